@@ -1,0 +1,262 @@
+"""
+TEST INFRASTRUCTURE ONLY -- freeze outputs of the real reference into tests/golden/.
+
+Run in the build container (where /root/reference exists):
+
+    python oracle/gen_golden.py
+
+For every case the reference itself (imported through oracle/ref_shim.py) is run
+on the seeded inputs of tests/cases.py, the NumPy restatement oracle/lime_oracle.py
+is run on the same inputs, the two are compared (the table is printed and stored
+in tests/golden/PINNING.json), and the REFERENCE output is written as a small
+.npz fixture.  The reference's own golden files examples/cor.dat + examples/dm.dat
+are converted to cavity_cor.npz verbatim (parsed, not recomputed).
+"""
+import io
+import os
+import sys
+import json
+import contextlib
+import warnings
+
+import numpy as np
+from scipy.sparse import csr_matrix
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+
+import ref_shim            # noqa: E402
+import lime_oracle as lo   # noqa: E402
+import cases               # noqa: E402
+
+GOLD = os.path.join(ROOT, 'tests', 'golden')
+report = {}
+
+
+def relerr(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    d = np.max(np.abs(a - b)) if a.size else 0.0
+    s = np.max(np.abs(b)) if b.size else 1.0
+    return float(d / s) if s > 0 else float(d)
+
+
+def quiet(f, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        return f(*a, **k)
+
+
+def note(name, **errs):
+    report[name] = errs
+    print('%-28s %s' % (name, '  '.join('%s=%.3g' % kv for kv in errs.items())))
+
+
+def main():
+    lime = ref_shim.load()
+    import lime.oqs as oqs
+    import lime.phys as phys
+    import lime.heom.heom as heom
+    import lime.signal.sos as sos
+    import lime.superoperator as sop
+    os.makedirs(GOLD, exist_ok=True)
+
+    # ---- 1. the reference's own golden: examples/cor.dat, dm.dat ----------------
+    ex = os.path.join(ref_shim.REFERENCE_ROOT, 'examples')
+    cor = np.genfromtxt(os.path.join(ex, 'cor.dat'), dtype=complex)
+    dm = np.genfromtxt(os.path.join(ex, 'dm.dat'), dtype=complex)
+    t_gold = cor[:, 0].real
+    cor_gold = cor[:, 1]
+    dm_gold = dm[:, 1:].reshape(-1, 10, 10)
+    H, rho0, ops, c_ops, tlist = cases.thermal_cavity()
+    # replay with the reference's own rk4 + liouvillian (CSR operands)
+    rho = ops[2].dot(rho0.dot(ops[0]))
+    dt = tlist[1] - tlist[0]
+    cr, dr = [], []
+    for k in range(len(tlist)):
+        rho = phys.rk4(rho, phys.liouvillian, dt, H, c_ops)
+        cr.append(ops[1].dot(rho).diagonal().sum())
+        dr.append(rho.toarray())
+    t_o, cor_o, dm_o = lo.correlation_3p_1t(H, rho0, ops, c_ops, tlist)
+    note('cavity_cor', ref_replay_vs_file=max(relerr(cr, cor_gold), relerr(dr, dm_gold)),
+         oracle_vs_file=max(relerr(cor_o, cor_gold), relerr(dm_o, dm_gold), relerr(t_o, t_gold)))
+    np.savez_compressed(os.path.join(GOLD, 'cavity_cor.npz'), t=t_gold, cor=cor_gold, dm=dm_gold)
+
+    # ---- 2. config 1: examples/redfield.py ---------------------------------------
+    H, a_ops, spectra, rho0, dt, Nt, e_ops, tlist = cases.redfield_example()
+    solver = oqs.Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = quiet(solver.redfield_tensor)
+    res = quiet(solver.evolve, rho0, evecs=evecs, dt=dt, Nt=Nt, e_ops=e_ops)
+    Ro, evo = lo.redfield_tensor(H, a_ops, spectra)
+    obs_o, rl_o = lo.redfield(Ro, rho0, evecs=evo, Nt=Nt, dt=dt, e_ops=e_ops)
+    t8 = tlist[:8]
+    U_sos = quiet(solver.propagator, t8, 'SOS').copy()
+    c4 = quiet(solver.correlation_4op_3t, rho0, [e_ops[0]] * 4, 'llll', t8)
+    ex_ref = solver.expect(rho0, e_ops)
+    U_eom = quiet(solver.propagator, t8, 'EOM').copy()
+    note('redfield_example', R=relerr(Ro.toarray(), R.toarray()), evecs=relerr(evo, evecs),
+         obs=relerr(obs_o, res.observables), rholist=relerr(rl_o, res.rholist),
+         U_sos=relerr(lo.redfield_propagator(Ro, t8, 'SOS'), U_sos),
+         U_eom=relerr(lo.redfield_propagator(Ro, t8, 'EOM'), U_eom),
+         expect=relerr(lo.redfield_expect(U_sos, evecs, rho0, e_ops), ex_ref),
+         corr4=relerr(lo.redfield_correlation_4op_3t(-1j * U_sos, 2, rho0, [e_ops[0]] * 4, 'llll'), c4))
+    np.savez_compressed(os.path.join(GOLD, 'redfield_example.npz'), R=R.toarray(), evecs=evecs,
+                        observables=res.observables, rholist=np.array(res.rholist),
+                        U_sos=U_sos, U_eom=U_eom, corr4=c4, expect=ex_ref)
+
+    # ---- 2b. multi-level Redfield with two baths -----------------------------------
+    H, a_ops, spectra, rho0 = cases.redfield_multilevel()
+    solver = oqs.Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = quiet(solver.redfield_tensor)
+    e_ops = [a_ops[0], cases.rand_herm(5, 99)]
+    res = quiet(solver.evolve, rho0, dt=0.02, Nt=60, e_ops=e_ops)
+    Ro, evo = lo.redfield_tensor(H, a_ops, spectra)
+    obs_o, rl_o = lo.redfield(Ro, rho0, evecs=evo, Nt=60, dt=0.02, e_ops=e_ops)
+    note('redfield_multilevel', R=relerr(Ro.toarray(), R.toarray()),
+         obs=relerr(obs_o, res.observables), rholist=relerr(rl_o, res.rholist))
+    np.savez_compressed(os.path.join(GOLD, 'redfield_multilevel.npz'), R=R.toarray(), evecs=evecs,
+                        observables=res.observables, rholist=np.array(res.rholist), e1=e_ops[1])
+
+    # ---- 3. Lindblad dense -------------------------------------------------------
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense()
+    res = oqs._lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=80, dt=0.01)
+    obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=80, dt=0.01)
+    rhs_ref = oqs.liouvillian(rho0, H, c_ops)
+    Lsup = sop.liouvillian(H, c_ops)
+    note('lindblad_dense', obs=relerr(obs_o, res.observables), rholist=relerr(rl_o, res.rholist),
+         rhs=relerr(lo.liouvillian(rho0, H, c_ops), rhs_ref),
+         superop=relerr(lo.liouvillian_super(H, c_ops).toarray(), Lsup.toarray()),
+         superop_vs_rhs=relerr(Lsup.dot(rho0.flatten()), rhs_ref.flatten()))
+    np.savez_compressed(os.path.join(GOLD, 'lindblad_dense.npz'), observables=res.observables,
+                        rholist=np.array(res.rholist), rhs=rhs_ref, superop=Lsup.toarray())
+
+    # ---- 3b. Lindblad Jaynes-Cummings, CSR operands (config-2 shape, small cutoff) --
+    H, c_ops, e_ops, rho0 = cases.jc_point(ncav=8)
+    res = oqs._lindblad(csr_matrix(H), csr_matrix(rho0), [csr_matrix(c) for c in c_ops],
+                        e_ops=[csr_matrix(e) for e in e_ops], Nt=100, dt=0.01)
+    obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=100, dt=0.01)
+    Ho, co, eo = lo.jaynes_cummings(1.0, 1.05, 0.1, 8, 0.05)
+    rl_ref = np.array([r.toarray() for r in res.rholist])
+    note('lindblad_jc', obs=relerr(obs_o, res.observables), rholist=relerr(rl_o, rl_ref),
+         builder=max(relerr(Ho.toarray(), H), relerr(co[0].toarray(), c_ops[0])))
+    np.savez_compressed(os.path.join(GOLD, 'lindblad_jc.npz'), observables=res.observables,
+                        rho_final=rl_ref[-1], rho_mid=rl_ref[49])
+
+    # ---- 3c. driven Lindblad ---------------------------------------------------------
+    H0, c_ops, e_ops, rho0 = cases.lindblad_dense(n=4, M=1, E=1, seed=77)
+    H1 = cases.rand_herm(4, 78)
+
+    def f1(t):
+        return 0.3 * np.exp(-(t - 0.4) ** 2 / 0.02) * np.exp(-1j * 2.0 * t)
+    Hlist = [H0.copy(), [H1, f1]]
+    res = oqs._lindblad_driven(Hlist, rho0, c_ops=c_ops, e_ops=e_ops, Nt=60, dt=0.01, t0=0.1)
+    obs_o, rl_o = lo.lindblad_driven([H0.copy(), [H1, f1]], rho0, c_ops, e_ops, Nt=60, dt=0.01,
+                                     t0=0.1, strict_parity=True)
+    obs_f, rl_f = lo.lindblad_driven([H0.copy(), [H1, f1]], rho0, c_ops, e_ops, Nt=60, dt=0.01, t0=0.1)
+    note('lindblad_driven', obs_strict=relerr(obs_o, res.observables),
+         rholist_strict=relerr(rl_o, res.rholist), fixed_vs_strict=relerr(obs_f, obs_o))
+    np.savez_compressed(os.path.join(GOLD, 'lindblad_driven.npz'), observables_strict=res.observables,
+                        rho_final_strict=res.rholist[-1], H1=H1)
+
+    # ---- 3d. Lindblad correlation functions -------------------------------------------
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=4, M=2, E=1, seed=31)
+    ops3 = [cases.rand_cplx(4, 32, 0.5), cases.rand_herm(4, 33), cases.rand_cplx(4, 34, 0.5)]
+    solver = oqs.Lindblad_solver(H, c_ops=c_ops)
+    c1 = solver.correlation_3op_1t(rho0, ops3, dt=0.02, Nt=30)
+    c2 = solver.correlation_3op_2t(rho0, ops3, dt=0.02, Nt=6, Ntau=7)
+    note('lindblad_corr', c3op1t=relerr(lo.lindblad_correlation_3op_1t(H, c_ops, rho0, ops3, 0.02, 30), c1),
+         c3op2t=relerr(lo.lindblad_correlation_3op_2t(H, c_ops, rho0, ops3, 0.02, 6, 7), c2))
+    np.savez_compressed(os.path.join(GOLD, 'lindblad_corr.npz'), c3op1t=c1, c3op2t=c2,
+                        A=ops3[0], B=ops3[1], C=ops3[2])
+
+    # ---- 4. HEOM ---------------------------------------------------------------------------
+    H, sz, rho0 = cases.spin_boson_heom()[:3]
+    fn = '/tmp/_heom_dl_golden.dat'
+    out = quiet(oqs._heom_dl, H, rho0, sz, None, 300.0, 0.002, 0.0005, 12, 0.05, 200, fn)
+    traj = np.genfromtxt(fn, dtype=complex)[:, 1:].reshape(-1, 2, 2)
+    ado_o, traj_o = lo.heom_dl(H, rho0, sz, 300.0, 0.002, 0.0005, 12, 0.05, 200)
+    note('heom_dl', final=relerr(ado_o[:, :, 0], out), traj=relerr(traj_o, traj))
+    np.savez_compressed(os.path.join(GOLD, 'heom_dl.npz'), rho_final=out, traj=traj)
+
+    tables = {}
+    worst = 0
+    for dims, exc in [([3, 3], 2), ([5, 5], 4), ([13, 13], 12), ([4, 3, 2], 3), ([3] * 4, 0),
+                      ([5] * 6, 4), ([3] * 8, 2), ([5] * 14, 4)]:
+        n, s2i, i2s = heom.enr_state_dictionaries(dims, exc)
+        arr = np.array([np.asarray(i2s[i]) for i in range(n)], dtype=np.int64).reshape(n, len(dims))
+        assert all(s2i[tuple(arr[i])] == i for i in range(n))
+        no, s2io, i2so = lo.enr_state_dictionaries(dims, exc)
+        arro = np.array([np.asarray(i2so[i]) for i in range(no)], dtype=np.int64).reshape(no, len(dims))
+        worst = max(worst, 0 if (n == no and np.array_equal(arr, arro)) else 1)
+        if exc:
+            worst = max(worst, 0 if np.array_equal(lo.enr_states_fast(dims, exc), arr) else 1)
+        tables['d' + '_'.join(map(str, dims)) + '_x' + str(exc)] = arr.astype(np.int16)
+    # excitations=None: state_number_enumerate yields ndarrays (lime/heom/heom.py:66),
+    # which enr_state_dictionaries cannot hash (:104) -> TypeError in the reference
+    try:
+        heom.enr_state_dictionaries([2, 2], None)
+        none_raises = 0
+    except TypeError:
+        none_raises = 1
+    note('heom_tables', none_raises_TypeError=none_raises, mismatches=worst, fmo_nhe=int(tables['d' + '_'.join(['5'] * 14) + '_x4'].shape[0]))
+    np.savez_compressed(os.path.join(GOLD, 'heom_tables.npz'), **tables)
+
+    mats = {}
+    worst = 0.0
+    for i, (K, lam, gam, T) in enumerate([(2, 0.2, 1.0, 1.0), (4, 35 / 219474.6305, 1 / (50 / 2.41888432651e-2), 300 / 315775.13),
+                                          (1, 0.1, 0.5, 2.0), (3, 1.0, 2.0, 0.25)]):
+        c, nu = heom._calc_matsubara_params(K, lam, gam, T)
+        co, nuo = lo.calc_matsubara_params(K, lam, gam, T)
+        worst = max(worst, relerr(co, c), relerr(nuo, nu))
+        mats['c%d' % i] = np.array(c, dtype=complex)
+        mats['nu%d' % i] = np.array(nu, dtype=float)
+        mats['par%d' % i] = np.array([K, lam, gam, T])
+    note('heom_matsubara', err=worst)
+    np.savez_compressed(os.path.join(GOLD, 'heom_matsubara.npz'), **mats)
+
+    # ---- 5. sum-over-states response functions ------------------------------------------------
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    au2ev = 27.211386
+    w1 = np.linspace(1.4, 2.1, 12) / au2ev
+    w3 = np.linspace(1.3, 2.2, 12) / au2ev
+    t2 = 30.0 / 2.41888432651e-2
+    g = {}
+    g['GSB'] = sos.GSB(E, dip, w1, w3, t2, g_idx, e_idx, gamma)
+    g['SE'] = sos.SE(E, dip, w1, w3, t2, g_idx, e_idx, gamma)
+    g['ESA'] = sos.ESA(E, dip, w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    g['PE'] = sos._photon_echo(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    g['SE_t3'] = sos._SE(E, dip, -w1, w3, t2, g_idx, e_idx, gamma, dephasing=0.01 / au2ev)
+    g['ESA_t3'] = sos._ESA(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma, dephasing=0.01 / au2ev)
+    w2 = np.linspace(3.0, 4.0, 10) / au2ev
+    w1b = np.linspace(1.4, 2.1, 10) / au2ev
+    g['R1_t3'] = sos.DQC_R1(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    g['R2_t3'] = sos.DQC_R2(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    g['R1_t1'] = sos.DQC_R1(E, dip, omega2=w2, omega3=w1b, tau1=50.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    g['R2_t1'] = sos.DQC_R2(E, dip, omega2=w2, omega3=w1b, tau1=50.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    g['TPA2D'] = sos.TPA2D(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma)
+    g['TPA2D_to'] = sos.TPA2D_time_order(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma)
+    o = {}
+    o['GSB'] = lo.GSB(E, dip, w1, w3, t2, g_idx, e_idx, gamma)
+    o['SE'] = lo.SE(E, dip, w1, w3, t2, g_idx, e_idx, gamma)
+    o['ESA'] = lo.ESA(E, dip, w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    o['PE'] = lo.photon_echo_core(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    o['SE_t3'] = lo.SE_t3(E, dip, -w1, w3, t2, g_idx, e_idx, gamma, dephasing=0.01 / au2ev)
+    o['ESA_t3'] = lo.ESA_t3(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma, dephasing=0.01 / au2ev)
+    o['R1_t3'] = lo.DQC_R1(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    o['R2_t3'] = lo.DQC_R2(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    o['R1_t1'] = lo.DQC_R1(E, dip, omega2=w2, omega3=w1b, tau1=50.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    o['R2_t1'] = lo.DQC_R2(E, dip, omega2=w2, omega3=w1b, tau1=50.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    o['TPA2D'] = lo.TPA2D(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma)
+    o['TPA2D_to'] = lo.TPA2D_time_order(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma)
+    note('sos', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'sos.npz'), w1=w1, w3=w3, w2=w2, w1b=w1b, t2=t2, **g)
+
+    with open(os.path.join(GOLD, 'PINNING.json'), 'w') as f:
+        json.dump({'generated_by': 'oracle/gen_golden.py', 'reference': 'binggu56/lime @ /root/reference',
+                   'numpy': np.__version__, 'oracle_vs_reference_max_rel_err': report}, f, indent=1)
+    print('wrote', GOLD)
+
+
+if __name__ == '__main__':
+    main()
