@@ -1,0 +1,49 @@
+"""
+Device plumbing: PyTorch owns device memory and streams, nothing else.  complex128 numpy
+arrays go to the device as torch.complex128 tensors (same interleaved bytes as double2).
+"""
+import ctypes as C
+import numpy as np
+import torch
+
+from ._lib import LimeB200Error
+
+
+def device(index=None):
+    if not torch.cuda.is_available():
+        raise LimeB200Error('no CUDA device visible: lime_b200 has no CPU fallback')
+    if index is None:
+        index = torch.cuda.current_device()
+    return torch.device('cuda', index)
+
+
+def to_dev(a, dtype=np.complex128, dev=None, pinned=False):
+    """numpy -> contiguous device tensor of the given numpy dtype"""
+    a = np.ascontiguousarray(a, dtype=dtype)
+    t = torch.from_numpy(a)
+    if pinned:
+        t = t.pin_memory()
+    return t.to(device() if dev is None else dev, non_blocking=pinned)
+
+
+def empty(shape, dtype=torch.complex128, dev=None):
+    return torch.empty(shape, dtype=dtype, device=device() if dev is None else dev)
+
+
+def ptr(t):
+    """raw device pointer of a tensor (or None)"""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def as_c128(a):
+    """dense C-contiguous complex128 numpy array from ndarray / scipy.sparse / np.matrix"""
+    if hasattr(a, 'toarray'):
+        a = a.toarray()
+    return np.ascontiguousarray(np.asarray(a), dtype=np.complex128)

@@ -1,0 +1,691 @@
+// Host side of the quantum-master-equation plan: operator analysis, kernel selection,
+// launch loops.  C ABI declared in include/lime_b200.h.
+#include "../../include/lime_b200.h"
+#include "common.cuh"
+#include "qme_dense.cuh"
+#include "qme_sparse.cuh"
+#include "qme_cluster.cuh"
+#include <algorithm>
+#include <memory>
+
+namespace {
+
+struct HostOp {                 // one operator as handed over by the caller
+    bool given = false;
+    bool is_csr = false;
+    int nb = 1;
+    std::vector<hcplx> dense;                   // [nb][N*N]
+    std::vector<int> indptr, indices;           // csr pattern
+    std::vector<hcplx> data;                    // [nb][nnz]
+};
+
+struct EllHost {
+    int w = 0;
+    std::vector<int> col;       // [N][w]
+    std::vector<hcplx> val;     // [nb][N][w]
+};
+
+}  // namespace
+
+struct limeb200_qme_s {
+    int N = 0, device = 0;
+    int path_req = 0, path = 0;
+    bool finalized = false;
+    int nb = 1;
+    HostOp G;
+    std::vector<HostOp> X, Z;
+    std::vector<std::vector<hcplx>> D;          // drives, dense
+    std::vector<hcplx> eops;                    // [E][N*N]
+    int E = 0;
+    long long launches = 0;
+
+    // ---- device copies, dense path
+    DevBuf dG, dGh, dX, dZh, dD, dDh, deT;
+    // ---- device copies, sparse path
+    DevBuf dGcol, dGval;
+    DevBuf dXcol[QME_MAXS], dXval[QME_MAXS], dZcol[QME_MAXS], dZval[QME_MAXS];
+    int wG = 0, wX[QME_MAXS] = {0}, wZ[QME_MAXS] = {0};
+    int bandwidth = 0;                          // max |row - col| over all sparse operators (permuted basis)
+    DevBuf dperm;                               // [N] new -> old (cluster path)
+    bool permuted = false;
+    DevBuf deptr, deidx, deval;
+    // ---- scratch
+    DevBuf s_y, s_acc, s_tmp, s_gk;
+    int scratch_B = 0;
+    int sm_count = 148;
+    long long smem_optin = 0;
+};
+
+namespace {
+
+void densify(const HostOp& op, int N, std::vector<hcplx>& out) {
+    const size_t NN = (size_t)N * N;
+    if (!op.is_csr) { out = op.dense; return; }
+    out.assign((size_t)op.nb * NN, hcplx(0, 0));
+    const size_t nnz = op.indices.size();
+    for (int b = 0; b < op.nb; ++b)
+        for (int i = 0; i < N; ++i)
+            for (int p = op.indptr[i]; p < op.indptr[i + 1]; ++p)
+                out[b * NN + (size_t)i * N + op.indices[p]] += op.data[b * nnz + p];
+}
+
+// union sparsity pattern over the batch -> ELL (padded with (col=row, val=0)) of the
+// basis-permuted operator A'[i'][j'] = A[perm[i']][perm[j']]  (inv[old] = new)
+void to_ell(const HostOp& op, int N, EllHost& e, int& bw, const std::vector<int>& perm,
+            const std::vector<int>& inv) {
+    const size_t NN = (size_t)N * N;
+    std::vector<std::vector<std::pair<int, int>>> cols(N);   // per new row: (new col, source slot)
+    for (int in = 0; in < N; ++in) {
+        const int io = perm[in];
+        if (op.is_csr) {
+            for (int p = op.indptr[io]; p < op.indptr[io + 1]; ++p) cols[in].push_back({inv[op.indices[p]], p});
+        } else {
+            for (int jo = 0; jo < N; ++jo) {
+                bool nz = false;
+                for (int b = 0; b < op.nb && !nz; ++b) nz = op.dense[b * NN + (size_t)io * N + jo] != hcplx(0, 0);
+                if (nz) cols[in].push_back({inv[jo], jo});
+            }
+        }
+        std::sort(cols[in].begin(), cols[in].end());
+    }
+    // distinct columns per row (csr input may hold duplicates, which scipy sums)
+    std::vector<std::vector<int>> ucol(N);
+    int w = 1;
+    for (int i = 0; i < N; ++i) {
+        for (auto& c : cols[i])
+            if (ucol[i].empty() || ucol[i].back() != c.first) ucol[i].push_back(c.first);
+        w = std::max(w, (int)ucol[i].size());
+        for (int c : ucol[i]) bw = std::max(bw, std::abs(c - i));
+    }
+    e.w = w;
+    e.col.assign((size_t)N * w, 0);
+    e.val.assign((size_t)op.nb * N * w, hcplx(0, 0));
+    const size_t nnz = op.indices.size();
+    for (int i = 0; i < N; ++i) {
+        for (int q = 0; q < w; ++q) e.col[(size_t)i * w + q] = (q < (int)ucol[i].size()) ? ucol[i][q] : i;
+        const int io = perm[i];
+        for (auto& c : cols[i]) {
+            int q = int(std::lower_bound(ucol[i].begin(), ucol[i].end(), c.first) - ucol[i].begin());
+            for (int b = 0; b < op.nb; ++b) {
+                hcplx v = op.is_csr ? op.data[b * nnz + c.second] : op.dense[b * NN + (size_t)io * N + c.second];
+                e.val[((size_t)b * N + i) * w + q] += v;
+            }
+        }
+    }
+}
+
+// reverse Cuthill-McKee ordering of the symmetrised union pattern; returns perm[new] = old
+std::vector<int> rcm_order(int N, const std::vector<std::vector<int>>& adj) {
+    std::vector<int> order;
+    order.reserve(N);
+    std::vector<char> seen(N, 0);
+    auto deg = [&](int v) { return (int)adj[v].size(); };
+    while ((int)order.size() < N) {
+        int start = -1;
+        for (int v = 0; v < N; ++v)
+            if (!seen[v] && (start < 0 || deg(v) < deg(start))) start = v;
+        // pseudo-peripheral start: repeat BFS from the farthest lowest-degree node
+        for (int it = 0; it < 4; ++it) {
+            std::vector<int> dist(N, -1), q{start};
+            dist[start] = 0;
+            for (size_t h = 0; h < q.size(); ++h)
+                for (int u : adj[q[h]])
+                    if (!seen[u] && dist[u] < 0) { dist[u] = dist[q[h]] + 1; q.push_back(u); }
+            int far = q.back(), best = far;
+            for (int v : q)
+                if (dist[v] == dist[far] && deg(v) < deg(best)) best = v;
+            if (best == start) break;
+            start = best;
+        }
+        std::vector<int> q{start};
+        seen[start] = 1;
+        for (size_t h = 0; h < q.size(); ++h) {
+            std::vector<int> nb;
+            for (int u : adj[q[h]])
+                if (!seen[u]) { seen[u] = 1; nb.push_back(u); }
+            std::sort(nb.begin(), nb.end(), [&](int x, int y) { return deg(x) != deg(y) ? deg(x) < deg(y) : x < y; });
+            q.insert(q.end(), nb.begin(), nb.end());
+        }
+        order.insert(order.end(), q.begin(), q.end());
+    }
+    std::reverse(order.begin(), order.end());
+    return order;
+}
+
+void add_pattern(const HostOp& op, int N, std::vector<std::vector<int>>& adj) {
+    const size_t NN = (size_t)N * N;
+    auto link = [&](int i, int j) { if (i != j) { adj[i].push_back(j); adj[j].push_back(i); } };
+    if (op.is_csr) {
+        for (int i = 0; i < N; ++i)
+            for (int p = op.indptr[i]; p < op.indptr[i + 1]; ++p) link(i, op.indices[p]);
+    } else {
+        for (int i = 0; i < N; ++i)
+            for (int j = 0; j < N; ++j) {
+                bool nz = false;
+                for (int b = 0; b < op.nb && !nz; ++b) nz = op.dense[b * NN + (size_t)i * N + j] != hcplx(0, 0);
+                if (nz) link(i, j);
+            }
+    }
+}
+
+int pattern_bandwidth(const std::vector<std::vector<int>>& adj, const std::vector<int>& inv) {
+    int bw = 0;
+    for (size_t i = 0; i < adj.size(); ++i)
+        for (int j : adj[i]) bw = std::max(bw, std::abs(inv[i] - inv[j]));
+    return bw;
+}
+
+int max_row_nnz(const HostOp& op, int N) {
+    EllHost e; int bw = 0;
+    std::vector<int> id(N);
+    for (int i = 0; i < N; ++i) id[i] = i;
+    to_ell(op, N, e, bw, id, id);
+    return e.w;
+}
+
+void replicate(std::vector<hcplx>& v, size_t per, int nb) {   // [1][per] -> [nb][per]
+    std::vector<hcplx> out((size_t)nb * per);
+    for (int b = 0; b < nb; ++b) std::copy(v.begin(), v.begin() + per, out.begin() + (size_t)b * per);
+    v.swap(out);
+}
+
+void adjoint(const hcplx* in, hcplx* out, int N) {
+    for (int i = 0; i < N; ++i)
+        for (int j = 0; j < N; ++j) out[(size_t)j * N + i] = std::conj(in[(size_t)i * N + j]);
+}
+
+int set_op_dense(limeb200_qme_t p, HostOp& op, const double* h, int nb) {
+    LB_REQUIRE(p && h, "null argument");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(nb >= 1, "nb must be >= 1");
+    const size_t NN = (size_t)p->N * p->N;
+    op.given = true; op.is_csr = false; op.nb = nb;
+    const hcplx* c = reinterpret_cast<const hcplx*>(h);
+    op.dense.assign(c, c + (size_t)nb * NN);
+    return LB_OK;
+}
+
+int set_op_csr(limeb200_qme_t p, HostOp& op, const int* indptr, const int* indices, const double* data,
+               int nnz, int nb) {
+    LB_REQUIRE(p && indptr && (nnz == 0 || (indices && data)), "null argument");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(nb >= 1 && nnz >= 0, "bad nb/nnz");
+    LB_REQUIRE(indptr[0] == 0 && indptr[p->N] == nnz, "csr indptr inconsistent with nnz");
+    for (int i = 0; i < nnz; ++i) LB_REQUIRE(indices[i] >= 0 && indices[i] < p->N, "csr column out of range");
+    op.given = true; op.is_csr = true; op.nb = nb;
+    op.indptr.assign(indptr, indptr + p->N + 1);
+    op.indices.assign(indices, indices + nnz);
+    const hcplx* c = reinterpret_cast<const hcplx*>(data);
+    op.data.assign(c, c + (size_t)nb * nnz);
+    return LB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int limeb200_qme_create(limeb200_qme_t* plan, int N, int device) {
+    LB_REQUIRE(plan, "null plan pointer");
+    LB_REQUIRE(N >= 1 && N <= 8192, "N out of range (1..8192)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        limeb200::set_error("no CUDA device available (%s): liblime_b200 has no CPU fallback",
+                            e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return LB_ERR_CUDA;
+    }
+    LB_REQUIRE(device >= 0 && device < ndev, "device %d out of range", device);
+    LB_CUDA(cudaSetDevice(device));
+    auto* p = new limeb200_qme_s();
+    p->N = N; p->device = device;
+    cudaDeviceProp prop;
+    LB_CUDA(cudaGetDeviceProperties(&prop, device));
+    p->sm_count = prop.multiProcessorCount;
+    p->smem_optin = (long long)prop.sharedMemPerBlockOptin;
+    *plan = p;
+    return LB_OK;
+}
+
+int limeb200_qme_destroy(limeb200_qme_t plan) {
+    if (plan) { cudaSetDevice(plan->device); delete plan; }
+    return LB_OK;
+}
+
+int limeb200_qme_set_generator_dense(limeb200_qme_t p, const double* h_G, int nb) {
+    LB_REQUIRE(p, "null plan");
+    return set_op_dense(p, p->G, h_G, nb);
+}
+int limeb200_qme_set_generator_csr(limeb200_qme_t p, const int* indptr, const int* indices,
+                                   const double* h_data, int nnz, int nb) {
+    LB_REQUIRE(p, "null plan");
+    return set_op_csr(p, p->G, indptr, indices, h_data, nnz, nb);
+}
+int limeb200_qme_add_sandwich_dense(limeb200_qme_t p, const double* h_X, const double* h_Z, int nb) {
+    LB_REQUIRE(p, "null plan");
+    p->X.emplace_back(); p->Z.emplace_back();
+    int r = set_op_dense(p, p->X.back(), h_X, nb);
+    if (r == LB_OK) r = set_op_dense(p, p->Z.back(), h_Z, nb);
+    if (r != LB_OK) { p->X.pop_back(); p->Z.pop_back(); }
+    return r;
+}
+int limeb200_qme_add_sandwich_csr(limeb200_qme_t p,
+                                  const int* x_indptr, const int* x_indices, const double* h_xdata, int x_nnz,
+                                  const int* z_indptr, const int* z_indices, const double* h_zdata, int z_nnz,
+                                  int nb) {
+    LB_REQUIRE(p, "null plan");
+    p->X.emplace_back(); p->Z.emplace_back();
+    int r = set_op_csr(p, p->X.back(), x_indptr, x_indices, h_xdata, x_nnz, nb);
+    if (r == LB_OK) r = set_op_csr(p, p->Z.back(), z_indptr, z_indices, h_zdata, z_nnz, nb);
+    if (r != LB_OK) { p->X.pop_back(); p->Z.pop_back(); }
+    return r;
+}
+int limeb200_qme_add_drive_dense(limeb200_qme_t p, const double* h_D) {
+    LB_REQUIRE(p && h_D, "null argument");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    const hcplx* c = reinterpret_cast<const hcplx*>(h_D);
+    p->D.emplace_back(c, c + (size_t)p->N * p->N);
+    return LB_OK;
+}
+int limeb200_qme_set_observables(limeb200_qme_t p, const double* h_e, int E) {
+    LB_REQUIRE(p && (E == 0 || h_e), "null argument");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(E >= 0 && E <= 64, "E out of range (0..64)");
+    const hcplx* c = reinterpret_cast<const hcplx*>(h_e);
+    p->eops.assign(c, c + (size_t)E * p->N * p->N);
+    p->E = E;
+    return LB_OK;
+}
+int limeb200_qme_set_path(limeb200_qme_t p, int path) {
+    LB_REQUIRE(p, "null plan");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(path >= 0 && path <= 4, "path must be 0..4");
+    p->path_req = path;
+    return LB_OK;
+}
+int limeb200_qme_get_path(limeb200_qme_t p) { return p ? p->path : LB_ERR_ARG; }
+long long limeb200_qme_last_launches(limeb200_qme_t p) { return p ? p->launches : -1; }
+
+int limeb200_qme_finalize(limeb200_qme_t p) {
+    LB_REQUIRE(p, "null plan");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(p->G.given, "generator not set");
+    LB_CUDA(cudaSetDevice(p->device));
+    const int N = p->N, S = (int)p->X.size(), nd = (int)p->D.size();
+    const size_t NN = (size_t)N * N;
+    // operator batch
+    int nb = p->G.nb;
+    for (int s = 0; s < S; ++s) nb = std::max(nb, std::max(p->X[s].nb, p->Z[s].nb));
+    auto okb = [&](const HostOp& o) { return o.nb == 1 || o.nb == nb; };
+    LB_REQUIRE(okb(p->G), "generator batch %d incompatible with %d", p->G.nb, nb);
+    for (int s = 0; s < S; ++s)
+        LB_REQUIRE(okb(p->X[s]) && okb(p->Z[s]), "sandwich %d batch incompatible with %d", s, nb);
+    p->nb = nb;
+
+    // ---- choose path
+    int wg = max_row_nnz(p->G, N), wprod = 1;
+    for (int s = 0; s < S; ++s) wprod = std::max(wprod, max_row_nnz(p->X[s], N) * max_row_nnz(p->Z[s], N));
+    const bool sparse_ok = (nd == 0) && S <= QME_MAXS && wg <= 16 && wprod <= 16;
+    const bool dense_mem_ok = (double)nb * NN * 16.0 * (2 + 2 * S) < 8e9;
+    int path = p->path_req;
+    if (path == 0) {
+        if (N >= 24 && sparse_ok && wg * 4 <= N) path = 4;          // structured mid/large N
+        else if (N <= 64 && dense_mem_ok) path = 1;
+        else if (dense_mem_ok) path = 2;
+        else path = 3;
+    }
+    // sparse paths work in a bandwidth-reducing basis order (cluster path only)
+    std::vector<int> perm(N), inv(N);
+    for (int i = 0; i < N; ++i) perm[i] = inv[i] = i;
+    if (path == 4) {
+        bool fits = sparse_ok;
+        if (fits) {
+            std::vector<std::vector<int>> adj(N);
+            add_pattern(p->G, N, adj);
+            for (int s = 0; s < S; ++s) { add_pattern(p->X[s], N, adj); add_pattern(p->Z[s], N, adj); }
+            for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+            int bw_id = pattern_bandwidth(adj, inv);
+            std::vector<int> cand = rcm_order(N, adj), cinv(N);
+            for (int i = 0; i < N; ++i) cinv[cand[i]] = i;
+            int bw_rcm = pattern_bandwidth(adj, cinv);
+            if (bw_rcm < bw_id) { perm = cand; inv = cinv; p->permuted = true; }
+            int wX[QME_MAXS], wZ[QME_MAXS];
+            for (int s = 0; s < S; ++s) { wX[s] = max_row_nnz(p->X[s], N); wZ[s] = max_row_nnz(p->Z[s], N); }
+            int C, R; size_t sm;
+            fits = qme_cluster_geometry(N, S, wg, wX, wZ, p->E, std::min(bw_id, bw_rcm), p->smem_optin, &C, &R, &sm);
+        }
+        if (!fits) {
+            LB_REQUIRE(p->path_req != 4, "sparse cluster path does not fit this problem (N=%d)", N);
+            path = 3;
+            for (int i = 0; i < N; ++i) perm[i] = inv[i] = i;
+            p->permuted = false;
+        }
+    }
+    if (path == 1) LB_REQUIRE(N <= 64, "dense on-chip path needs N <= 64 (N=%d)", N);
+    if (path == 3 || path == 4) {
+        LB_REQUIRE(nd == 0, "sparse paths do not support drive operators");
+        LB_REQUIRE(S <= QME_MAXS, "sparse paths support at most %d sandwich terms", QME_MAXS);
+    }
+    if (path == 1 || path == 2) LB_REQUIRE(dense_mem_ok, "dense operator batch too large (nb=%d, N=%d)", nb, N);
+    p->path = path;
+
+    if (path == 1 || path == 2) {
+        std::vector<hcplx> g, gh, x, zh;
+        densify(p->G, N, g);
+        if (p->G.nb < nb) replicate(g, NN, nb);
+        gh.resize(g.size());
+        for (int b = 0; b < nb; ++b) adjoint(&g[b * NN], &gh[b * NN], N);
+        x.resize((size_t)nb * S * NN);
+        zh.resize((size_t)nb * S * NN);
+        for (int s = 0; s < S; ++s) {
+            std::vector<hcplx> xs, zs;
+            densify(p->X[s], N, xs);
+            densify(p->Z[s], N, zs);
+            if (p->X[s].nb < nb) replicate(xs, NN, nb);
+            if (p->Z[s].nb < nb) replicate(zs, NN, nb);
+            for (int b = 0; b < nb; ++b) {
+                std::copy(xs.begin() + b * NN, xs.begin() + (b + 1) * NN, x.begin() + ((size_t)b * S + s) * NN);
+                adjoint(&zs[b * NN], &zh[((size_t)b * S + s) * NN], N);
+            }
+        }
+        LB_CUDA(p->dG.upload(g.data(), g.size() * 16));
+        LB_CUDA(p->dGh.upload(gh.data(), gh.size() * 16));
+        LB_CUDA(p->dX.upload(x.data(), x.size() * 16));
+        LB_CUDA(p->dZh.upload(zh.data(), zh.size() * 16));
+        if (nd > 0) {
+            LB_REQUIRE(nb == 1, "drive operators need a shared (nb = 1) generator");
+            std::vector<hcplx> d((size_t)nd * NN), dh((size_t)nd * NN);
+            for (int i = 0; i < nd; ++i) {
+                std::copy(p->D[i].begin(), p->D[i].end(), d.begin() + i * NN);
+                adjoint(p->D[i].data(), &dh[i * NN], N);
+            }
+            LB_CUDA(p->dD.upload(d.data(), d.size() * 16));
+            LB_CUDA(p->dDh.upload(dh.data(), dh.size() * 16));
+        }
+        std::vector<hcplx> et((size_t)p->E * NN);
+        for (int e = 0; e < p->E; ++e)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) et[e * NN + (size_t)i * N + j] = p->eops[e * NN + (size_t)j * N + i];
+        LB_CUDA(p->deT.upload(et.data(), et.size() * 16));
+    } else {
+        int bw = 0;
+        auto up = [&](const HostOp& op, DevBuf& dcol, DevBuf& dval, int& w) -> cudaError_t {
+            EllHost e;
+            to_ell(op, N, e, bw, perm, inv);
+            if (op.nb < nb) replicate(e.val, (size_t)N * e.w, nb);
+            w = e.w;
+            cudaError_t r = dcol.upload(e.col.data(), e.col.size() * sizeof(int));
+            if (r != cudaSuccess) return r;
+            return dval.upload(e.val.data(), e.val.size() * 16);
+        };
+        LB_CUDA(up(p->G, p->dGcol, p->dGval, p->wG));
+        for (int s = 0; s < S; ++s) {
+            LB_CUDA(up(p->X[s], p->dXcol[s], p->dXval[s], p->wX[s]));
+            LB_CUDA(up(p->Z[s], p->dZcol[s], p->dZval[s], p->wZ[s]));
+        }
+        p->bandwidth = bw;
+        if (p->permuted) LB_CUDA(p->dperm.upload(perm.data(), N * sizeof(int)));
+        // observables as COO over rho's (permuted) linear index:
+        // Tr(e rho) = sum_{ij} e[j][i] rho[i][j] = sum_{i'j'} e[perm j'][perm i'] rho'[i'][j']
+        std::vector<int> eptr(p->E + 1, 0), eidx;
+        std::vector<hcplx> eval;
+        for (int e = 0; e < p->E; ++e) {
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < N; ++j) {
+                    hcplx v = p->eops[e * NN + (size_t)perm[j] * N + perm[i]];
+                    if (v != hcplx(0, 0)) { eidx.push_back(i * N + j); eval.push_back(v); }
+                }
+            eptr[e + 1] = (int)eidx.size();
+        }
+        if (eidx.empty()) { eidx.push_back(0); eval.push_back(hcplx(0, 0)); }
+        LB_CUDA(p->deptr.upload(eptr.data(), eptr.size() * sizeof(int)));
+        LB_CUDA(p->deidx.upload(eidx.data(), eidx.size() * sizeof(int)));
+        LB_CUDA(p->deval.upload(eval.data(), eval.size() * 16));
+    }
+    p->finalized = true;
+    return LB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+__global__ void qme_build_gk(const cplx* G, const cplx* Gh, const cplx* D, const cplx* Dh,
+                             const cplx* coef, int nd, int NN, cplx* Gk, cplx* Gkh) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NN) return;
+    cplx v = G[i], vh = Gh[i];
+    for (int d = 0; d < nd; ++d) {
+        cplx c = coef[d];
+        cfma(v, c, D[(size_t)d * NN + i]);
+        cfma(vh, cconj(c), Dh[(size_t)d * NN + i]);
+    }
+    Gk[i] = v; Gkh[i] = vh;
+}
+
+void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
+    a.N = p->N; a.S = (int)p->X.size(); a.E = p->E; a.B = B; a.nb = p->nb;
+    a.G.w = p->wG; a.G.col = p->dGcol.as<int>(); a.G.val = p->dGval.as<cplx>();
+    for (int s = 0; s < a.S; ++s) {
+        a.X[s].w = p->wX[s]; a.X[s].col = p->dXcol[s].as<int>(); a.X[s].val = p->dXval[s].as<cplx>();
+        a.Z[s].w = p->wZ[s]; a.Z[s].col = p->dZcol[s].as<int>(); a.Z[s].val = p->dZval[s].as<cplx>();
+    }
+    a.eptr = p->deptr.as<int>(); a.eidx = p->deidx.as<int>(); a.eval = p->deval.as<cplx>();
+}
+
+int run_dense_onchip(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, const cplx* coef,
+                     cplx* obs, cplx* traj, int traj_every, cudaStream_t st, bool* handled) {
+    const int N = p->N, NN = N * N, S = (int)p->X.size(), nd = (int)p->D.size();
+    *handled = false;
+    QmeDenseArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.S = S; a.E = p->E; a.nd = nd; a.B = B; a.nsteps = nsteps;
+    a.traj_every = traj_every > 0 ? traj_every : 1;
+    a.nb = p->nb;
+    a.G = p->dG.as<cplx>(); a.Gh = p->dGh.as<cplx>(); a.X = p->dX.as<cplx>(); a.Zh = p->dZh.as<cplx>();
+    a.D = p->dD.as<cplx>(); a.Dh = p->dDh.as<cplx>(); a.eT = p->deT.as<cplx>();
+    a.coef = coef; a.rho = rho; a.obs = obs; a.traj = traj; a.dt = dt;
+    int ept = 1, tps;
+    if (NN <= 4) tps = 4;
+    else if (NN <= 16) tps = 16;
+    else {
+        if (NN > 2048) ept = 4; else if (NN > 1024) ept = 2;
+        tps = ceil_div(ceil_div(NN, ept), 32) * 32;
+    }
+    int slots = std::max(1, 256 / tps);
+    slots = std::min(slots, std::max(1, B));
+    // fill the machine: prefer >= 2 CTAs per SM worth of blocks when the batch is small
+    while (slots > 1 && ceil_div(B, slots) < 2 * p->sm_count) slots >>= 1;
+    const size_t ops_bytes = (size_t)(2 + 2 * S) * NN * 16;
+    auto smem_for = [&](int sl, bool ops) { return (size_t)sl * (2 * NN + 32) * 16 + (ops ? ops_bytes : 0); };
+    bool ops = (p->nb == 1) && smem_for(slots, true) <= (size_t)p->smem_optin;
+    if (nd > 0 && !ops) return LB_OK;            // caller falls back to per-step launches
+    if (smem_for(slots, ops) > (size_t)p->smem_optin) return LB_OK;
+    a.slots = slots; a.tps = tps; a.ops_in_smem = ops ? 1 : 0;
+    const size_t smem = smem_for(slots, ops);
+    dim3 grid(ceil_div(B, slots)), block(slots * tps);
+    void (*kern)(QmeDenseArgs) = ept == 1 ? qme_dense_onchip<1> : (ept == 2 ? qme_dense_onchip<2> : qme_dense_onchip<4>);
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, block, smem, st>>>(a);
+    LB_CUDA(cudaGetLastError());
+    p->launches += 1;
+    *handled = true;
+    return LB_OK;
+}
+
+int ensure_scratch(limeb200_qme_t p, int B, int ny, bool need_tmp) {
+    const size_t NN = (size_t)p->N * p->N;
+    const int S = (int)p->X.size();
+    if (B > p->scratch_B || !p->s_y.p) {
+        LB_CUDA(p->s_y.alloc((size_t)ny * B * NN * 16));
+        LB_CUDA(p->s_acc.alloc((size_t)B * NN * 16));
+        if (need_tmp && S > 0) LB_CUDA(p->s_tmp.alloc((size_t)S * B * NN * 16));
+        p->scratch_B = B;
+    }
+    return LB_OK;
+}
+
+int run_dense_stage(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, const cplx* coef,
+                    cplx* obs, cplx* traj, int traj_every, cudaStream_t st) {
+    const int N = p->N, S = (int)p->X.size(), nd = (int)p->D.size();
+    const size_t NN = (size_t)N * N;
+    int r = ensure_scratch(p, B, 2, true);
+    if (r != LB_OK) return r;
+    if (nd > 0 && !p->s_gk.p) LB_CUDA(p->s_gk.alloc(2 * NN * 16));
+    cplx* y[2] = {p->s_y.as<cplx>(), p->s_y.as<cplx>() + (size_t)B * NN};
+    cplx* acc = p->s_acc.as<cplx>();
+    cplx* tmp = p->s_tmp.as<cplx>();
+    const long long sOp = (p->nb > 1) ? (long long)NN : 0;
+    const cplx* G = p->dG.as<cplx>();
+    const cplx* Gh = p->dGh.as<cplx>();
+    dim3 grid(ceil_div(N, 32), ceil_div(N, 32), B);
+    for (int step = 0; step < nsteps; ++step) {
+        if (nd > 0) {
+            cplx* gk = p->s_gk.as<cplx>();
+            qme_build_gk<<<ceil_div((int)NN, 256), 256, 0, st>>>(p->dG.as<cplx>(), p->dGh.as<cplx>(), p->dD.as<cplx>(),
+                                                                p->dDh.as<cplx>(), coef + (size_t)step * nd, nd,
+                                                                (int)NN, gk, gk + NN);
+            p->launches++;
+            G = gk; Gh = gk + NN;
+        }
+        for (int stage = 0; stage < 4; ++stage) {
+            const cplx* yin = (stage == 0) ? rho : y[(stage - 1) & 1];
+            cplx* yout = y[stage & 1];
+            for (int s = 0; s < S; ++s) {           // tmp_s = yin Z_s^H
+                QmeStageArgs a;
+                memset(&a, 0, sizeof(a));
+                a.N = N; a.B = B; a.nprod = 1;
+                a.A[0] = yin; a.sA[0] = (long long)NN;
+                a.Bm[0] = p->dZh.as<cplx>() + (size_t)s * NN; a.sB[0] = (p->nb > 1) ? (long long)S * NN : 0;
+                a.mode = 0; a.out = tmp + (size_t)s * B * NN; a.sOut = (long long)NN; a.dt = dt;
+                qme_dense_stage<<<grid, 256, 0, st>>>(a);
+                p->launches++;
+            }
+            QmeStageArgs a;
+            memset(&a, 0, sizeof(a));
+            a.N = N; a.B = B; a.nprod = 2 + S;
+            LB_REQUIRE(a.nprod <= QME_MAXPROD, "too many sandwich terms for the dense stage kernel");
+            a.A[0] = G; a.sA[0] = sOp; a.Bm[0] = yin; a.sB[0] = (long long)NN;
+            a.A[1] = yin; a.sA[1] = (long long)NN; a.Bm[1] = Gh; a.sB[1] = sOp;
+            for (int s = 0; s < S; ++s) {
+                a.A[2 + s] = p->dX.as<cplx>() + (size_t)s * NN; a.sA[2 + s] = (p->nb > 1) ? (long long)S * NN : 0;
+                a.Bm[2 + s] = tmp + (size_t)s * B * NN; a.sB[2 + s] = (long long)NN;
+            }
+            a.mode = stage + 1; a.rho = rho; a.acc = acc; a.ynext = yout; a.dt = dt;
+            qme_dense_stage<<<grid, 256, 0, st>>>(a);
+            p->launches++;
+        }
+        if (obs && p->E > 0) {
+            qme_trace_obs<<<dim3(p->E, B), 256, 0, st>>>(p->deT.as<cplx>(), rho, obs + (size_t)step * B * p->E,
+                                                         (int)NN, p->E, (long long)p->E);
+            p->launches++;
+        }
+        if (traj && ((step + 1) % traj_every) == 0) {
+            LB_CUDA(cudaMemcpyAsync(traj + (size_t)(step / traj_every) * B * NN, rho, (size_t)B * NN * 16,
+                                    cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nsteps,
+                     const double* d_coef, double* d_obs, double* d_traj, int traj_every,
+                     void* stream) {
+    LB_REQUIRE(p && p->finalized, "plan not finalized");
+    LB_REQUIRE(d_rho && B >= 1 && nsteps >= 0, "bad arguments");
+    LB_REQUIRE(p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
+    LB_REQUIRE(p->D.empty() || d_coef, "drive operators present but d_coef is NULL");
+    LB_REQUIRE(!d_traj || traj_every >= 1, "traj_every must be >= 1");
+    LB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    p->launches = 0;
+    if (nsteps == 0) return LB_OK;
+    cplx* rho = (cplx*)d_rho;
+    const cplx* coef = (const cplx*)d_coef;
+    cplx* obs = (p->E > 0) ? (cplx*)d_obs : nullptr;
+    cplx* traj = (cplx*)d_traj;
+    if (!d_traj) traj_every = 1;
+    if (p->path == 1) {
+        bool handled = false;
+        int r = run_dense_onchip(p, rho, B, dt, nsteps, coef, obs, traj, traj_every, st, &handled);
+        if (r != LB_OK) return r;
+        if (handled) return LB_OK;
+        return run_dense_stage(p, rho, B, dt, nsteps, coef, obs, traj, traj_every, st);
+    }
+    if (p->path == 2) return run_dense_stage(p, rho, B, dt, nsteps, coef, obs, traj, traj_every, st);
+    QmeEllArgs a;
+    memset(&a, 0, sizeof(a));
+    fill_ell_args(p, a, B);
+    a.nsteps = nsteps; a.traj_every = traj_every; a.rho = rho; a.obs = obs; a.traj = traj; a.dt = dt;
+    if (p->path == 4) {
+        int r = qme_cluster_launch(a, p->bandwidth, p->permuted ? p->dperm.as<int>() : nullptr, p->smem_optin, st);
+        if (r == LB_OK) { p->launches += 1; return LB_OK; }
+        if (r != LB_ERR_UNSUPPORTED) return r;
+        // geometry does not fit the cluster kernel: use the global-scratch kernel
+    }
+    int r = ensure_scratch(p, B, 2, false);
+    if (r != LB_OK) return r;
+    a.ybuf = p->s_y.as<cplx>(); a.accbuf = p->s_acc.as<cplx>();
+    const int NN = p->N * p->N;
+    int threads = std::min(1024, ceil_div(NN, 32) * 32);
+    qme_ell_global<<<B, threads, 0, st>>>(a);
+    LB_CUDA(cudaGetLastError());
+    p->launches += 1;
+    return LB_OK;
+}
+
+int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B, void* stream) {
+    LB_REQUIRE(p && p->finalized, "plan not finalized");
+    LB_REQUIRE(d_in && d_out && B >= 1, "bad arguments");
+    LB_REQUIRE(p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
+    LB_REQUIRE(p->D.empty(), "rhs with drive operators is not supported");
+    LB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int N = p->N, S = (int)p->X.size();
+    const size_t NN = (size_t)N * N;
+    p->launches = 0;
+    if (p->path == 1 || p->path == 2) {
+        int r = ensure_scratch(p, B, 2, true);
+        if (r != LB_OK) return r;
+        cplx* tmp = p->s_tmp.as<cplx>();
+        const cplx* yin = (const cplx*)d_in;
+        dim3 grid(ceil_div(N, 32), ceil_div(N, 32), B);
+        const long long sOp = (p->nb > 1) ? (long long)NN : 0;
+        for (int s = 0; s < S; ++s) {
+            QmeStageArgs a;
+            memset(&a, 0, sizeof(a));
+            a.N = N; a.B = B; a.nprod = 1;
+            a.A[0] = yin; a.sA[0] = (long long)NN;
+            a.Bm[0] = p->dZh.as<cplx>() + (size_t)s * NN; a.sB[0] = (p->nb > 1) ? (long long)S * NN : 0;
+            a.mode = 0; a.out = tmp + (size_t)s * B * NN; a.sOut = (long long)NN;
+            qme_dense_stage<<<grid, 256, 0, st>>>(a);
+            p->launches++;
+        }
+        QmeStageArgs a;
+        memset(&a, 0, sizeof(a));
+        a.N = N; a.B = B; a.nprod = 2 + S;
+        a.A[0] = p->dG.as<cplx>(); a.sA[0] = sOp; a.Bm[0] = yin; a.sB[0] = (long long)NN;
+        a.A[1] = yin; a.sA[1] = (long long)NN; a.Bm[1] = p->dGh.as<cplx>(); a.sB[1] = sOp;
+        for (int s = 0; s < S; ++s) {
+            a.A[2 + s] = p->dX.as<cplx>() + (size_t)s * NN; a.sA[2 + s] = (p->nb > 1) ? (long long)S * NN : 0;
+            a.Bm[2 + s] = tmp + (size_t)s * B * NN; a.sB[2 + s] = (long long)NN;
+        }
+        a.mode = 0; a.out = (cplx*)d_out; a.sOut = (long long)NN;
+        qme_dense_stage<<<grid, 256, 0, st>>>(a);
+        p->launches++;
+    } else {
+        QmeEllArgs a;
+        memset(&a, 0, sizeof(a));
+        fill_ell_args(p, a, B);
+        qme_ell_rhs<<<dim3(ceil_div((int)NN, 256), B), 256, 0, st>>>(a, (const cplx*)d_in, (cplx*)d_out);
+        p->launches++;
+    }
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,329 @@
+// Dense-operator kernels for the quantum master equation in generator/sandwich form
+//
+//     d rho/dt = G rho + rho G^H + sum_s X_s rho Z_s^H
+//
+// which covers lime's Lindblad RHS (lime/oqs.py:706-723: G = -iH - 1/2 sum l^H l,
+// X_s = Z_s = l_s) and the operator form of its Redfield RHS (lime/oqs.py:840-850,
+// the same generator lime/oqs.py:528-579 expands into an N^2 x N^2 CSR matrix:
+// G = -i diag(eps) - sum_k A_k Lam_k, sandwiches (A_k, Lam_k) and (Lam_k, A_k)).
+//
+// Two kernels:
+//   qme_dense_onchip : N <= 64.  rho, the RK4 accumulator and the stage vector stay in
+//                      registers / shared memory for ALL nsteps steps; HBM sees rho once
+//                      on the way in and once on the way out (+ observables).
+//   qme_dense_stage  : any N.  One launch per RK stage, 32x32 output tiles, the RK4
+//                      axpy chain fused into the epilogue.
+#pragma once
+#include "common.cuh"
+
+struct QmeDenseArgs {
+    int N, S, E, nd, B, nsteps, traj_every;
+    int nb;                 // operator batch: 1 (shared) or B (per-item values)
+    const cplx* G;          // [nb][N*N]
+    const cplx* Gh;         // [nb][N*N]   G^H
+    const cplx* X;          // [nb][S][N*N]
+    const cplx* Zh;         // [nb][S][N*N] Z_s^H
+    const cplx* D;          // [nd][N*N]   drive generators:  G_k = G + sum_i coef[k][i] D_i
+    const cplx* Dh;         // [nd][N*N]   D_i^H            G_k^H = G^H + sum_i conj(coef) D_i^H
+    const cplx* eT;         // [E][N*N]    observables, transposed: Tr(e rho) = sum eT[idx] rho[idx]
+    const cplx* coef;       // [nsteps][nd]
+    cplx* rho;              // [B][N*N] in/out
+    cplx* obs;              // [nsteps][B][E] or null
+    cplx* traj;             // [nsteps/traj_every][B][N*N] or null
+    double dt;
+    int slots;              // density matrices per CTA
+    int tps;                // threads per slot
+    int ops_in_smem;        // G,Gh,X,Zh staged in shared memory (nb == 1 only)
+};
+
+// --------------------------------------------------------------------------------
+// on-chip kernel
+// --------------------------------------------------------------------------------
+template <int EPT>
+__global__ void __launch_bounds__(1024, 1)
+qme_dense_onchip(QmeDenseArgs a) {
+    extern __shared__ double2 smem[];
+    const int N = a.N, NN = N * N, S = a.S;
+    const int tps = a.tps;
+    const int slot = threadIdx.x / tps;
+    const int t = threadIdx.x - slot * tps;
+    const int b = blockIdx.x * a.slots + slot;
+    const bool active = b < a.B;
+
+    cplx* y = smem + (size_t)slot * 2 * NN;
+    cplx* tmp = y + NN;
+    cplx* red = smem + (size_t)a.slots * 2 * NN;             // [slots][32]
+    cplx* opsm = red + a.slots * 32;
+
+    const size_t ob = (a.nb > 1 && active) ? (size_t)b : 0;
+    const cplx* Gs = a.G + ob * NN;
+    const cplx* Ghs = a.Gh + ob * NN;
+    const cplx* Xs = a.X + ob * S * NN;
+    const cplx* Zhs = a.Zh + ob * S * NN;
+    if (a.ops_in_smem) {
+        cplx* g = opsm;
+        cplx* gh = g + NN;
+        cplx* x = gh + NN;
+        cplx* zh = x + (size_t)S * NN;
+        for (int i = threadIdx.x; i < NN; i += blockDim.x) { g[i] = a.G[i]; gh[i] = a.Gh[i]; }
+        for (int i = threadIdx.x; i < S * NN; i += blockDim.x) { x[i] = a.X[i]; zh[i] = a.Zh[i]; }
+        Gs = g; Ghs = gh; Xs = x; Zhs = zh;
+    }
+
+    int ei[EPT], ej[EPT];
+    bool ok[EPT];
+    cplx rho[EPT], acc[EPT];
+#pragma unroll
+    for (int e = 0; e < EPT; ++e) {
+        int idx = t + e * tps;
+        ok[e] = idx < NN;
+        ei[e] = ok[e] ? idx / N : 0;
+        ej[e] = ok[e] ? idx - ei[e] * N : 0;
+        rho[e] = (ok[e] && active) ? a.rho[(size_t)b * NN + idx] : cmake(0, 0);
+        acc[e] = cmake(0, 0);
+        if (ok[e]) y[idx] = rho[e];
+    }
+    __syncthreads();
+
+    const double dt = a.dt, hdt = 0.5 * a.dt;
+    for (int step = 0; step < a.nsteps; ++step) {
+        if (a.nd > 0) {          // time-dependent generator for this step (ops_in_smem guaranteed)
+            cplx* g = opsm;
+            cplx* gh = g + NN;
+            for (int i = threadIdx.x; i < NN; i += blockDim.x) {
+                cplx v = a.G[i], vh = a.Gh[i];
+                for (int d = 0; d < a.nd; ++d) {
+                    cplx c = a.coef[(size_t)step * a.nd + d];
+                    cfma(v, c, a.D[(size_t)d * NN + i]);
+                    cfma(vh, cconj(c), a.Dh[(size_t)d * NN + i]);
+                }
+                g[i] = v; gh[i] = vh;
+            }
+            __syncthreads();
+        }
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            cplx k[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                cplx s = cmake(0, 0);
+                if (ok[e]) {
+                    const cplx* gr = Gs + ei[e] * N;
+                    const cplx* yr = y + ei[e] * N;
+                    const int j = ej[e];
+                    for (int q = 0; q < N; ++q) {
+                        cfma(s, gr[q], y[q * N + j]);
+                        cfma(s, yr[q], Ghs[q * N + j]);
+                    }
+                }
+                k[e] = s;
+            }
+            for (int sw = 0; sw < S; ++sw) {
+                const cplx* zh = Zhs + (size_t)sw * NN;
+                const cplx* xs = Xs + (size_t)sw * NN;
+                cplx tv[EPT];
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    cplx s = cmake(0, 0);
+                    if (ok[e]) {
+                        const cplx* yr = y + ei[e] * N;
+                        const int j = ej[e];
+                        for (int q = 0; q < N; ++q) cfma(s, yr[q], zh[q * N + j]);
+                    }
+                    tv[e] = s;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if (ok[e]) tmp[t + e * tps] = tv[e];
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < EPT; ++e) {
+                    if (ok[e]) {
+                        const cplx* xr = xs + ei[e] * N;
+                        const int j = ej[e];
+                        cplx s = k[e];
+                        for (int q = 0; q < N; ++q) cfma(s, xr[q], tmp[q * N + j]);
+                        k[e] = s;
+                    }
+                }
+            }
+            cplx yn[EPT];
+#pragma unroll
+            for (int e = 0; e < EPT; ++e) {
+                if (stage == 0) {
+                    acc[e] = k[e];
+                    yn[e] = cmake(fma(hdt, k[e].x, rho[e].x), fma(hdt, k[e].y, rho[e].y));
+                } else if (stage == 1) {
+                    rfma(acc[e], 2.0, k[e]);
+                    yn[e] = cmake(fma(hdt, k[e].x, rho[e].x), fma(hdt, k[e].y, rho[e].y));
+                } else if (stage == 2) {
+                    rfma(acc[e], 2.0, k[e]);
+                    yn[e] = cmake(fma(dt, k[e].x, rho[e].x), fma(dt, k[e].y, rho[e].y));
+                } else {
+                    cplx tot = cadd(acc[e], k[e]);
+                    rho[e].x += tot.x / 6.0 * dt;
+                    rho[e].y += tot.y / 6.0 * dt;
+                    yn[e] = rho[e];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (ok[e]) y[t + e * tps] = yn[e];
+            __syncthreads();
+        }
+        // ---- observables Tr(e rho) of the state AFTER this step (lime/oqs.py:1674-1682)
+        if (a.obs) {
+            for (int eo = 0; eo < a.E; ++eo) {
+                cplx v = cmake(0, 0);
+#pragma unroll
+                for (int e = 0; e < EPT; ++e)
+                    if (ok[e]) cfma(v, a.eT[(size_t)eo * NN + t + e * tps], rho[e]);
+                if (tps >= 32) {
+                    for (int off = 16; off > 0; off >>= 1) {
+                        v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+                        v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+                    }
+                    if ((t & 31) == 0) red[slot * 32 + (t >> 5)] = v;
+                    __syncthreads();
+                    if (t == 0 && active) {
+                        cplx s = cmake(0, 0);
+                        for (int w = 0; w < tps / 32; ++w) s = cadd(s, red[slot * 32 + w]);
+                        a.obs[((size_t)step * a.B + b) * a.E + eo] = s;
+                    }
+                    __syncthreads();
+                } else {
+                    for (int off = tps >> 1; off > 0; off >>= 1) {
+                        v.x += __shfl_xor_sync(0xffffffffu, v.x, off);
+                        v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+                    }
+                    if (t == 0 && active) a.obs[((size_t)step * a.B + b) * a.E + eo] = v;
+                }
+            }
+        }
+        if (a.traj && ((step + 1) % a.traj_every) == 0 && active) {
+            cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * NN;
+#pragma unroll
+            for (int e = 0; e < EPT; ++e)
+                if (ok[e]) dst[t + e * tps] = rho[e];
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int e = 0; e < EPT; ++e)
+            if (ok[e]) a.rho[(size_t)b * NN + t + e * tps] = rho[e];
+    }
+}
+
+// --------------------------------------------------------------------------------
+// stage-wise tiled kernel (any N): out = sum_p A_p B_p with fused RK4 epilogue
+// --------------------------------------------------------------------------------
+#define QME_MAXPROD 18
+struct QmeStageArgs {
+    int N, B, nprod;
+    const cplx* A[QME_MAXPROD];      // left factors
+    const cplx* Bm[QME_MAXPROD];     // right factors
+    long long sA[QME_MAXPROD];       // batch strides (elements); 0 = shared
+    long long sB[QME_MAXPROD];
+    // epilogue
+    int mode;                        // 0: out = k ; 1..4: RK4 stage
+    cplx* out;                       // mode 0: [B][N*N] (stride sOut)
+    long long sOut;
+    cplx* rho;                       // [B][N*N]
+    cplx* acc;                       // [B][N*N]
+    cplx* ynext;                     // [B][N*N]
+    double dt;
+};
+
+__global__ void __launch_bounds__(256)
+qme_dense_stage(QmeStageArgs a) {
+    // 32x32 output tile, 256 threads, 2x2 outputs per thread, k-tile 16
+    __shared__ cplx As[32][17];
+    __shared__ cplx Bs[16][33];
+    const int N = a.N;
+    const int b = blockIdx.z;
+    const int ti = blockIdx.y * 32, tj = blockIdx.x * 32;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16
+    cplx c00 = cmake(0, 0), c01 = c00, c10 = c00, c11 = c00;
+    for (int p = 0; p < a.nprod; ++p) {
+        const cplx* Ap = a.A[p] + (size_t)b * a.sA[p];
+        const cplx* Bp = a.Bm[p] + (size_t)b * a.sB[p];
+        for (int k0 = 0; k0 < N; k0 += 16) {
+            for (int l = threadIdx.x; l < 32 * 16; l += 256) {
+                int r = l >> 4, c = l & 15;
+                int gi = ti + r, gk = k0 + c;
+                As[r][c] = (gi < N && gk < N) ? Ap[(size_t)gi * N + gk] : cmake(0, 0);
+            }
+            for (int l = threadIdx.x; l < 16 * 32; l += 256) {
+                int r = l >> 5, c = l & 31;
+                int gk = k0 + r, gj = tj + c;
+                Bs[r][c] = (gk < N && gj < N) ? Bp[(size_t)gk * N + gj] : cmake(0, 0);
+            }
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                cplx a0 = As[ty][q], a1 = As[ty + 16][q];
+                cplx b0 = Bs[q][tx], b1 = Bs[q][tx + 16];
+                cfma(c00, a0, b0); cfma(c01, a0, b1);
+                cfma(c10, a1, b0); cfma(c11, a1, b1);
+            }
+            __syncthreads();
+        }
+    }
+    cplx kk[4] = {c00, c01, c10, c11};
+    const double dt = a.dt, hdt = 0.5 * a.dt;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        int gi = ti + ty + ((q >> 1) ? 16 : 0);
+        int gj = tj + tx + ((q & 1) ? 16 : 0);
+        if (gi >= N || gj >= N) continue;
+        size_t idx = (size_t)gi * N + gj;
+        cplx k = kk[q];
+        if (a.mode == 0) {
+            a.out[(size_t)b * a.sOut + idx] = k;
+        } else {
+            size_t o = (size_t)b * N * N + idx;
+            cplx r = a.rho[o];
+            if (a.mode == 1) {
+                a.acc[o] = k;
+                a.ynext[o] = cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y));
+            } else if (a.mode == 2) {
+                cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                a.ynext[o] = cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y));
+            } else if (a.mode == 3) {
+                cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                a.ynext[o] = cmake(fma(dt, k.x, r.x), fma(dt, k.y, r.y));
+            } else {
+                cplx tot = cadd(a.acc[o], k);
+                r.x += tot.x / 6.0 * dt;
+                r.y += tot.y / 6.0 * dt;
+                a.rho[o] = r;
+                a.ynext[o] = r;
+            }
+        }
+    }
+}
+
+// obs[b][e] = sum_idx eT[e][idx] * rho[b][idx]; one CTA per (e, b)
+__global__ void __launch_bounds__(256)
+qme_trace_obs(const cplx* __restrict__ eT, const cplx* __restrict__ rho, cplx* __restrict__ obs,
+              int NN, int E, long long obs_stride_b) {
+    __shared__ cplx red[8];
+    const int e = blockIdx.x, b = blockIdx.y;
+    const cplx* et = eT + (size_t)e * NN;
+    const cplx* r = rho + (size_t)b * NN;
+    cplx v = cmake(0, 0);
+    for (int i = threadIdx.x; i < NN; i += 256) cfma(v, et[i], r[i]);
+    for (int off = 16; off > 0; off >>= 1) {
+        v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+        v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+    }
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        cplx s = cmake(0, 0);
+        for (int w = 0; w < 8; ++w) s = cadd(s, red[w]);
+        obs[(size_t)b * obs_stride_b + e] = s;
+    }
+}

@@ -1,0 +1,618 @@
+"""
+Open-quantum-system solvers with lime's call signatures (lime/oqs.py), running on the
+CUDA engine.
+
+    Lindblad_solver / _lindblad / _lindblad_driven     lime/oqs.py:1117-1331, 1590-1800
+    Redfield_solver / _redfield / redfield_tensor      lime/oqs.py:40-371, 373-472, 528-579
+    HEOMSolverDL / _heom_dl                            lime/oqs.py:1335-1431, 1802-1865
+    liouvillian / lindbladian                          lime/oqs.py:706-723
+
+Set-up that lime does once per solve on the host (building the generator from H and the
+collapse operators, the eigenbasis change, the Redfield tensor from Python spectral-density
+callbacks) stays on the host; every time loop -- the four RK4 stages, the observables, the
+stored trajectory -- is one CUDA launch (lime_b200/csrc).  Extensions over lime are marked
+[ext]: batched propagation (`evolve_batch`) and the multi-index HEOM propagator.
+"""
+import sys
+import numpy as np
+import scipy.linalg
+from scipy.sparse import issparse, csr_matrix, identity, kron
+
+from .mol import Result
+from .phys import dag, transform, isherm, obs_dm
+from .superoperator import op2sop, left, right, dm2vec, operator_to_superoperator
+from . import superoperator as superop
+from .units import au2k
+from . import engine
+from . import _dev
+
+
+# ---------------------------------------------------------------------------------------
+# generator assembly (host set-up)
+# ---------------------------------------------------------------------------------------
+def _all_sparse(ops):
+    return all(issparse(o) for o in ops)
+
+
+def lindblad_generator(H, c_ops):
+    """G = -iH - 1/2 sum_m l_m^dag l_m (sparse if every operand is sparse)"""
+    c_ops = [] if c_ops is None else list(c_ops)
+    if _all_sparse([H] + c_ops):
+        G = (-1j) * csr_matrix(H).astype(complex)
+        for l in c_ops:
+            l = csr_matrix(l).astype(complex)
+            G = G - 0.5 * (l.conj().T @ l)
+        return csr_matrix(G), [csr_matrix(l).astype(complex) for l in c_ops]
+    Hd = _dev.as_c128(H)
+    G = -1j * Hd
+    ls = [_dev.as_c128(l) for l in c_ops]
+    for l in ls:
+        G = G - 0.5 * (l.conj().T @ l)
+    return G, ls
+
+
+def _lindblad_plan(H, c_ops, e_ops, path=None, device_index=None):
+    N = H.shape[-1]
+    G, ls = lindblad_generator(H, c_ops)
+    plan = engine.QmePlan(N, device_index)
+    plan.set_generator(G)
+    for l in ls:
+        plan.add_sandwich(l, l)
+    plan.set_observables(e_ops)
+    if path is not None:
+        plan.set_path(path)
+    return plan.finalize()
+
+
+def liouvillian(rho, H, c_ops):
+    """-i[H,rho] + sum_m (l rho l^dag - 1/2 {l^dag l, rho}); lime/oqs.py:706-713.
+    One device right-hand side; returns an ndarray."""
+    plan = _lindblad_plan(H, c_ops, None)
+    return plan.rhs(rho)
+
+
+def lindbladian(l, rho):
+    """l rho l^dag - 1/2 {l^dag l, rho}; lime/oqs.py:716-723"""
+    N = l.shape[-1]
+    ld = _dev.as_c128(l)
+    plan = engine.QmePlan(N)
+    plan.set_generator(-0.5 * (ld.conj().T @ ld))
+    plan.add_sandwich(ld, ld)
+    plan.finalize()
+    return plan.rhs(rho)
+
+
+# ---------------------------------------------------------------------------------------
+# Lindblad
+# ---------------------------------------------------------------------------------------
+def _write_obs_file(fname, times, obs):
+    with open(fname, 'w') as f:
+        fmt = '{} ' * (obs.shape[1] + 1) + '\n'
+        for t, row in zip(times, obs):
+            f.write(fmt.format(t, *row))
+
+
+def _lindblad(H, rho0, c_ops, e_ops=None, Nt=1, dt=0.005, return_result=True):
+    """Nt RK4 steps of the Lindblad master equation; lime/oqs.py:1590-1688.
+
+    return_result=True  -> Result(observables (Nt,E) complex, rholist = Nt arrays);
+                           sample k is the state AFTER step k+1 (lime/oqs.py:1674-1682).
+    return_result=False -> writes obs.dat (observables BEFORE each step, as lime does,
+                           lime/oqs.py:1629-1661) and returns the final rho."""
+    if e_ops is None:
+        e_ops = []
+    rho = _dev.as_c128(rho0)
+    plan = _lindblad_plan(H, c_ops, e_ops)
+    if return_result:
+        rho_f, obs, traj = plan.run(rho, dt, Nt, traj_every=1)
+        result = Result(dt=dt, Nt=Nt, rho0=rho0)
+        result.observables = obs if obs is not None else np.zeros((Nt, 0), dtype=complex)
+        result.rholist = [traj[k] for k in range(Nt)]
+        return result
+    rho_f, obs, _ = plan.run(rho, dt, Nt)
+    if len(e_ops):
+        first = np.array([[obs_dm(rho, _dev.as_c128(e)) for e in e_ops]], dtype=complex)
+        before = np.concatenate([first, obs[:-1]], axis=0) if Nt > 0 else first[:0]
+    else:
+        before = np.zeros((Nt, 0), dtype=complex)
+    _write_obs_file('obs.dat', dt * (np.arange(Nt) + 1), before)
+    return rho_f
+
+
+def _lindblad_driven(H, rho0, c_ops=None, e_ops=None, Nt=1, dt=0.005, t0=0.,
+                     return_result=True, strict_parity=False):
+    """Driven Lindblad equation, H = [H0, [H1, f1], ...], H(t) = H0 - sum_i f_i(t) H_i evaluated
+    once per step at t+dt and frozen over the four stages; lime/oqs.py:1691-1800.
+
+    lime's calculateH aliases H[0] (`Ht = H[0]; Ht += ...`, lime/oqs.py:1717-1724), so the
+    drive ACCUMULATES into H[0] from step to step.  strict_parity=True reproduces that (the
+    effective coefficient at step k is the running sum of f_i, and the caller's H[0] is
+    left modified, as in lime); the default evaluates H(t) afresh each step."""
+    if c_ops is None:
+        c_ops = []
+    if e_ops is None:
+        e_ops = []
+    H0 = _dev.as_c128(H[0])
+    N = H0.shape[-1]
+    nd = len(H) - 1
+    times = t0 + dt * (np.arange(Nt) + 1)
+    f = np.array([[complex(H[i][1](t)) for i in range(1, len(H))] for t in times],
+                 dtype=complex).reshape(Nt, nd)
+    if strict_parity:
+        f = np.cumsum(f, axis=0)
+    # G_k = G0 + sum_i f_i(t_k) * (i H_i)
+    G0, ls = lindblad_generator(H0, [_dev.as_c128(c) for c in c_ops])
+    plan = engine.QmePlan(N)
+    plan.set_generator(G0)
+    for l in ls:
+        plan.add_sandwich(l, l)
+    for i in range(1, len(H)):
+        plan.add_drive(1j * _dev.as_c128(H[i][0]))
+    plan.set_observables(e_ops)
+    plan.finalize()
+    rho_f, obs, traj = plan.run(_dev.as_c128(rho0), dt, Nt, coef=f, traj_every=1 if return_result else 0)
+    if strict_parity and Nt > 0 and not issparse(H[0]):
+        try:       # lime leaves the accumulated drive in the caller's H[0]
+            H[0] += -sum(f[-1, i - 1] * _dev.as_c128(H[i][0]) for i in range(1, len(H)))
+        except Exception:
+            pass
+    if return_result:
+        result = Result(dt=dt, Nt=Nt, rho0=rho0)
+        result.observables = obs if obs is not None else np.zeros((Nt, 0), dtype=complex)
+        result.rholist = [traj[k] for k in range(Nt)]
+        return result
+    _write_obs_file('obs.dat', times, obs if obs is not None else np.zeros((Nt, 0), dtype=complex))
+    return rho_f
+
+
+class Lindblad_solver():
+    """lime/oqs.py:1117-1331"""
+
+    def __init__(self, H=None, c_ops=None, e_ops=None):
+        self.c_ops = c_ops
+        self.e_ops = e_ops
+        self.H = H
+
+    def set_c_ops(self, c_ops):
+        self.c_ops = c_ops
+
+    def set_e_ops(self, e_ops):
+        self.e_ops = e_ops
+
+    def setH(self, H):
+        self.H = H
+
+    def configure(self, c_ops, e_ops):
+        self.c_ops = c_ops
+        self.e_ops = e_ops
+
+    def liouvillian(self):
+        """Liouville-space superoperator (scipy.sparse), lime/oqs.py:1145-1148"""
+        return superop.liouvillian(self.H, self.c_ops)
+
+    def evolve(self, rho0, dt, Nt, t0=0., e_ops=None, return_result=True):
+        """lime/oqs.py:1152-1190"""
+        if isinstance(self.H, list):
+            return _lindblad_driven(self.H, rho0=rho0, c_ops=self.c_ops, e_ops=e_ops, Nt=Nt, dt=dt, t0=t0)
+        return _lindblad(self.H, rho0, c_ops=self.c_ops, e_ops=e_ops, Nt=Nt, dt=dt,
+                         return_result=return_result)
+
+    def evolve_batch(self, rho0, dt, Nt, e_ops=None, H_batch=None, store_every=0, path=None,
+                     device_index=None, return_device=False):
+        """[ext] propagate a batch of density matrices in one launch.
+
+        rho0    : [B,N,N] (or [N,N], broadcast to the operator batch)
+        H_batch : None (all share self.H) or a list/array of B Hamiltonians with the SAME
+                  sparsity pattern (parameter scans: coupling x detuning grids)
+        returns (rho_final [B,N,N], observables [Nt,B,E], rholist [Nt//store_every,B,N,N] or None)"""
+        c_ops = [] if self.c_ops is None else list(self.c_ops)
+        if H_batch is None:
+            plan = _lindblad_plan(self.H, c_ops, e_ops, path=path, device_index=device_index)
+            B = None
+        else:
+            plan, B = _lindblad_plan_batch(H_batch, c_ops, e_ops, path=path, device_index=device_index)
+        r = _dev.as_c128(rho0)
+        if r.ndim == 2:
+            r = np.broadcast_to(r, ((B or 1),) + r.shape)
+        if return_device:
+            d = _dev.to_dev(r, dev=plan.dev)
+            obs, traj = plan.run_device(d, dt, Nt, traj_every=store_every)
+            return d, obs, traj
+        return plan.run(r, dt, Nt, traj_every=store_every)
+
+    # ---- correlation functions (quantum regression), lime/oqs.py:1196-1331 ---------
+    def correlation_3op_1t(self, rho0, oplist, dt=0.005, Nt=1):
+        """<A B(t) C>, lime/oqs.py:1227-1246"""
+        a_op, b_op, c_op = oplist
+        return _lindblad(self.H, rho0=c_op @ rho0 @ a_op, c_ops=self.c_ops, e_ops=[b_op],
+                         dt=dt, Nt=Nt).observables[:, 0]
+
+    def correlation_3op_2t(self, rho0, ops, dt, Nt, Ntau):
+        """<A(t) B(t+tau) C(t)>, lime/oqs.py:1268-1299.  lime runs Nt independent
+        propagations of Ntau steps in a Python loop; here they are ONE batched launch."""
+        a_op, b_op, c_op = [_dev.as_c128(o) for o in ops]
+        plan = _lindblad_plan(self.H, self.c_ops, [b_op])
+        _, _, rho_t = plan.run(_dev.as_c128(rho0), dt, Nt, traj_every=1)
+        batch = np.ascontiguousarray(c_op[None] @ rho_t @ a_op[None])
+        _, obs, _ = plan.run(batch, dt, Ntau)
+        return np.ascontiguousarray(obs[:, :, 0].T)
+
+    def correlation_4op_1t(self, rho0, ops, dt, nt):
+        """<A B(t) C(t) D>, lime/oqs.py:1301-1315"""
+        if len(ops) != 4:
+            raise ValueError('Number of operators is not 4.')
+        a, b, c, d = ops
+        return self.correlation_3op_1t(rho0, [a, b @ c, d], dt, nt)
+
+    def correlation_4op_2t(self, rho0, ops, dt, nt, ntau):
+        """<A(t) B(t+tau) C(t+tau) D(t)>, lime/oqs.py:1317-1331"""
+        if len(ops) != 4:
+            raise ValueError('Number of operators is not 4.')
+        a, b, c, d = ops
+        return self.correlation_3op_2t(rho0, [a, b @ c, d], dt, nt, ntau)
+
+
+def _lindblad_plan_batch(H_batch, c_ops, e_ops, path=None, device_index=None):
+    """plan for B Hamiltonians sharing one sparsity pattern (values differ).
+    H_batch: sequence of B matrices (ndarray or scipy.sparse), or a tuple
+    (pattern, values[B, nnz]) with `pattern` a scipy.sparse matrix whose CSR order
+    (sorted indices) indexes `values` -- the cheap form for large parameter scans."""
+    if isinstance(H_batch, tuple):
+        pat, hvals = H_batch
+        pat = csr_matrix(pat)
+        pat.sort_indices()
+        hvals = np.asarray(hvals, dtype=np.complex128)
+        B, N = hvals.shape[0], pat.shape[0]
+        sparse = True
+    else:
+        Hs = list(H_batch)
+        B, N = len(Hs), Hs[0].shape[-1]
+        sparse = all(issparse(h) for h in Hs)
+    plan = engine.QmePlan(N, device_index)
+    if sparse and _all_sparse(c_ops):
+        ls = [csr_matrix(l).astype(complex) for l in c_ops]
+        diss = csr_matrix((N, N), dtype=complex)
+        for l in ls:
+            diss = diss - 0.5 * (l.conj().T @ l)
+        if isinstance(H_batch, tuple):
+            hpat = pat.copy()
+        else:
+            hpat = csr_matrix((N, N))
+            for h in Hs:
+                a = abs(csr_matrix(h))
+                a.data[:] = 1.0
+                hpat = hpat + a
+        upat = abs(csr_matrix(hpat)) + abs(diss)
+        upat = csr_matrix(upat)
+        upat.sum_duplicates()
+        upat.sort_indices()
+        rows = np.repeat(np.arange(N), np.diff(upat.indptr))
+        cols = upat.indices
+        dvals = np.asarray(diss.todense())[rows, cols]
+        data = np.empty((B, upat.nnz), dtype=np.complex128)
+        if isinstance(H_batch, tuple):
+            # position of every pattern entry inside the union pattern
+            prow = np.repeat(np.arange(N), np.diff(pat.indptr))
+            key_u = rows.astype(np.int64) * N + cols
+            key_p = prow.astype(np.int64) * N + pat.indices
+            pos = np.searchsorted(key_u, key_p)
+            data[:] = dvals[None, :]
+            data[:, pos] += -1j * hvals
+        else:
+            for b, h in enumerate(Hs):
+                data[b] = -1j * np.asarray(csr_matrix(h).todense())[rows, cols] + dvals
+        upat.data[:] = 1.0
+        plan.set_generator_csr_batch(upat, data)
+        for l in ls:
+            plan.add_sandwich(l, l)
+    else:
+        if isinstance(H_batch, tuple):
+            raise ValueError('(pattern, values) Hamiltonian batches need sparse collapse operators')
+        G = np.stack([lindblad_generator(_dev.as_c128(h), [_dev.as_c128(c) for c in c_ops])[0] for h in Hs])
+        plan.set_generator(G)
+        for c in c_ops:
+            plan.add_sandwich(_dev.as_c128(c), _dev.as_c128(c))
+    plan.set_observables(e_ops)
+    if path is not None:
+        plan.set_path(path)
+    return plan.finalize(), B
+
+
+# ---------------------------------------------------------------------------------------
+# Redfield
+# ---------------------------------------------------------------------------------------
+def _redfield_pieces(H, a_ops, spectra):
+    for a in a_ops:
+        if issparse(a):
+            if not isherm(a.todense()):
+                raise TypeError("Operators in a_ops must be Hermitian.")
+        elif not isherm(a):
+            raise TypeError("Operators in a_ops must be Hermitian.")
+    evals, evecs = scipy.linalg.eigh(H.todense() if issparse(H) else H)
+    W = np.real(evals[:, np.newaxis] - evals[np.newaxis, :])
+    N = len(evals)
+    A, Lam = [], []
+    for k, a in enumerate(a_ops):
+        c = np.zeros((N, N))
+        for n in range(N):
+            for m in range(N):
+                c[n, m] = spectra[k](-W[n, m])        # host callback, as in lime/oqs.py:553-561
+        ak = transform(a, evecs)
+        A.append(ak)
+        Lam.append(c * ak)
+    return evals, evecs, A, Lam
+
+
+def redfield_tensor(H, a_ops, spectra, secular=False):
+    """Eigenbasis Redfield generator as an N^2 x N^2 CSR matrix, d/dt vec(rho) = R vec(rho)
+    (row-major vec); lime/oqs.py:528-579.  `secular` is accepted and ignored, as in lime.
+    Host set-up: the spectral densities are Python callbacks."""
+    evals, evecs, A, Lam = _redfield_pieces(H, a_ops, spectra)
+    R = 0
+    for a, l in zip(A, Lam):
+        R += op2sop(a).dot(left(l) - right(dag(l)))
+    return csr_matrix(-1j * op2sop(np.diag(evals)) - R), evecs
+
+
+def _redfield(R, rho0, evecs=None, Nt=1, dt=0.005, t0=0, e_ops=[], return_result=True):
+    """RK4 propagation of d/dt vec(rho) = R vec(rho); lime/oqs.py:373-468.  Observables are
+    taken in the eigenbasis, rholist is transformed back with v rho v^dag (:458-462)."""
+    N = rho0.shape[0]
+    if e_ops is None:
+        e_ops = []
+    if evecs is not None:
+        rho0 = transform(rho0, evecs)
+        e_ops = [transform(e, evecs) for e in e_ops]
+    v0 = dm2vec(np.array(rho0)).astype(complex)
+    e_rows = [np.asarray(_dev.as_c128(e)).T.reshape(-1) for e in e_ops]
+    if return_result:
+        v, obs, traj = engine.liouville_rk4(R, v0, dt, Nt, e_rows=e_rows, traj_every=1)
+        result = Result(dt=dt, Nt=Nt, rho0=rho0)
+        result.observables = obs if obs is not None else np.zeros((Nt, 0), dtype=complex)
+        m = traj.reshape(Nt, N, N)
+        if evecs is None:
+            raise TypeError("unsupported operand: evecs is None")    # lime calls dag(None) here (:459)
+        vd = dag(evecs)
+        result.rholist = list(np.einsum('ia,kab,bj->kij', dag(vd), m, vd)) if Nt else []
+        return result
+    v, obs, _ = engine.liouville_rk4(R, v0, dt, Nt, e_rows=e_rows)
+    if len(e_ops):
+        first = np.array([[obs_dm(np.reshape(v0, (N, N)), e) for e in e_ops]], dtype=complex)
+        before = np.concatenate([first, obs[:-1]], axis=0) if Nt > 0 else first[:0]
+    else:
+        before = np.zeros((Nt, 0), dtype=complex)
+    _write_obs_file('obs.dat', t0 + dt * (np.arange(Nt) + 1), before)
+    return v
+
+
+class Redfield_solver:
+    """lime/oqs.py:40-371"""
+
+    def __init__(self, H, c_ops=None, spectra=None, e_ops=None):
+        self.H = H
+        self.c_ops = c_ops
+        self.R = None
+        self.spectra = spectra
+        self.evecs = None
+        self.dim = H.shape[0]
+        self.U = None
+        self.G = None
+        self.e_ops = e_ops
+        self._pieces = None
+
+    def idm(self, sp=True):
+        if sp:
+            return dm2vec(identity(self.dim))
+        return dm2vec(identity(self.dim).toarray())
+
+    def configure(self, H, c_ops, e_ops):
+        self.c_ops = c_ops
+        self.e_ops = e_ops
+        self.H = H
+
+    def redfield_tensor(self, secular=False):
+        """lime/oqs.py:92-125"""
+        if self.spectra is None:
+            raise TypeError('Specify the bath spectral function.')
+        evals, evecs, A, Lam = _redfield_pieces(self.H, self.c_ops, self.spectra)
+        self._pieces = (evals, A, Lam)
+        R = 0
+        for a, l in zip(A, Lam):
+            R += op2sop(a).dot(left(l) - right(dag(l)))
+        self.R = csr_matrix(-1j * op2sop(np.diag(evals)) - R)
+        self.evecs = evecs
+        return self.R, evecs
+
+    def evolve(self, rho0, dt, Nt, evecs=None, e_ops=[], store_states=False, t0=0, nout=1):
+        """lime/oqs.py:66-90 (the `evecs` argument is ignored in favour of self.evecs, as in lime)"""
+        if self.R is None:
+            self.redfield_tensor()
+        return _redfield(self.R, rho0, evecs=self.evecs, Nt=Nt, dt=dt, t0=t0, e_ops=e_ops)
+
+    def operator_plan(self, e_ops=None, path=None, device_index=None):
+        """[ext] O(K N^2)-storage operator form of the same generator:
+        d rho/dt = G rho + rho G^H + sum_k (A_k rho Lam_k^H + Lam_k rho A_k),
+        G = -i diag(eps) - sum_k A_k Lam_k  (what lime's `func`, lime/oqs.py:840-850, evaluates).
+        All operators in the eigenbasis of H."""
+        if self._pieces is None:
+            self.redfield_tensor()
+        evals, A, Lam = self._pieces
+        G = -1j * np.diag(evals).astype(complex)
+        for a, l in zip(A, Lam):
+            G = G - a @ l
+        plan = engine.QmePlan(self.dim, device_index)
+        plan.set_generator(G)
+        for a, l in zip(A, Lam):
+            plan.add_sandwich(a, l)
+            plan.add_sandwich(l, a)
+        plan.set_observables(e_ops)
+        if path is not None:
+            plan.set_path(path)
+        return plan.finalize()
+
+    def evolve_batch(self, rho0, dt, Nt, e_ops=None, store_every=0, form='tensor'):
+        """[ext] batch of initial states [B,N,N] (site basis) in one launch.
+        form='tensor': vec(rho) propagated with the CSR tensor R (lime's form);
+        form='operator': operator form (O(N^3) per right-hand side instead of O(N^4)).
+        Returns (rho_final [B,N,N] in the EIGENBASIS, observables [Nt,B,E])."""
+        if self.R is None:
+            self.redfield_tensor()
+        v = self.evecs
+        N = self.dim
+        r = _dev.as_c128(rho0)
+        if r.ndim == 2:
+            r = r[None]
+        r_eb = np.ascontiguousarray(dag(v)[None] @ r @ v[None])
+        e_eb = [transform(_dev.as_c128(e), v) for e in (e_ops or [])]
+        if form == 'operator':
+            plan = self.operator_plan(e_eb)
+            out, obs, _ = plan.run(r_eb, dt, Nt, traj_every=store_every)
+            return out, obs
+        e_rows = [e.T.reshape(-1) for e in e_eb]
+        out, obs, _ = engine.liouville_rk4(self.R, r_eb.reshape(-1, N * N), dt, Nt, e_rows=e_rows)
+        return out.reshape(-1, N, N), obs
+
+    def propagator(self, t, method='SOS'):
+        """U[a,b,k] = (e^{R t_k})_{ab}; lime/oqs.py:169-223.
+        'EOM' integrates dU/dt = R U with RK4 from U(t_0)=1 (lime/phys.py:1384-1401) -- the N^2
+        columns are one batched device launch; 'SOS'/'eseries' diagonalises R on the host."""
+        if self.R is None:
+            raise TypeError('Redfield tensor is not computed. Please call redfield_tensor()')
+        t = np.asarray(t)
+        D = self.dim ** 2
+        if method == 'EOM':
+            dt = t[1] - t[0]
+            nt = len(t)
+            eye = np.identity(D, dtype=complex)
+            if nt > 1:
+                _, _, traj = engine.liouville_rk4(self.R, eye, dt, nt - 1, traj_every=1)
+                # traj[k][b][a] = U(t_{k+1})[a][b]
+                U = np.concatenate([eye[None], traj.transpose(0, 2, 1)], axis=0)
+            else:
+                U = eye[None]
+            self.U = np.ascontiguousarray(U.transpose(1, 2, 0))
+        elif method in ['eseries', 'SOS']:
+            evals1, U1 = scipy.linalg.eig(self.R.toarray())
+            U2 = scipy.linalg.inv(U1)
+            E = np.exp(evals1[:, np.newaxis] * t[np.newaxis, :])
+            self.U = np.einsum('aj, jk, jb -> abk', U1, E, U2, optimize=True)
+        self.G = -1j * self.U
+        return self.U
+
+    def expect(self, rho0, e_ops):
+        """lime/oqs.py:225-252"""
+        evecs = self.evecs
+        U = self.U
+        rho0_eb = dm2vec(transform(rho0, evecs))
+        e_ops = [transform(e, evecs) for e in e_ops]
+        if isinstance(U, list):
+            out = np.zeros((len(U), len(e_ops)), dtype=complex)
+            for j, e in enumerate(e_ops):
+                out[:, j] = [np.vdot(e, u.dot(rho0_eb)) for u in U]
+            return out
+        out = np.zeros((U.shape[-1], len(e_ops)), dtype=complex)
+        rho = np.tensordot(U, rho0_eb, axes=([1], [0]))
+        for j, e in enumerate(e_ops):
+            out[:, j] = dm2vec(e).dot(rho)
+        return out
+
+    def correlation_2op_1t(self, rho0, a, b, tau):
+        """<<I|a G(tau) b|rho0>>, lime/oqs.py:254-275"""
+        if self.G is None:
+            self.propagator(tau)
+        idm = dm2vec(identity(self.dim))
+        if rho0.ndim == 2:
+            rho0 = dm2vec(rho0)
+        return idm.dot(a.dot(np.tensordot(self.G, b.dot(rho0), axes=([1], [0]))))
+
+    def correlation_4op_3t(self, rho0, oplist, signature, tau):
+        """<<I|A G(t3) B G(t2) C G(t1) D|rho0>>; result[i,j,k] with axis 0 the LAST interval;
+        lime/oqs.py:277-366.  Host contraction of the (device- or eig-built) propagator."""
+        if len(oplist) != 4:
+            raise ValueError('Number of operators is not 4.')
+        a, b, c, d = [operator_to_superoperator(o, s) for o, s in zip(oplist, signature)]
+        if self.G is None:
+            self.propagator(tau)
+        G = self.G
+        idm = self.idm(sp=False)
+        rho = d.dot(dm2vec(rho0.toarray() if issparse(rho0) else rho0))
+        tmp = np.tensordot(G, rho, axes=((1), (0)))
+        tmp = c.dot(tmp)
+        tmp = np.tensordot(G, tmp, axes=([1], [0]))
+        tmp = np.tensordot(np.asarray(b.todense()), tmp, axes=([1], [0]))
+        tmp = np.tensordot(G, tmp, axes=([1], [0]))
+        return np.einsum('a, ab, bijk -> ijk', idm, np.asarray(a.todense()), tmp, optimize=True)
+
+
+# ---------------------------------------------------------------------------------------
+# HEOM
+# ---------------------------------------------------------------------------------------
+def _heom_dl(H, rho0, c_ops, e_ops, temperature, cutoff, reorganization,
+             nado, dt, nt, fname=None, return_result=True):
+    """Single Drude mode, high-temperature HEOM with lime's in-place Gauss-Seidel Euler sweep
+    (tier 0 advanced twice per step, last tier frozen); lime/oqs.py:1802-1865.  `c_ops` is ONE
+    matrix (the system-bath coupling), `e_ops` is unused, T = temperature/au2k, a = pi*lambda*T,
+    b = 0.  Writes `t rho00 rho01 rho10 rho11` per step to `fname` and returns tier 0."""
+    H = _dev.as_c128(H)
+    nst = H.shape[0]
+    T = temperature / au2k
+    a = np.pi * reorganization * T
+    b = 0.0
+    print('Temperature of the environment = {}'.format(T))
+    print('High-Temperature check gamma/(kT) = {}'.format(cutoff / T))
+    if cutoff / T > 0.8:
+        print('WARNING: High-Temperature Approximation may fail.')
+    print('Reorganization energy = {}'.format(reorganization))
+    print('Amplitude of the fluctuations = {}'.format(a))
+    ado = np.zeros((1, nado, nst, nst), dtype=np.complex128)
+    ado[0, 0] = rho0
+    out, traj = engine.heom_dl_euler(H, c_ops, ado, [[cutoff, a, b]], dt, nt, want_traj=True)
+    if fname is not None:
+        with open(fname, 'w') as f:
+            fmt = '{} ' * 5 + '\n'
+            for k in range(nt):
+                r = traj[k, 0]
+                f.write(fmt.format(dt * (k + 1), r[0, 0], r[0, 1], r[1, 0], r[1, 1]))
+    return out[0, 0]
+
+
+class HEOMSolverDL():
+    """API shell of lime/oqs.py:1335-1431.  lime's `solve` literally runs the Lindblad
+    propagator (lime/oqs.py:1364-1366); that behaviour is kept for `solve`, and the
+    hierarchy itself is reachable through `solve_heom` [ext] (lime_b200.heom.heom.HEOM)."""
+
+    def __init__(self, H=None, c_ops=None, e_ops=None):
+        self.c_ops = c_ops
+        self.e_ops = e_ops
+        self.H = H
+
+    def set_c_ops(self, c_ops):
+        self.c_ops = c_ops
+
+    def set_e_ops(self, e_ops):
+        self.e_ops = e_ops
+
+    def setH(self, H):
+        self.H = H
+
+    def configure(self, c_ops, e_ops):
+        self.c_ops = c_ops
+        self.e_ops = e_ops
+
+    def solve(self, rho0, dt, Nt, return_result):
+        return _lindblad(self.H, rho0, self.c_ops, e_ops=self.e_ops, Nt=Nt, dt=dt,
+                         return_result=return_result)
+
+    def solve_heom(self, rho0, dt, Nt, coup_strength, cut_freq, temperature, N_exp=2, N_cut=4,
+                   Q=None, e_ops=None):
+        """[ext] multi-index Drude-Lorentz hierarchy with the rules of lime/heom/heom.py:156-216"""
+        from .heom.heom import HEOM
+        Q = self.c_ops if Q is None else Q
+        if isinstance(Q, (list, tuple)):
+            Q = Q[0]
+        h = HEOM(self.H, Q, coup_strength, cut_freq, temperature, N_exp=N_exp, N_cut=N_cut)
+        return h.evolve(rho0, dt, Nt, e_ops=self.e_ops if e_ops is None else e_ops)
+
+    def correlation_3op_2t(self, rho0, ops, dt, Nt, Ntau):
+        """lime/oqs.py:1399-1431 (Lindblad regression, as in lime)"""
+        return Lindblad_solver(self.H, self.c_ops).correlation_3op_2t(rho0, ops, dt, Nt, Ntau)

@@ -1,0 +1,105 @@
+"""
+L1 primitives of lime/phys.py that sit on the density-matrix path.
+
+The algebraic helpers (comm, dag, transform ...) are host-side conveniences with lime's
+exact semantics (they are used for set-up: building generators, changing basis).  The two
+functions lime's solvers actually spend their time in -- `liouvillian` and `rk4` applied to
+it -- are served by the CUDA engine: see lime_b200.oqs.
+"""
+import numpy as np
+from scipy.sparse import lil_matrix, issparse
+
+
+def dag(a):
+    """lime/phys.py:758-759"""
+    return a.conjugate().transpose()
+
+
+dagger = dag
+
+
+def comm(A, B):
+    """lime/phys.py:741-743"""
+    assert A.shape == B.shape
+    return np.dot(A, B) - np.dot(B, A)
+
+
+def anticomm(A, B):
+    """lime/phys.py:746-748"""
+    assert A.shape == B.shape
+    return np.dot(A, B) + np.dot(B, A)
+
+
+def commutator(A, B):
+    """lime/phys.py:736-738"""
+    assert A.shape == B.shape
+    return A.dot(B) - B.dot(A)
+
+
+def anticommutator(A, B):
+    """lime/phys.py:750-752"""
+    assert A.shape == B.shape
+    return A.dot(B) + B.dot(A)
+
+
+def transform(A, v):
+    """v^dag A v, lime/phys.py:706-718"""
+    return dag(v).dot(A.dot(v))
+
+
+def obs_dm(rho, d):
+    """Tr(d rho), lime/phys.py:837-844 (O(N^2) form of the same number)"""
+    if issparse(d) or issparse(rho):
+        return d.dot(rho).diagonal().sum()
+    return np.sum(np.asarray(d).T * np.asarray(rho))
+
+
+def isherm(a):
+    """lime/phys.py:1429"""
+    return np.allclose(a, dag(a))
+
+
+def pauli():
+    """lime/phys.py:773-786"""
+    s0 = np.identity(2)
+    sx = np.array([[0., 1.], [1., 0.]])
+    sy = np.array([[0., -1j], [1j, 0.]])
+    sz = np.array([[1., 0.], [0., -1.]])
+    return s0, sx, sy, sz
+
+
+def basis(N, j):
+    """lime/phys.py:879-899"""
+    b = np.zeros(N)
+    b[j] = 1.0
+    return b
+
+
+def ket2dm(psi):
+    """lime/phys.py:579-594"""
+    return np.einsum("i, j -> ij", psi, psi.conj())
+
+
+def destroy(N):
+    """lime/phys.py:615-633"""
+    a = lil_matrix((N, N))
+    a.setdiag(np.sqrt(np.arange(1, N)), 1)
+    return a.tocsr()
+
+
+def lorentzian(x, width=1.):
+    """lime/phys.py:669-688"""
+    return 1. / np.pi * width / (width ** 2 + (x) ** 2)
+
+
+def rk4(rho, fun, dt, *args):
+    """lime/phys.py:636-649: generic RK4 driver for an arbitrary Python right-hand side;
+    updates `rho` in place and returns it.  (The solvers do not loop over this function:
+    their whole time loop runs inside one CUDA launch.)"""
+    dt2 = dt / 2.0
+    k1 = fun(rho, *args)
+    k2 = fun(rho + k1 * dt2, *args)
+    k3 = fun(rho + k2 * dt2, *args)
+    k4 = fun(rho + k3 * dt, *args)
+    rho += (k1 + 2 * k2 + 2 * k3 + k4) / 6. * dt
+    return rho

@@ -1,0 +1,360 @@
+"""
+Sum-over-states nonlinear response functions with lime's signatures (lime/signal/sos.py),
+evaluated on the device in factorised form.
+
+Each pathway of sos.py is a sum over state triples (b,c,d) of four dipole elements times two
+frequency-domain Green's functions G(w) = 1/(w - dE + i Gamma) (one per scanned axis) and one
+propagator at the fixed delay.  Grouping by the index the first-axis factor depends on,
+
+    S[r][c] = sum_q A[q][r] * B[q][c],      B[q][c] = sum_d W[q][d] G(w_c; pole_{q,d})
+
+so the O(states^3) weights W are assembled on the host (numpy, microseconds) and the O(grid)
+work -- factor tables and the rank-R outer product, one complex store per grid point -- is two
+CUDA kernels (limeb200_sos_factor / limeb200_sos_outer).  Results differ from lime's only by
+floating-point re-association (~1e-15 relative).
+
+Conventions kept from lime: np.meshgrid(omega1, omega3) uses 'xy' indexing, so the returned
+array is indexed [omega3, omega1] (lime/signal/sos.py:379-388); DQC_R1 evaluates G_ba at the
+second axis (lime/signal/sos.py:949).
+[ext]: the *_batch variants take a vector of delays and return [T, n3, n1] in one launch.
+"""
+import numpy as np
+import torch
+
+from .. import engine
+from .. import _dev
+from ..units import au2mev
+from ..phys import lorentzian  # noqa: F401  (re-exported like lime)
+
+
+def _z(w):
+    return _dev.to_dev(np.asarray(w, dtype=np.float64).reshape(-1), np.float64)
+
+
+def _simple_factor(z, e, g):
+    """A[q][n] = 1/(z_n - e_q + i g_q) -> device [1,R,n]"""
+    e = np.asarray(e, dtype=float).reshape(-1)
+    g = np.asarray(g, dtype=float).reshape(-1)
+    R = len(e)
+    W = np.ones((1, R, 1), dtype=complex)
+    p = np.stack([e, g], axis=-1).reshape(R, 1, 2)
+    return engine.sos_factor(z, W, p)
+
+
+def _U(E, gamma, x, y, tau, extra=None):
+    """-i exp(-i (E_x - E_y) tau - Gamma_xy tau) for index arrays x, y (broadcast) and delays tau[T]"""
+    tau = np.asarray(tau, dtype=float).reshape(-1, *([1] * np.ndim(np.broadcast_arrays(x, y)[0])))
+    dE = E[x] - E[y]
+    G = (gamma[x] + gamma[y]) / 2.0
+    if extra is not None:
+        G = G + extra
+    return -1j * np.exp(-1j * dE * tau - G * tau)
+
+
+def _finish(out, single):
+    r = out.cpu().numpy()
+    return r[0] if single else r
+
+
+def _check_grid(n1, n3):
+    # lime adds (n3,n1) arrays into zeros((n1,n3)): only broadcast-compatible shapes work
+    np.broadcast_shapes((n1, n3), (n3, n1))
+
+
+# ---------------------------------------------------------------------------------------
+# photon echo: GSB, SE, ESA  (frequency-frequency at waiting time tau2)
+# ---------------------------------------------------------------------------------------
+def _pe_terms(evals, dip, tau2, g_idx, e_idx, f_idx, gamma, parts):
+    """weights and poles of the requested pathways, grouped by b (the omega1 index).
+    returns W[T,R,D], poles[R,D,2], (eA[R], gA[R])"""
+    E = np.asarray(evals, dtype=float)
+    dip = np.asarray(dip)
+    gamma = np.asarray(gamma, dtype=float)
+    a = 0
+    eb = np.array(list(e_idx), dtype=int)
+    taus = np.atleast_1d(np.asarray(tau2, dtype=float))
+    T, R = len(taus), len(eb)
+    Ws, Ps = [], []
+    if 'GSB' in parts:
+        c = 0
+        d = eb
+        w = (dip[a, eb][:, None] * dip[eb, c][:, None]) * (dip[c, d] * dip[d, a])[None, :]       # [b,d]
+        Ws.append(np.broadcast_to(w[None].astype(complex), (T, R, len(d))))
+        pe = np.broadcast_to((E[d] - E[c])[None, :], (R, len(d)))
+        pg = np.broadcast_to(((gamma[d] + gamma[c]) / 2.0)[None, :], (R, len(d)))
+        Ps.append(np.stack([pe, pg], axis=-1))
+    if 'SE' in parts:
+        cc = eb
+        dd = np.array(list(g_idx), dtype=int)
+        U = _U(E, gamma, cc[None, :], eb[:, None], taus)                                        # [T,b,c]
+        w = (dip[a, eb][:, None, None] * dip[cc, a][None, :, None]
+             * dip[dd[None, :], cc[:, None]][None, :, :] * dip[eb[:, None], dd[None, :]][:, None, :])  # [b,c,d]
+        Ws.append((U[:, :, :, None] * w[None]).reshape(T, R, -1))
+        pe = np.broadcast_to((E[cc][:, None] - E[dd][None, :])[None], (R, len(cc), len(dd))).reshape(R, -1)
+        pg = np.broadcast_to(((gamma[cc][:, None] + gamma[dd][None, :]) / 2.0)[None], (R, len(cc), len(dd))).reshape(R, -1)
+        Ps.append(np.stack([pe, pg], axis=-1))
+    if 'ESA' in parts:
+        cc = eb
+        dd = np.array(list(f_idx), dtype=int)
+        U = _U(E, gamma, cc[None, :], eb[:, None], taus)                                        # [T,b,c]
+        m = dip[cc, a][:, None] * dip[dd[None, :], cc[:, None]]                                  # [c,d]
+        inner = np.einsum('tbc,cd->tbd', U, m)
+        w = -(dip[eb, a][:, None] * dip[eb[:, None], dd[None, :]])[None] * inner                # [T,b,d]
+        Ws.append(w)
+        pe = E[dd][None, :] - E[eb][:, None]
+        pg = (gamma[dd][None, :] + gamma[eb][:, None]) / 2.0
+        Ps.append(np.stack([pe, pg], axis=-1))
+    W = np.concatenate(Ws, axis=2)
+    P = np.concatenate(Ps, axis=1)
+    eA = E[a] - E[eb]
+    gA = (gamma[a] + gamma[eb]) / 2.0
+    return W, P, (eA, gA)
+
+
+def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts):
+    single = np.ndim(tau2) == 0
+    n1, n3 = len(omega1), len(omega3)
+    _check_grid(n1, n3)
+    if len(list(e_idx)) == 0:
+        T = 1 if single else len(tau2)
+        z = np.zeros((T, n3, n1), dtype=complex)
+        return z[0] if single else z
+    W, P, (eA, gA) = _pe_terms(evals, dip, tau2, g_idx, e_idx, f_idx, gamma, parts)
+    z1, z3 = _z(omega1), _z(omega3)
+    A = _simple_factor(z1, eA, gA)                 # [1,R,n1]  G_ab(omega1)
+    Bf = engine.sos_factor(z3, W, P)               # [T,R,n3]
+    out = engine.sos_outer(Bf, A, W.shape[0])      # [T,n3,n1]
+    return _finish(out, single)
+
+
+def GSB(evals, dip, omega1, omega3, tau2, g_idx, e_idx, gamma):
+    """ground-state bleach; lime/signal/sos.py:478-528"""
+    return _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, [], gamma, ('GSB',))
+
+
+def SE(evals, dip, omega1, omega3, tau2, g_idx, e_idx, gamma):
+    """stimulated emission; lime/signal/sos.py:576-635"""
+    return _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, [], gamma, ('SE',))
+
+
+def ESA(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma):
+    """excited-state absorption (sign -1); lime/signal/sos.py:348-407"""
+    return _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, ('ESA',))
+
+
+def _photon_echo(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma):
+    """GSB + SE + ESA at waiting time t2 (scalar, or [ext] a vector -> [T,n3,n1]);
+    lime/signal/sos.py:695-729"""
+    return _pe_eval(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma, ('GSB', 'SE', 'ESA'))
+
+
+def photon_echo(mol, pump, probe, t2=0., g_idx=[0], e_idx=None, f_idx=None, fname='signal',
+                plt_signal=False, pol=None):
+    """lime/signal/sos.py:812-902 (np.savez side effect kept; plotting is not part of the port)"""
+    E = mol.eigvals()
+    dip = mol.edip_rms
+    gamma = mol.gamma
+    if gamma is None:
+        raise ValueError('Please set the decay constants gamma first.')
+    N = mol.nstates
+    if e_idx is None:
+        e_idx = range(N)
+    if f_idx is None:
+        f_idx = range(N)
+    S = _photon_echo(E, dip, omega1=-np.asarray(pump), omega3=probe, t2=t2, g_idx=g_idx, e_idx=e_idx,
+                     f_idx=f_idx, gamma=gamma)
+    if fname is not None:
+        np.savez(fname, pump, probe, S)
+    return S
+
+
+# ---- (omega1, omega2) maps at detection time t3, with pure dephasing --------------------
+def _t3_eval(E, dip, omega1, omega2, t3, g_idx, e_idx, f_idx, gamma, dephasing, which):
+    E = np.asarray(E, dtype=float)
+    dip = np.asarray(dip)
+    gamma = np.asarray(gamma, dtype=float)
+    N = len(E)
+    gD = np.ones((N, N)) * dephasing
+    np.fill_diagonal(gD, 0)
+    a = 0
+    eb = np.array(list(e_idx), dtype=int)
+    cc = eb
+    single = np.ndim(t3) == 0
+    taus = np.atleast_1d(np.asarray(t3, dtype=float))
+    n1, n2 = len(omega1), len(omega2)
+    if which == 'SE':
+        dd = np.array(list(g_idx), dtype=int)
+        Gt = _U(E, gamma, cc[:, None], dd[None, :], taus, extra=gD[cc[:, None], dd[None, :]])   # [T,c,d]
+        w = (dip[a, eb][:, None, None] * dip[cc, a][None, :, None]
+             * dip[dd[None, :], cc[:, None]][None] * dip[eb[:, None], dd[None, :]][:, None, :])  # [b,c,d]
+        W = np.einsum('bcd,tcd->tbc', w, Gt)
+    else:
+        dd = np.array(list(f_idx), dtype=int)
+        Gt = _U(E, gamma, dd[None, :], eb[:, None], taus, extra=gD[dd[None, :], eb[:, None]])   # [T,b,d]
+        w = (dip[eb, a][:, None, None] * dip[cc, a][None, :, None]
+             * dip[dd[None, :], cc[:, None]][None] * dip[eb[:, None], dd[None, :]][:, None, :])  # [b,c,d]
+        W = -np.einsum('bcd,tbd->tbc', w, Gt)
+    pe = E[cc][None, :] - E[eb][:, None]
+    pg = (gamma[cc][None, :] + gamma[eb][:, None]) / 2.0 + gD[cc[None, :], eb[:, None]]
+    P = np.stack([pe, pg], axis=-1)
+    A = _simple_factor(_z(omega1), E[a] - E[eb], (gamma[a] + gamma[eb]) / 2.0 + gD[a, eb])
+    Bf = engine.sos_factor(_z(omega2), W, P)
+    out = engine.sos_outer(Bf, A, W.shape[0])          # [T, n2, n1]
+    return _finish(out, single)
+
+
+def _SE(E, dip, omega1, omega2, t3, g_idx, e_idx, gamma, dephasing=10 / au2mev):
+    """lime/signal/sos.py:638-692"""
+    return _t3_eval(E, dip, omega1, omega2, t3, g_idx, e_idx, [], gamma, dephasing, 'SE')
+
+
+def _ESA(evals, dip, omega1, omega2, t3, g_idx, e_idx, f_idx, gamma, dephasing=10 / au2mev):
+    """lime/signal/sos.py:410-476"""
+    return _t3_eval(evals, dip, omega1, omega2, t3, g_idx, e_idx, f_idx, gamma, dephasing, 'ESA')
+
+
+def photon_echo_t3(mol, omega1, omega2, t3, g_idx=[0], e_idx=None, f_idx=None,
+                   fname='2DES', plt_signal=False, separate=False):
+    """lime/signal/sos.py:731-810"""
+    E = mol.eigvals()
+    edip = mol.edip_rms
+    gamma = mol.gamma
+    dephasing = mol.dephasing
+    if gamma is None:
+        raise ValueError('Please set the decay constants gamma first.')
+    N = mol.nstates
+    if e_idx is None:
+        e_idx = range(1, N)
+    if f_idx is None:
+        f_idx = range(1, N)
+    se = _SE(E, edip, -np.asarray(omega1), omega2, t3, g_idx, e_idx, gamma, dephasing=dephasing)
+    esa = _ESA(E, edip, -np.asarray(omega1), omega2, t3, g_idx, e_idx, f_idx, gamma, dephasing=dephasing)
+    S = se + esa
+    if separate:
+        if fname is not None:
+            np.savez(fname, omega1, omega2, se, esa)
+        return se, esa
+    if fname is not None:
+        np.savez(fname, omega1, omega2, S)
+    return S
+
+
+# ---------------------------------------------------------------------------------------
+# double-quantum coherence
+# ---------------------------------------------------------------------------------------
+def _ones_factor(n):
+    return torch.ones((1, 1, n), dtype=torch.complex128, device=_dev.device())
+
+
+def DQC_R1(evals, dip, omega1=None, omega2=[], omega3=None, tau1=None, tau3=None,
+           g_idx=[0], e_idx=None, f_idx=None, gamma=None):
+    """gg -> eg -> fg -> fe' -> e'e'; lime/signal/sos.py:904-992"""
+    E = np.asarray(evals, dtype=float)
+    dip = np.asarray(dip)
+    gamma = np.asarray(gamma, dtype=float)
+    a = 0
+    eb = np.array(list(e_idx), dtype=int)
+    fc = np.array(list(f_idx), dtype=int)
+    ed = eb
+    if omega3 is None and tau3 is not None:
+        single = np.ndim(tau3) == 0
+        taus = np.atleast_1d(np.asarray(tau3, dtype=float))
+        U = _U(E, gamma, fc[:, None], ed[None, :], taus)                             # [T,c,d]
+        m = np.einsum('tcd,d,dc->tc', U, dip[ed, a], dip[ed[:, None], fc[None, :]])   # sum_d
+        Wbc = dip[eb, a][None, :, None] * dip[fc[None, :], eb[:, None]][None] * m[:, None, :]   # [T,b,c]
+        T = len(taus)
+        W = (-Wbc).reshape(T, 1, -1)
+        nb, nc = len(eb), len(fc)
+        p1 = np.stack([np.broadcast_to((E[eb] - E[a])[:, None], (nb, nc)),
+                       np.broadcast_to(((gamma[eb] + gamma[a]) / 2.0)[:, None], (nb, nc))], axis=-1).reshape(1, -1, 2)
+        p2 = np.stack([np.broadcast_to((E[fc] - E[a])[None, :], (nb, nc)),
+                       np.broadcast_to(((gamma[fc] + gamma[a]) / 2.0)[None, :], (nb, nc))], axis=-1).reshape(1, -1, 2)
+        Bf = engine.sos_factor(_z(omega2), W, p1, p2)          # [T,1,n2]  (both G's on omega2, :949)
+        A = _ones_factor(len(omega1))
+        return _finish(engine.sos_outer(A, Bf, T), single)     # [T, n1, n2]
+    elif omega1 is None and tau1 is not None:
+        single = np.ndim(tau1) == 0
+        taus = np.atleast_1d(np.asarray(tau1, dtype=float))
+        U = _U(E, gamma, eb, a, taus)                                                 # [T,b]
+        s = np.einsum('tb,b,cb->tc', U, dip[eb, a], dip[fc[:, None], eb[None, :]])    # sum_b
+        W = -(dip[ed, a][None, :] * dip[ed[None, :], fc[:, None]])[None] * s[:, :, None]        # [T,c,d]
+        pe = E[fc][:, None] - E[ed][None, :]
+        pg = (gamma[fc][:, None] + gamma[ed][None, :]) / 2.0
+        Bf = engine.sos_factor(_z(omega3), W, np.stack([pe, pg], axis=-1))
+        A = _simple_factor(_z(omega2), E[fc] - E[a], (gamma[fc] + gamma[a]) / 2.0)
+        return _finish(engine.sos_outer(A, Bf, len(taus)), single)                    # [T, n2, n3]
+    # lime falls through with `signal` undefined (UnboundLocalError); make the misuse explicit
+    raise Exception('Input Error! Please specify either omega1, tau3 or omega3, tau1.')
+
+
+def DQC_R2(evals, dip, omega1=None, omega2=[], omega3=None, tau1=None, tau3=None,
+           g_idx=[0], e_idx=None, f_idx=None, gamma=None):
+    """gg -> eg -> fg -> eg -> gg; lime/signal/sos.py:994-1099"""
+    E = np.asarray(evals, dtype=float)
+    dip = np.asarray(dip)
+    gamma = np.asarray(gamma, dtype=float)
+    a = 0
+    eb = np.array(list(e_idx), dtype=int)
+    fc = np.array(list(f_idx), dtype=int)
+    ed = eb
+    if omega3 is None and tau3 is not None:
+        single = np.ndim(tau3) == 0
+        taus = np.atleast_1d(np.asarray(tau3, dtype=float))
+        U = _U(E, gamma, ed, a, taus)                                                 # [T,d]
+        s = np.einsum('td,dc,d->tc', U, dip[ed[:, None], fc[None, :]], dip[a, ed])    # sum_d
+        W = (dip[eb, a][:, None] * dip[fc[None, :], eb[:, None]])[None] * s[:, None, :]         # [T,b,c]
+        pe = np.broadcast_to((E[fc] - E[a])[None, :], (len(eb), len(fc)))
+        pg = np.broadcast_to(((gamma[fc] + gamma[a]) / 2.0)[None, :], (len(eb), len(fc)))
+        Bf = engine.sos_factor(_z(omega2), W, np.stack([pe, pg], axis=-1))
+        A = _simple_factor(_z(omega1), E[eb] - E[a], (gamma[eb] + gamma[a]) / 2.0)
+        return _finish(engine.sos_outer(A, Bf, len(taus)), single)                    # [T, n1, n2]
+    elif omega1 is None and tau1 is not None:
+        single = np.ndim(tau1) == 0
+        taus = np.atleast_1d(np.asarray(tau1, dtype=float))
+        U = 1j * _U(E, gamma, eb, a, taus)              # no -i prefactor here (lime/signal/sos.py:1056)
+        s = np.einsum('tb,b,cb->tc', U, dip[eb, a], dip[fc[:, None], eb[None, :]])
+        W = (dip[ed[None, :], fc[:, None]] * dip[a, ed][None, :])[None] * s[:, :, None]          # [T,c,d]
+        pe = np.broadcast_to((E[ed] - E[a])[None, :], (len(fc), len(ed)))
+        pg = np.broadcast_to(((gamma[ed] + gamma[a]) / 2.0)[None, :], (len(fc), len(ed)))
+        Bf = engine.sos_factor(_z(omega3), W, np.stack([pe, pg], axis=-1))
+        A = _simple_factor(_z(omega2), E[fc] - E[a], (gamma[fc] + gamma[a]) / 2.0)
+        return _finish(engine.sos_outer(A, Bf, len(taus)), single)                    # [T, n2, n3]
+    raise Exception('Input Error! Please specify either omega1, tau3 or omega3, tau1.')
+
+
+# ---------------------------------------------------------------------------------------
+# two-photon absorption
+# ---------------------------------------------------------------------------------------
+def _tpa2d(E, dip, omegaps, omega1s, e_idx, f_idx, gamma, time_order):
+    from .._lib import lib, check
+    dev = _dev.device()
+    E = np.asarray(E, dtype=float)
+    N = len(E)
+    dE = _dev.to_dev(E, np.float64, dev)
+    dd = _dev.to_dev(np.asarray(dip, dtype=float).reshape(N, N), np.float64, dev)
+    dg = _dev.to_dev(np.asarray(gamma, dtype=float), np.float64, dev)
+    ei = _dev.to_dev(np.array(list(e_idx), dtype=np.int32), np.int32, dev)
+    fi = _dev.to_dev(np.array(list(f_idx), dtype=np.int32), np.int32, dev)
+    wp, w1 = _z(omegaps), _z(omega1s)
+    out = torch.empty((wp.shape[0], w1.shape[0]), dtype=torch.float64, device=dev)
+    check(lib().limeb200_sos_tpa2d(_dev.ptr(dE), _dev.ptr(dd), _dev.ptr(dg), N, _dev.ptr(ei), ei.shape[0],
+                                   _dev.ptr(fi), fi.shape[0], _dev.ptr(wp), wp.shape[0], _dev.ptr(w1), w1.shape[0],
+                                   1 if time_order else 0, _dev.ptr(out), _dev.stream_ptr()))
+    return out.cpu().numpy()
+
+
+def TPA2D(E, dip, omegaps, omega1s, g_idx, e_idx, f_idx, gamma):
+    """lime/signal/sos.py:230-256"""
+    return _tpa2d(E, dip, omegaps, omega1s, e_idx, f_idx, gamma, False)
+
+
+def TPA2D_time_order(E, dip, omegaps, omega1s, g_idx, e_idx, f_idx, gamma):
+    """lime/signal/sos.py:258-283"""
+    return _tpa2d(E, dip, omegaps, omega1s, e_idx, f_idx, gamma, True)
+
+
+def TPA(E, dip, omegap, g_idx, e_idx, f_idx, gamma, degenerate=True):
+    """lime/signal/sos.py:199-228 (degenerate pump: omega1 = omega2 = omegap/2)"""
+    if not degenerate:
+        raise UnboundLocalError("omega1 is not defined for degenerate=False (as in lime)")
+    return float(_tpa2d(E, dip, [omegap], [omegap * 0.5], e_idx, f_idx, gamma, False)[0, 0])

@@ -1,0 +1,341 @@
+"""GPU parity: the CUDA path (through the C ABI / lime-compatible Python surface) against the
+NumPy oracle on the same seeded inputs and against the frozen reference outputs in tests/golden.
+Tolerance: <= 1e-10 relative in complex128 (BASELINE.json north_star); integer tables bit-exact."""
+import numpy as np
+import pytest
+from scipy.sparse import csr_matrix
+
+import cases
+import lime_oracle as lo
+from conftest import golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-10
+
+
+# ---------------------------------------------------------------- Lindblad
+def test_reference_golden_cavity(cuda):
+    """examples/cor.dat + dm.dat: <a^dag (a^dag a)(t) a>, thermal cavity N=10, CSR operands"""
+    from lime_b200.oqs import Lindblad_solver
+    g = golden('cavity_cor')
+    H, rho0, ops, c_ops, tlist = cases.thermal_cavity()
+    dt = tlist[1] - tlist[0]
+    A, B, C = ops
+    s = Lindblad_solver(H, c_ops=c_ops)
+    res = s.evolve(C.dot(rho0.dot(A)).toarray(), dt, len(tlist), e_ops=[B])
+    assert relerr(res.observables[:, 0], g['cor']) <= TOL
+    assert relerr(np.array(res.rholist), g['dm']) <= TOL
+    cor = s.correlation_3op_1t(rho0.toarray(), [A.toarray(), B.toarray(), C.toarray()], dt=dt, Nt=len(tlist))
+    assert relerr(cor, g['cor']) <= TOL
+
+
+@pytest.mark.parametrize('path', [0, 1, 2])
+def test_lindblad_dense_paths(cuda, path):
+    from lime_b200 import oqs
+    g = golden('lindblad_dense')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense()
+    plan = oqs._lindblad_plan(H, c_ops, e_ops, path=path)
+    rho_f, obs, traj = plan.run(rho0, 0.01, 80, traj_every=1)
+    assert relerr(obs, g['observables']) <= TOL
+    assert relerr(traj, g['rholist']) <= TOL
+    assert relerr(rho_f, g['rholist'][-1]) <= TOL
+    assert relerr(plan.rhs(rho0), g['rhs']) <= 1e-13
+    assert plan.last_launches >= 1
+
+
+def test_lindblad_drop_in_surface(cuda):
+    from lime_b200 import oqs
+    g = golden('lindblad_dense')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense()
+    rho_in = rho0.copy()
+    res = oqs._lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=80, dt=0.01)
+    assert np.array_equal(rho0, rho_in)                       # input is copied, never mutated
+    assert res.observables.shape == (80, 2) and res.observables.dtype == np.complex128
+    assert len(res.rholist) == 80 and res.rholist[0].shape == (6, 6)
+    assert relerr(res.observables, g['observables']) <= TOL
+    assert relerr(oqs.liouvillian(rho0, H, c_ops), g['rhs']) <= 1e-13
+    ref = lo.lindbladian(c_ops[0], rho0)
+    assert relerr(oqs.lindbladian(c_ops[0], rho0), ref) <= 1e-13
+    res2 = oqs.Lindblad_solver(H, c_ops).evolve(rho0, 0.01, 80, e_ops=e_ops)
+    assert relerr(res2.observables, g['observables']) <= TOL
+    # no e_ops / no c_ops edge cases
+    r3 = oqs._lindblad(H, rho0, [], e_ops=None, Nt=5, dt=0.01)
+    o3, l3 = lo.lindblad(H, rho0, [], None, Nt=5, dt=0.01)
+    assert r3.observables.shape == (5, 0) and relerr(r3.rholist[-1], l3[-1]) <= TOL
+
+
+@pytest.mark.parametrize('path', [1, 2, 3, 4])
+@pytest.mark.parametrize('ncav', [8, 16])
+def test_lindblad_jc_every_kernel(cuda, path, ncav):
+    """Jaynes-Cummings (config-2 shape, small cutoffs) through every kernel family"""
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav)
+    obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=60, dt=0.01)
+    sp = path in (3, 4)
+    Hs = csr_matrix(H) if sp else H
+    cs = [csr_matrix(c) for c in c_ops] if sp else c_ops
+    plan = oqs._lindblad_plan(Hs, cs, e_ops, path=path)
+    assert plan.path == path
+    rho_f, obs, traj = plan.run(rho0, 0.01, 60, traj_every=20)
+    assert relerr(obs, obs_o) <= TOL
+    assert relerr(rho_f, rl_o[-1]) <= TOL
+    assert relerr(traj, np.array([rl_o[19], rl_o[39], rl_o[59]])) <= TOL
+    if ncav == 8:
+        g = golden('lindblad_jc')
+        p2 = oqs._lindblad_plan(Hs, cs, e_ops, path=path)
+        rf, ob, _ = p2.run(rho0, 0.01, 100)
+        assert relerr(ob, g['observables']) <= TOL and relerr(rf, g['rho_final']) <= TOL
+
+
+@pytest.mark.parametrize('path', [1, 3, 4])
+def test_lindblad_batch_parameter_scan(cuda, path):
+    """[ext] batch over coupling/detuning points with per-point Hamiltonian values"""
+    from lime_b200.oqs import Lindblad_solver
+    pts = [(0.05, -0.1), (0.1, 0.0), (0.15, 0.1), (0.2, 0.2), (0.08, 0.05)]
+    Hs, refs = [], []
+    for gc, det in pts:
+        H, c_ops, e_ops, rho0 = cases.jc_point(ncav=12, g=gc, detuning=det)
+        Hs.append(csr_matrix(H) if path != 1 else H)
+        refs.append(lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=40, dt=0.02))
+    cs = [csr_matrix(c) for c in c_ops] if path != 1 else c_ops
+    s = Lindblad_solver(None, c_ops=cs)
+    rho_f, obs, _ = s.evolve_batch(rho0, 0.02, 40, e_ops=e_ops, H_batch=Hs, path=path)
+    assert obs.shape == (40, len(pts), 2)
+    for b, (o, rl) in enumerate(refs):
+        assert relerr(obs[:, b], o) <= TOL
+        assert relerr(rho_f[b], rl[-1]) <= TOL
+
+
+def test_lindblad_non_hermitian_rho_and_ragged_sizes(cuda):
+    """correlation functions propagate non-Hermitian 'density matrices'; odd N; N=1"""
+    from lime_b200 import oqs
+    for n, M in [(1, 1), (3, 2), (5, 0), (7, 3), (11, 1), (33, 1)]:
+        H, c_ops, e_ops, _ = cases.lindblad_dense(n=n, M=M, E=1, seed=100 + n)
+        rho0 = cases.rand_cplx(n, 7)
+        o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=12, dt=0.01)
+        for path in ([1, 2] if n < 33 else [1, 2]):
+            plan = oqs._lindblad_plan(H, c_ops, e_ops, path=path)
+            rf, ob, _ = plan.run(rho0, 0.01, 12)
+            assert relerr(ob, o) <= TOL, (n, path)
+            assert relerr(rf, rl[-1]) <= TOL, (n, path)
+
+
+def test_lindblad_driven(cuda):
+    from lime_b200 import oqs
+    g = golden('lindblad_driven')
+    H0, c_ops, e_ops, rho0 = cases.lindblad_dense(n=4, M=1, E=1, seed=77)
+
+    def f1(t):
+        return 0.3 * np.exp(-(t - 0.4) ** 2 / 0.02) * np.exp(-1j * 2.0 * t)
+    res = oqs._lindblad_driven([H0.copy(), [g['H1'], f1]], rho0, c_ops=c_ops, e_ops=e_ops, Nt=60, dt=0.01,
+                               t0=0.1, strict_parity=True)
+    assert relerr(res.observables, g['observables_strict']) <= TOL
+    assert relerr(res.rholist[-1], g['rho_final_strict']) <= TOL
+    o, rl = lo.lindblad_driven([H0.copy(), [g['H1'], f1]], rho0, c_ops, e_ops, Nt=60, dt=0.01, t0=0.1)
+    res = oqs.Lindblad_solver([H0.copy(), [g['H1'], f1]], c_ops=c_ops).evolve(rho0, 0.01, 60, t0=0.1, e_ops=e_ops)
+    assert relerr(res.observables, o) <= TOL and relerr(res.rholist[-1], rl[-1]) <= TOL
+
+
+def test_lindblad_correlations(cuda):
+    from lime_b200.oqs import Lindblad_solver
+    g = golden('lindblad_corr')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=4, M=2, E=1, seed=31)
+    ops3 = [g['A'], g['B'], g['C']]
+    s = Lindblad_solver(H, c_ops=c_ops)
+    assert relerr(s.correlation_3op_1t(rho0, ops3, dt=0.02, Nt=30), g['c3op1t']) <= TOL
+    c2 = s.correlation_3op_2t(rho0, ops3, 0.02, 6, 7)
+    assert c2.shape == (6, 7) and relerr(c2, g['c3op2t']) <= TOL
+    with pytest.raises(ValueError):
+        s.correlation_4op_1t(rho0, ops3, 0.02, 4)
+    ops4 = [g['A'], g['B'], g['C'], g['A']]
+    ref = lo.lindblad_correlation_3op_2t(H, c_ops, rho0, [ops4[0], ops4[1] @ ops4[2], ops4[3]], 0.02, 4, 5)
+    assert relerr(s.correlation_4op_2t(rho0, ops4, 0.02, 4, 5), ref) <= TOL
+
+
+def test_lindblad_long_run_stability(cuda):
+    """2e4 steps, N=2: accumulated difference to the oracle stays far below 1e-10"""
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=2, M=1, E=1, seed=3)
+    o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=20000, dt=0.005)
+    plan = oqs._lindblad_plan(H, c_ops, e_ops)
+    rf, ob, _ = plan.run(rho0, 0.005, 20000)
+    assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+    assert abs(np.trace(rf) - 1) < 1e-11
+
+
+# ---------------------------------------------------------------- Redfield
+def test_redfield_example_config1(cuda):
+    from lime_b200.oqs import Redfield_solver
+    g = golden('redfield_example')
+    H, a_ops, spectra, rho0, dt, Nt, e_ops, tlist = cases.redfield_example()
+    s = Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = s.redfield_tensor()
+    res = s.evolve(rho0, evecs=evecs, dt=dt, Nt=Nt, e_ops=e_ops)
+    assert res.observables.shape == (200, 1)
+    assert relerr(res.observables, g['observables']) <= TOL
+    assert relerr(np.array(res.rholist), g['rholist']) <= TOL
+    t8 = tlist[:8]
+    assert relerr(s.propagator(t8, 'EOM'), g['U_eom']) <= TOL
+    U = s.propagator(t8, 'SOS')
+    assert relerr(U, g['U_sos']) <= 1e-10
+    assert relerr(s.expect(rho0, e_ops), g['expect']) <= 1e-10
+    assert relerr(s.correlation_4op_3t(rho0, [e_ops[0]] * 4, 'llll', t8), g['corr4']) <= 1e-10
+
+
+def test_redfield_multilevel_tensor_and_operator_forms(cuda):
+    from lime_b200.oqs import Redfield_solver, _redfield
+    g = golden('redfield_multilevel')
+    H, a_ops, spectra, rho0 = cases.redfield_multilevel()
+    s = Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = s.redfield_tensor()
+    e_ops = [a_ops[0], g['e1']]
+    res = s.evolve(rho0, dt=0.02, Nt=60, e_ops=e_ops)
+    assert relerr(res.observables, g['observables']) <= TOL
+    assert relerr(np.array(res.rholist), g['rholist']) <= TOL
+    res = _redfield(R, rho0, evecs=evecs, Nt=60, dt=0.02, e_ops=e_ops)
+    assert relerr(res.observables, g['observables']) <= TOL
+    # [ext] batched, both forms; final state returned in the eigenbasis
+    batch = cases.rand_dm_batch(9, 5, 4)
+    for form in ('tensor', 'operator'):
+        out, obs = s.evolve_batch(batch, 0.02, 30, e_ops=e_ops, form=form)
+        for b in range(9):
+            o, rl = lo.redfield(R, batch[b], evecs=evecs, Nt=30, dt=0.02, e_ops=e_ops)
+            assert relerr(obs[:, b], o) <= TOL, form
+            assert relerr(evecs @ out[b] @ evecs.conj().T, rl[-1]) <= TOL, form
+
+
+# ---------------------------------------------------------------- HEOM
+def test_heom_dl_exact(cuda):
+    import io, contextlib, os, tempfile
+    from lime_b200.oqs import _heom_dl
+    g = golden('heom_dl')
+    H, sz, rho0 = cases.spin_boson_heom()[:3]
+    fn = os.path.join(tempfile.mkdtemp(), 'heom.dat')
+    with contextlib.redirect_stdout(io.StringIO()):
+        out = _heom_dl(H, rho0, sz, None, 300.0, 0.002, 0.0005, 12, 0.05, 200, fn)
+    assert relerr(out, g['rho_final']) <= TOL
+    traj = np.genfromtxt(fn, dtype=complex)[:, 1:].reshape(-1, 2, 2)
+    assert relerr(traj, g['traj']) <= TOL
+
+
+@pytest.mark.parametrize('path', [1, 2])
+def test_heom_spin_boson_multi_index(cuda, path):
+    """config-3 shape: K=2 Matsubara terms, depth 12 -> 91 ADOs, 312 couplings (diagonal Q)"""
+    from lime_b200.heom.heom import HEOM
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=12)
+    h = HEOM(H, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    assert h.nhe == 91
+    h.plan.set_path(path)
+    sx = np.array([[0, 1.], [1, 0]])
+    res = h.evolve(rho0, 0.01, 50, e_ops=[sz, sx])
+    ado_o, obs_o, traj_o = lo.heom_rk4(h.initial(rho0), H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64),
+                                       h.dn.astype(np.int64), h.up.astype(np.int64), 0.01, 50,
+                                       e_ops=[sz, sx], store=True)
+    assert h.plan.path == path
+    assert relerr(res.ado, ado_o) <= TOL
+    assert relerr(res.observables, obs_o) <= TOL
+    assert relerr(np.array(res.rholist), np.array(traj_o)) <= TOL
+    assert relerr(h.plan.rhs(ado_o), lo.heom_rhs(ado_o, H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64),
+                                                 h.dn.astype(np.int64), h.up.astype(np.int64))) <= 1e-12
+
+
+@pytest.mark.parametrize('path', [1, 2])
+def test_heom_dense_q_and_multibath(cuda, path):
+    """non-diagonal coupling operators, 2 baths with their own Q, n=3"""
+    from lime_b200.heom.heom import HEOM
+    n = 3
+    H = cases.rand_herm(n, 1)
+    Q = [cases.rand_herm(n, 2), cases.rand_herm(n, 3)]
+    rho0 = cases.rand_dm(n, 4)
+    h = HEOM(H, Q, [0.1, 0.2], [0.8, 1.3], 1.5, N_exp=2, N_cut=3)
+    h.plan.set_path(path)
+    res = h.evolve(rho0, 0.01, 25, e_ops=[H])
+    st = h.states.astype(np.int64)
+    ado_o, obs_o, _ = lo.heom_rk4(h.initial(rho0), H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                  h.up.astype(np.int64), 0.01, 25, e_ops=[H])
+    assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
+
+
+def test_heom_fmo_shape_stagewise_and_batch(cuda):
+    """config-4 shape at reduced depth: 7 sites, 7 baths x K=2, depth 2 (120 ADOs of 7x7);
+    projector coupling operators (diagonal-Q gather path); batch of 3 hierarchies"""
+    from lime_b200 import engine
+    import lime_b200.heom.heom as hh
+    n = 7
+    H = cases.rand_herm(n, 21, 0.5) + np.diag(np.arange(n) * 0.3)
+    Q = [np.diag((np.arange(n) == j).astype(float)) for j in range(n)]
+    h = hh.HEOM(H, Q, 0.05, 0.6, 1.2, N_exp=2, N_cut=2)
+    assert h.nhe == 120
+    st = h.states.astype(np.int64)
+    rng = np.random.default_rng(5)
+    ado0 = rng.standard_normal((3, h.nhe, n, n)) + 1j * rng.standard_normal((3, h.nhe, n, n))
+    ado0 *= 0.1
+    out, obs, traj = h.plan.run(ado0, 0.02, 10, e_ops=[H])
+    for b in range(3):
+        ado_o, obs_o, _ = lo.heom_rk4(ado0[b], H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                      h.up.astype(np.int64), 0.02, 10, e_ops=[H])
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+
+
+def test_heom_parameter_batch(cuda):
+    """[ext] config-3 throughput variant: hierarchies differing in (lambda, beta)"""
+    from lime_b200 import engine
+    from lime_b200.heom.heom import _calc_matsubara_params
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=5)
+    states, dn, up = engine.heom_tables([depth + 1] * K, depth)
+    pars = [(0.1, 1.0), (0.2, 0.7), (0.3, 1.4), (0.05, 2.0)]
+    cs, nus = [], []
+    for lam_b, T_b in pars:
+        c, nu = _calc_matsubara_params(K, lam_b, gam, T_b)
+        cs.append(c)
+        nus.append(nu)
+    plan = engine.HeomPlan(H, sz, [0] * K, np.array(cs), np.array(nus), states, dn, up)
+    ado0 = np.zeros((len(pars), states.shape[0], 2, 2), dtype=complex)
+    ado0[:, 0] = rho0
+    out, obs, _ = plan.run(ado0, 0.01, 40, e_ops=[sz])
+    for b in range(len(pars)):
+        ado_o, obs_o, _ = lo.heom_rk4(ado0[b], H, sz[None], [0] * K, cs[b], nus[b], states.astype(np.int64),
+                                      dn.astype(np.int64), up.astype(np.int64), 0.01, 40, e_ops=[sz])
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+
+
+# ---------------------------------------------------------------- SOS
+def test_sos_all_pathways(cuda):
+    from lime_b200.signal import sos
+    g = golden('sos')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    w1, w3, w2, w1b, t2 = g['w1'], g['w3'], g['w2'], g['w1b'], float(g['t2'])
+    au2ev = 27.211386
+    assert relerr(sos.GSB(E, dip, w1, w3, t2, g_idx, e_idx, gamma), g['GSB']) <= TOL
+    assert relerr(sos.SE(E, dip, w1, w3, t2, g_idx, e_idx, gamma), g['SE']) <= TOL
+    assert relerr(sos.ESA(E, dip, w1, w3, t2, g_idx, e_idx, f_idx, gamma), g['ESA']) <= TOL
+    pe = sos._photon_echo(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    assert pe.shape == (12, 12) and pe.dtype == np.complex128
+    assert relerr(pe, g['PE']) <= TOL
+    assert relerr(sos._SE(E, dip, -w1, w3, t2, g_idx, e_idx, gamma, dephasing=0.01 / au2ev), g['SE_t3']) <= TOL
+    assert relerr(sos._ESA(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma, dephasing=0.01 / au2ev), g['ESA_t3']) <= TOL
+    kw = dict(g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    assert relerr(sos.DQC_R1(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, **kw), g['R1_t3']) <= TOL
+    assert relerr(sos.DQC_R2(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, **kw), g['R2_t3']) <= TOL
+    assert relerr(sos.DQC_R1(E, dip, omega2=w2, omega3=w1b, tau1=50.0, **kw), g['R1_t1']) <= TOL
+    assert relerr(sos.DQC_R2(E, dip, omega2=w2, omega3=w1b, tau1=50.0, **kw), g['R2_t1']) <= TOL
+    assert relerr(sos.TPA2D(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D']) <= TOL
+    assert relerr(sos.TPA2D_time_order(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D_to']) <= TOL
+    with pytest.raises(Exception):
+        sos.DQC_R2(E, dip, omega2=w2, **kw)
+
+
+def test_sos_waiting_time_batch_and_ragged_grid(cuda):
+    """[ext] vector of waiting times in one launch; non-multiple-of-tile grid; N=32 config-5 shape"""
+    from lime_b200.signal import sos
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system(N=32, ne=15, seed=0)
+    au2ev, au2fs = 27.211386, 2.41888432651e-2
+    w = np.linspace(1.4, 2.1, 45) / au2ev
+    T = np.linspace(0, 630, 5) / au2fs
+    pe = sos._photon_echo(E, dip, -w, w, T, g_idx, e_idx, f_idx, gamma)
+    assert pe.shape == (5, 45, 45)
+    for t in (0, 2, 4):
+        assert relerr(pe[t], lo.photon_echo_core(E, dip, -w, w, T[t], g_idx, e_idx, f_idx, gamma)) <= TOL
+    # linearity in the dipole scale: S ~ mu^4
+    pe2 = sos._photon_echo(E, 2.0 * dip, -w, w, T[1], g_idx, e_idx, f_idx, gamma)
+    assert relerr(pe2, 16.0 * pe[1]) <= 1e-12

@@ -1,0 +1,114 @@
+"""CPU: host logic of the product package -- the C ABI loads and exports every symbol the
+header declares, the native HEOM table builder is bit-exact against the reference goldens,
+and compute entry points fail loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import cases
+from conftest import golden, relerr, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    from lime_b200 import _lib
+    hdr = open(os.path.join(ROOT, 'include', 'lime_b200.h')).read()
+    declared = set(re.findall(r'\b(limeb200_\w+)\s*\(', hdr))
+    assert declared, 'no declarations found'
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    l = _lib.lib()
+    for name in declared:
+        assert hasattr(l, name), name
+    assert l.limeb200_version() == 100
+
+
+def test_heom_tables_native_bit_exact():
+    from lime_b200 import engine
+    g = golden('heom_tables')
+    for key in g.files:
+        dpart, x = key[1:].split('_x')
+        dims = [int(v) for v in dpart.split('_')]
+        states, dn, up = engine.heom_tables(dims, int(x))
+        assert states.dtype == np.int32
+        assert np.array_equal(states, g[key].astype(np.int32)), key
+    import lime_oracle as lo
+    for dims, exc in [([13, 13], 12), ([4, 3, 2], 3), ([5] * 6, 4), ([3, 3], 0)]:
+        states, dn, up = engine.heom_tables(dims, exc)
+        so, dno, upo = lo.heom_tables(dims, exc)
+        assert np.array_equal(states, so) and np.array_equal(dn, dno) and np.array_equal(up, upo)
+    states, dn, up = engine.heom_tables([5] * 14, 4)
+    assert states.shape == (3060, 14)
+    assert (dn >= 0).sum() + (up >= 0).sum() == 19040
+    tiers = np.bincount(states.sum(axis=1))
+    assert list(tiers) == [1, 14, 105, 560, 2380]
+
+
+def test_enr_state_dictionaries_drop_in():
+    from lime_b200.heom.heom import enr_state_dictionaries, state_number_enumerate, _calc_matsubara_params
+    import lime_oracle as lo
+    for dims, exc in [([3, 3], 2), ([4, 3, 2], 3), ([3] * 4, 0)]:
+        n, s2i, i2s = enr_state_dictionaries(dims, exc)
+        no, s2io, i2so = lo.enr_state_dictionaries(dims, exc)
+        assert n == no and s2i == s2io and i2s == i2so
+        assert list(s2i.keys()) == list(s2io.keys())           # same insertion order
+        assert all(isinstance(k, tuple) for k in s2i)
+    with pytest.raises(TypeError):
+        enr_state_dictionaries([2, 2], None)
+    assert [tuple(s) for s in state_number_enumerate([2, 2])] == [(0, 0), (0, 1), (1, 0), (1, 1)]
+    g = golden('heom_matsubara')
+    for i in range(4):
+        K, lam, gam, T = g['par%d' % i]
+        c, nu = _calc_matsubara_params(int(K), lam, gam, T)
+        assert isinstance(c, list) and isinstance(nu, list)
+        assert relerr(c, g['c%d' % i]) == 0 and relerr(nu, g['nu%d' % i]) == 0
+
+
+def test_redfield_tensor_host_setup_matches_golden():
+    import io, contextlib
+    from lime_b200.oqs import Redfield_solver, redfield_tensor
+    g = golden('redfield_example')
+    H, a_ops, spectra, rho0, dt, Nt, e_ops, tlist = cases.redfield_example()
+    s = Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = s.redfield_tensor()
+    assert relerr(R.toarray(), g['R']) <= 1e-14 and relerr(evecs, g['evecs']) == 0
+    R2, _ = redfield_tensor(H, a_ops, spectra)
+    assert relerr(R2.toarray(), g['R']) <= 1e-14
+    with pytest.raises(TypeError):
+        Redfield_solver(H, c_ops=a_ops).redfield_tensor()              # no spectra
+    with pytest.raises(TypeError):
+        redfield_tensor(H, [np.array([[0, 1.], [0, 0]])], spectra)      # non-Hermitian a_op
+    with pytest.raises(TypeError):
+        Redfield_solver(H, c_ops=a_ops, spectra=spectra).propagator(tlist)
+    with pytest.raises(ValueError):
+        s.correlation_4op_3t(rho0, [e_ops[0]] * 3, 'lll', tlist[:4])
+
+
+def test_superoperator_algebra_matches_golden():
+    from lime_b200 import superoperator as sop
+    g = golden('lindblad_dense')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense()
+    L = sop.liouvillian(H, c_ops)
+    assert relerr(L.toarray(), g['superop']) <= 1e-14
+    with pytest.raises(ValueError):
+        sop.operator_to_superoperator(H, 'x')
+
+
+def test_result_defaults():
+    from lime_b200.mol import Result
+    r = Result(dt=0.1, Nt=5, rho0=np.eye(2))
+    assert np.allclose(r.times, 0.1 * np.arange(5)) and r.timesteps == 5
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason='checks the no-GPU failure mode')
+def test_no_cpu_fallback():
+    from lime_b200 import _lib
+    from lime_b200.oqs import _lindblad
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense()
+    with pytest.raises(_lib.LimeB200Error):
+        _lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=2, dt=0.01)
+    h = ctypes.c_void_p()
+    rc = _lib.lib().limeb200_qme_create(ctypes.byref(h), 4, 0)
+    assert rc < 0 and b'no CUDA device' in _lib.lib().limeb200_last_error()
