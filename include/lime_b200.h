@@ -34,7 +34,7 @@ int limeb200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor
 /* ------------------------------------------------------------------------------------
  * Quantum master equation in generator/sandwich form
  *
- *      d rho/dt = G rho + rho G^H + sum_s X_s rho Z_s^H
+ *      d rho/dt = G rho + rho Gr + sum_s X_s rho Z_s^H        (Gr = G^H unless set)
  *
  * replaces: liouvillian/lindbladian  lime/oqs.py:706-723 (= lime/phys.py:561-577)
  *             G = -iH - 1/2 sum_m l_m^H l_m,   (X_s, Z_s) = (l_s, l_s)
@@ -65,9 +65,16 @@ int limeb200_qme_add_sandwich_csr(limeb200_qme_t plan,
                                   const int* x_indptr, const int* x_indices, const double* h_xdata, int x_nnz,
                                   const int* z_indptr, const int* z_indices, const double* h_zdata, int z_nnz,
                                   int nb);
-/* time-dependent generator G_k = G + sum_i coef[k][i] D_i, frozen over the four stages of
- * step k (lime/oqs.py:1786-1790 evaluates H(t) once per step at t+dt); D_i dense [N][N]. */
-int limeb200_qme_add_drive_dense(limeb200_qme_t plan, const double* h_D);
+/* optional explicit right generator (dense paths only).  lime's liouvillian is the plain
+ * commutator -i(H rho - rho H) even for a non-Hermitian H (lime/oqs.py:706-713), i.e.
+ * Gr = +iH - 1/2 sum l^H l, which equals G^H only when H is Hermitian.                    */
+int limeb200_qme_set_right_generator_dense(limeb200_qme_t plan, const double* h_Gr, int nb);
+/* time-dependent generator, frozen over the four stages of step k (lime/oqs.py:1786-1790
+ * evaluates H(t) once per step at t+dt):  G_k = G + sum_i coef[k][i] D_i and
+ *   h_Dr given : Gr_k = Gr + sum_i coef[k][i] Dr_i      (complex drives, lime's Pulse.efield)
+ *   h_Dr NULL  : Gr_k = Gr + sum_i conj(coef[k][i]) D_i^H
+ * D_i, Dr_i dense [N][N].                                                                  */
+int limeb200_qme_add_drive_dense(limeb200_qme_t plan, const double* h_D, const double* h_Dr);
 /* observables e[E][N][N] (dense host): obs = Tr(e rho), lime/phys.py:837-844 */
 int limeb200_qme_set_observables(limeb200_qme_t plan, const double* h_e, int E);
 /* kernel selection: 0 auto, 1 dense on-chip, 2 dense stage-wise, 3 sparse global-scratch,

@@ -24,7 +24,8 @@ SIGNATURES = {
     'limeb200_qme_set_generator_csr': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int]),
     'limeb200_qme_add_sandwich_dense': (c_int, [c_vp, c_vp, c_vp, c_int]),
     'limeb200_qme_add_sandwich_csr': (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int]),
-    'limeb200_qme_add_drive_dense': (c_int, [c_vp, c_vp]),
+    'limeb200_qme_set_right_generator_dense': (c_int, [c_vp, c_vp, c_int]),
+    'limeb200_qme_add_drive_dense': (c_int, [c_vp, c_vp, c_vp]),
     'limeb200_qme_set_observables': (c_int, [c_vp, c_vp, c_int]),
     'limeb200_qme_set_path': (c_int, [c_vp, c_int]),
     'limeb200_qme_finalize': (c_int, [c_vp]),

@@ -32,9 +32,10 @@ struct limeb200_qme_s {
     int path_req = 0, path = 0;
     bool finalized = false;
     int nb = 1;
-    HostOp G;
+    HostOp G, Gr;                               // left generator, optional right generator (default G^H)
     std::vector<HostOp> X, Z;
-    std::vector<std::vector<hcplx>> D;          // drives, dense
+    std::vector<std::vector<hcplx>> D, Dr;      // drives, dense: G_k += c D, Gr_k += c Dr (or conj(c) D^H)
+    bool drive_conj = true;
     std::vector<hcplx> eops;                    // [E][N*N]
     int E = 0;
     long long launches = 0;
@@ -279,11 +280,27 @@ int limeb200_qme_add_sandwich_csr(limeb200_qme_t p,
     if (r != LB_OK) { p->X.pop_back(); p->Z.pop_back(); }
     return r;
 }
-int limeb200_qme_add_drive_dense(limeb200_qme_t p, const double* h_D) {
+int limeb200_qme_set_right_generator_dense(limeb200_qme_t p, const double* h_Gr, int nb) {
+    LB_REQUIRE(p, "null plan");
+    return set_op_dense(p, p->Gr, h_Gr, nb);
+}
+int limeb200_qme_add_drive_dense(limeb200_qme_t p, const double* h_D, const double* h_Dr) {
     LB_REQUIRE(p && h_D, "null argument");
     LB_REQUIRE(!p->finalized, "plan already finalized");
+    LB_REQUIRE(p->D.empty() || (h_Dr != nullptr) == !p->drive_conj, "all drives must agree on passing h_Dr");
+    const size_t NN = (size_t)p->N * p->N;
     const hcplx* c = reinterpret_cast<const hcplx*>(h_D);
-    p->D.emplace_back(c, c + (size_t)p->N * p->N);
+    p->D.emplace_back(c, c + NN);
+    if (h_Dr) {
+        const hcplx* r = reinterpret_cast<const hcplx*>(h_Dr);
+        p->Dr.emplace_back(r, r + NN);
+        p->drive_conj = false;
+    } else {
+        std::vector<hcplx> dh(NN);
+        adjoint(c, dh.data(), p->N);
+        p->Dr.push_back(dh);
+        p->drive_conj = true;
+    }
     return LB_OK;
 }
 int limeb200_qme_set_observables(limeb200_qme_t p, const double* h_e, int E) {
@@ -324,7 +341,7 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     // ---- choose path
     int wg = max_row_nnz(p->G, N), wprod = 1;
     for (int s = 0; s < S; ++s) wprod = std::max(wprod, max_row_nnz(p->X[s], N) * max_row_nnz(p->Z[s], N));
-    const bool sparse_ok = (nd == 0) && S <= QME_MAXS && wg <= 16 && wprod <= 16;
+    const bool sparse_ok = (nd == 0) && !p->Gr.given && S <= QME_MAXS && wg <= 16 && wprod <= 16;
     const bool dense_mem_ok = (double)nb * NN * 16.0 * (2 + 2 * S) < 8e9;
     int path = p->path_req;
     if (path == 0) {
@@ -363,6 +380,7 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     if (path == 1) LB_REQUIRE(N <= 64, "dense on-chip path needs N <= 64 (N=%d)", N);
     if (path == 3 || path == 4) {
         LB_REQUIRE(nd == 0, "sparse paths do not support drive operators");
+        LB_REQUIRE(!p->Gr.given, "sparse paths need the right generator to be G^H");
         LB_REQUIRE(S <= QME_MAXS, "sparse paths support at most %d sandwich terms", QME_MAXS);
     }
     if (path == 1 || path == 2) LB_REQUIRE(dense_mem_ok, "dense operator batch too large (nb=%d, N=%d)", nb, N);
@@ -372,8 +390,14 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
         std::vector<hcplx> g, gh, x, zh;
         densify(p->G, N, g);
         if (p->G.nb < nb) replicate(g, NN, nb);
-        gh.resize(g.size());
-        for (int b = 0; b < nb; ++b) adjoint(&g[b * NN], &gh[b * NN], N);
+        if (p->Gr.given) {
+            LB_REQUIRE(p->Gr.nb == 1 || p->Gr.nb == nb, "right generator batch incompatible with %d", nb);
+            densify(p->Gr, N, gh);
+            if (p->Gr.nb < nb) replicate(gh, NN, nb);
+        } else {
+            gh.resize(g.size());
+            for (int b = 0; b < nb; ++b) adjoint(&g[b * NN], &gh[b * NN], N);
+        }
         x.resize((size_t)nb * S * NN);
         zh.resize((size_t)nb * S * NN);
         for (int s = 0; s < S; ++s) {
@@ -396,7 +420,7 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
             std::vector<hcplx> d((size_t)nd * NN), dh((size_t)nd * NN);
             for (int i = 0; i < nd; ++i) {
                 std::copy(p->D[i].begin(), p->D[i].end(), d.begin() + i * NN);
-                adjoint(p->D[i].data(), &dh[i * NN], N);
+                std::copy(p->Dr[i].begin(), p->Dr[i].end(), dh.begin() + i * NN);
             }
             LB_CUDA(p->dD.upload(d.data(), d.size() * 16));
             LB_CUDA(p->dDh.upload(dh.data(), dh.size() * 16));
@@ -450,14 +474,14 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
 namespace {
 
 __global__ void qme_build_gk(const cplx* G, const cplx* Gh, const cplx* D, const cplx* Dh,
-                             const cplx* coef, int nd, int NN, cplx* Gk, cplx* Gkh) {
+                             const cplx* coef, int nd, int NN, int conj_r, cplx* Gk, cplx* Gkh) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= NN) return;
     cplx v = G[i], vh = Gh[i];
     for (int d = 0; d < nd; ++d) {
         cplx c = coef[d];
         cfma(v, c, D[(size_t)d * NN + i]);
-        cfma(vh, cconj(c), Dh[(size_t)d * NN + i]);
+        cfma(vh, conj_r ? cconj(c) : c, Dh[(size_t)d * NN + i]);
     }
     Gk[i] = v; Gkh[i] = vh;
 }
@@ -484,6 +508,7 @@ int run_dense_onchip(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, 
     a.G = p->dG.as<cplx>(); a.Gh = p->dGh.as<cplx>(); a.X = p->dX.as<cplx>(); a.Zh = p->dZh.as<cplx>();
     a.D = p->dD.as<cplx>(); a.Dh = p->dDh.as<cplx>(); a.eT = p->deT.as<cplx>();
     a.coef = coef; a.rho = rho; a.obs = obs; a.traj = traj; a.dt = dt;
+    a.drive_conj = p->drive_conj ? 1 : 0;
     int ept = 1, tps;
     if (NN <= 4) tps = 4;
     else if (NN <= 16) tps = 16;
@@ -543,7 +568,7 @@ int run_dense_stage(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, c
             cplx* gk = p->s_gk.as<cplx>();
             qme_build_gk<<<ceil_div((int)NN, 256), 256, 0, st>>>(p->dG.as<cplx>(), p->dGh.as<cplx>(), p->dD.as<cplx>(),
                                                                 p->dDh.as<cplx>(), coef + (size_t)step * nd, nd,
-                                                                (int)NN, gk, gk + NN);
+                                                                (int)NN, p->drive_conj ? 1 : 0, gk, gk + NN);
             p->launches++;
             G = gk; Gh = gk + NN;
         }

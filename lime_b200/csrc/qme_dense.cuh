@@ -20,11 +20,11 @@ struct QmeDenseArgs {
     int N, S, E, nd, B, nsteps, traj_every;
     int nb;                 // operator batch: 1 (shared) or B (per-item values)
     const cplx* G;          // [nb][N*N]
-    const cplx* Gh;         // [nb][N*N]   G^H
+    const cplx* Gh;         // [nb][N*N]   right generator (G^H unless set explicitly)
     const cplx* X;          // [nb][S][N*N]
     const cplx* Zh;         // [nb][S][N*N] Z_s^H
     const cplx* D;          // [nd][N*N]   drive generators:  G_k = G + sum_i coef[k][i] D_i
-    const cplx* Dh;         // [nd][N*N]   D_i^H            G_k^H = G^H + sum_i conj(coef) D_i^H
+    const cplx* Dh;         // [nd][N*N]   right drives     Gr_k = Gr + sum_i (conj?)(coef) Dr_i
     const cplx* eT;         // [E][N*N]    observables, transposed: Tr(e rho) = sum eT[idx] rho[idx]
     const cplx* coef;       // [nsteps][nd]
     cplx* rho;              // [B][N*N] in/out
@@ -34,6 +34,7 @@ struct QmeDenseArgs {
     int slots;              // density matrices per CTA
     int tps;                // threads per slot
     int ops_in_smem;        // G,Gh,X,Zh staged in shared memory (nb == 1 only)
+    int drive_conj;         // 1: Gr_k += conj(c) Dh ; 0: Gr_k += c Dh
 };
 
 // --------------------------------------------------------------------------------
@@ -95,7 +96,7 @@ qme_dense_onchip(QmeDenseArgs a) {
                 for (int d = 0; d < a.nd; ++d) {
                     cplx c = a.coef[(size_t)step * a.nd + d];
                     cfma(v, c, a.D[(size_t)d * NN + i]);
-                    cfma(vh, cconj(c), a.Dh[(size_t)d * NN + i]);
+                    cfma(vh, a.drive_conj ? cconj(c) : c, a.Dh[(size_t)d * NN + i]);
                 }
                 g[i] = v; gh[i] = vh;
             }

@@ -92,11 +92,18 @@ class QmePlan:
                 z = np.ascontiguousarray(np.broadcast_to(z, (nb, self.N, self.N)))
             check(lib().limeb200_qme_add_sandwich_dense(self._h, hptr(x), hptr(z), nb))
 
-    def add_drive(self, D):
+    def set_right_generator(self, Gr):
+        """explicit right generator (rho Gr); needed when H is not Hermitian"""
+        a, nb = _dense_batch(Gr, self.N)
+        check(lib().limeb200_qme_set_right_generator_dense(self._h, hptr(a), nb))
+
+    def add_drive(self, D, Dr=None):
+        """G_k += c_k D ; Gr_k += c_k Dr  (Dr None: Gr_k += conj(c_k) D^H)"""
         a, nb = _dense_batch(D, self.N)
         if nb != 1:
             raise ValueError('drive operators are not batched')
-        check(lib().limeb200_qme_add_drive_dense(self._h, hptr(a)))
+        r = None if Dr is None else _dense_batch(Dr, self.N)[0]
+        check(lib().limeb200_qme_add_drive_dense(self._h, hptr(a), hptr(r)))
         self.ndrive += 1
 
     def set_observables(self, e_ops):

@@ -34,28 +34,44 @@ def _all_sparse(ops):
     return all(issparse(o) for o in ops)
 
 
+def _is_hermitian(H):
+    if issparse(H):
+        d = (H - H.conj().T)
+        return d.nnz == 0 or abs(d).max() == 0
+    H = np.asarray(H)
+    return np.array_equal(H, H.conj().T)
+
+
 def lindblad_generator(H, c_ops):
-    """G = -iH - 1/2 sum_m l_m^dag l_m (sparse if every operand is sparse)"""
+    """(G, Gr, [l_m]) with d rho/dt = G rho + rho Gr + sum_m l_m rho l_m^dag:
+    G = -iH - 1/2 sum_m l_m^dag l_m,  Gr = +iH - 1/2 sum_m l_m^dag l_m.
+    lime's liouvillian is the plain commutator even for a non-Hermitian H
+    (lime/oqs.py:706-713), so Gr == G^dag only for Hermitian H; Gr is returned as None
+    in that case (the engine then uses G^dag, which the sparse kernels require).
+    Sparse operands stay sparse."""
     c_ops = [] if c_ops is None else list(c_ops)
-    if _all_sparse([H] + c_ops):
+    herm = _is_hermitian(H)
+    if herm and _all_sparse([H] + c_ops):
         G = (-1j) * csr_matrix(H).astype(complex)
-        for l in c_ops:
-            l = csr_matrix(l).astype(complex)
+        ls = [csr_matrix(l).astype(complex) for l in c_ops]
+        for l in ls:
             G = G - 0.5 * (l.conj().T @ l)
-        return csr_matrix(G), [csr_matrix(l).astype(complex) for l in c_ops]
+        return csr_matrix(G), None, ls
     Hd = _dev.as_c128(H)
-    G = -1j * Hd
     ls = [_dev.as_c128(l) for l in c_ops]
+    diss = np.zeros_like(Hd)
     for l in ls:
-        G = G - 0.5 * (l.conj().T @ l)
-    return G, ls
+        diss = diss - 0.5 * (l.conj().T @ l)
+    return -1j * Hd + diss, (None if herm else 1j * Hd + diss), ls
 
 
 def _lindblad_plan(H, c_ops, e_ops, path=None, device_index=None):
     N = H.shape[-1]
-    G, ls = lindblad_generator(H, c_ops)
+    G, Gr, ls = lindblad_generator(H, c_ops)
     plan = engine.QmePlan(N, device_index)
     plan.set_generator(G)
+    if Gr is not None:
+        plan.set_right_generator(Gr)
     for l in ls:
         plan.add_sandwich(l, l)
     plan.set_observables(e_ops)
@@ -140,14 +156,18 @@ def _lindblad_driven(H, rho0, c_ops=None, e_ops=None, Nt=1, dt=0.005, t0=0.,
                  dtype=complex).reshape(Nt, nd)
     if strict_parity:
         f = np.cumsum(f, axis=0)
-    # G_k = G0 + sum_i f_i(t_k) * (i H_i)
-    G0, ls = lindblad_generator(H0, [_dev.as_c128(c) for c in c_ops])
+    # H(t_k) = H0 - sum_i f_i H_i  ->  G_k = G0 + sum_i f_i (i H_i),  Gr_k = Gr0 + sum_i f_i (-i H_i);
+    # f_i may be complex (lime's Pulse.efield), H(t) is then not Hermitian and lime still
+    # evaluates the plain commutator
+    G0, Gr0, ls = lindblad_generator(H0, [_dev.as_c128(c) for c in c_ops])
     plan = engine.QmePlan(N)
     plan.set_generator(G0)
+    plan.set_right_generator(G0.conj().T if Gr0 is None else Gr0)
     for l in ls:
         plan.add_sandwich(l, l)
     for i in range(1, len(H)):
-        plan.add_drive(1j * _dev.as_c128(H[i][0]))
+        Hi = _dev.as_c128(H[i][0])
+        plan.add_drive(1j * Hi, -1j * Hi)
     plan.set_observables(e_ops)
     plan.finalize()
     rho_f, obs, traj = plan.run(_dev.as_c128(rho0), dt, Nt, coef=f, traj_every=1 if return_result else 0)
@@ -308,8 +328,10 @@ def _lindblad_plan_batch(H_batch, c_ops, e_ops, path=None, device_index=None):
     else:
         if isinstance(H_batch, tuple):
             raise ValueError('(pattern, values) Hamiltonian batches need sparse collapse operators')
-        G = np.stack([lindblad_generator(_dev.as_c128(h), [_dev.as_c128(c) for c in c_ops])[0] for h in Hs])
-        plan.set_generator(G)
+        gens = [lindblad_generator(_dev.as_c128(h), [_dev.as_c128(c) for c in c_ops]) for h in Hs]
+        plan.set_generator(np.stack([g[0] for g in gens]))
+        if any(g[1] is not None for g in gens):
+            plan.set_right_generator(np.stack([g[0].conj().T if g[1] is None else g[1] for g in gens]))
         for c in c_ops:
             plan.add_sandwich(_dev.as_c128(c), _dev.as_c128(c))
     plan.set_observables(e_ops)

@@ -120,6 +120,21 @@ def test_lindblad_non_hermitian_rho_and_ragged_sizes(cuda):
             assert relerr(rf, rl[-1]) <= TOL, (n, path)
 
 
+def test_lindblad_non_hermitian_hamiltonian(cuda):
+    """lime evaluates the plain commutator -i[H,rho] even when H is not Hermitian
+    (lime/oqs.py:706-713): the right generator is then not G^dag"""
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=5, M=1, E=1, seed=9)
+    H = H + 0.1j * cases.rand_herm(5, 10)
+    o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=30, dt=0.01)
+    for path in (1, 2):
+        plan = oqs._lindblad_plan(H, c_ops, e_ops, path=path)
+        rf, ob, _ = plan.run(rho0, 0.01, 30)
+        assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+    res = oqs._lindblad(csr_matrix(H), rho0, [csr_matrix(c) for c in c_ops], e_ops=e_ops, Nt=30, dt=0.01)
+    assert relerr(res.observables, o) <= TOL
+
+
 def test_lindblad_driven(cuda):
     from lime_b200 import oqs
     g = golden('lindblad_driven')
