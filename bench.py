@@ -1,0 +1,687 @@
+#!/usr/bin/env python
+"""
+bench.py -- throughput of the density-matrix hot path on B200 (BASELINE.json metric:
+Lindblad rho-steps/s and HEOM ADO-steps/s; % of the HBM roof).
+
+    python bench.py --gpus N --steps K --warmup W [--workload NAME] [--impl reference]
+
+One bench "step" = one pass of the hot path over one batch of synthetic input = ONE launch of
+the fused propagator that advances every density matrix (or hierarchy) of the batch by
+`--rk-steps` RK4 steps, observables included.  Workloads:
+
+    jc_lindblad   (default) config 2: Jaynes-Cummings, Fock cutoff 64 (N = 128), 4096
+                  coupling x detuning points PER GPU, c_ops = [sqrt(kappa) a], e_ops = [a^dag a, s+s-]
+    heom_fmo      config 4: FMO 7 sites, 7 Drude baths x 2 exponentials, depth 4 (3060 ADOs);
+                  ADO-sharded over the ranks with one exchange per RK4 stage (strong scaling)
+    heom_sb       config 3 throughput variant: spin-boson, K = 2, depth 12 (91 ADOs), batch of
+                  hierarchies differing in (lambda, beta)
+    sos_2des      config 5: photon-echo (GSB+SE+ESA) 256 x 256 grid x 64 waiting times, N = 32
+
+The JSON line carries `value` (inputs resident in HBM), `e2e` (same metric through the
+lime-compatible public API with pinned HOST buffers, H2D/D2H inside the timed region),
+`roofline` (algorithmic bytes / CUDA-event duration of the dominant kernel against
+MEASURED_PEAKS.json) and `cpu_baseline` (the NumPy/SciPy port of lime's CPU path, oracle/,
+timed on the host cores on a bounded sample).  `--impl reference` times that CPU port alone.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT,):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return float(p['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+# ---------------------------------------------------------------------------------------
+# clocks during the timed region (B200_PROFILING.md recipe)
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_id):
+        self.gpu_id = gpu_id
+        self.proc = None
+        self.path = '/tmp/limeb200_clocks_%d_%s.csv' % (os.getpid(), str(gpu_id).replace('/', '_'))
+
+    def start(self):
+        try:
+            self.f = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_id), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': [], 'samples': 0}
+        if self.proc is None:
+            return out
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        try:
+            for line in open(self.path):
+                c = [x.strip() for x in line.split(',')]
+                if len(c) < 9:
+                    continue
+                try:
+                    sm.append(float(c[1])); mx.append(float(c[2])); pw.append(float(c[3]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, c[5:9]):
+                    if v.lower() == 'active':
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), power_w_max=max(pw),
+                       reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------
+# workloads
+# ---------------------------------------------------------------------------------------
+class JCLindblad:
+    """config 2: batched Jaynes-Cummings Lindblad RK4, N = 2 x 64."""
+    name = 'jc_lindblad'
+    metric = 'lindblad_rho_steps_per_s'
+    unit = 'rho-steps/s'
+    dtype = 'complex128 (f64 arithmetic)'
+    scaling = 'weak'
+    bound = 'hbm'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        from lime_b200 import models
+        self.ncav, self.ng, self.ndet = 64, 64, 64
+        if args.batch:
+            self.ng = max(1, args.batch // self.ndet) if args.batch >= self.ndet else 1
+            self.ndet = min(self.ndet, args.batch)
+        self.N = 2 * self.ncav
+        self.B = self.ng * self.ndet
+        self.rk = args.rk_steps or 1000
+        self.dt, self.kappa, self.omega0 = 0.01, 0.05, 1.0
+        self.rank, self.world = rank, world
+        # weak scaling: the detuning axis is refined to 64*world points, rank r takes block r
+        gs = np.linspace(0.01, 0.2, self.ng) * self.omega0
+        dets = np.linspace(-0.2, 0.2, self.ndet * world)[rank * self.ndet:(rank + 1) * self.ndet] * self.omega0
+        G, Dt = np.meshgrid(gs, dets, indexing='ij')
+        self.g_pts, self.det_pts = G.reshape(-1), Dt.reshape(-1)
+        self.pat, self.vals, self.c_ops, self.e_ops, self.rho0 = models.jaynes_cummings_batch(
+            self.omega0, self.omega0 + self.det_pts, self.g_pts, self.ncav, self.kappa)
+        self.alg_bytes_per_unit = 2 * 16 * self.N * self.N          # read rho_n, write rho_{n+1}
+        self.units_per_step = self.B * self.rk
+        self.launches = 0
+        if need_gpu:
+            import torch
+            from lime_b200 import oqs
+            self.torch = torch
+            self.plan, _ = oqs._lindblad_plan_batch((self.pat, self.vals), self.c_ops, self.e_ops)
+            self.rho = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(self.rho0, (self.B, self.N, self.N)))).cuda()
+            self.kernel = {1: 'qme_dense_onchip', 2: 'qme_dense_stage', 3: 'qme_ell_global',
+                           4: 'qme_ell_cluster'}[self.plan.path]
+
+    def config(self):
+        return {'workload': 'jc_lindblad: Jaynes-Cummings (no RWA) Fock cutoff 64 -> N=128, '
+                            '%d coupling x %d detuning points per GPU, kappa=%g, dt=%g, %d RK4 steps per launch, '
+                            'E=2 observables per step' % (self.ng, self.ndet, self.kappa, self.dt, self.rk),
+                'N': self.N, 'batch_per_gpu': self.B, 'rk4_steps_per_launch': self.rk,
+                'state_bytes_per_gpu': self.B * self.N * self.N * 16,
+                'l2_policy': 'inputs larger than L2 (state %.2f GiB per GPU)' % (self.B * self.N * self.N * 16 / 2 ** 30),
+                'state': 'dynamics continue across bench steps (no re-initialisation, no work skipped)',
+                'sharding': 'parameter points split across ranks, no collective'}
+
+    def step(self):
+        self.obs, _ = self.plan.run_device(self.rho, self.dt, self.rk)
+        self.launches += self.plan.last_launches
+
+    def check(self):
+        tr = self.torch.einsum('bii->b', self.rho).cpu().numpy()
+        err = float(np.max(np.abs(tr - 1.0)))
+        assert err < 1e-9, 'trace drifted: %g' % err
+        return {'max_trace_error': err}
+
+    def e2e_setup(self):
+        t = self.torch
+        self.h_rho = t.from_numpy(np.ascontiguousarray(np.broadcast_to(self.rho0, (self.B, self.N, self.N)))).pin_memory()
+
+    def e2e_step(self):
+        """public API, host buffers in and out: lime's Lindblad_solver with the batch extension"""
+        from lime_b200.oqs import Lindblad_solver
+        s = Lindblad_solver(None, c_ops=self.c_ops)
+        rho_f, obs, _ = s.evolve_batch(self.h_rho, self.dt, self.rk, e_ops=self.e_ops,
+                                       H_batch=(self.pat, self.vals), pinned=True)
+        self.launches_e2e = 1
+        h2d = self.h_rho.numel() * 16 + self.vals.nbytes
+        d2h = rho_f.nbytes + obs.nbytes
+        return h2d, d2h
+
+    # ---- CPU port of lime's path (oracle/): bounded sample
+    def cpu_point(self, idx, variant, nsteps):
+        """nsteps RK4 steps of parameter point idx with lime's algorithm; returns seconds"""
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        from scipy.sparse import csr_matrix
+        H, c_ops, e_ops = lo.jaynes_cummings(self.omega0, self.omega0 + self.det_pts[idx % self.B],
+                                             self.g_pts[idx % self.B], self.ncav, self.kappa)
+        if variant == 'dense':      # Lindblad_solver.evolve -> _lindblad (np.dot), lime/oqs.py:1590-1688
+            Hd, cd, ed = H.toarray(), [c.toarray() for c in c_ops], [e.toarray() for e in e_ops]
+            t = time.perf_counter()
+            lo.lindblad(Hd, self.rho0, cd, ed, Nt=nsteps, dt=self.dt)
+            return time.perf_counter() - t
+        # CSR operands and CSR rho through phys.liouvillian (lime/phys.py:561-577), the route of
+        # lime/correlation.py; rho starts as the full-pattern mixed state so fill-in is not hidden
+        rng = np.random.default_rng(idx)
+        a = rng.standard_normal((self.N, self.N)) + 1j * rng.standard_normal((self.N, self.N))
+        rho = a @ a.conj().T
+        rho = csr_matrix(rho / np.trace(rho))
+        t = time.perf_counter()
+        for _ in range(nsteps):
+            rho = lo.rk4(rho, lo.liouvillian_sp, self.dt, H, c_ops)
+            [e.dot(rho).diagonal().sum() for e in e_ops]
+        return time.perf_counter() - t
+
+
+class HeomBase:
+    metric = 'heom_ado_steps_per_s'
+    unit = 'ADO-steps/s'
+    dtype = 'complex128 (f64 arithmetic)'
+    bound = 'hbm'
+
+
+class HeomSpinBoson(HeomBase):
+    """config 3 throughput variant: B hierarchies of 91 ADOs (2x2), per-hierarchy (lambda, beta)"""
+    name = 'heom_sb'
+    scaling = 'weak'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        from lime_b200 import engine
+        from lime_b200.heom.heom import _calc_matsubara_params
+        self.B = args.batch or 32768
+        self.rk = args.rk_steps or 200
+        self.dt, self.depth, self.K = 0.01, 12, 2
+        sx = np.array([[0., 1.], [1., 0.]], dtype=complex)
+        sz = np.array([[1., 0.], [0., -1.]], dtype=complex)
+        self.H = 0.5 * 1.0 * sz + 0.5 * 0.5 * sx
+        self.sz = sz
+        lam = np.linspace(0.05, 0.4, self.B * world)[rank * self.B:(rank + 1) * self.B]
+        beta = np.linspace(0.5, 2.0, self.B * world)[::-1][rank * self.B:(rank + 1) * self.B]
+        cs, nus = [], []
+        for l, b in zip(lam, beta):
+            c, nu = _calc_matsubara_params(self.K, l, 1.0, 1.0 / b)
+            cs.append(c); nus.append(nu)
+        self.c, self.nu = np.array(cs, dtype=complex), np.array(nus, dtype=float)
+        self.n = 2
+        self.alg_bytes_per_unit = 2 * 16 * self.n * self.n
+        self.launches = 0
+        if need_gpu:
+            import torch
+            self.torch = torch
+            self.states, self.dn, self.up = engine.heom_tables([self.depth + 1] * self.K, self.depth)
+            self.nhe = self.states.shape[0]
+            self.plan = engine.HeomPlan(self.H, sz, [0] * self.K, self.c, self.nu, self.states, self.dn, self.up)
+            ado = np.zeros((self.B, self.nhe, 2, 2), dtype=complex)
+            ado[:, 0, 0, 0] = 1.0
+            self.h_ado = ado
+            self.ado = torch.from_numpy(ado).cuda()
+            self.eT = torch.from_numpy(np.ascontiguousarray(np.stack([sz.T, sx.T]))).cuda()
+            self.units_per_step = self.B * self.nhe * self.rk
+            self.kernel = 'heom_onchip_kernel'
+
+    def config(self):
+        return {'workload': 'heom_sb: spin-boson Drude-Lorentz HEOM, K=2 exponentials, depth 12 (91 ADOs, 312 couplings), '
+                            '%d hierarchies per GPU differing in (lambda, beta), dt=%g, %d RK4 steps per launch'
+                            % (self.B, self.dt, self.rk),
+                'batch_per_gpu': self.B, 'rk4_steps_per_launch': self.rk, 'n_ado': 91,
+                'l2_policy': 'inputs larger than L2 (state %.0f MiB per GPU)' % (self.B * 91 * 4 * 16 / 2 ** 20),
+                'sharding': 'hierarchies split across ranks, no collective'}
+
+    def step(self):
+        self.obs, _ = self.plan.run_device(self.ado, self.dt, self.rk, eT=self.eT)
+        self.launches += self.plan.last_launches
+
+    def check(self):
+        tr = (self.ado[:, 0, 0, 0] + self.ado[:, 0, 1, 1]).cpu().numpy()
+        err = float(np.max(np.abs(tr - 1.0)))
+        assert err < 1e-9, 'trace drifted: %g' % err
+        return {'max_trace_error': err}
+
+    def e2e_setup(self):
+        self.h_pin = self.torch.from_numpy(self.h_ado).pin_memory()
+
+    def e2e_step(self):
+        from lime_b200 import _dev
+        d = _dev.h2d(self.h_pin)
+        obs, _ = self.plan.run_device(d, self.dt, self.rk, eT=self.eT)
+        out = _dev.d2h(d, True)
+        o = _dev.d2h(obs, True)
+        return self.h_pin.numel() * 16, out.nbytes + o.nbytes
+
+    def cpu_point(self, idx, variant, nsteps):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        states, dn, up = lo.heom_tables([self.depth + 1] * self.K, self.depth)
+        ado = np.zeros((states.shape[0], 2, 2), dtype=complex)
+        ado[0, 0, 0] = 1.0
+        t = time.perf_counter()
+        lo.heom_rk4(ado, self.H, self.sz[None], [0] * self.K, self.c[idx % self.B], self.nu[idx % self.B],
+                    states, dn, up, self.dt, nsteps, e_ops=[self.sz])
+        return time.perf_counter() - t
+
+
+class HeomFMO(HeomBase):
+    """config 4: FMO 7 sites x 7 Drude baths x K=2, depth 4 -> 3060 ADOs of 7x7.
+    world == 1: `--batch` independent hierarchies (default 1 = the single-hierarchy case).
+    world  > 1: ONE hierarchy, ADO-sharded, all-gather of the stage vector after each stage."""
+    name = 'heom_fmo'
+    scaling = 'strong'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        from lime_b200 import models
+        from lime_b200.units import au2fs
+        self.B = args.batch or 1
+        self.rk = args.rk_steps or 200
+        self.depth = args.depth or 4
+        self.rank, self.world = rank, world
+        self.Hm, self.Q, self.lam, self.gam, self.kT = models.fmo_heom_inputs()
+        self.dt = 0.5 / au2fs
+        self.n = 7
+        self.alg_bytes_per_unit = 2 * 16 * 49
+        self.launches = 0
+        from lime_b200 import engine
+        self.nhe = engine.heom_tables([self.depth + 1] * 14, self.depth)[0].shape[0]   # host table builder
+        if need_gpu:
+            import torch
+            from lime_b200.heom.heom import HEOM
+            self.torch = torch
+            if world > 1:
+                from lime_b200.heom.sharded import ShardedHEOM
+                self.h = ShardedHEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
+                self.nhe = self.h.nhe
+                self.kernel = 'heom_stage_kernel + all_gather'
+            else:
+                self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
+                self.nhe = self.h.nhe
+                self.kernel = 'heom_stage_kernel'
+            rho0 = np.zeros((7, 7), dtype=complex)
+            rho0[0, 0] = 1.0
+            ado = np.zeros((self.B, self.nhe, 7, 7), dtype=complex)
+            ado[:, 0] = rho0
+            self.h_ado = ado
+            self.ado = torch.from_numpy(ado).cuda()
+            self.eT = torch.from_numpy(np.ascontiguousarray(np.stack([q.T for q in self.Q]))).cuda()
+            self.units_per_step = self.B * self.nhe * self.rk / (world if world > 1 else 1)
+
+    def config(self):
+        return {'workload': 'heom_fmo: FMO 7-site (Adolphs-Renger), 7 Drude baths (35 cm^-1, 50 fs, 300 K) x K=2, '
+                            'depth %d -> %d ADOs of 7x7, dt=0.5 fs, %d RK4 steps per bench step, %d hierarchies'
+                            % (self.depth, self.nhe, self.rk, self.B),
+                'n_ado': self.nhe, 'rk4_steps_per_launch': self.rk, 'batch': self.B,
+                'l2_policy': 'single hierarchy (%.2f MiB) is L2 resident by construction; L2 flushed between bench steps'
+                             % (self.nhe * 49 * 16 / 2 ** 20) if self.B * self.nhe * 49 * 16 < 2 ** 27 else 'inputs larger than L2',
+                'sharding': 'one hierarchy, ADO ranges per rank, all-gather of each stage vector (4 per RK4 step)'
+                            if self.world > 1 else 'none'}
+
+    def step(self):
+        if self.world > 1:
+            self.h.run_device(self.ado, self.dt, self.rk)
+            self.launches += self.h.last_launches
+        else:
+            self.obs, _ = self.h.plan.run_device(self.ado, self.dt, self.rk, eT=self.eT)
+            self.launches += self.h.plan.last_launches
+
+    def check(self):
+        tr = self.torch.einsum('bii->b', self.ado[:, 0]).cpu().numpy()
+        err = float(np.max(np.abs(tr - 1.0)))
+        assert err < 1e-9, 'trace drifted: %g' % err
+        return {'max_trace_error': err}
+
+    def e2e_setup(self):
+        pass
+
+    def e2e_step(self):
+        """public API: HEOM.evolve(rho0, dt, Nt, e_ops) -> Result (host in, host out)"""
+        rho0 = np.zeros((7, 7), dtype=complex)
+        rho0[0, 0] = 1.0
+        if self.world > 1:
+            res = self.h.evolve(rho0, self.dt, self.rk)
+            return rho0.nbytes, res.ado.nbytes
+        res = self.h.evolve(rho0, self.dt, self.rk, e_ops=self.Q, store_states=False)
+        return self.nhe * 49 * 16, res.ado.nbytes + res.observables.nbytes
+
+    def cpu_point(self, idx, variant, nsteps):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        c, nu, qmap = [], [], []
+        for b in range(7):
+            cb, nub = lo.calc_matsubara_params(2, self.lam, self.gam, self.kT)
+            c += cb; nu += nub; qmap += [b, b]
+        states, dn, up = lo.heom_tables([self.depth + 1] * 14, self.depth)
+        ado = np.zeros((states.shape[0], 7, 7), dtype=complex)
+        ado[0, 0, 0] = 1.0
+        t = time.perf_counter()
+        lo.heom_rk4(ado, self.Hm, np.stack(self.Q), qmap, np.array(c), np.array(nu), states, dn, up,
+                    self.dt, nsteps, e_ops=[self.Q[0]])
+        return time.perf_counter() - t
+
+
+class Sos2DES:
+    """config 5: photon echo GSB+SE+ESA on a 256x256 (omega1, omega3) grid x 64 waiting times"""
+    name = 'sos_2des'
+    metric = 'sos_grid_points_per_s'
+    unit = 'grid-points/s'
+    dtype = 'complex128 (f64 arithmetic)'
+    scaling = 'weak'
+    bound = 'hbm'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        au2ev, au2fs = 27.211386, 2.41888432651e-2
+        self.n = 256
+        self.T = args.batch or 64
+        rng = np.random.default_rng(0)
+        N, ne = 32, 15
+        nf = N - 1 - ne
+        E = np.zeros(N)
+        E[1:1 + ne] = np.sort(rng.uniform(1.5, 2.0, ne)) / au2ev
+        E[1 + ne:] = np.sort(rng.uniform(3.2, 3.8, nf)) / au2ev
+        dip = np.zeros((N, N))
+        ge = rng.standard_normal(ne)
+        dip[0, 1:1 + ne] = ge; dip[1:1 + ne, 0] = ge
+        ef = rng.standard_normal((ne, nf))
+        dip[1:1 + ne, 1 + ne:] = ef; dip[1 + ne:, 1:1 + ne] = ef.T
+        gamma = np.ones(N) * 0.05 / au2ev
+        gamma[0] = 0.0
+        self.sys = (E, dip, gamma, [0], list(range(1, 1 + ne)), list(range(1 + ne, N)))
+        self.w = np.linspace(1.4, 2.1, self.n) / au2ev
+        Tall = np.linspace(0, 630, self.T * world) / au2fs
+        self.taus = Tall[rank * self.T:(rank + 1) * self.T]
+        self.alg_bytes_per_unit = 16
+        self.units_per_step = self.T * self.n * self.n
+        self.launches = 0
+        self.kernel = 'sos_outer_kernel'
+        if need_gpu:
+            import torch
+            self.torch = torch
+
+    def config(self):
+        return {'workload': 'sos_2des: _photon_echo (GSB+SE+ESA) N=32 (15 e, 16 f), 256x256 grid, %d waiting times per GPU'
+                            % self.T, 'l2_policy': 'output (%d MiB) rewritten each step; L2 flushed between steps'
+                            % (self.units_per_step * 16 // 2 ** 20),
+                'sharding': 'waiting times split across ranks, no collective'}
+
+    def step(self):
+        from lime_b200.signal import sos
+        E, dip, gamma, g, e, f = self.sys
+        self.out = sos._photon_echo(E, dip, -self.w, self.w, self.taus, g, e, f, gamma, return_device=True)
+        self.launches += 3          # pole factor, weighted factor, rank-R outer product
+
+    def check(self):
+        return {}
+
+    def e2e_setup(self):
+        pass
+
+    def e2e_step(self):
+        from lime_b200.signal import sos
+        E, dip, gamma, g, e, f = self.sys
+        out = sos._photon_echo(E, dip, -self.w, self.w, self.taus, g, e, f, gamma)
+        return 2 * self.w.nbytes + dip.nbytes, out.nbytes
+
+    def cpu_point(self, idx, variant, nsteps):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        E, dip, gamma, g, e, f = self.sys
+        t = time.perf_counter()
+        for k in range(nsteps):
+            lo.photon_echo_core(E, dip, -self.w, self.w, self.taus[(idx + k) % self.T], g, e, f, gamma)
+        return time.perf_counter() - t
+
+
+WORKLOADS = {c.name: c for c in (JCLindblad, HeomFMO, HeomSpinBoson, Sos2DES)}
+# units one cpu_point "step" stands for
+CPU_UNITS = {'jc_lindblad': lambda w: 1, 'heom_sb': lambda w: 91, 'heom_fmo': lambda w: None,
+             'sos_2des': lambda w: w.n * w.n}
+
+
+def _cpu_worker(job):
+    wname, argd, idx, variant, nsteps = job
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+    args = argparse.Namespace(**argd)
+    w = WORKLOADS[wname](args, 0, 1, need_gpu=False)
+    return w.cpu_point(idx, variant, nsteps)
+
+
+def cpu_units(w):
+    u = CPU_UNITS[w.name](w)
+    return w.nhe if u is None else u
+
+
+def cpu_throughput(w, args, budget_s, cores):
+    """lime's CPU algorithm (oracle/ port) on a bounded sample of workload `w`, fanned out over
+    `cores` processes (one parameter point / hierarchy / waiting time per process, BLAS
+    threads pinned to 1).  Returns (units per second, description)."""
+    import multiprocessing as mp
+    argd = vars(args)
+    variants = ['dense', 'csr'] if w.name == 'jc_lindblad' else ['port']
+    per_step = {}
+    for v in variants:                           # calibrate on one step, single process
+        t1 = _cpu_worker((w.name, argd, 0, v, 1))
+        per_step[v] = t1
+    best = min(per_step, key=per_step.get)
+    nsteps = int(max(1, min(200, budget_s / max(per_step[best], 1e-6))))
+    units = cpu_units(w)
+    ctx = mp.get_context('spawn')
+    jobs = [(w.name, argd, i, best, nsteps) for i in range(cores)]
+    t = time.perf_counter()
+    if cores > 1:
+        with ctx.Pool(cores) as pool:
+            pool.map(_cpu_worker, jobs[:cores])          # spawn + import warm-up (untimed)
+            t = time.perf_counter()
+            pool.map(_cpu_worker, jobs)
+            wall = time.perf_counter() - t
+    else:
+        _cpu_worker(jobs[0])
+        wall = time.perf_counter() - t
+    value = cores * nsteps * units / wall
+    desc = ('%d processes x %d RK4 steps/evaluations of one %s each, variant=%s (single-process calibration: %s s/step)'
+            % (cores, nsteps, 'point' if w.name != 'sos_2des' else 'waiting time', best,
+               ', '.join('%s %.4g' % kv for kv in per_step.items())))
+    return value, desc, best
+
+
+# ---------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload](args, 0, 1, need_gpu=False)
+    cores = os.cpu_count() or 1
+    vals = []
+    desc = ''
+    total = args.warmup + args.steps
+    budget = max(1.0, min(8.0, 150.0 / max(total, 1) / 2.0))
+    t_all = time.perf_counter()
+    for i in range(total):
+        v, desc, variant = cpu_throughput(w, args, budget, cores)
+        if i >= args.warmup:
+            vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = float(np.mean(vals)) if vals else 0.0
+    cfg = w.config()
+    line = {'impl': 'reference', 'metric': w.metric, 'value': value, 'unit': w.unit, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': 1e3 * wall / max(total, 1), 'higher_is_better': True, 'scaling': w.scaling,
+            'vs_baseline': None, 'dtype': w.dtype, 'data': 'synthetic', 'config': cfg,
+            'cpu_baseline': {'value': value, 'unit': w.unit, 'cores': cores, 'kind': 'port', 'sample': desc},
+            'e2e': {'value': value, 'unit': w.unit, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0,
+            'note': "lime's own NumPy/SciPy algorithm (oracle/lime_oracle.py, a call-for-call port; /root/reference is "
+                    "absent on the GPU box) on the host cores; lime itself is single-threaded Python, the fan-out over "
+                    "points is the most its CPU path can use"}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w = WORKLOADS[args.workload](args, rank, world)
+    flush = None
+    if 'flushed' in json.dumps(w.config()):
+        flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device='cuda')
+    st = torch.cuda.current_stream()
+    for _ in range(args.warmup):
+        w.step()
+    barrier()
+    w.launches = 0
+    try:
+        gpu_id = 'GPU-' + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_id = local
+    sampler = ClockSampler(gpu_id)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall = time.perf_counter()
+    for k in range(args.steps):
+        if flush is not None:
+            flush.fill_(k & 0xff)
+        ev[k][0].record(st)
+        w.step()
+        ev[k][1].record(st)
+    barrier()
+    t_wall = time.perf_counter() - t_wall
+    clocks = sampler.stop()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(ms)], dtype=torch.float64, device='cuda')
+    launches = torch.tensor([w.launches], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(launches, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    chk = w.check()
+    units_all = w.units_per_step * world * args.steps
+    value = units_all / (total_ms * 1e-3)
+    peak, peak_src = measured_peaks()
+    kernel_s = (sum(ms) / len(ms)) * 1e-3
+    achieved = w.alg_bytes_per_unit * w.units_per_step / kernel_s / 1e9
+
+    # ---- end to end through the public API with host buffers
+    w.e2e_setup()
+    w.e2e_step()                                  # warm (pinned pools, plan caches)
+    barrier()
+    ne2e = max(1, min(args.steps, 3))
+    t0 = time.perf_counter()
+    for _ in range(ne2e):
+        h2d, d2h = w.e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = w.units_per_step * world * ne2e / float(e2e_t.item())
+
+    line = {'metric': w.metric, 'value': value, 'unit': w.unit, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': w.scaling, 'vs_baseline': None, 'dtype': w.dtype, 'data': 'synthetic',
+            'config': w.config(),
+            'e2e': {'value': e2e_val, 'unit': w.unit, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                    'api': 'lime_b200 public API, pinned host buffers, %d steps, wall clock incl. plan set-up' % ne2e},
+            'gpu_launches': int(launches.item()),
+            'clocks': clocks,
+            'roofline': {'bound': w.bound, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': TRAFFIC.get(w.name),
+                         'kernel': w.kernel, 'peak_source': peak_src,
+                         'algorithmic_bytes_per_unit': w.alg_bytes_per_unit,
+                         'units_per_launch': w.units_per_step,
+                         'note': 'state stays on chip for all %s RK4 steps of a launch; achieved = algorithmic bytes '
+                                 '(one read + one write of every rho/ADO per RK4 step) / CUDA-event time, so it is a '
+                                 'throughput normalised to the HBM roof, not measured DRAM traffic (see traffic)'
+                                 % getattr(w, 'rk', 1)},
+            'wall_s_timed_region': t_wall, 'check': chk}
+    if rank == 0:
+        if world == 1 and not args.no_cpu:
+            cores = os.cpu_count() or 1
+            v, desc, variant = cpu_throughput(w, args, args.cpu_seconds, cores)
+            line['cpu_baseline'] = {'value': v, 'unit': w.unit, 'cores': cores, 'kind': 'port', 'sample': desc}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+# `ncu --set full` capture summarised under profiles/ (same command, same sizes); None = not captured
+TRAFFIC = {}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='jc_lindblad', choices=sorted(WORKLOADS))
+    ap.add_argument('--rk-steps', type=int, default=0, help='RK4 steps per launch (0 = workload default)')
+    ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
+    ap.add_argument('--depth', type=int, default=0, help='HEOM depth for heom_fmo (0 = 4)')
+    ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')
+    ap.add_argument('--no-cpu', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == 'ours':
+        log('note: fewer than 3 warm-up steps requested')
+    if args.impl == 'reference':
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

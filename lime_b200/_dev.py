@@ -26,6 +26,35 @@ def to_dev(a, dtype=np.complex128, dev=None, pinned=False):
     return t.to(device() if dev is None else dev, non_blocking=pinned)
 
 
+def h2d(a, dtype=np.complex128, dev=None):
+    """host -> device.  A torch CPU tensor is copied as it is (asynchronously when it is
+    pinned); anything else goes through numpy (pageable)."""
+    if isinstance(a, torch.Tensor):
+        assert a.device.type == 'cpu' and a.is_contiguous()
+        return a.to(device() if dev is None else dev, non_blocking=a.is_pinned())
+    return to_dev(a, dtype, dev)
+
+
+_pinned_pool = {}
+
+
+def d2h(t, pinned=False):
+    """device -> host numpy array; pinned=True stages through a cached page-locked buffer
+    (the returned array is a view of it and is overwritten by the next call of that shape)"""
+    if t is None:
+        return None
+    if not pinned:
+        return t.cpu().numpy()
+    key = (tuple(t.shape), t.dtype)
+    buf = _pinned_pool.get(key)
+    if buf is None:
+        buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        _pinned_pool[key] = buf
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy()
+
+
 def empty(shape, dtype=torch.complex128, dev=None):
     return torch.empty(shape, dtype=dtype, device=device() if dev is None else dev)
 

@@ -145,18 +145,20 @@ class QmePlan:
                                      _dev.ptr(obs), _dev.ptr(traj), int(traj_every), _dev.stream_ptr()))
         return obs, traj
 
-    def run(self, rho0, dt, nsteps, coef=None, traj_every=0):
-        """host in / host out: rho0 [N,N] or [B,N,N] -> (rho_final, obs, traj) as numpy"""
-        r = _dev.as_c128(rho0)
+    def run(self, rho0, dt, nsteps, coef=None, traj_every=0, pinned=False):
+        """host in / host out: rho0 [N,N] or [B,N,N] -> (rho_final, obs, traj) as numpy.
+        rho0 may be a (pinned) torch CPU tensor; pinned=True returns views of cached
+        page-locked buffers (asynchronous copies in both directions)."""
+        r = rho0 if isinstance(rho0, torch.Tensor) else _dev.as_c128(rho0)
         single = r.ndim == 2
         if single:
             r = r[None]
-        d = _dev.to_dev(r, dev=self.dev)
+        d = _dev.h2d(r, dev=self.dev)
         c = None if coef is None else _dev.to_dev(np.asarray(coef).reshape(nsteps, -1), dev=self.dev)
         obs, traj = self.run_device(d, dt, nsteps, coef=c, traj_every=traj_every)
-        out = d.cpu().numpy()
-        obs = None if obs is None else obs.cpu().numpy()
-        traj = None if traj is None else traj.cpu().numpy()
+        out = _dev.d2h(d, pinned)
+        obs = _dev.d2h(obs, pinned)
+        traj = _dev.d2h(traj, pinned)
         if single:
             out = out[0]
             obs = None if obs is None else obs[:, 0]

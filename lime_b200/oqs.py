@@ -16,6 +16,7 @@ stored trajectory -- is one CUDA launch (lime_b200/csrc).  Extensions over lime 
 import sys
 import numpy as np
 import scipy.linalg
+import torch
 from scipy.sparse import issparse, csr_matrix, identity, kron
 
 from .mol import Result
@@ -218,7 +219,7 @@ class Lindblad_solver():
                          return_result=return_result)
 
     def evolve_batch(self, rho0, dt, Nt, e_ops=None, H_batch=None, store_every=0, path=None,
-                     device_index=None, return_device=False):
+                     device_index=None, return_device=False, pinned=False):
         """[ext] propagate a batch of density matrices in one launch.
 
         rho0    : [B,N,N] (or [N,N], broadcast to the operator batch)
@@ -231,14 +232,17 @@ class Lindblad_solver():
             B = None
         else:
             plan, B = _lindblad_plan_batch(H_batch, c_ops, e_ops, path=path, device_index=device_index)
-        r = _dev.as_c128(rho0)
-        if r.ndim == 2:
-            r = np.broadcast_to(r, ((B or 1),) + r.shape)
+        if isinstance(rho0, torch.Tensor):          # (pinned) host tensor [B,N,N], copied as it is
+            r = rho0
+        else:
+            r = _dev.as_c128(rho0)
+            if r.ndim == 2:
+                r = np.broadcast_to(r, ((B or 1),) + r.shape)
         if return_device:
-            d = _dev.to_dev(r, dev=plan.dev)
+            d = _dev.h2d(r, dev=plan.dev)
             obs, traj = plan.run_device(d, dt, Nt, traj_every=store_every)
             return d, obs, traj
-        return plan.run(r, dt, Nt, traj_every=store_every)
+        return plan.run(r, dt, Nt, traj_every=store_every, pinned=pinned)
 
     # ---- correlation functions (quantum regression), lime/oqs.py:1196-1331 ---------
     def correlation_3op_1t(self, rho0, oplist, dt=0.005, Nt=1):

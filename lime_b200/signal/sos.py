@@ -111,7 +111,7 @@ def _pe_terms(evals, dip, tau2, g_idx, e_idx, f_idx, gamma, parts):
     return W, P, (eA, gA)
 
 
-def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts):
+def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts, return_device=False):
     single = np.ndim(tau2) == 0
     n1, n3 = len(omega1), len(omega3)
     _check_grid(n1, n3)
@@ -124,6 +124,8 @@ def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts
     A = _simple_factor(z1, eA, gA)                 # [1,R,n1]  G_ab(omega1)
     Bf = engine.sos_factor(z3, W, P)               # [T,R,n3]
     out = engine.sos_outer(Bf, A, W.shape[0])      # [T,n3,n1]
+    if return_device:
+        return out
     return _finish(out, single)
 
 
@@ -142,10 +144,11 @@ def ESA(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma):
     return _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, ('ESA',))
 
 
-def _photon_echo(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma):
+def _photon_echo(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma, return_device=False):
     """GSB + SE + ESA at waiting time t2 (scalar, or [ext] a vector -> [T,n3,n1]);
-    lime/signal/sos.py:695-729"""
-    return _pe_eval(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma, ('GSB', 'SE', 'ESA'))
+    lime/signal/sos.py:695-729.  [ext] return_device=True leaves the [T,n3,n1] result on the GPU."""
+    return _pe_eval(evals, edip, omega1, omega3, t2, g_idx, e_idx, f_idx, gamma, ('GSB', 'SE', 'ESA'),
+                    return_device=return_device)
 
 
 def photon_echo(mol, pump, probe, t2=0., g_idx=[0], e_idx=None, f_idx=None, fname='signal',
