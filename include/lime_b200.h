@@ -78,7 +78,9 @@ int limeb200_qme_add_drive_dense(limeb200_qme_t plan, const double* h_D, const d
 /* observables e[E][N][N] (dense host): obs = Tr(e rho), lime/phys.py:837-844 */
 int limeb200_qme_set_observables(limeb200_qme_t plan, const double* h_e, int E);
 /* kernel selection: 0 auto, 1 dense on-chip, 2 dense stage-wise, 3 sparse global-scratch,
- * 4 sparse cluster-resident (tests force each path)                                      */
+ * 4 sparse cluster-resident (generic ELL), 5 sparse cluster-resident register-tiled
+ * (at most 4 off-diagonal entries per row of G, one entry per row of X_s/Z_s, N <= 128);
+ * tests force each path                                                                  */
 int limeb200_qme_set_path(limeb200_qme_t plan, int path);
 /* analyse operators, choose the kernel, upload.  B_hint sizes scratch (may grow later). */
 int limeb200_qme_finalize(limeb200_qme_t plan);

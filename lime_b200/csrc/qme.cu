@@ -5,6 +5,7 @@
 #include "qme_dense.cuh"
 #include "qme_sparse.cuh"
 #include "qme_cluster.cuh"
+#include "qme_band.cuh"
 #include <algorithm>
 #include <memory>
 
@@ -50,6 +51,10 @@ struct limeb200_qme_s {
     DevBuf dperm;                               // [N] new -> old (cluster path)
     bool permuted = false;
     DevBuf deptr, deidx, deval;
+    // ---- band path (qme_band.cuh)
+    DevBuf dbgd, dbgcol, dbgval, dbxcol[QME_BAND_MAXS], dbxval[QME_BAND_MAXS], dbzcol[QME_BAND_MAXS], dbzval[QME_BAND_MAXS];
+    int band_noff = 0, band_gt = 0, band_xt = 0, band_C = 0, band_R = 0;
+    size_t band_smem = 0;
     // ---- scratch
     DevBuf s_y, s_acc, s_tmp, s_gk;
     int scratch_B = 0;
@@ -195,6 +200,110 @@ void adjoint(const hcplx* in, hcplx* out, int N) {
         for (int j = 0; j < N; ++j) out[(size_t)j * N + i] = std::conj(in[(size_t)i * N + j]);
 }
 
+// Cuthill-McKee from every start node of every connected component; keeps the ordering with
+// the smallest bandwidth (N is at most a few hundred on the paths that use it)
+std::vector<int> best_cm_order(int N, const std::vector<std::vector<int>>& adj) {
+    std::vector<int> comp(N, -1), order;
+    order.reserve(N);
+    int nc = 0;
+    for (int s = 0; s < N; ++s) {
+        if (comp[s] >= 0) continue;
+        std::vector<int> members{s};
+        comp[s] = nc;
+        for (size_t hd = 0; hd < members.size(); ++hd)
+            for (int u : adj[members[hd]])
+                if (comp[u] < 0) { comp[u] = nc; members.push_back(u); }
+        std::vector<int> best;
+        int best_bw = N + 1;
+        std::vector<int> pos(N, -1);
+        for (int start : members) {
+            std::vector<int> q{start};
+            std::vector<char> seen(N, 0);
+            seen[start] = 1;
+            for (size_t hd = 0; hd < q.size(); ++hd) {
+                std::vector<int> nbv;
+                for (int u : adj[q[hd]])
+                    if (!seen[u]) { seen[u] = 1; nbv.push_back(u); }
+                std::sort(nbv.begin(), nbv.end(), [&](int x, int y) {
+                    return adj[x].size() != adj[y].size() ? adj[x].size() < adj[y].size() : x < y; });
+                q.insert(q.end(), nbv.begin(), nbv.end());
+            }
+            for (size_t i = 0; i < q.size(); ++i) pos[q[i]] = (int)i;
+            int bw = 0;
+            for (int v : q)
+                for (int u : adj[v]) bw = std::max(bw, std::abs(pos[v] - pos[u]));
+            if (bw < best_bw) { best_bw = bw; best = q; }
+        }
+        order.insert(order.end(), best.begin(), best.end());
+        ++nc;
+    }
+    return order;
+}
+
+struct BandHost {
+    int noff = 0, gt = 1, xt = 1, bw = 0;
+    std::vector<hcplx> gd, gval;           // [nb][N], [nb][NOFF][N]
+    std::vector<int> gcol;                 // [NOFF][N]
+    std::vector<int> xcol[QME_BAND_MAXS], zcol[QME_BAND_MAXS];
+    std::vector<hcplx> xval[QME_BAND_MAXS], zval[QME_BAND_MAXS];
+};
+
+
+// split the (permuted) operators into the tables of qme_band.cuh; false when the structure is
+// outside what that kernel handles (more than 4 off-diagonal entries per row of G, more than
+// one entry per row of an X_s / Z_s, more than 2 sandwich terms)
+bool build_band_host(const HostOp& G, const std::vector<HostOp>& X, const std::vector<HostOp>& Z, int N, int nb,
+                     const std::vector<int>& perm, const std::vector<int>& inv, BandHost& o) {
+    const int S = (int)X.size();
+    if (S > QME_BAND_MAXS || N > 128) return false;
+    EllHost eg;
+    to_ell(G, N, eg, o.bw, perm, inv);
+    if (G.nb < nb) replicate(eg.val, (size_t)N * eg.w, nb);
+    int noff = 0;
+    for (int i = 0; i < N; ++i) {
+        int c = 0;
+        for (int q = 0; q < eg.w; ++q) c += eg.col[(size_t)i * eg.w + q] != i;
+        noff = std::max(noff, c);
+    }
+    if (noff > 4) return false;
+    o.noff = noff <= 2 ? 2 : 4;
+    o.gd.assign((size_t)nb * N, hcplx(0, 0));
+    o.gcol.assign((size_t)o.noff * N, 0);
+    o.gval.assign((size_t)nb * o.noff * N, hcplx(0, 0));
+    for (int i = 0; i < N; ++i) {
+        int slot = 0;
+        for (int q = 0; q < o.noff; ++q) o.gcol[(size_t)q * N + i] = i;
+        for (int q = 0; q < eg.w; ++q) {
+            const int c = eg.col[(size_t)i * eg.w + q];
+            for (int b = 0; b < nb; ++b) {
+                const hcplx v = eg.val[((size_t)b * N + i) * eg.w + q];
+                if (c == i) o.gd[(size_t)b * N + i] += v;
+                else {
+                    o.gval[((size_t)b * o.noff + slot) * N + i] = v;
+                    if (v.real() != 0.0) o.gt = 0;
+                }
+            }
+            if (c != i) { o.gcol[(size_t)slot * N + i] = c; ++slot; }
+        }
+    }
+    for (int s = 0; s < S; ++s) {
+        const HostOp* ops[2] = {&X[s], &Z[s]};
+        std::vector<int>* cols[2] = {&o.xcol[s], &o.zcol[s]};
+        std::vector<hcplx>* vals[2] = {&o.xval[s], &o.zval[s]};
+        for (int t = 0; t < 2; ++t) {
+            EllHost e;
+            to_ell(*ops[t], N, e, o.bw, perm, inv);
+            if (e.w != 1) return false;
+            if (ops[t]->nb < nb) replicate(e.val, (size_t)N, nb);
+            *cols[t] = e.col;
+            *vals[t] = e.val;
+            for (const hcplx& v : e.val)
+                if (v.imag() != 0.0) o.xt = 0;
+        }
+    }
+    return true;
+}
+
 int set_op_dense(limeb200_qme_t p, HostOp& op, const double* h, int nb) {
     LB_REQUIRE(p && h, "null argument");
     LB_REQUIRE(!p->finalized, "plan already finalized");
@@ -315,7 +424,7 @@ int limeb200_qme_set_observables(limeb200_qme_t p, const double* h_e, int E) {
 int limeb200_qme_set_path(limeb200_qme_t p, int path) {
     LB_REQUIRE(p, "null plan");
     LB_REQUIRE(!p->finalized, "plan already finalized");
-    LB_REQUIRE(path >= 0 && path <= 4, "path must be 0..4");
+    LB_REQUIRE(path >= 0 && path <= 5, "path must be 0..5");
     p->path_req = path;
     return LB_OK;
 }
@@ -345,40 +454,60 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     const bool dense_mem_ok = (double)nb * NN * 16.0 * (2 + 2 * S) < 8e9;
     int path = p->path_req;
     if (path == 0) {
-        if (N >= 24 && sparse_ok && wg * 4 <= N) path = 4;          // structured mid/large N
+        if (N >= 24 && sparse_ok && wg * 4 <= N) path = 5;          // structured mid/large N
         else if (N <= 64 && dense_mem_ok) path = 1;
         else if (dense_mem_ok) path = 2;
         else path = 3;
     }
-    // sparse paths work in a bandwidth-reducing basis order (cluster path only)
+    // the cluster paths work in a bandwidth-reducing basis order
     std::vector<int> perm(N), inv(N);
     for (int i = 0; i < N; ++i) perm[i] = inv[i] = i;
-    if (path == 4) {
+    BandHost band;
+    if (path == 4 || path == 5) {
         bool fits = sparse_ok;
         if (fits) {
             std::vector<std::vector<int>> adj(N);
             add_pattern(p->G, N, adj);
             for (int s = 0; s < S; ++s) { add_pattern(p->X[s], N, adj); add_pattern(p->Z[s], N, adj); }
             for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
-            int bw_id = pattern_bandwidth(adj, inv);
-            std::vector<int> cand = rcm_order(N, adj), cinv(N);
-            for (int i = 0; i < N; ++i) cinv[cand[i]] = i;
-            int bw_rcm = pattern_bandwidth(adj, cinv);
-            if (bw_rcm < bw_id) { perm = cand; inv = cinv; p->permuted = true; }
-            int wX[QME_MAXS], wZ[QME_MAXS];
-            for (int s = 0; s < S; ++s) { wX[s] = max_row_nnz(p->X[s], N); wZ[s] = max_row_nnz(p->Z[s], N); }
-            int C, R; size_t sm;
-            fits = qme_cluster_geometry(N, S, wg, wX, wZ, p->E, std::min(bw_id, bw_rcm), p->smem_optin, &C, &R, &sm);
+            int bw_best = pattern_bandwidth(adj, inv);
+            std::vector<std::vector<int>> cands;
+            cands.push_back(rcm_order(N, adj));
+            if (N <= 512) {
+                cands.push_back(best_cm_order(N, adj));
+                cands.push_back(cands.back());
+                std::reverse(cands.back().begin(), cands.back().end());
+            }
+            for (auto& cand : cands) {
+                std::vector<int> cinv(N);
+                for (int i = 0; i < N; ++i) cinv[cand[i]] = i;
+                int bw = pattern_bandwidth(adj, cinv);
+                if (bw < bw_best) { bw_best = bw; perm = cand; inv = cinv; p->permuted = true; }
+            }
+            if (path == 5) {
+                bool ok5 = build_band_host(p->G, p->X, p->Z, N, nb, perm, inv, band) &&
+                           qme_band_geometry(N, p->E, band.bw, p->smem_optin, &p->band_C, &p->band_R, &p->band_smem);
+                if (!ok5) {
+                    LB_REQUIRE(p->path_req != 5, "band path does not fit this problem (N=%d)", N);
+                    path = 4;
+                }
+            }
+            if (path == 4) {
+                int wX[QME_MAXS], wZ[QME_MAXS];
+                for (int s = 0; s < S; ++s) { wX[s] = max_row_nnz(p->X[s], N); wZ[s] = max_row_nnz(p->Z[s], N); }
+                int C, R; size_t sm;
+                fits = qme_cluster_geometry(N, S, wg, wX, wZ, p->E, bw_best, p->smem_optin, &C, &R, &sm);
+            }
         }
         if (!fits) {
-            LB_REQUIRE(p->path_req != 4, "sparse cluster path does not fit this problem (N=%d)", N);
+            LB_REQUIRE(p->path_req != 4 && p->path_req != 5, "sparse cluster path does not fit this problem (N=%d)", N);
             path = 3;
             for (int i = 0; i < N; ++i) perm[i] = inv[i] = i;
             p->permuted = false;
         }
     }
     if (path == 1) LB_REQUIRE(N <= 64, "dense on-chip path needs N <= 64 (N=%d)", N);
-    if (path == 3 || path == 4) {
+    if (path >= 3) {
         LB_REQUIRE(nd == 0, "sparse paths do not support drive operators");
         LB_REQUIRE(!p->Gr.given, "sparse paths need the right generator to be G^H");
         LB_REQUIRE(S <= QME_MAXS, "sparse paths support at most %d sandwich terms", QME_MAXS);
@@ -447,6 +576,18 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
             LB_CUDA(up(p->Z[s], p->dZcol[s], p->dZval[s], p->wZ[s]));
         }
         p->bandwidth = bw;
+        if (path == 5) {
+            p->band_noff = band.noff; p->band_gt = band.gt; p->band_xt = band.xt;
+            LB_CUDA(p->dbgd.upload(band.gd.data(), band.gd.size() * 16));
+            LB_CUDA(p->dbgcol.upload(band.gcol.data(), band.gcol.size() * sizeof(int)));
+            LB_CUDA(p->dbgval.upload(band.gval.data(), band.gval.size() * 16));
+            for (int s = 0; s < S; ++s) {
+                LB_CUDA(p->dbxcol[s].upload(band.xcol[s].data(), band.xcol[s].size() * sizeof(int)));
+                LB_CUDA(p->dbxval[s].upload(band.xval[s].data(), band.xval[s].size() * 16));
+                LB_CUDA(p->dbzcol[s].upload(band.zcol[s].data(), band.zcol[s].size() * sizeof(int)));
+                LB_CUDA(p->dbzval[s].upload(band.zval[s].data(), band.zval[s].size() * 16));
+            }
+        }
         if (p->permuted) LB_CUDA(p->dperm.upload(perm.data(), N * sizeof(int)));
         // observables as COO over rho's (permuted) linear index:
         // Tr(e rho) = sum_{ij} e[j][i] rho[i][j] = sum_{i'j'} e[perm j'][perm i'] rho'[i'][j']
@@ -484,6 +625,18 @@ __global__ void qme_build_gk(const cplx* G, const cplx* Gh, const cplx* D, const
         cfma(vh, conj_r ? cconj(c) : c, Dh[(size_t)d * NN + i]);
     }
     Gk[i] = v; Gkh[i] = vh;
+}
+
+// dst[b][i'][j'] = src[b][perm i'][perm j'] (gather != 0) or dst[b][perm i'][perm j'] = src[b][i'][j']
+__global__ void qme_permute(const cplx* __restrict__ src, cplx* __restrict__ dst, const int* __restrict__ perm,
+                            int N, int gather) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= N * N) return;
+    const int i = idx / N, j = idx - i * N;
+    const size_t base = (size_t)blockIdx.y * N * N;
+    const size_t o = (size_t)perm[i] * N + perm[j];
+    if (gather) dst[base + idx] = src[base + o];
+    else dst[base + o] = src[base + idx];
 }
 
 void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
@@ -646,6 +799,29 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
     memset(&a, 0, sizeof(a));
     fill_ell_args(p, a, B);
     a.nsteps = nsteps; a.traj_every = traj_every; a.rho = rho; a.obs = obs; a.traj = traj; a.dt = dt;
+    if (p->path == 5) {
+        QmeBandArgs g;
+        memset(&g, 0, sizeof(g));
+        g.N = p->N; g.E = p->E; g.B = B; g.nsteps = nsteps; g.traj_every = traj_every; g.nb = p->nb;
+        g.R = p->band_R; g.h = p->bandwidth; g.C = p->band_C;
+        g.gd = p->dbgd.as<cplx>(); g.gcol = p->dbgcol.as<int>(); g.gval = p->dbgval.as<cplx>();
+        const int S = (int)p->X.size();
+        for (int s = 0; s < S; ++s) {
+            g.xcol[s] = p->dbxcol[s].as<int>(); g.xval[s] = p->dbxval[s].as<cplx>();
+            g.zcol[s] = p->dbzcol[s].as<int>(); g.zval[s] = p->dbzval[s].as<cplx>();
+        }
+        g.perm = p->permuted ? p->dperm.as<int>() : nullptr;
+        g.eptr = p->deptr.as<int>(); g.eidx = p->deidx.as<int>(); g.eval = p->deval.as<cplx>();
+        g.rho = rho; g.obs = obs; g.traj = traj; g.dt = dt;
+        int r;
+        if (p->N <= 64) r = p->band_noff == 2 ? qme_band_launch_tc2_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
+                                              : qme_band_launch_tc2_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
+        else r = p->band_noff == 2 ? qme_band_launch_tc4_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
+                                   : qme_band_launch_tc4_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
+        if (r != LB_OK) return r;
+        p->launches += 1;
+        return LB_OK;
+    }
     if (p->path == 4) {
         int r = qme_cluster_launch(a, p->bandwidth, p->permuted ? p->dperm.as<int>() : nullptr, p->smem_optin, st);
         if (r == LB_OK) { p->launches += 1; return LB_OK; }
@@ -706,8 +882,20 @@ int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B,
         QmeEllArgs a;
         memset(&a, 0, sizeof(a));
         fill_ell_args(p, a, B);
-        qme_ell_rhs<<<dim3(ceil_div((int)NN, 256), B), 256, 0, st>>>(a, (const cplx*)d_in, (cplx*)d_out);
-        p->launches++;
+        dim3 grid(ceil_div((int)NN, 256), B);
+        if (p->permuted) {          // operators live in the permuted basis
+            int r = ensure_scratch(p, B, 2, false);
+            if (r != LB_OK) return r;
+            cplx* t0 = p->s_y.as<cplx>();
+            cplx* t1 = t0 + (size_t)B * NN;
+            qme_permute<<<grid, 256, 0, st>>>((const cplx*)d_in, t0, p->dperm.as<int>(), N, 1);
+            qme_ell_rhs<<<grid, 256, 0, st>>>(a, t0, t1);
+            qme_permute<<<grid, 256, 0, st>>>(t1, (cplx*)d_out, p->dperm.as<int>(), N, 0);
+            p->launches += 3;
+        } else {
+            qme_ell_rhs<<<grid, 256, 0, st>>>(a, (const cplx*)d_in, (cplx*)d_out);
+            p->launches++;
+        }
     }
     LB_CUDA(cudaGetLastError());
     return LB_OK;

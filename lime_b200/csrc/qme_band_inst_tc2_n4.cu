@@ -1,0 +1,3 @@
+// explicit instantiations of the register-tiled cluster propagator (see qme_band.cuh)
+#include "qme_band.cuh"
+QME_BAND_DEFINE_LAUNCH(qme_band_launch_tc2_n4, 2, 4)

@@ -64,14 +64,16 @@ def test_lindblad_drop_in_surface(cuda):
     assert r3.observables.shape == (5, 0) and relerr(r3.rholist[-1], l3[-1]) <= TOL
 
 
-@pytest.mark.parametrize('path', [1, 2, 3, 4])
-@pytest.mark.parametrize('ncav', [8, 16])
+@pytest.mark.parametrize('path', [1, 2, 3, 4, 5])
+@pytest.mark.parametrize('ncav', [8, 16, 37, 64])
 def test_lindblad_jc_every_kernel(cuda, path, ncav):
     """Jaynes-Cummings (config-2 shape, small cutoffs) through every kernel family"""
     from lime_b200 import oqs
     H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav)
     obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=60, dt=0.01)
-    sp = path in (3, 4)
+    if path == 1 and 2 * ncav > 64:
+        pytest.skip('dense on-chip path is N <= 64')
+    sp = path in (3, 4, 5)
     Hs = csr_matrix(H) if sp else H
     cs = [csr_matrix(c) for c in c_ops] if sp else c_ops
     plan = oqs._lindblad_plan(Hs, cs, e_ops, path=path)
@@ -87,7 +89,7 @@ def test_lindblad_jc_every_kernel(cuda, path, ncav):
         assert relerr(ob, g['observables']) <= TOL and relerr(rf, g['rho_final']) <= TOL
 
 
-@pytest.mark.parametrize('path', [1, 3, 4])
+@pytest.mark.parametrize('path', [1, 3, 4, 5])
 def test_lindblad_batch_parameter_scan(cuda, path):
     """[ext] batch over coupling/detuning points with per-point Hamiltonian values"""
     from lime_b200.oqs import Lindblad_solver
@@ -133,6 +135,30 @@ def test_lindblad_non_hermitian_hamiltonian(cuda):
         assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
     res = oqs._lindblad(csr_matrix(H), rho0, [csr_matrix(c) for c in c_ops], e_ops=e_ops, Nt=30, dt=0.01)
     assert relerr(res.observables, o) <= TOL
+
+
+def test_lindblad_band_variants_and_sparse_rhs(cuda):
+    """register-tiled cluster kernel: RWA Hamiltonian (other sparsity), complex couplings (generic
+    complex off-diagonal G), two collapse operators, no collapse operator, non-Hermitian rho;
+    liouvillian() on sparse operands goes through the permuted-basis right-hand side"""
+    from lime_b200 import oqs
+    for ncav, rwa, cplx_g, M in [(20, True, False, 1), (20, False, True, 2), (33, False, False, 0), (64, True, True, 2)]:
+        H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav, rwa=rwa)
+        N = 2 * ncav
+        if cplx_g:
+            ph = np.exp(1j * np.linspace(0, 1, N))
+            H = ph[:, None] * H * ph.conj()[None, :]
+            H = (H + H.conj().T) / 2
+        a = c_ops[0]
+        cs = [a, 0.3 * a.conj().T * (1 + (0.5j if cplx_g else 0))][:M]
+        rho0 = rho0 + 0.01 * cases.rand_cplx(N, 3)
+        o, rl = lo.lindblad(H, rho0, cs, e_ops=e_ops, Nt=25, dt=0.01)
+        plan = oqs._lindblad_plan(csr_matrix(H), [csr_matrix(c) for c in cs], e_ops, path=5)
+        assert plan.path == 5
+        rf, ob, _ = plan.run(rho0, 0.01, 25)
+        assert relerr(ob, o) <= TOL, (ncav, rwa, cplx_g, M)
+        assert relerr(rf, rl[-1]) <= TOL, (ncav, rwa, cplx_g, M)
+        assert relerr(plan.rhs(rho0), lo.liouvillian(rho0, H, cs)) <= 1e-13
 
 
 def test_lindblad_driven(cuda):
