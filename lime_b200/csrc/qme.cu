@@ -486,7 +486,7 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
             }
             if (path == 5) {
                 bool ok5 = build_band_host(p->G, p->X, p->Z, N, nb, perm, inv, band) &&
-                           qme_band_geometry(N, p->E, band.bw, p->smem_optin, &p->band_C, &p->band_R, &p->band_smem);
+                           qme_band_geometry(N, p->E, band.bw, band.noff, S, p->smem_optin, &p->band_C, &p->band_R, &p->band_smem);
                 if (!ok5) {
                     LB_REQUIRE(p->path_req != 5, "band path does not fit this problem (N=%d)", N);
                     path = 4;

@@ -25,6 +25,13 @@ namespace cgb = cooperative_groups;
 
 #define QME_BAND_MAXS 2
 
+// cluster-wide barrier with release/acquire semantics at cluster scope (what cg::cluster_group::sync()
+// does, minus the GPU-scope MEMBAR and the L1 invalidate it adds): orders this CTA's local and
+// distributed-shared-memory stores before the neighbours' loads of the next stage
+__device__ __forceinline__ void cluster_barrier() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 struct QmeBandArgs {
     int N, E, B, nsteps, traj_every, nb;
     int R, h, C;                 // rows per CTA, halo rows, CTAs per cluster
@@ -46,6 +53,11 @@ struct QmeBandArgs {
 };
 
 // GT: 0 complex off-diagonal G, 1 purely imaginary.  XT: 0 complex X/Z, 1 real.
+//
+// Shared memory (element = double2, all indices 32-bit so that every access is an LDS/STS with
+// a register base + immediate): two stage buffers of (R + 2h) rows x N (+128 pad: lanes whose
+// column l + 32u lies beyond N read into the next row and are never stored), the reduction
+// scratch, and the row-side coefficient tables of this CTA's rows.
 template <int TR, int TC, int NOFF, int S, int GT, int XT>
 __global__ void __launch_bounds__(256, 1)
 qme_band_kernel(QmeBandArgs a) {
@@ -61,64 +73,84 @@ qme_band_kernel(QmeBandArgs a) {
     const int row0 = row_lo - h;
     const int T = blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int SS = S > 0 ? S : 1;
 
-    cplx* ybuf0 = smem;
-    cplx* ybuf1 = ybuf0 + (size_t)buf_rows * N;
-    cplx* red = ybuf1 + (size_t)buf_rows * N;          // [32]
-    cplx* part = red + 32;                             // [2][C][E] (rank 0)
+    const int buf_elems = buf_rows * N + 128;
+    const int o_buf1 = buf_elems;
+    const int o_red = 2 * buf_elems;                   // [32]
+    const int o_part = o_red + 32;                     // [2][C][E] (rank 0)
+    const int o_lgd = o_part + 2 * C * max(a.E, 1);    // [R]        G_ii
+    const int o_lgv = o_lgd + R;                       // [NOFF][R]  G[i][c(i,q)]
+    const int o_lxv = o_lgv + NOFF * R;                // [S][R]     X_s[i]
+    int* lgo = reinterpret_cast<int*>(smem + o_lxv + SS * R);     // [NOFF][R] byte offset of row c(i,q) in a buffer
+    int* lxo = lgo + NOFF * R;                                    // [S][R]
+    cplx* part = smem + o_part;
 
     // ---- load rho (own + halo rows, permuted basis) into stage buffer 0
     const cplx* grho = a.rho + (size_t)b * N * N;
-    for (int l = threadIdx.x; l < buf_rows * N; l += T) {
+    for (int l = threadIdx.x; l < buf_elems; l += T) {
         int r = row0 + l / N, c = l % N;
         cplx v = cmake(0, 0);
-        if (r >= 0 && r < N) {
+        if (l < buf_rows * N && r >= 0 && r < N) {
             int gr = a.perm ? a.perm[r] : r, gc = a.perm ? a.perm[c] : c;
             v = grho[(size_t)gr * N + gc];
         }
-        ybuf0[l] = v;
-        ybuf1[l] = cmake(0, 0);
+        smem[l] = v;
+        smem[o_buf1 + l] = cmake(0, 0);
+    }
+    // ---- row-side coefficient tables (rows beyond row_hi: zero coefficients, own row)
+    for (int l = threadIdx.x; l < R; l += T) {
+        const int i = row_lo + l;
+        const bool ok = i < row_hi;
+        smem[o_lgd + l] = ok ? a.gd[vb * N + i] : cmake(0, 0);
+        for (int q = 0; q < NOFF; ++q) {
+            smem[o_lgv + q * R + l] = ok ? a.gval[(vb * NOFF + q) * N + i] : cmake(0, 0);
+            lgo[q * R + l] = ((ok ? a.gcol[q * N + i] : row_lo) - row0) * N * 16;
+        }
+        for (int s = 0; s < S; ++s) {
+            smem[o_lxv + s * R + l] = ok ? a.xval[s][vb * N + i] : cmake(0, 0);
+            lxo[s * R + l] = ((ok ? a.xcol[s][i] : row_lo) - row0) * N * 16;
+        }
     }
     // ---- column-side coefficients (registers, whole launch)
-    int jc[TC];
     bool okc[TC];
     cplx gdj[TC];                    // conj(G_jj)
     int offR[NOFF][TC];              // byte offset of column c(j,q) inside a row
     cplx valR[NOFF][TC];             // conj(G[j][q])   (GT == 1: only .y is used)
-    int offZ[S > 0 ? S : 1][TC];
-    cplx valZ[S > 0 ? S : 1][TC];    // conj(Z[j])      (XT == 1: only .x is used)
+    int offZ[SS][TC];
+    cplx valZ[SS][TC];               // conj(Z[j])      (XT == 1: only .x is used)
 #pragma unroll
     for (int u = 0; u < TC; ++u) {
         const int j = lane + 32 * u;
         okc[u] = j < N;
-        jc[u] = okc[u] ? j : 0;
-        gdj[u] = okc[u] ? cconj(a.gd[vb * N + jc[u]]) : cmake(0, 0);
+        const int jj = okc[u] ? j : 0;
+        gdj[u] = okc[u] ? cconj(a.gd[vb * N + jj]) : cmake(0, 0);
 #pragma unroll
         for (int q = 0; q < NOFF; ++q) {
-            offR[q][u] = a.gcol[q * N + jc[u]] * 16;
-            valR[q][u] = okc[u] ? cconj(a.gval[(vb * NOFF + q) * N + jc[u]]) : cmake(0, 0);
+            offR[q][u] = a.gcol[q * N + jj] * 16;
+            valR[q][u] = okc[u] ? cconj(a.gval[(vb * NOFF + q) * N + jj]) : cmake(0, 0);
         }
 #pragma unroll
         for (int s = 0; s < S; ++s) {
-            offZ[s][u] = a.zcol[s][jc[u]] * 16;
-            valZ[s][u] = okc[u] ? cconj(a.zval[s][vb * N + jc[u]]) : cmake(0, 0);
+            offZ[s][u] = a.zcol[s][jj] * 16;
+            valZ[s][u] = okc[u] ? cconj(a.zval[s][vb * N + jj]) : cmake(0, 0);
         }
     }
     __syncthreads();
     cplx rho[TR][TC], acc[TR][TC];
-    const int i0 = row_lo + warp * TR;
+    const int l0 = warp * TR;                          // first own row, relative to row_lo
 #pragma unroll
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
-            const int i = i0 + r;
-            rho[r][u] = (i < row_hi && okc[u]) ? ybuf0[(size_t)(i - row0) * N + jc[u]] : cmake(0, 0);
+            const int i = row_lo + l0 + r;
+            rho[r][u] = (i < row_hi && okc[u]) ? smem[(l0 + r + h) * N + lane + 32 * u] : cmake(0, 0);
             acc[r][u] = cmake(0, 0);
         }
-    cplx* up0 = nullptr; cplx* up1 = nullptr; cplx* dn0 = nullptr; cplx* dn1 = nullptr;
+    cplx* up = nullptr; cplx* dn = nullptr;            // neighbours' shared-memory windows (generic DSMEM pointers)
     if (C > 1) {
-        if (rank > 0) { up0 = cluster.map_shared_rank(ybuf0, rank - 1); up1 = cluster.map_shared_rank(ybuf1, rank - 1); }
-        if (rank < C - 1) { dn0 = cluster.map_shared_rank(ybuf0, rank + 1); dn1 = cluster.map_shared_rank(ybuf1, rank + 1); }
+        if (rank > 0) up = cluster.map_shared_rank(smem, rank - 1);
+        if (rank < C - 1) dn = cluster.map_shared_rank(smem, rank + 1);
         cluster.sync();
     }
     cplx* part0 = (C > 1) ? cluster.map_shared_rank(part, 0) : part;
@@ -127,96 +159,113 @@ qme_band_kernel(QmeBandArgs a) {
     for (int step = 0; step < a.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
-            const cplx* yin = (stage & 1) ? ybuf1 : ybuf0;
-            cplx* yout = (stage & 1) ? ybuf0 : ybuf1;
-            cplx* rup = (stage & 1) ? up0 : up1;
-            cplx* rdn = (stage & 1) ? dn0 : dn1;
+            const int yin = (stage & 1) ? o_buf1 : 0;
+            const int yout = (stage & 1) ? 0 : o_buf1;
             const double cy = (stage == 2) ? dt : hdt;
+            const char* yinb = reinterpret_cast<const char*>(smem + yin);          // stage input, row 0
+            const char* yinl = yinb + lane * 16;                                    // ... at this lane's column
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
-                const int i = i0 + r;
-                if (i >= row_hi) break;                           // warp-uniform
-                const char* yrow = reinterpret_cast<const char*>(yin + (size_t)(i - row0) * N);
-                const cplx gdi = __ldg(a.gd + vb * N + i);
-                cplx k[TC];
-#pragma unroll
-                for (int u = 0; u < TC; ++u) {
-                    const cplx y = *reinterpret_cast<const cplx*>(yrow + jc[u] * 16);
-                    const double dr = gdi.x + gdj[u].x, di = gdi.y + gdj[u].y;
-                    k[u].x = dr * y.x - di * y.y;
-                    k[u].y = dr * y.y + di * y.x;
-                }
-#pragma unroll
-                for (int q = 0; q < NOFF; ++q) {
-                    // left: G[i][c] y[c][j]  (c, value warp-uniform)
-                    const int c = __ldg(a.gcol + q * N + i);
-                    const cplx v = __ldg(a.gval + (vb * NOFF + q) * N + i);
-                    const cplx* yl = yin + (size_t)(c - row0) * N;
+                const int li = l0 + r;                            // row relative to row_lo (warp-uniform)
+                if (row_lo + li < row_hi) {
+                    const int ownoff = (li + h) * N * 16;
+                    const char* ownb = yinb + ownoff;             // y[i][0]
+                    const char* ownl = yinl + ownoff;             // y[i][lane]
+                    const cplx gdi = smem[o_lgd + li];
+                    cplx k[TC];
 #pragma unroll
                     for (int u = 0; u < TC; ++u) {
-                        const cplx y = yl[jc[u]];
-                        if (GT == 1) {
-                            k[u].x = fma(-v.y, y.y, k[u].x);
-                            k[u].y = fma(v.y, y.x, k[u].y);
-                        } else {
-                            cfma(k[u], v, y);
+                        const cplx y = *reinterpret_cast<const cplx*>(ownl + 512 * u);
+                        const double dr = gdi.x + gdj[u].x, di = gdi.y + gdj[u].y;
+                        k[u].x = dr * y.x - di * y.y;
+                        k[u].y = dr * y.y + di * y.x;
+                    }
+#pragma unroll
+                    for (int q = 0; q < NOFF; ++q) {
+                        // left: G[i][c] y[c][j]  (c, value warp-uniform)
+                        const char* lrow = yinl + lgo[q * R + li];
+                        const cplx v = smem[o_lgv + q * R + li];
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            const cplx y = *reinterpret_cast<const cplx*>(lrow + 512 * u);
+                            if (GT == 1) {
+                                k[u].x = fma(-v.y, y.y, k[u].x);
+                                k[u].y = fma(v.y, y.x, k[u].y);
+                            } else {
+                                cfma(k[u], v, y);
+                            }
+                        }
+                        // right: y[i][c(j,q)] conj(G[j][q])
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            const cplx y = *reinterpret_cast<const cplx*>(ownb + offR[q][u]);
+                            if (GT == 1) {
+                                k[u].x = fma(-valR[q][u].y, y.y, k[u].x);
+                                k[u].y = fma(valR[q][u].y, y.x, k[u].y);
+                            } else {
+                                cfma(k[u], valR[q][u], y);
+                            }
                         }
                     }
-                    // right: y[i][c(j,q)] conj(G[j][q])
 #pragma unroll
-                    for (int u = 0; u < TC; ++u) {
-                        const cplx y = *reinterpret_cast<const cplx*>(yrow + offR[q][u]);
-                        if (GT == 1) {
-                            k[u].x = fma(-valR[q][u].y, y.y, k[u].x);
-                            k[u].y = fma(valR[q][u].y, y.x, k[u].y);
-                        } else {
-                            cfma(k[u], valR[q][u], y);
+                    for (int s = 0; s < S; ++s) {
+                        const char* xrowb = yinb + lxo[s * R + li];
+                        const cplx xv = smem[o_lxv + s * R + li];
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            const cplx y = *reinterpret_cast<const cplx*>(xrowb + offZ[s][u]);
+                            if (XT == 1) {
+                                const double cf = xv.x * valZ[s][u].x;
+                                k[u].x = fma(cf, y.x, k[u].x);
+                                k[u].y = fma(cf, y.y, k[u].y);
+                            } else {
+                                cfma(k[u], cmul(xv, valZ[s][u]), y);
+                            }
                         }
                     }
-                }
-#pragma unroll
-                for (int s = 0; s < S; ++s) {
-                    const int cx = __ldg(a.xcol[s] + i);
-                    const cplx xv = __ldg(a.xval[s] + vb * N + i);
-                    const char* ys = reinterpret_cast<const char*>(yin + (size_t)(cx - row0) * N);
-#pragma unroll
-                    for (int u = 0; u < TC; ++u) {
-                        const cplx y = *reinterpret_cast<const cplx*>(ys + offZ[s][u]);
-                        if (XT == 1) {
-                            const double cf = xv.x * valZ[s][u].x;
-                            k[u].x = fma(cf, y.x, k[u].x);
-                            k[u].y = fma(cf, y.y, k[u].y);
-                        } else {
-                            cfma(k[u], cmul(xv, valZ[s][u]), y);
-                        }
-                    }
-                }
-                // RK4 stage algebra (lime/phys.py:636-649) and write-out of the next stage vector
-                const int lr = i - row0;
-                const bool pu = rup && (i - row_lo < h);
-                const bool pd = rdn && (i >= row_lo + R - h);
-#pragma unroll
-                for (int u = 0; u < TC; ++u) {
-                    cplx yn;
+                    // RK4 stage algebra (lime/phys.py:636-649) and write-out of the next stage vector
+                    cplx yn[TC];
                     if (stage == 0) {
-                        acc[r][u] = k[u];
-                        yn = cmake(fma(cy, k[u].x, rho[r][u].x), fma(cy, k[u].y, rho[r][u].y));
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            acc[r][u] = k[u];
+                            yn[u] = cmake(fma(cy, k[u].x, rho[r][u].x), fma(cy, k[u].y, rho[r][u].y));
+                        }
                     } else if (stage < 3) {
-                        rfma(acc[r][u], 2.0, k[u]);
-                        yn = cmake(fma(cy, k[u].x, rho[r][u].x), fma(cy, k[u].y, rho[r][u].y));
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            rfma(acc[r][u], 2.0, k[u]);
+                            yn[u] = cmake(fma(cy, k[u].x, rho[r][u].x), fma(cy, k[u].y, rho[r][u].y));
+                        }
                     } else {
-                        rho[r][u].x = fma(w6, acc[r][u].x + k[u].x, rho[r][u].x);
-                        rho[r][u].y = fma(w6, acc[r][u].y + k[u].y, rho[r][u].y);
-                        yn = rho[r][u];
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) {
+                            rho[r][u].x = fma(w6, acc[r][u].x + k[u].x, rho[r][u].x);
+                            rho[r][u].y = fma(w6, acc[r][u].y + k[u].y, rho[r][u].y);
+                            yn[u] = rho[r][u];
+                        }
                     }
-                    if (okc[u]) {
-                        yout[(size_t)lr * N + jc[u]] = yn;
-                        if (pu) rup[(size_t)(i - row_lo + R + h) * N + jc[u]] = yn;
-                        if (pd) rdn[(size_t)(i - row_lo - R + h) * N + jc[u]] = yn;
+                    cplx* oo = smem + (yout + (li + h) * N + lane);
+#pragma unroll
+                    for (int u = 0; u < TC; ++u)
+                        if (okc[u]) oo[32 * u] = yn[u];
+                    // own row li sits at local row li + R + h in the upper neighbour's buffer and at
+                    // li - R + h in the lower neighbour's
+                    if (up != nullptr && li < h) {
+                        cplx* d = up + (yout + (li + R + h) * N + lane);
+#pragma unroll
+                        for (int u = 0; u < TC; ++u)
+                            if (okc[u]) d[32 * u] = yn[u];
+                    }
+                    if (dn != nullptr && li >= R - h) {
+                        cplx* d = dn + (yout + (li - R + h) * N + lane);
+#pragma unroll
+                        for (int u = 0; u < TC; ++u)
+                            if (okc[u]) d[32 * u] = yn[u];
                     }
                 }
             }
-            if (C > 1) cluster.sync(); else __syncthreads();
+            if (C > 1) cluster_barrier(); else __syncthreads();
             if (stage == 0 && a.obs && step > 0 && rank == 0 && threadIdx.x < a.E) {
                 const cplx* pp = part + (size_t)((step - 1) & 1) * C * a.E;
                 cplx sum = cmake(0, 0);
@@ -224,25 +273,25 @@ qme_band_kernel(QmeBandArgs a) {
                 a.obs[((size_t)(step - 1) * a.B + b) * a.E + threadIdx.x] = sum;
             }
         }
-        // ybuf0 now holds rho_{n+1} (own + halo rows)
+        // buffer 0 now holds rho_{n+1} (own + halo rows)
         if (a.obs) {
             for (int e = 0; e < a.E; ++e) {
                 cplx v = cmake(0, 0);
                 for (int n = a.eptr[e] + threadIdx.x; n < a.eptr[e + 1]; n += T) {
                     int idx = a.eidx[n];
                     int i = idx / N;
-                    if (i >= row_lo && i < row_hi) cfma(v, a.eval[n], ybuf0[(size_t)(i - row0) * N + (idx - i * N)]);
+                    if (i >= row_lo && i < row_hi) cfma(v, a.eval[n], smem[(i - row0) * N + (idx - i * N)]);
                 }
                 for (int off = 16; off > 0; off >>= 1) {
                     v.x += __shfl_down_sync(0xffffffffu, v.x, off);
                     v.y += __shfl_down_sync(0xffffffffu, v.y, off);
                 }
                 __syncthreads();
-                if (lane == 0) red[warp] = v;
+                if (lane == 0) smem[o_red + warp] = v;
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     cplx sum = cmake(0, 0);
-                    for (int w = 0; w < (T + 31) / 32; ++w) sum = cadd(sum, red[w]);
+                    for (int w = 0; w < (T + 31) / 32; ++w) sum = cadd(sum, smem[o_red + w]);
                     part0[(size_t)(step & 1) * C * a.E + rank * a.E + e] = sum;
                 }
             }
@@ -253,9 +302,9 @@ qme_band_kernel(QmeBandArgs a) {
             for (int r = 0; r < TR; ++r)
 #pragma unroll
                 for (int u = 0; u < TC; ++u) {
-                    const int i = i0 + r;
+                    const int i = row_lo + l0 + r, j = lane + 32 * u;
                     if (i < row_hi && okc[u]) {
-                        int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[jc[u]] : jc[u];
+                        int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                         dst[(size_t)gr * N + gc] = rho[r][u];
                     }
                 }
@@ -275,17 +324,25 @@ qme_band_kernel(QmeBandArgs a) {
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
-            const int i = i0 + r;
+            const int i = row_lo + l0 + r, j = lane + 32 * u;
             if (i < row_hi && okc[u]) {
-                int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[jc[u]] : jc[u];
+                int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                 out[(size_t)gr * N + gc] = rho[r][u];
             }
         }
     if (C > 1) cluster.sync();      // keep shared memory alive until the neighbours' remote stores are done
 }
 
+// shared-memory bytes of qme_band_kernel for a given geometry
+static inline size_t qme_band_smem(int N, int R, int h, int C, int E, int NOFF, int S) {
+    const size_t SS = S > 0 ? S : 1;
+    size_t elems = (size_t)2 * ((size_t)(R + 2 * h) * N + 128) + 32 + (size_t)2 * C * (E > 0 ? E : 1) +
+                   (size_t)R * (1 + NOFF + SS);
+    return elems * 16 + (size_t)R * (NOFF + SS) * 4 + 16;
+}
+
 // geometry: smallest cluster with R = ceil(N/C) <= 32 rows per CTA that fits shared memory
-static inline bool qme_band_geometry(int N, int E, int bandwidth, long long smem_optin,
+static inline bool qme_band_geometry(int N, int E, int bandwidth, int NOFF, int S, long long smem_optin,
                                      int* Cout, int* Rout, size_t* smem_out) {
     if (N > 128) return false;
     const int h = bandwidth;
@@ -293,7 +350,7 @@ static inline bool qme_band_geometry(int N, int E, int bandwidth, long long smem
         int r = (N + c - 1) / c;
         if (r > 32) continue;
         if (c > 1 && h > r) break;
-        size_t need = (size_t)2 * (r + 2 * h) * N * 16 + (size_t)(32 + 2 * c * (E > 0 ? E : 1)) * 16;
+        size_t need = qme_band_smem(N, r, h, c, E, NOFF, S);
         if (need <= (size_t)smem_optin) { *Cout = c; *Rout = r; *smem_out = need; return true; }
     }
     return false;
