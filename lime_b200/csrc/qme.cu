@@ -813,11 +813,10 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
         g.perm = p->permuted ? p->dperm.as<int>() : nullptr;
         g.eptr = p->deptr.as<int>(); g.eidx = p->deidx.as<int>(); g.eval = p->deval.as<cplx>();
         g.rho = rho; g.obs = obs; g.traj = traj; g.dt = dt;
+        { const char* dbg = getenv("LIMEB200_DEBUG_FLAGS"); g.debug_flags = dbg ? atoi(dbg) : 0; }
         int r;
-        if (p->N <= 64) r = p->band_noff == 2 ? qme_band_launch_tc2_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
-                                              : qme_band_launch_tc2_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
-        else r = p->band_noff == 2 ? qme_band_launch_tc4_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
-                                   : qme_band_launch_tc4_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
+        r = p->band_noff == 2 ? qme_band_launch_tc2_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
+                              : qme_band_launch_tc2_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
         if (r != LB_OK) return r;
         p->launches += 1;
         return LB_OK;

@@ -21,6 +21,7 @@
 #pragma once
 #include "common.cuh"
 #include <cooperative_groups.h>
+#include <cstdlib>
 namespace cgb = cooperative_groups;
 
 #define QME_BAND_MAXS 2
@@ -30,6 +31,39 @@ namespace cgb = cooperative_groups;
 // distributed-shared-memory stores before the neighbours' loads of the next stage
 __device__ __forceinline__ void cluster_barrier() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// ---- mbarrier / st.async plumbing for the halo exchange ------------------------------------
+// Halo rows are pushed into the neighbour CTA with st.async, which signals an mbarrier in the
+// DESTINATION CTA as the bytes land; the consumer waits on its own mbarrier for the expected
+// byte count.  No cluster-wide barrier, no fence (a cluster-scope release compiles to
+// MEMBAR.ALL.GPU + CCTL.IVALL on sm_100a) in the time loop.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n"
+        "LIMEB_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra LIMEB_DONE_%=;\n\t"
+        "bra LIMEB_WAIT_%=;\n"
+        "LIMEB_DONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+template <int IMM>
+__device__ __forceinline__ void st_async_c128(unsigned raddr, cplx v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0+%4], {%1, %2}, [%3];"
+                 ::"r"(raddr), "d"(v.x), "d"(v.y), "r"(rbar), "n"(IMM) : "memory");
 }
 
 struct QmeBandArgs {
@@ -50,6 +84,7 @@ struct QmeBandArgs {
     cplx* obs;                   // [nsteps][B][E] or null
     cplx* traj;                  // [nsteps/traj_every][B][N][N] or null
     double dt;
+    int debug_flags;             // bit 0: skip the halo exchange (timing experiments only; wrong results)
 };
 
 // GT: 0 complex off-diagonal G, 1 purely imaginary.  XT: 0 complex X/Z, 1 real.
@@ -59,7 +94,7 @@ struct QmeBandArgs {
 // column l + 32u lies beyond N read into the next row and are never stored), the reduction
 // scratch, and the row-side coefficient tables of this CTA's rows.
 template <int TR, int TC, int NOFF, int S, int GT, int XT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(512, 1)
 qme_band_kernel(QmeBandArgs a) {
     extern __shared__ double2 smem[];
     cgb::cluster_group cluster = cgb::this_cluster();
@@ -73,12 +108,15 @@ qme_band_kernel(QmeBandArgs a) {
     const int row0 = row_lo - h;
     const int T = blockDim.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int CB = (N + 32 * TC - 1) / (32 * TC);      // column blocks of 32*TC columns; warp -> (row group, column block)
+    const int jb = (warp % CB) * 32 * TC + lane;       // this thread's columns: jb + 32 u
     constexpr int SS = S > 0 ? S : 1;
 
     const int buf_elems = buf_rows * N + 128;
     const int o_buf1 = buf_elems;
-    const int o_red = 2 * buf_elems;                   // [32]
-    const int o_part = o_red + 32;                     // [2][C][E] (rank 0)
+    const int o_bar = 2 * buf_elems;                   // 4 mbarriers (8 B each): halo[2], partial sums[2]
+    const int o_red = o_bar + 2;                       // [E][16]
+    const int o_part = o_red + 16 * max(a.E, 1);        // [2][C][E] (rank 0)
     const int o_lgd = o_part + 2 * C * max(a.E, 1);    // [R]        G_ii
     const int o_lgv = o_lgd + R;                       // [NOFF][R]  G[i][c(i,q)]
     const int o_lxv = o_lgv + NOFF * R;                // [S][R]     X_s[i]
@@ -121,7 +159,7 @@ qme_band_kernel(QmeBandArgs a) {
     cplx valZ[SS][TC];               // conj(Z[j])      (XT == 1: only .x is used)
 #pragma unroll
     for (int u = 0; u < TC; ++u) {
-        const int j = lane + 32 * u;
+        const int j = jb + 32 * u;
         okc[u] = j < N;
         const int jj = okc[u] ? j : 0;
         gdj[u] = okc[u] ? cconj(a.gd[vb * N + jj]) : cmake(0, 0);
@@ -138,22 +176,34 @@ qme_band_kernel(QmeBandArgs a) {
     }
     __syncthreads();
     cplx rho[TR][TC], acc[TR][TC];
-    const int l0 = warp * TR;                          // first own row, relative to row_lo
+    const int l0 = (warp / CB) * TR;                   // first own row, relative to row_lo
 #pragma unroll
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
             const int i = row_lo + l0 + r;
-            rho[r][u] = (i < row_hi && okc[u]) ? smem[(l0 + r + h) * N + lane + 32 * u] : cmake(0, 0);
+            rho[r][u] = (i < row_hi && okc[u]) ? smem[(l0 + r + h) * N + jb + 32 * u] : cmake(0, 0);
             acc[r][u] = cmake(0, 0);
         }
-    cplx* up = nullptr; cplx* dn = nullptr;            // neighbours' shared-memory windows (generic DSMEM pointers)
+    // ---- neighbours: mapped shared-memory windows and mbarriers
+    const unsigned bar0 = smem_u32(smem + o_bar);      // halo mbarriers bar0 + 8*p, partial-sum mbarriers bar0 + 16 + 8*p
+    const bool has_up = C > 1 && rank > 0 && !(a.debug_flags & 1), has_dn = C > 1 && rank < C - 1 && !(a.debug_flags & 1);
+    unsigned up_base = 0, dn_base = 0, up_bar = 0, dn_bar = 0, r0_part = 0, r0_bar = 0, halo_bytes = 0;
     if (C > 1) {
-        if (rank > 0) up = cluster.map_shared_rank(smem, rank - 1);
-        if (rank < C - 1) dn = cluster.map_shared_rank(smem, rank + 1);
+        if (threadIdx.x == 0) {
+            for (int m = 0; m < 4; ++m) mbar_init(bar0 + 8 * m, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        const unsigned sbase = smem_u32(smem);
+        if (has_up) { up_base = mapa_u32(sbase, rank - 1); up_bar = mapa_u32(bar0, rank - 1); halo_bytes += h * N * 16; }
+        if (has_dn) {
+            dn_base = mapa_u32(sbase, rank + 1); dn_bar = mapa_u32(bar0, rank + 1);
+            halo_bytes += min(h, min(N, row_lo + 2 * R) - (row_lo + R)) * N * 16;
+        }
+        r0_part = mapa_u32(smem_u32(smem + o_part), 0);
+        r0_bar = mapa_u32(bar0 + 16, 0);
         cluster.sync();
     }
-    cplx* part0 = (C > 1) ? cluster.map_shared_rank(part, 0) : part;
 
     const double dt = a.dt, hdt = 0.5 * a.dt, w6 = a.dt / 6.0;
     for (int step = 0; step < a.nsteps; ++step) {
@@ -162,15 +212,16 @@ qme_band_kernel(QmeBandArgs a) {
             const int yin = (stage & 1) ? o_buf1 : 0;
             const int yout = (stage & 1) ? 0 : o_buf1;
             const double cy = (stage == 2) ? dt : hdt;
+            if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * (stage & 1), halo_bytes);
             const char* yinb = reinterpret_cast<const char*>(smem + yin);          // stage input, row 0
-            const char* yinl = yinb + lane * 16;                                    // ... at this lane's column
+            const char* yinl = yinb + jb * 16;                                      // ... at this thread's first column
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
                 const int li = l0 + r;                            // row relative to row_lo (warp-uniform)
                 if (row_lo + li < row_hi) {
                     const int ownoff = (li + h) * N * 16;
                     const char* ownb = yinb + ownoff;             // y[i][0]
-                    const char* ownl = yinl + ownoff;             // y[i][lane]
+                    const char* ownl = yinl + ownoff;             // y[i][jb]
                     const cplx gdi = smem[o_lgd + li];
                     cplx k[TC];
 #pragma unroll
@@ -245,32 +296,44 @@ qme_band_kernel(QmeBandArgs a) {
                             yn[u] = rho[r][u];
                         }
                     }
-                    cplx* oo = smem + (yout + (li + h) * N + lane);
+                    cplx* oo = smem + (yout + (li + h) * N + jb);
 #pragma unroll
                     for (int u = 0; u < TC; ++u)
                         if (okc[u]) oo[32 * u] = yn[u];
                     // own row li sits at local row li + R + h in the upper neighbour's buffer and at
-                    // li - R + h in the lower neighbour's
-                    if (up != nullptr && li < h) {
-                        cplx* d = up + (yout + (li + R + h) * N + lane);
-#pragma unroll
-                        for (int u = 0; u < TC; ++u)
-                            if (okc[u]) d[32 * u] = yn[u];
+                    // li - R + h in the lower neighbour's; the bytes are counted on the neighbour's mbarrier
+                    if (has_up && li < h) {
+                        const unsigned d = up_base + (unsigned)(yout + (li + R + h) * N + jb) * 16u;
+                        const unsigned rb = up_bar + 8 * (stage & 1);
+                        if (okc[0]) st_async_c128<0>(d, yn[0], rb);
+                        if (TC > 1 && okc[TC > 1 ? 1 : 0]) st_async_c128<512>(d, yn[TC > 1 ? 1 : 0], rb);
+                        if (TC > 2 && okc[TC > 2 ? 2 : 0]) st_async_c128<1024>(d, yn[TC > 2 ? 2 : 0], rb);
+                        if (TC > 3 && okc[TC > 3 ? 3 : 0]) st_async_c128<1536>(d, yn[TC > 3 ? 3 : 0], rb);
                     }
-                    if (dn != nullptr && li >= R - h) {
-                        cplx* d = dn + (yout + (li - R + h) * N + lane);
-#pragma unroll
-                        for (int u = 0; u < TC; ++u)
-                            if (okc[u]) d[32 * u] = yn[u];
+                    if (has_dn && li >= R - h) {
+                        const unsigned d = dn_base + (unsigned)(yout + (li - R + h) * N + jb) * 16u;
+                        const unsigned rb = dn_bar + 8 * (stage & 1);
+                        if (okc[0]) st_async_c128<0>(d, yn[0], rb);
+                        if (TC > 1 && okc[TC > 1 ? 1 : 0]) st_async_c128<512>(d, yn[TC > 1 ? 1 : 0], rb);
+                        if (TC > 2 && okc[TC > 2 ? 2 : 0]) st_async_c128<1024>(d, yn[TC > 2 ? 2 : 0], rb);
+                        if (TC > 3 && okc[TC > 3 ? 3 : 0]) st_async_c128<1536>(d, yn[TC > 3 ? 3 : 0], rb);
                     }
                 }
             }
-            if (C > 1) cluster_barrier(); else __syncthreads();
-            if (stage == 0 && a.obs && step > 0 && rank == 0 && threadIdx.x < a.E) {
-                const cplx* pp = part + (size_t)((step - 1) & 1) * C * a.E;
-                cplx sum = cmake(0, 0);
-                for (int c = 0; c < C; ++c) sum = cadd(sum, pp[c * a.E + threadIdx.x]);
-                a.obs[((size_t)(step - 1) * a.B + b) * a.E + threadIdx.x] = sum;
+            // local writes visible / local reads of the old stage vector finished ...
+            __syncthreads();
+            // ... and the neighbours' halo rows have landed (phase (g >> 1) & 1 of mbarrier g & 1, g = 4 step + stage)
+            if (C > 1) mbar_wait(bar0 + 8 * (stage & 1), (unsigned)((step * 2 + (stage >> 1)) & 1));
+            if (C > 1 && stage == 0 && a.obs && step > 0 && rank == 0) {
+                // partial sums of the previous step (pushed by the other CTAs with st.async) are complete
+                const int sp = step - 1;
+                for (int e = threadIdx.x; e < a.E; e += T) {
+                    mbar_wait(bar0 + 16 + 8 * (sp & 1), (unsigned)((sp >> 1) & 1));
+                    const cplx* pp = part + (size_t)(sp & 1) * C * a.E;
+                    cplx sum = cmake(0, 0);
+                    for (int c = 0; c < C; ++c) sum = cadd(sum, pp[c * a.E + e]);
+                    a.obs[((size_t)sp * a.B + b) * a.E + e] = sum;
+                }
             }
         }
         // buffer 0 now holds rho_{n+1} (own + halo rows)
@@ -286,15 +349,20 @@ qme_band_kernel(QmeBandArgs a) {
                     v.x += __shfl_down_sync(0xffffffffu, v.x, off);
                     v.y += __shfl_down_sync(0xffffffffu, v.y, off);
                 }
-                __syncthreads();
-                if (lane == 0) smem[o_red + warp] = v;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    cplx sum = cmake(0, 0);
-                    for (int w = 0; w < (T + 31) / 32; ++w) sum = cadd(sum, smem[o_red + w]);
-                    part0[(size_t)(step & 1) * C * a.E + rank * a.E + e] = sum;
-                }
+                if (lane == 0) smem[o_red + e * 16 + warp] = v;
             }
+            __syncthreads();
+            if (C > 1 && rank == 0 && threadIdx.x == 0)
+                mbar_arrive_expect_tx(bar0 + 16 + 8 * (step & 1), (unsigned)((C - 1) * a.E * 16));
+            for (int e = threadIdx.x; e < a.E; e += T) {
+                cplx sum = cmake(0, 0);
+                for (int w = 0; w < (T + 31) / 32; ++w) sum = cadd(sum, smem[o_red + e * 16 + w]);
+                if (C == 1) a.obs[((size_t)step * a.B + b) * a.E + e] = sum;
+                else if (rank == 0) part[(size_t)(step & 1) * C * a.E + e] = sum;
+                else st_async_c128<0>(r0_part + (unsigned)(((step & 1) * C + rank) * a.E + e) * 16u, sum,
+                                      r0_bar + 8 * (step & 1));
+            }
+            __syncthreads();          // red[] is reused by the next step
         }
         if (a.traj && ((step + 1) % a.traj_every) == 0) {
             cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * N * N;
@@ -302,7 +370,7 @@ qme_band_kernel(QmeBandArgs a) {
             for (int r = 0; r < TR; ++r)
 #pragma unroll
                 for (int u = 0; u < TC; ++u) {
-                    const int i = row_lo + l0 + r, j = lane + 32 * u;
+                    const int i = row_lo + l0 + r, j = jb + 32 * u;
                     if (i < row_hi && okc[u]) {
                         int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                         dst[(size_t)gr * N + gc] = rho[r][u];
@@ -310,13 +378,14 @@ qme_band_kernel(QmeBandArgs a) {
                 }
         }
     }
-    if (a.obs && a.nsteps > 0) {
-        if (C > 1) cluster.sync(); else __syncthreads();
-        if (rank == 0 && threadIdx.x < a.E) {
-            const cplx* pp = part + (size_t)((a.nsteps - 1) & 1) * C * a.E;
+    if (C > 1 && a.obs && a.nsteps > 0 && rank == 0) {
+        const int sp = a.nsteps - 1;
+        for (int e = threadIdx.x; e < a.E; e += T) {
+            mbar_wait(bar0 + 16 + 8 * (sp & 1), (unsigned)((sp >> 1) & 1));
+            const cplx* pp = part + (size_t)(sp & 1) * C * a.E;
             cplx sum = cmake(0, 0);
-            for (int c = 0; c < C; ++c) sum = cadd(sum, pp[c * a.E + threadIdx.x]);
-            a.obs[((size_t)(a.nsteps - 1) * a.B + b) * a.E + threadIdx.x] = sum;
+            for (int c = 0; c < C; ++c) sum = cadd(sum, pp[c * a.E + e]);
+            a.obs[((size_t)sp * a.B + b) * a.E + e] = sum;
         }
     }
     cplx* out = a.rho + (size_t)b * N * N;
@@ -324,7 +393,7 @@ qme_band_kernel(QmeBandArgs a) {
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
-            const int i = row_lo + l0 + r, j = lane + 32 * u;
+            const int i = row_lo + l0 + r, j = jb + 32 * u;
             if (i < row_hi && okc[u]) {
                 int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                 out[(size_t)gr * N + gc] = rho[r][u];
@@ -336,7 +405,7 @@ qme_band_kernel(QmeBandArgs a) {
 // shared-memory bytes of qme_band_kernel for a given geometry
 static inline size_t qme_band_smem(int N, int R, int h, int C, int E, int NOFF, int S) {
     const size_t SS = S > 0 ? S : 1;
-    size_t elems = (size_t)2 * ((size_t)(R + 2 * h) * N + 128) + 32 + (size_t)2 * C * (E > 0 ? E : 1) +
+    size_t elems = (size_t)2 * ((size_t)(R + 2 * h) * N + 128) + 2 + (size_t)(16 + 2 * C) * (E > 0 ? E : 1) +
                    (size_t)R * (1 + NOFF + SS);
     return elems * 16 + (size_t)R * (NOFF + SS) * 4 + 16;
 }
@@ -346,9 +415,11 @@ static inline bool qme_band_geometry(int N, int E, int bandwidth, int NOFF, int 
                                      int* Cout, int* Rout, size_t* smem_out) {
     if (N > 128) return false;
     const int h = bandwidth;
+    const char* force = getenv("LIMEB200_BAND_C");           // tuning/experiments: force the cluster size
     for (int c = 1; c <= 8; c *= 2) {
         int r = (N + c - 1) / c;
         if (r > 32) continue;
+        if (force && atoi(force) != c) continue;
         if (c > 1 && h > r) break;
         size_t need = qme_band_smem(N, r, h, c, E, NOFF, S);
         if (need <= (size_t)smem_optin) { *Cout = c; *Rout = r; *smem_out = need; return true; }
@@ -359,15 +430,13 @@ static inline bool qme_band_geometry(int N, int E, int bandwidth, int NOFF, int 
 // implemented in qme_band_inst_*.cu (one translation unit per (TC, NOFF) so that make -j compiles them in parallel)
 int qme_band_launch_tc2_n2(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
 int qme_band_launch_tc2_n4(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
-int qme_band_launch_tc4_n2(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
-int qme_band_launch_tc4_n4(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
 
 template <int TC, int NOFF, int S, int GT, int XT>
 static int qme_band_launch_one(const QmeBandArgs& a, size_t smem, cudaStream_t st) {
     constexpr int TR = 4;
     auto kern = qme_band_kernel<TR, TC, NOFF, S, GT, XT>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int W = (a.R + TR - 1) / TR;
+    const int W = ((a.R + TR - 1) / TR) * ((a.N + 32 * TC - 1) / (32 * TC));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)a.B * a.C);
     cfg.blockDim = dim3(32 * W);
