@@ -331,7 +331,7 @@ class HeomFMO(HeomBase):
             else:
                 self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
                 self.nhe = self.h.nhe
-                self.kernel = 'heom_stage_kernel'
+                self.kernel = {1: 'heom_onchip', 2: 'heom_stage_kernel', 3: 'heom_persist_kernel'}
             rho0 = np.zeros((7, 7), dtype=complex)
             rho0[0, 0] = 1.0
             ado = np.zeros((self.B, self.nhe, 7, 7), dtype=complex)

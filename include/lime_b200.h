@@ -150,7 +150,9 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
                                  const int* states, const int* dn, const int* up,
                                  long long row_lo, long long row_hi);
 int limeb200_heom_destroy(limeb200_heom_t plan);
-int limeb200_heom_set_path(limeb200_heom_t plan, int path);   /* 0 auto, 1 on-chip, 2 stage-wise */
+/* 0 auto, 1 on-chip (one CTA per hierarchy, all steps fused), 2 one launch per RK4 stage,
+ * 3 persistent cooperative kernel (all steps in one launch, one grid barrier per stage)   */
+int limeb200_heom_set_path(limeb200_heom_t plan, int path);
 int limeb200_heom_get_path(limeb200_heom_t plan);
 /* nsteps RK4 steps (lime/phys.py:636-649) of B hierarchies d_ado[B][nhe][n][n], in place.
  * d_eT [E][n][n] TRANSPOSED observables of tier 0, d_obs [nsteps][B][E],

@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <memory>
+#include <cooperative_groups.h>
 
 // ====================================================================================
 // host: index tables
@@ -117,13 +118,17 @@ struct HeomDev {
     long long nhe;
     const cplx* H;          // [n][n]
     const cplx* Q;          // [nq][n][n]
-    const double* qdiag;    // [nq][n] real diagonal (valid when diagq)
-    int diagq;
-    const int* qstart;      // [nq+1] into qmodes
+    int diagq;              // every Q_q is real diagonal
+    const int* qstart;      // [nq+1] into qmodes              (dense-Q path)
     const int* qmodes;      // modes sorted by q
+    // diagonal-Q path: per matrix element (i,j) the modes k with (Q_qk)_ii != 0 or (Q_qk)_jj != 0
+    const int* em_start;    // [nn+1]
+    const int* em_mode;     // mode index
+    const double2* em_v;    // ((Q_q)_ii, (Q_q)_jj)
     const cplx* cdn;        // [npar][nmodes]  pref_dn * c_k
     const cplx* cdnR;       // [npar][nmodes]  pref_dn * conj(c_k)
     const double* nu;       // [npar][nmodes]
+    const double* damp;     // [nhe] sum_k n_k nu_k, or null when npar > 1
     cplx pref_up;
     const int* states;      // [nhe][nmodes]
     const int* dn;          // [nhe][nmodes]
@@ -139,23 +144,21 @@ struct HeomStageArgs {
     int apc;                // ADOs per CTA
 };
 
-// L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (hierarchy base)
-__device__ __forceinline__ void heom_combos(const HeomDev& d, int par, long long a, int q, int idx,
-                                            const cplx* y, cplx& L, cplx& R) {
+// L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
+// st/dn/up: the ADO's rows of the index tables (global memory, or a shared-memory copy)
+__device__ __forceinline__ void heom_combos(const HeomDev& d, int par, const int* st, const int* dn, const int* up,
+                                            int q, int idx, const cplx* y, cplx& L, cplx& R) {
     L = cmake(0, 0); R = cmake(0, 0);
-    const int* st = d.states + a * d.nmodes;
-    const int* dn = d.dn + a * d.nmodes;
-    const int* up = d.up + a * d.nmodes;
     for (int m = __ldg(d.qstart + q); m < __ldg(d.qstart + q + 1); ++m) {
         const int k = __ldg(d.qmodes + m);
-        const int id = __ldg(dn + k);
+        const int id = dn[k];
         if (id >= 0) {
-            const double nk = (double)__ldg(st + k);
+            const double nk = (double)st[k];
             const cplx v = y[(size_t)id * d.nn + idx];
             cfma(L, cscale(nk, __ldg(d.cdn + (size_t)par * d.nmodes + k)), v);
             cfma(R, cscale(nk, __ldg(d.cdnR + (size_t)par * d.nmodes + k)), v);
         }
-        const int iu = __ldg(up + k);
+        const int iu = up[k];
         if (iu >= 0) {
             const cplx v = y[(size_t)iu * d.nn + idx];
             cfma(L, d.pref_up, v);
@@ -164,95 +167,359 @@ __device__ __forceinline__ void heom_combos(const HeomDev& d, int par, long long
     }
 }
 
+// coefficient of rho_{n-e_k}[i][j] in d rho_n[i][j]/dt for diagonal Q:  n_k (q_i pref_dn c_k - q_j pref_dn conj c_k)
+__device__ __forceinline__ cplx heom_dn_coef(const HeomDev& d, int par, int k, double nk, double2 v) {
+    const cplx cl = __ldg(d.cdn + (size_t)par * d.nmodes + k);
+    const cplx cr = __ldg(d.cdnR + (size_t)par * d.nmodes + k);
+    return cmake(nk * (v.x * cl.x - v.y * cr.x), nk * (v.x * cl.y - v.y * cr.y));
+}
+
+// bath part of the right-hand side, diagonal Q: a pure neighbour gather over the element's own mode list
+__device__ __forceinline__ void heom_bath_diag(const HeomDev& d, int par, const int* st, const int* dn,
+                                               const int* up, int idx, const cplx* y, cplx& k) {
+    const int t1 = __ldg(d.em_start + idx + 1);
+#pragma unroll 4
+    for (int t = __ldg(d.em_start + idx); t < t1; ++t) {
+        const int m = __ldg(d.em_mode + t);
+        const double2 v = __ldg(d.em_v + t);
+        const int id = dn[m], iu = up[m];
+        // clamp instead of branching so that both neighbour loads are issued back to back
+        const cplx yd = y[(size_t)max(id, 0) * d.nn + idx];
+        const cplx yu = y[(size_t)max(iu, 0) * d.nn + idx];
+        if (id >= 0) cfma(k, heom_dn_coef(d, par, m, (double)st[m], v), yd);
+        if (iu >= 0) cfma(k, cscale(v.x - v.y, d.pref_up), yu);
+    }
+}
+
 __device__ __forceinline__ double heom_damp(const HeomDev& d, int par, long long a) {
+    if (d.damp) return __ldg(d.damp + a);
     double s = 0.0;
     const int* st = d.states + a * d.nmodes;
     for (int k = 0; k < d.nmodes; ++k) s = fma((double)__ldg(st + k), __ldg(d.nu + (size_t)par * d.nmodes + k), s);
     return s;
 }
 
-// -i [H, Y]_{ij} with Y a full n x n matrix at ya
-__device__ __forceinline__ cplx heom_sys(const HeomDev& d, const cplx* ya, int i, int j) {
+// -i [H, Y]_{ij} with Y a full n x n matrix at ya (shared memory), Hs the system Hamiltonian
+__device__ __forceinline__ cplx heom_sys(const cplx* Hs, int n, const cplx* ya, int i, int j) {
     cplx s = cmake(0, 0);
-    const int n = d.n;
     for (int m = 0; m < n; ++m) {
-        cfma(s, __ldg(d.H + i * n + m), ya[m * n + j]);
-        cplx t = cmul(ya[i * n + m], __ldg(d.H + m * n + j));
+        cfma(s, Hs[i * n + m], ya[m * n + j]);
+        cplx t = cmul(ya[i * n + m], Hs[m * n + j]);
         s.x -= t.x; s.y -= t.y;
     }
     return cmake(s.y, -s.x);          // -i * s
 }
 
-// stage-wise kernel: grid (ceil(nown/apc), B); block apc*nn threads; dynamic smem 3*apc*nn cplx
-__global__ void __launch_bounds__(1024)
-heom_stage_kernel(HeomStageArgs a) {
-    extern __shared__ double2 smem[];
+// RK4 stage algebra (lime/phys.py:636-649) for one element; returns the next stage vector element
+__device__ __forceinline__ cplx heom_rk_update(int stage, cplx k, cplx& r, cplx& ac, double dt) {
+    const double hdt = 0.5 * dt;
+    if (stage == 0) { ac = k; return cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y)); }
+    if (stage == 1) { rfma(ac, 2.0, k); return cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y)); }
+    if (stage == 2) { rfma(ac, 2.0, k); return cmake(fma(dt, k.x, r.x), fma(dt, k.y, r.y)); }
+    const double w6 = dt / 6.0;
+    r.x = fma(w6, ac.x + k.x, r.x);
+    r.y = fma(w6, ac.y + k.y, r.y);
+    return r;
+}
+
+// one tile (apc ADOs x nn elements) of one RK4 stage; shared: Hs[nn], ys/Ls/Rs[apc*nn].
+// Items are the owned ADOs of all B hierarchies in flat order: item = b * nown + (ado - row_lo).
+// tabs: shared-memory copy [apc][3][nmodes] of the tile's (states, dn, up) rows, or null (read global).
+// rreg/areg: the element's rho / RK accumulator kept in registers by a persistent caller, or null.
+__device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long long item0, double2* smem,
+                                                const int* tabs, cplx* rreg, cplx* areg) {
     const HeomDev& d = a.d;
     const int nn = d.nn, n = d.n;
     const int g = threadIdx.x / nn;
     const int idx = threadIdx.x - g * nn;
     const int i = idx / n, j = idx - i * n;
-    const long long ado = a.row_lo + (long long)blockIdx.x * a.apc + g;
-    const bool act = ado < a.row_hi;
-    const int b = blockIdx.y;
+    const long long nown = a.row_hi - a.row_lo;
+    const long long item = item0 + g;
+    const bool act = g < a.apc && item < nown * a.B;
+    const int b = act ? (int)(item / nown) : 0;
+    const long long ado = act ? a.row_lo + (item - (long long)b * nown) : a.row_lo;
     const int par = d.npar > 1 ? b : 0;
     const cplx* y = a.yin + (size_t)b * d.nhe * nn;
-    cplx* ys = smem + (size_t)g * nn;
-    cplx* Ls = smem + (size_t)(a.apc + g) * nn;
-    cplx* Rs = smem + (size_t)(2 * a.apc + g) * nn;
+    cplx* Hs = smem;
+    cplx* ys = Hs + nn + (size_t)g * nn;
+    cplx* Ls = Hs + nn + (size_t)(a.apc + g) * nn;
+    cplx* Rs = Hs + nn + (size_t)(2 * a.apc + g) * nn;
 
     cplx yv = act ? y[(size_t)ado * nn + idx] : cmake(0, 0);
-    ys[idx] = yv;
+    if (g < a.apc) ys[idx] = yv;
     __syncthreads();
     cplx k = cmake(0, 0);
     if (act) {
-        k = heom_sys(d, ys, i, j);
+        k = heom_sys(Hs, n, ys, i, j);
         const double damp = heom_damp(d, par, ado);
         k.x = fma(-damp, yv.x, k.x);
         k.y = fma(-damp, yv.y, k.y);
     }
-    for (int q = 0; q < d.nq; ++q) {
-        cplx L = cmake(0, 0), R = cmake(0, 0);
-        if (act) heom_combos(d, par, ado, q, idx, y, L, R);
-        if (d.diagq) {
-            rfma(k, __ldg(d.qdiag + q * n + i), L);
-            rfma(k, -__ldg(d.qdiag + q * n + j), R);
-        } else {
+    const int nm = d.nmodes;
+    const int* st = tabs ? tabs + (size_t)(3 * g) * nm : d.states + ado * nm;
+    const int* dn = tabs ? tabs + (size_t)(3 * g + 1) * nm : d.dn + ado * nm;
+    const int* up = tabs ? tabs + (size_t)(3 * g + 2) * nm : d.up + ado * nm;
+    if (d.diagq) {
+        if (act) heom_bath_diag(d, par, st, dn, up, idx, y, k);
+    } else {
+        for (int q = 0; q < d.nq; ++q) {
+            cplx L = cmake(0, 0), R = cmake(0, 0);
+            if (act) heom_combos(d, par, st, dn, up, q, idx, y, L, R);
             __syncthreads();
-            Ls[idx] = L; Rs[idx] = R;
+            if (g < a.apc) { Ls[idx] = L; Rs[idx] = R; }
             __syncthreads();
-            const cplx* Qq = d.Q + (size_t)q * nn;
-            for (int m = 0; m < n; ++m) {
-                cfma(k, __ldg(Qq + i * n + m), Ls[m * n + j]);
-                cplx t = cmul(Rs[i * n + m], __ldg(Qq + m * n + j));
-                k.x -= t.x; k.y -= t.y;
+            if (act) {
+                const cplx* Qq = d.Q + (size_t)q * nn;
+                for (int m = 0; m < n; ++m) {
+                    cfma(k, __ldg(Qq + i * n + m), Ls[m * n + j]);
+                    cplx t = cmul(Rs[i * n + m], __ldg(Qq + m * n + j));
+                    k.x -= t.x; k.y -= t.y;
+                }
             }
         }
     }
     if (!act) return;
     const size_t o = ((size_t)b * d.nhe + ado) * nn + idx;
-    const double dt = a.dt, hdt = 0.5 * a.dt;
     if (a.stage < 0) { a.ynext[o] = k; return; }
+    if (rreg) {
+        a.ynext[o] = heom_rk_update(a.stage, k, *rreg, *areg, a.dt);
+        if (a.stage == 3) a.rho[o] = *rreg;
+        return;
+    }
     cplx r = a.rho[o];
-    if (a.stage == 0) {
-        a.acc[o] = k;
-        a.ynext[o] = cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y));
-    } else if (a.stage == 1) {
-        cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
-        a.ynext[o] = cmake(fma(hdt, k.x, r.x), fma(hdt, k.y, r.y));
-    } else if (a.stage == 2) {
-        cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
-        a.ynext[o] = cmake(fma(dt, k.x, r.x), fma(dt, k.y, r.y));
-    } else {
-        cplx tot = cadd(a.acc[o], k);
-        r.x += tot.x / 6.0 * dt;
-        r.y += tot.y / 6.0 * dt;
-        a.rho[o] = r;
-        a.ynext[o] = r;
+    cplx ac = (a.stage == 0) ? cmake(0, 0) : a.acc[o];
+    const cplx yn = heom_rk_update(a.stage, k, r, ac, a.dt);
+    if (a.stage < 3) a.acc[o] = ac; else a.rho[o] = r;
+    a.ynext[o] = yn;
+}
+
+// stage-wise kernel: grid ceil(items/apc); block >= apc*nn threads; dynamic smem (1 + 3*apc)*nn cplx
+__global__ void __launch_bounds__(1024)
+heom_stage_kernel(HeomStageArgs a) {
+    extern __shared__ double2 smem[];
+    for (int l = threadIdx.x; l < a.d.nn; l += blockDim.x) smem[l] = a.d.H[l];
+    heom_stage_tile(a, (long long)blockIdx.x * a.apc, smem, nullptr, nullptr, nullptr);
+}
+
+// persistent variant: the whole RK4 loop in ONE cooperative launch; tiles are distributed
+// grid-stride, stage vectors stay in L2, one grid barrier per stage.  Used when the hierarchy
+// is too large for one CTA's shared memory but small enough that per-stage launches dominate.
+struct HeomPersistArgs {
+    HeomStageArgs s;        // rho, acc set; yin/ynext = ping-pong buffers y0 (holds rho on entry), y1
+    cplx* y0; cplx* y1;
+    int nsteps, E, traj_every;
+    const cplx* eT; cplx* obs; cplx* traj;
+    unsigned* barrier;      // zero-initialised counter
+};
+
+// grid-wide barrier on a monotonic counter (zeroed by the host before the launch): one release
+// reduction per CTA, polling with relaxed L2 loads, ONE acquire fence (which invalidates L1) at
+// the end.  cooperative_groups' grid.sync() polls through an L1-invalidating load (CCTL.IVALL per
+// poll), measured at ~6 us per barrier with 444 CTAs; the kernel is still launched cooperatively so
+// that all CTAs are co-resident.
+__device__ __forceinline__ void heom_grid_barrier(unsigned* ctr, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+heom_persist_kernel(HeomPersistArgs p) {
+    extern __shared__ double2 smem[];
+    HeomStageArgs a = p.s;
+    unsigned bar_target = 0;
+    const HeomDev& d = a.d;
+    const int nn = d.nn;
+    for (int l = threadIdx.x; l < nn; l += blockDim.x) smem[l] = d.H[l];
+    const long long nown = a.row_hi - a.row_lo;
+    const long long nitems = nown * a.B;
+    const long long ntiles = (nitems + a.apc - 1) / a.apc;
+    // one tile per CTA for the whole run: index tables of the tile in shared memory, rho and the RK4
+    // accumulator of the thread's element in registers (only the stage vectors travel through L2)
+    const bool fixed = ntiles <= (long long)gridDim.x;
+    int* tabs = reinterpret_cast<int*>(smem + (size_t)(1 + 3 * a.apc) * nn);
+    cplx rreg = cmake(0, 0), areg = cmake(0, 0);
+    if (fixed) {
+        const int nm = d.nmodes;
+        for (int l = threadIdx.x; l < a.apc * nm; l += blockDim.x) {
+            const int g = l / nm, k = l - g * nm;
+            const long long item = (long long)blockIdx.x * a.apc + g;
+            if (item < nitems) {
+                const long long ado = a.row_lo + item % nown;
+                tabs[(3 * g) * nm + k] = d.states[ado * nm + k];
+                tabs[(3 * g + 1) * nm + k] = d.dn[ado * nm + k];
+                tabs[(3 * g + 2) * nm + k] = d.up[ado * nm + k];
+            }
+        }
+        const int g = threadIdx.x / nn;
+        const long long item = (long long)blockIdx.x * a.apc + g;
+        if (g < a.apc && item < nitems) {
+            const long long b = item / nown;
+            rreg = a.rho[((size_t)b * d.nhe + a.row_lo + (item - b * nown)) * nn + (threadIdx.x - g * nn)];
+        }
+    }
+    __syncthreads();
+    for (int step = 0; step < p.nsteps; ++step) {
+        for (int stage = 0; stage < 4; ++stage) {
+            a.stage = stage;
+            a.yin = (stage & 1) ? p.y1 : p.y0;
+            a.ynext = (stage & 1) ? p.y0 : p.y1;
+            if (fixed) {
+                if (blockIdx.x < ntiles) heom_stage_tile(a, (long long)blockIdx.x * a.apc, smem, tabs, &rreg, &areg);
+            } else {
+                for (long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+                    heom_stage_tile(a, t * a.apc, smem, nullptr, nullptr, nullptr);
+                    __syncthreads();
+                }
+            }
+            bar_target += gridDim.x;
+            heom_grid_barrier(p.barrier, bar_target);
+        }
+        // y0 == rho_{n+1}; tier-0 observables / trajectory: one warp per (hierarchy, observable)
+        const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        const int nwarps = (gridDim.x * blockDim.x) >> 5;
+        if (p.obs)
+            for (int w = warp; w < a.B * p.E; w += nwarps) {
+                const int b = w / p.E, e = w - b * p.E;
+                const cplx* r = a.rho + (size_t)b * d.nhe * nn;
+                cplx v = cmake(0, 0);
+                for (int l = lane; l < nn; l += 32) cfma(v, __ldg(p.eT + (size_t)e * nn + l), r[l]);
+                for (int off = 16; off > 0; off >>= 1) {
+                    v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+                    v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+                }
+                if (lane == 0) p.obs[((size_t)step * a.B + b) * p.E + e] = v;
+            }
+        if (p.traj && ((step + 1) % p.traj_every) == 0)
+            for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < (long long)a.B * nn;
+                 l += (long long)gridDim.x * blockDim.x) {
+                const long long b = l / nn;
+                p.traj[((size_t)(step / p.traj_every) * a.B + b) * nn + (l - b * nn)] =
+                    a.rho[(size_t)b * d.nhe * nn + (l - b * nn)];
+            }
     }
 }
 
-// on-chip kernel: one CTA per hierarchy, all nsteps fused.  smem: y0,y1 [nhe*nn] (+ L,R if dense Q)
+// Persistent kernel, diagonal Q, ONE element per thread for the whole run (apc ADOs per CTA,
+// every item has its own CTA slot): the element's <= NE neighbour offsets and coefficients are
+// computed once and kept in shared memory (structure-of-arrays, conflict-free), rho / the RK4
+// accumulator / the damping rate in registers.  Per stage a thread issues its neighbour loads
+// (independent L2 reads), exchanges its own stage value through shared memory for -i[H, .],
+// and writes one element of the next stage vector; then the grid barrier.
+#define HEOM_PC_NE 8
+template <int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB)
+heom_persist_cached_kernel(HeomPersistArgs p) {
+    extern __shared__ double2 smem[];
+    const HeomStageArgs& a = p.s;
+    const HeomDev& d = a.d;
+    const int nn = d.nn, n = d.n, T = blockDim.x;
+    cplx* Hs = smem;                                   // [nn]
+    cplx* ys = Hs + nn;                                // [apc*nn]
+    cplx* ecf = ys + (size_t)a.apc * nn;               // [NE][T]
+    int* eoff = reinterpret_cast<int*>(ecf + (size_t)HEOM_PC_NE * T);   // [NE][T]
+    for (int l = threadIdx.x; l < nn; l += T) Hs[l] = d.H[l];
+    const long long nown = a.row_hi - a.row_lo;
+    const long long nitems = nown * a.B;
+    const int g = threadIdx.x / nn;
+    const int idx = threadIdx.x - g * nn;
+    const int i = idx / n, j = idx - i * n;
+    const long long item = (long long)blockIdx.x * a.apc + g;
+    const bool act = g < a.apc && item < nitems;
+    const int b = act ? (int)(item / nown) : 0;
+    const long long ado = act ? a.row_lo + (item - (long long)b * nown) : a.row_lo;
+    const int par = d.npar > 1 ? b : 0;
+    const size_t hb = (size_t)b * d.nhe * nn;          // hierarchy base
+    const size_t own = hb + (size_t)ado * nn + idx;
+    cplx rreg = act ? a.rho[own] : cmake(0, 0), areg = cmake(0, 0);
+    const double damp = act ? heom_damp(d, par, ado) : 0.0;
+    {
+        int ne = 0;
+        if (act) {
+            const int* st = d.states + ado * d.nmodes;
+            const int* dn = d.dn + ado * d.nmodes;
+            const int* up = d.up + ado * d.nmodes;
+            for (int t = d.em_start[idx]; t < d.em_start[idx + 1]; ++t) {
+                const int m = d.em_mode[t];
+                const double2 v = d.em_v[t];
+                const int id = dn[m], iu = up[m];
+                if (id >= 0 && ne < HEOM_PC_NE) {
+                    eoff[ne * T + threadIdx.x] = (int)(hb + (size_t)id * nn + idx);
+                    ecf[ne * T + threadIdx.x] = heom_dn_coef(d, par, m, (double)st[m], v);
+                    ++ne;
+                }
+                if (iu >= 0 && v.x != v.y && ne < HEOM_PC_NE) {
+                    eoff[ne * T + threadIdx.x] = (int)(hb + (size_t)iu * nn + idx);
+                    ecf[ne * T + threadIdx.x] = cscale(v.x - v.y, d.pref_up);
+                    ++ne;
+                }
+            }
+        }
+        for (; ne < HEOM_PC_NE; ++ne) {
+            eoff[ne * T + threadIdx.x] = (int)own;
+            ecf[ne * T + threadIdx.x] = cmake(0, 0);
+        }
+    }
+    __syncthreads();
+    unsigned bar_target = 0;
+    for (int step = 0; step < p.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            const cplx* yin = (stage & 1) ? p.y1 : p.y0;
+            cplx* yout = (stage & 1) ? p.y0 : p.y1;
+            cplx nb[HEOM_PC_NE];
+#pragma unroll
+            for (int e = 0; e < HEOM_PC_NE; ++e) nb[e] = yin[eoff[e * T + threadIdx.x]];
+            const cplx yv = yin[own];
+            if (g < a.apc) ys[threadIdx.x] = yv;
+            __syncthreads();
+            cplx k = heom_sys(Hs, n, ys + (size_t)g * nn, i, j);
+            k.x = fma(-damp, yv.x, k.x);
+            k.y = fma(-damp, yv.y, k.y);
+#pragma unroll
+            for (int e = 0; e < HEOM_PC_NE; ++e) cfma(k, ecf[e * T + threadIdx.x], nb[e]);
+            const cplx yn = heom_rk_update(stage, k, rreg, areg, a.dt);
+            if (act) {
+                yout[own] = yn;
+                if (stage == 3) a.rho[own] = rreg;
+            }
+            bar_target += gridDim.x;
+            heom_grid_barrier(p.barrier, bar_target);
+        }
+        // tier-0 observables / trajectory (a.rho was written before the barrier)
+        const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        const int nwarps = (gridDim.x * blockDim.x) >> 5;
+        if (p.obs)
+            for (int w = warp; w < a.B * p.E; w += nwarps) {
+                const int bb = w / p.E, e = w - bb * p.E;
+                const cplx* r = a.rho + (size_t)bb * d.nhe * nn;
+                cplx v = cmake(0, 0);
+                for (int l = lane; l < nn; l += 32) cfma(v, __ldg(p.eT + (size_t)e * nn + l), r[l]);
+                for (int off = 16; off > 0; off >>= 1) {
+                    v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+                    v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+                }
+                if (lane == 0) p.obs[((size_t)step * a.B + bb) * p.E + e] = v;
+            }
+        if (p.traj && ((step + 1) % p.traj_every) == 0)
+            for (long long l = (long long)blockIdx.x * blockDim.x + threadIdx.x; l < (long long)a.B * nn;
+                 l += (long long)gridDim.x * blockDim.x) {
+                const long long bb = l / nn;
+                p.traj[((size_t)(step / p.traj_every) * a.B + bb) * nn + (l - bb * nn)] =
+                    a.rho[(size_t)bb * d.nhe * nn + (l - bb * nn)];
+            }
+    }
+}
+
+// on-chip kernel: one CTA per hierarchy, all nsteps fused.  smem: Hs[nn], y0,y1 [nhe*nn] (+ L,R if dense Q)
 struct HeomChipArgs {
     HeomDev d;
     int B, nsteps, traj_every, E, T;
@@ -260,17 +527,105 @@ struct HeomChipArgs {
     double dt;
 };
 
+// tier-0 observables / trajectory from a shared-memory hierarchy (ADO 0 = reduced density matrix)
+__device__ __forceinline__ void heom_chip_outputs(const HeomChipArgs& a, const cplx* y0, int b, int step) {
+    const int nn = a.d.nn;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (a.obs)
+        for (int e = warp; e < a.E; e += nw) {
+            cplx v = cmake(0, 0);
+            for (int l = lane; l < nn; l += 32) cfma(v, __ldg(a.eT + (size_t)e * nn + l), y0[l]);
+            for (int off = 16; off > 0; off >>= 1) {
+                v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+                v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+            }
+            if (lane == 0) a.obs[((size_t)step * a.B + b) * a.E + e] = v;
+        }
+    if (a.traj && ((step + 1) % a.traj_every) == 0) {
+        cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * nn;
+        for (int l = threadIdx.x; l < nn; l += blockDim.x) dst[l] = y0[l];
+    }
+}
+
+// diagonal Q, one element per thread, at most NE/2 modes per element: neighbour offsets and
+// coefficients are computed ONCE and stay in registers for the whole launch
+template <int NE>
+__global__ void __launch_bounds__(1024, 1)
+heom_onchip_cached(HeomChipArgs a) {
+    extern __shared__ double2 smem[];
+    const HeomDev& d = a.d;
+    const int nn = d.nn, n = d.n;
+    const int total = (int)d.nhe * nn;
+    const int b = blockIdx.x;
+    const int par = d.npar > 1 ? b : 0;
+    cplx* Hs = smem;
+    cplx* y0 = Hs + nn;
+    cplx* y1 = y0 + total;
+    cplx* gado = a.ado + (size_t)b * total;
+    const int l = threadIdx.x;
+    const bool ok = l < total;
+    const int ado = ok ? l / nn : 0, idx = ok ? l - ado * nn : 0;
+    const int i = idx / n, j = idx - i * n;
+    for (int t = threadIdx.x; t < nn; t += blockDim.x) Hs[t] = d.H[t];
+    cplx rho = ok ? gado[l] : cmake(0, 0), acc = cmake(0, 0);
+    if (ok) y0[l] = rho;
+    const double damp = ok ? heom_damp(d, par, ado) : 0.0;
+    int eoff[NE];
+    cplx ecf[NE];
+    {
+        const int t0 = __ldg(d.em_start + idx), t1 = __ldg(d.em_start + idx + 1);
+#pragma unroll
+        for (int s = 0; s < NE / 2; ++s) {
+            eoff[2 * s] = eoff[2 * s + 1] = 0;
+            ecf[2 * s] = ecf[2 * s + 1] = cmake(0, 0);
+            if (ok && t0 + s < t1) {
+                const int m = __ldg(d.em_mode + t0 + s);
+                const double2 v = __ldg(d.em_v + t0 + s);
+                const int id = __ldg(d.dn + (size_t)ado * d.nmodes + m);
+                if (id >= 0) {
+                    eoff[2 * s] = id * nn + idx;
+                    ecf[2 * s] = heom_dn_coef(d, par, m, (double)__ldg(d.states + (size_t)ado * d.nmodes + m), v);
+                }
+                const int iu = __ldg(d.up + (size_t)ado * d.nmodes + m);
+                if (iu >= 0) {
+                    eoff[2 * s + 1] = iu * nn + idx;
+                    ecf[2 * s + 1] = cscale(v.x - v.y, d.pref_up);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int step = 0; step < a.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            const cplx* yin = (stage & 1) ? y1 : y0;
+            cplx* yout = (stage & 1) ? y0 : y1;
+            const cplx yv = yin[ok ? l : 0];
+            cplx k = heom_sys(Hs, n, yin + (size_t)ado * nn, i, j);
+            k.x = fma(-damp, yv.x, k.x);
+            k.y = fma(-damp, yv.y, k.y);
+#pragma unroll
+            for (int e = 0; e < NE; ++e) cfma(k, ecf[e], yin[eoff[e]]);
+            const cplx yn = heom_rk_update(stage, k, rho, acc, a.dt);
+            if (ok) yout[l] = yn;
+            __syncthreads();
+        }
+        heom_chip_outputs(a, y0, b, step);
+    }
+    if (ok) gado[l] = rho;
+}
+
 template <int EPT>
 __global__ void __launch_bounds__(1024, 1)
 heom_onchip_kernel(HeomChipArgs a) {
     extern __shared__ double2 smem[];
-    __shared__ cplx red[32];
     const HeomDev& d = a.d;
     const int nn = d.nn, n = d.n, T = a.T;
     const int total = (int)d.nhe * nn;
     const int b = blockIdx.x;
     const int par = d.npar > 1 ? b : 0;
-    cplx* y0 = smem;
+    cplx* Hs = smem;
+    cplx* y0 = Hs + nn;
     cplx* y1 = y0 + total;
     cplx* Ls = y1 + total;
     cplx* Rs = Ls + total;
@@ -278,6 +633,7 @@ heom_onchip_kernel(HeomChipArgs a) {
     cplx rho[EPT], acc[EPT];
     double damp[EPT];
     bool ok[EPT];
+    for (int t = threadIdx.x; t < nn; t += T) Hs[t] = d.H[t];
 #pragma unroll
     for (int e = 0; e < EPT; ++e) {
         int l = threadIdx.x + e * T;
@@ -288,7 +644,6 @@ heom_onchip_kernel(HeomChipArgs a) {
         if (ok[e]) y0[l] = rho[e];
     }
     __syncthreads();
-    const double dt = a.dt, hdt = 0.5 * a.dt;
     for (int step = 0; step < a.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
@@ -302,28 +657,26 @@ heom_onchip_kernel(HeomChipArgs a) {
                 const int l = threadIdx.x + e * T;
                 const int ado = l / nn, idx = l - ado * nn;
                 const int i = idx / n, j = idx - i * n;
-                cplx s = heom_sys(d, yin + (size_t)ado * nn, i, j);
+                cplx s = heom_sys(Hs, n, yin + (size_t)ado * nn, i, j);
                 const cplx yv = yin[l];
                 s.x = fma(-damp[e], yv.x, s.x);
                 s.y = fma(-damp[e], yv.y, s.y);
+                if (d.diagq) heom_bath_diag(d, par, d.states + (size_t)ado * d.nmodes, d.dn + (size_t)ado * d.nmodes,
+                                            d.up + (size_t)ado * d.nmodes, idx, yin, s);
                 k[e] = s;
             }
-            for (int q = 0; q < d.nq; ++q) {
-                cplx L[EPT], R[EPT];
+            if (!d.diagq) {
+                for (int q = 0; q < d.nq; ++q) {
+                    cplx L[EPT], R[EPT];
 #pragma unroll
-                for (int e = 0; e < EPT; ++e) {
-                    L[e] = cmake(0, 0); R[e] = cmake(0, 0);
-                    if (!ok[e]) continue;
-                    const int l = threadIdx.x + e * T;
-                    const int ado = l / nn, idx = l - ado * nn;
-                    heom_combos(d, par, ado, q, idx, yin, L[e], R[e]);
-                    if (d.diagq) {
-                        const int i = idx / n, j = idx - i * n;
-                        rfma(k[e], __ldg(d.qdiag + q * n + i), L[e]);
-                        rfma(k[e], -__ldg(d.qdiag + q * n + j), R[e]);
+                    for (int e = 0; e < EPT; ++e) {
+                        L[e] = cmake(0, 0); R[e] = cmake(0, 0);
+                        if (!ok[e]) continue;
+                        const int l = threadIdx.x + e * T;
+                        const int ado = l / nn, idx = l - ado * nn;
+                        heom_combos(d, par, d.states + (size_t)ado * d.nmodes, d.dn + (size_t)ado * d.nmodes,
+                                    d.up + (size_t)ado * d.nmodes, q, idx, yin, L[e], R[e]);
                     }
-                }
-                if (!d.diagq) {
                     __syncthreads();
 #pragma unroll
                     for (int e = 0; e < EPT; ++e)
@@ -349,54 +702,17 @@ heom_onchip_kernel(HeomChipArgs a) {
 #pragma unroll
             for (int e = 0; e < EPT; ++e) {
                 if (!ok[e]) continue;
-                cplx yn;
-                if (stage == 0) {
-                    acc[e] = k[e];
-                    yn = cmake(fma(hdt, k[e].x, rho[e].x), fma(hdt, k[e].y, rho[e].y));
-                } else if (stage == 1) {
-                    rfma(acc[e], 2.0, k[e]);
-                    yn = cmake(fma(hdt, k[e].x, rho[e].x), fma(hdt, k[e].y, rho[e].y));
-                } else if (stage == 2) {
-                    rfma(acc[e], 2.0, k[e]);
-                    yn = cmake(fma(dt, k[e].x, rho[e].x), fma(dt, k[e].y, rho[e].y));
-                } else {
-                    cplx tot = cadd(acc[e], k[e]);
-                    rho[e].x += tot.x / 6.0 * dt;
-                    rho[e].y += tot.y / 6.0 * dt;
-                    yn = rho[e];
-                }
-                yout[threadIdx.x + e * T] = yn;
+                yout[threadIdx.x + e * T] = heom_rk_update(stage, k[e], rho[e], acc[e], a.dt);
             }
             __syncthreads();
         }
-        // y0 holds the new hierarchy; tier 0 is ADO 0
-        if (a.obs) {
-            for (int eo = 0; eo < a.E; ++eo) {
-                cplx v = cmake(0, 0);
-                for (int l = threadIdx.x; l < nn; l += T) cfma(v, __ldg(a.eT + (size_t)eo * nn + l), y0[l]);
-                for (int off = 16; off > 0; off >>= 1) {
-                    v.x += __shfl_down_sync(0xffffffffu, v.x, off);
-                    v.y += __shfl_down_sync(0xffffffffu, v.y, off);
-                }
-                if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    cplx s = cmake(0, 0);
-                    for (int w = 0; w < (T + 31) / 32; ++w) s = cadd(s, red[w]);
-                    a.obs[((size_t)step * a.B + b) * a.E + eo] = s;
-                }
-                __syncthreads();
-            }
-        }
-        if (a.traj && ((step + 1) % a.traj_every) == 0) {
-            cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * nn;
-            for (int l = threadIdx.x; l < nn; l += T) dst[l] = y0[l];
-        }
+        heom_chip_outputs(a, y0, b, step);      // y0 holds the new hierarchy; tier 0 is ADO 0
     }
 #pragma unroll
     for (int e = 0; e < EPT; ++e)
         if (ok[e]) gado[threadIdx.x + e * T] = rho[e];
 }
+
 
 // tier-0 observables / trajectory for the stage-wise path
 __global__ void heom_tier0_obs(const cplx* __restrict__ ado, long long hier_stride, int nn,
@@ -502,8 +818,9 @@ struct limeb200_heom_s {
     int path_req = 0, path = 0;
     bool diagq = false;
     cplx pref_up;
-    DevBuf dH, dQ, dqdiag, dqstart, dqmodes, dcdn, dcdnR, dnu, dstates, ddn, dup;
-    DevBuf s_y, s_acc;
+    DevBuf dH, dQ, dqstart, dqmodes, dems, demm, demv, ddamp, dcdn, dcdnR, dnu, dstates, ddn, dup;
+    int max_modes_per_elem = 0;
+    DevBuf s_y, s_acc, dbar;
     int scratch_B = 0;
     long long launches = 0;
     long long smem_optin = 0;
@@ -511,8 +828,10 @@ struct limeb200_heom_s {
     HeomDev dev() const {
         HeomDev d;
         d.n = n; d.nn = n * n; d.nmodes = nmodes; d.nq = nq; d.npar = npar; d.nhe = nhe;
-        d.H = dH.as<cplx>(); d.Q = dQ.as<cplx>(); d.qdiag = dqdiag.as<double>(); d.diagq = diagq ? 1 : 0;
+        d.H = dH.as<cplx>(); d.Q = dQ.as<cplx>(); d.diagq = diagq ? 1 : 0;
         d.qstart = dqstart.as<int>(); d.qmodes = dqmodes.as<int>();
+        d.em_start = dems.as<int>(); d.em_mode = demm.as<int>(); d.em_v = demv.as<double2>();
+        d.damp = (npar == 1) ? ddamp.as<double>() : nullptr;
         d.cdn = dcdn.as<cplx>(); d.cdnR = dcdnR.as<cplx>(); d.nu = dnu.as<double>();
         d.pref_up = pref_up;
         d.states = dstates.as<int>(); d.dn = ddn.as<int>(); d.up = dup.as<int>();
@@ -593,7 +912,34 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
     p->pref_up = cmake(pref_up[0], pref_up[1]);
     LB_CUDA(p->dH.upload(h_H, (size_t)nn * 16));
     LB_CUDA(p->dQ.upload(h_Q, (size_t)nq * nn * 16));
-    LB_CUDA(p->dqdiag.upload(qd.data(), qd.size() * 8));
+    {   // per matrix element: the modes whose (diagonal) coupling operator touches row i or column j
+        std::vector<int> ems(nn + 1, 0), emm;
+        std::vector<double> emv;
+        int mx = 0;
+        for (int idx = 0; idx < nn; ++idx) {
+            const int i = idx / n, j = idx % n;
+            for (int k = 0; k < nmodes; ++k) {
+                const double vi = qd[qmap[k] * n + i], vj = qd[qmap[k] * n + j];
+                if (vi != 0.0 || vj != 0.0) { emm.push_back(k); emv.push_back(vi); emv.push_back(vj); }
+            }
+            ems[idx + 1] = (int)emm.size();
+            mx = std::max(mx, ems[idx + 1] - ems[idx]);
+        }
+        p->max_modes_per_elem = mx;
+        if (emm.empty()) { emm.push_back(0); emv.push_back(0.0); emv.push_back(0.0); }
+        LB_CUDA(p->dems.upload(ems.data(), ems.size() * 4));
+        LB_CUDA(p->demm.upload(emm.data(), emm.size() * 4));
+        LB_CUDA(p->demv.upload(emv.data(), emv.size() * 8));
+    }
+    if (npar == 1) {
+        std::vector<double> damp((size_t)nhe, 0.0);
+        for (long long a = 0; a < nhe; ++a) {
+            double sd = 0.0;          // same fma order as the device loop
+            for (int k = 0; k < nmodes; ++k) sd = std::fma((double)states[a * nmodes + k], h_nu[k], sd);
+            damp[a] = sd;
+        }
+        LB_CUDA(p->ddamp.upload(damp.data(), damp.size() * 8));
+    }
     LB_CUDA(p->dqstart.upload(qstart.data(), qstart.size() * 4));
     LB_CUDA(p->dqmodes.upload(qmodes.data(), qmodes.size() * 4));
     LB_CUDA(p->dcdn.upload(cdn.data(), cdn.size() * 16));
@@ -611,7 +957,7 @@ int limeb200_heom_destroy(limeb200_heom_t p) {
     return LB_OK;
 }
 int limeb200_heom_set_path(limeb200_heom_t p, int path) {
-    LB_REQUIRE(p && path >= 0 && path <= 2, "bad arguments");
+    LB_REQUIRE(p && path >= 0 && path <= 3, "bad arguments");
     p->path_req = path;
     return LB_OK;
 }
@@ -628,11 +974,11 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
     a.apc = std::max(1, 256 / nn);
-    size_t smem = (size_t)3 * a.apc * nn * 16;
-    dim3 grid((unsigned)ceil_div(nown, (long long)a.apc), B);
+    size_t smem = (size_t)(1 + 3 * a.apc) * nn * 16;
+    dim3 grid((unsigned)ceil_div(nown * B, (long long)a.apc));
     if (smem > 48 * 1024)
         LB_CUDA(cudaFuncSetAttribute(heom_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    heom_stage_kernel<<<grid, a.apc * nn, smem, st>>>(a);
+    heom_stage_kernel<<<grid, ceil_div(a.apc * nn, 32) * 32, smem, st>>>(a);
     p->launches++;
     return LB_OK;
 }
@@ -679,10 +1025,10 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     const long long total = p->nhe * nn;
     // ---- on-chip path: whole hierarchy in one CTA's shared memory
     const int nbuf = p->diagq ? 2 : 4;
-    const size_t smem_chip = (size_t)nbuf * total * 16;
+    const size_t smem_chip = ((size_t)nbuf * total + nn) * 16;
     bool chip_ok = total <= 8 * 1024 && smem_chip + 1024 <= (size_t)p->smem_optin;
     int path = p->path_req;
-    if (path == 0) path = (chip_ok && (B >= p->sm_count / 2 || total <= 4096)) ? 1 : 2;
+    if (path == 0) path = (chip_ok && (B >= p->sm_count / 2 || total <= 4096)) ? 1 : 3;
     LB_REQUIRE(path != 1 || chip_ok, "hierarchy (%lld elements) does not fit the on-chip path", total);
     p->path = path;
     if (path == 1) {
@@ -697,18 +1043,74 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         a.T = T;
         void (*kern)(HeomChipArgs) = EPT == 1 ? heom_onchip_kernel<1> : EPT == 2 ? heom_onchip_kernel<2>
                                    : EPT == 4 ? heom_onchip_kernel<4> : heom_onchip_kernel<8>;
+        if (p->diagq && EPT == 1 && p->max_modes_per_elem <= 4)       // register-cached neighbour lists
+            kern = p->max_modes_per_elem <= 2 ? heom_onchip_cached<4> : heom_onchip_cached<8>;
         LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chip));
         kern<<<B, T, smem_chip, st>>>(a);
         LB_CUDA(cudaGetLastError());
         p->launches++;
         return LB_OK;
     }
-    // ---- stage-wise path
+    // ---- scratch shared by the persistent and the stage-wise paths
     if (B > p->scratch_B || !p->s_y.p) {
         LB_CUDA(p->s_y.alloc((size_t)2 * B * total * 16));
         LB_CUDA(p->s_acc.alloc((size_t)B * total * 16));
         p->scratch_B = B;
     }
+    if (path == 3) {
+        // persistent cooperative kernel: all steps in one launch, one grid barrier per stage
+        HeomPersistArgs pa;
+        pa.s.d = p->dev();
+        pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = 0; pa.s.row_hi = p->nhe;
+        pa.s.rho = (cplx*)d_ado; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
+        pa.s.dt = dt;
+        pa.y0 = p->s_y.as<cplx>(); pa.y1 = p->s_y.as<cplx>() + (size_t)B * total;
+        pa.nsteps = nsteps; pa.E = E; pa.traj_every = traj_every;
+        pa.eT = (const cplx*)d_eT; pa.obs = E > 0 ? (cplx*)d_obs : nullptr; pa.traj = (cplx*)d_traj;
+        int coop = 0;
+        LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+        // balanced tiles: one tile per CTA for the whole run when the items fit in (1 or 2 CTAs per SM) x
+        // at most (1024 or 576) threads; larger problems loop over tiles of up to 1024 threads
+        const long long nitems = p->nhe * B;
+        const int nmodes_ = p->nmodes;
+        void (*kern)(HeomPersistArgs) = heom_persist_kernel<1024, 1>;
+        int per_sm = 1;
+        {
+            long long apc1 = ceil_div(nitems, (long long)p->sm_count);
+            long long apc2 = ceil_div(nitems, 2LL * p->sm_count);
+            if (apc1 * nn <= 1024) pa.s.apc = (int)std::max<long long>(1, apc1);
+            else if (apc2 * nn <= 576) { pa.s.apc = (int)apc2; kern = heom_persist_kernel<576, 2>; per_sm = 2; }
+            else pa.s.apc = std::max(1, 1024 / nn);
+        }
+        const int threads = ceil_div(pa.s.apc * nn, 32) * 32;
+        size_t smem = (size_t)(1 + 3 * pa.s.apc) * nn * 16 + (size_t)3 * pa.s.apc * nmodes_ * 4;
+        const bool one_tile_per_cta = ceil_div(nitems, (long long)pa.s.apc) <= (long long)per_sm * p->sm_count;
+        const size_t smem_c = (size_t)(1 + pa.s.apc) * nn * 16 + (size_t)HEOM_PC_NE * threads * 20;
+        if (p->diagq && one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
+            (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
+            kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
+            smem = smem_c;
+        }
+        LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;
+        LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+        per_sm = std::min(per_sm, occ);
+        const long long ntiles = ceil_div(nitems, (long long)pa.s.apc);
+        if (per_sm >= 1 && coop) {
+            const int grid = (int)std::min<long long>(ntiles, (long long)per_sm * p->sm_count);
+            if (!p->dbar.p) LB_CUDA(p->dbar.alloc(64));
+            LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
+            pa.barrier = p->dbar.as<unsigned>();
+            LB_CUDA(cudaMemcpyAsync(pa.y0, d_ado, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
+            void* kargs[] = {&pa};
+            LB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), kargs, smem, st));
+            p->launches += 1;
+            return LB_OK;
+        }
+        LB_REQUIRE(p->path_req != 3, "cooperative launch is not available on this device");
+        p->path = 2;
+    }
+    // ---- stage-wise path
     cplx* rho = (cplx*)d_ado;
     cplx* y[2] = {p->s_y.as<cplx>(), p->s_y.as<cplx>() + (size_t)B * total};
     cplx* acc = p->s_acc.as<cplx>();

@@ -259,7 +259,7 @@ def test_heom_dl_exact(cuda):
     assert relerr(traj, g['traj']) <= TOL
 
 
-@pytest.mark.parametrize('path', [1, 2])
+@pytest.mark.parametrize('path', [1, 2, 3])
 def test_heom_spin_boson_multi_index(cuda, path):
     """config-3 shape: K=2 Matsubara terms, depth 12 -> 91 ADOs, 312 couplings (diagonal Q)"""
     from lime_b200.heom.heom import HEOM
@@ -280,7 +280,7 @@ def test_heom_spin_boson_multi_index(cuda, path):
                                                  h.dn.astype(np.int64), h.up.astype(np.int64))) <= 1e-12
 
 
-@pytest.mark.parametrize('path', [1, 2])
+@pytest.mark.parametrize('path', [1, 2, 3])
 def test_heom_dense_q_and_multibath(cuda, path):
     """non-diagonal coupling operators, 2 baths with their own Q, n=3"""
     from lime_b200.heom.heom import HEOM
@@ -297,7 +297,8 @@ def test_heom_dense_q_and_multibath(cuda, path):
     assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
 
 
-def test_heom_fmo_shape_stagewise_and_batch(cuda):
+@pytest.mark.parametrize('path', [0, 2, 3])
+def test_heom_fmo_shape_stagewise_and_batch(cuda, path):
     """config-4 shape at reduced depth: 7 sites, 7 baths x K=2, depth 2 (120 ADOs of 7x7);
     projector coupling operators (diagonal-Q gather path); batch of 3 hierarchies"""
     from lime_b200 import engine
@@ -311,7 +312,9 @@ def test_heom_fmo_shape_stagewise_and_batch(cuda):
     rng = np.random.default_rng(5)
     ado0 = rng.standard_normal((3, h.nhe, n, n)) + 1j * rng.standard_normal((3, h.nhe, n, n))
     ado0 *= 0.1
-    out, obs, traj = h.plan.run(ado0, 0.02, 10, e_ops=[H])
+    h.plan.set_path(path)
+    out, obs, traj = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
+    assert relerr(traj[-1], out[:, 0]) == 0
     for b in range(3):
         ado_o, obs_o, _ = lo.heom_rk4(ado0[b], H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
                                       h.up.astype(np.int64), 0.02, 10, e_ops=[H])
