@@ -1,0 +1,130 @@
+"""
+ADO-sharded HEOM propagation over the ranks of a torch.distributed group (BASELINE config 4:
+one large hierarchy partitioned by ADO index across the GPUs of one box).
+
+Partition: contiguous blocks of `chunk = ceil(N_he / world)` ADOs in the lexicographic order of
+lime's index tables (lime/heom/heom.py:21-108).  Every rank keeps the full stage vector, computes
+the RK4 stage (lime/phys.py:636-649) of the ADOs it OWNS with limeb200_heom_stage, and the new
+stage vector is exchanged with ONE all-gather per stage (4 per RK4 step) -- with this ordering
+the rows a rank needs from its peers are at least as many as the rows it owns, so a
+halo exchange would move about the same bytes.  rho and the RK4 accumulator are only ever
+touched on the owned rows, so they need no communication; after stage 3 the gathered stage vector
+IS rho_{n+1}.
+
+The data path is: CUDA stage kernel -> NCCL all-gather over NVLink, both on the current stream.
+`stage_fn` is a seam for the world_size-2 gloo tests of this host logic (they plug a CPU stage
+function built from the oracle); the product path always uses the CUDA plan.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .. import engine
+from .. import _dev
+from .heom import _calc_matsubara_params
+
+
+def partition(nhe, world):
+    """(chunk, [(lo, hi)] per rank): contiguous, equal chunks (the last one may be short or empty)"""
+    chunk = -(-nhe // world)
+    return chunk, [(min(nhe, r * chunk), min(nhe, (r + 1) * chunk)) for r in range(world)]
+
+
+class ShardedHEOM:
+    def __init__(self, H, Q, coup_strength, cut_freq, temperature, N_exp=2, N_cut=4,
+                 pref_dn=-1j, pref_up=-1j, group=None, stage_fn=None, device=None):
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.H = _dev.as_c128(H)
+        self.n = self.H.shape[0]
+        Qs = [_dev.as_c128(q) for q in Q] if isinstance(Q, (list, tuple)) else [_dev.as_c128(Q)]
+        nbath = len(Qs)
+        lam = np.broadcast_to(np.asarray(coup_strength, dtype=float), (nbath,))
+        gam = np.broadcast_to(np.asarray(cut_freq, dtype=float), (nbath,))
+        c, nu, qmap = [], [], []
+        for b in range(nbath):
+            cb, nub = _calc_matsubara_params(N_exp, lam[b], gam[b], temperature)
+            c += cb
+            nu += nub
+            qmap += [b] * N_exp
+        self.c = np.array(c, dtype=complex)
+        self.nu = np.array(nu, dtype=float)
+        self.qmap = np.array(qmap, dtype=np.int32)
+        self.Q = np.stack(Qs)
+        self.nmodes = nbath * N_exp
+        self.states, self.dn, self.up = engine.heom_tables([N_cut + 1] * self.nmodes, N_cut)
+        self.nhe = self.states.shape[0]
+        self.chunk, self.ranges = partition(self.nhe, self.world)
+        self.nhe_pad = self.chunk * self.world
+        self.lo, self.hi = self.ranges[self.rank]
+        self.last_launches = 0
+        self._stage_fn = stage_fn
+        self._graph = None
+        if stage_fn is None:
+            self.dev = _dev.device() if device is None else device
+            self.plan = engine.HeomPlan(self.H, self.Q, self.qmap, self.c, self.nu, self.states, self.dn, self.up,
+                                        pref_dn=pref_dn, pref_up=pref_up, row_range=(self.lo, self.hi),
+                                        device_index=self.dev.index)
+        else:
+            self.dev = torch.device('cpu') if device is None else device
+            self.plan = None
+
+    # ---- one RK4 stage of the owned rows, then the exchange --------------------------------
+    def _stage(self, stage, rho, yin, ynext, acc, dt):
+        if self._stage_fn is not None:
+            self._stage_fn(self, stage, rho, yin, ynext, acc, dt)
+        else:
+            self.plan.stage(stage, rho, yin, ynext, acc, dt)
+            self.last_launches += 1
+
+    def _exchange(self, y):
+        """all-gather of the stage vector y [1, nhe_pad, n, n]: every rank contributes its chunk"""
+        if self.world == 1:
+            return
+        flat = y.view(self.world, -1)
+        if dist.get_backend(self.group) == 'nccl':
+            dist.all_gather_into_tensor(y.view(-1), flat[self.rank], group=self.group)     # in place
+        else:
+            chunks = [torch.empty_like(flat[0]) for _ in range(self.world)]
+            dist.all_gather(chunks, flat[self.rank].clone(), group=self.group)
+            for r in range(self.world):
+                flat[r].copy_(chunks[r])
+        self.last_launches += 1
+
+    def run_device(self, ado, dt, nsteps):
+        """ado: [1, N_he, n, n] complex128 on self.dev, identical on every rank; advanced in place by
+        nsteps RK4 steps (every rank ends up with the full hierarchy)."""
+        assert ado.shape == (1, self.nhe, self.n, self.n) and ado.dtype == torch.complex128
+        shape = (1, self.nhe_pad, self.n, self.n)
+        y = [torch.zeros(shape, dtype=torch.complex128, device=ado.device) for _ in range(2)]
+        acc = torch.zeros(shape, dtype=torch.complex128, device=ado.device)
+        rho = torch.zeros(shape, dtype=torch.complex128, device=ado.device)
+        rho[:, :self.nhe] = ado
+        y[0].copy_(rho)
+        self.last_launches = 0
+        for _ in range(nsteps):
+            for stage in range(4):
+                yin, ynext = y[stage & 1], y[(stage + 1) & 1]
+                self._stage(stage, rho, yin, ynext, acc, dt)
+                self._exchange(ynext)
+        ado.copy_(y[0][:, :self.nhe])        # after stage 3 the gathered stage vector is rho_{n+1}
+        return ado
+
+    def initial(self, rho0):
+        a = np.zeros((1, self.nhe, self.n, self.n), dtype=np.complex128)
+        a[0, 0] = rho0
+        return a
+
+    def evolve(self, rho0, dt, Nt):
+        """host in / host out; returns a lime Result whose rholist holds the final reduced density matrix and
+        `ado` the final hierarchy"""
+        from ..mol import Result
+        d = torch.from_numpy(self.initial(rho0)).to(self.dev)
+        self.run_device(d, dt, Nt)
+        out = d.cpu().numpy()[0]
+        res = Result(dt=dt, Nt=Nt, rho0=rho0)
+        res.observables = np.zeros((Nt, 0), dtype=complex)
+        res.rholist = [out[0]]
+        res.ado = out
+        return res

@@ -1,0 +1,133 @@
+"""ADO-sharded HEOM (lime_b200/heom/sharded.py): host logic under gloo with world_size 2 on CPU
+(the CUDA stage kernel is replaced by an oracle-based stage function through the `stage_fn` seam),
+and the real CUDA + NCCL path when at least two GPUs are visible."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import cases
+import lime_oracle as lo
+from conftest import relerr
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _problem(depth=3):
+    n = 3
+    H = cases.rand_herm(n, 1)
+    Q = [np.diag([1.0, -0.5, 0.25]), np.diag([0.0, 1.0, 0.0])]
+    rho0 = cases.rand_dm(n, 4)
+    return H, Q, [0.1, 0.2], [0.8, 1.3], 1.5, depth, rho0
+
+
+def _oracle_stage(sh, stage, rho, yin, ynext, acc, dt):
+    """CPU stand-in for limeb200_heom_stage: RK4 stage algebra of lime/phys.py:636-649 on the owned rows"""
+    st = sh.states.astype(np.int64)
+    y = yin[0, :sh.nhe].numpy()
+    k = lo.heom_rhs(y, sh.H, sh.Q, sh.qmap, sh.c, sh.nu, st, sh.dn.astype(np.int64), sh.up.astype(np.int64))
+    sl = slice(sh.lo, sh.hi)
+    r, a, out = rho[0].numpy(), acc[0].numpy(), ynext[0].numpy()
+    if stage == 0:
+        a[sl] = k[sl]
+        out[sl] = r[sl] + 0.5 * dt * k[sl]
+    elif stage == 1:
+        a[sl] += 2 * k[sl]
+        out[sl] = r[sl] + 0.5 * dt * k[sl]
+    elif stage == 2:
+        a[sl] += 2 * k[sl]
+        out[sl] = r[sl] + dt * k[sl]
+    else:
+        r[sl] += (a[sl] + k[sl]) / 6.0 * dt
+        out[sl] = r[sl]
+
+
+def _worker(rank, world, port, backend, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group(backend, rank=rank, world_size=world)
+    try:
+        from lime_b200.heom.sharded import ShardedHEOM
+        H, Q, lam, gam, T, depth, rho0 = _problem()
+        if backend == 'nccl':
+            torch.cuda.set_device(rank)
+            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth)
+        else:
+            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, stage_fn=_oracle_stage)
+        ado = torch.from_numpy(sh.initial(rho0)).to(sh.dev)
+        sh.run_device(ado, 0.01, 12)
+        q.put((rank, ado.cpu().numpy()[0], sh.ranges, sh.nhe))
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(world, backend):
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=300) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    return sorted(res, key=lambda t: t[0])
+
+
+def _reference():
+    from lime_b200.heom.heom import _calc_matsubara_params
+    H, Q, lam, gam, T, depth, rho0 = _problem()
+    c, nu, qmap = [], [], []
+    for b in range(2):
+        cb, nub = _calc_matsubara_params(2, lam[b], gam[b], T)
+        c += cb
+        nu += nub
+        qmap += [b, b]
+    states, dn, up = lo.heom_tables([depth + 1] * 4, depth)
+    ado0 = np.zeros((states.shape[0], 3, 3), dtype=complex)
+    ado0[0] = rho0
+    out, _, _ = lo.heom_rk4(ado0, H, np.stack(Q).astype(complex), qmap, np.array(c), np.array(nu), states, dn, up,
+                            0.01, 12)
+    return out
+
+
+def test_partition():
+    from lime_b200.heom.sharded import partition
+    chunk, r = partition(35, 2)
+    assert chunk == 18 and r == [(0, 18), (18, 35)]
+    chunk, r = partition(3060, 8)
+    assert chunk == 383 and r[-1] == (2681, 3060) and sum(h - l for l, h in r) == 3060
+    chunk, r = partition(3, 8)
+    assert chunk == 1 and r[3] == (3, 3)
+
+
+def test_sharded_heom_gloo_world2():
+    res = _run(2, 'gloo')
+    ref = _reference()
+    assert res[0][3] == ref.shape[0] == 35
+    for rank, ado, ranges, nhe in res:
+        assert ranges == [(0, 18), (18, 35)]
+        assert relerr(ado, ref) <= 1e-12, rank
+    assert np.array_equal(res[0][1], res[1][1])          # every rank ends with the same full hierarchy
+
+
+@pytest.mark.gpu
+def test_sharded_heom_nccl_world2():
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    res = _run(2, 'nccl')
+    ref = _reference()
+    for rank, ado, ranges, nhe in res:
+        assert relerr(ado, ref) <= 1e-10, rank
+    assert np.array_equal(res[0][1], res[1][1])
