@@ -312,6 +312,7 @@ class HeomFMO(HeomBase):
         self.rk = args.rk_steps or 200
         self.depth = args.depth or 4
         self.rank, self.world = rank, world
+        self.exchange = args.exchange
         self.Hm, self.Q, self.lam, self.gam, self.kT = models.fmo_heom_inputs()
         self.dt = 0.5 / au2fs
         self.n = 7
@@ -325,9 +326,11 @@ class HeomFMO(HeomBase):
             self.torch = torch
             if world > 1:
                 from lime_b200.heom.sharded import ShardedHEOM
-                self.h = ShardedHEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
+                self.h = ShardedHEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth,
+                                     exchange=args.exchange)
                 self.nhe = self.h.nhe
-                self.kernel = 'heom_stage_kernel + all_gather'
+                self.kernel = ('heom_persist_cached_kernel (fused peer stores + flag barrier)' if args.exchange == 'p2p'
+                               else 'heom_stage_kernel + NCCL all_gather (CUDA graph)')
             else:
                 self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
                 self.nhe = self.h.nhe
@@ -348,7 +351,7 @@ class HeomFMO(HeomBase):
                 'n_ado': self.nhe, 'rk4_steps_per_launch': self.rk, 'batch': self.B,
                 'l2_policy': 'single hierarchy (%.2f MiB) is L2 resident by construction; L2 flushed between bench steps'
                              % (self.nhe * 49 * 16 / 2 ** 20) if self.B * self.nhe * 49 * 16 < 2 ** 27 else 'inputs larger than L2',
-                'sharding': 'one hierarchy, ADO ranges per rank, all-gather of each stage vector (4 per RK4 step)'
+                'sharding': ('one hierarchy, ADO ranges per rank, exchange=%s, 4 exchanges per RK4 step' % self.exchange)
                             if self.world > 1 else 'none'}
 
     def step(self):
@@ -673,6 +676,7 @@ def main():
     ap.add_argument('--rk-steps', type=int, default=0, help='RK4 steps per launch (0 = workload default)')
     ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
     ap.add_argument('--depth', type=int, default=0, help='HEOM depth for heom_fmo (0 = 4)')
+    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded heom_fmo: fused peer-memory kernel or stage kernel + NCCL all-gather')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()

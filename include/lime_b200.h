@@ -169,6 +169,30 @@ int limeb200_heom_stage(limeb200_heom_t plan, int stage, double* d_rho, const do
                         double* d_ynext, double* d_acc, int B, double dt, void* stream);
 long long limeb200_heom_last_launches(limeb200_heom_t plan);
 
+/* ADO-sharded propagation of ONE hierarchy over the GPUs of one box (one process per GPU): the
+ * fused compute + exchange path.  Every rank runs a persistent kernel over the ADO range its plan
+ * owns; each new stage-vector element is stored into the local stage vector AND, through peer
+ * (CUDA IPC / NVLink) pointers, into the same element of every peer's stage vector; a flag
+ * barrier across the GPUs separates the RK4 stages.  No host round trip and no collective library
+ * call inside the time loop (the alternative is limeb200_heom_stage + an all-gather per stage).
+ *   limeb200_peer_alloc : cudaMalloc + zero + export (handle64 = cudaIpcMemHandle_t bytes)
+ *   limeb200_peer_open  : map a peer's allocation into this process
+ *   d_y0/d_y1[world]    : every rank's two stage vectors [nhe_pad][n][n] (index = rank; own entry local)
+ *   d_flags[world]      : every rank's flag array (>= world unsigned, zero-initialised)
+ *   d_rho               : local [nhe_pad][n][n]; only the owned rows are read and written
+ *   epoch               : flags are monotonic; pass the number of stages run so far (4 * steps)
+ * On entry every rank's d_y0[rank] holds the full state; on return it holds the full new state.  */
+int limeb200_memcpy_d2d(void* d_dst, const void* d_src, long long bytes, void* stream);   /* async, stream-ordered */
+int limeb200_peer_alloc(int device, long long bytes, void** d_ptr, unsigned char* handle64);
+int limeb200_peer_open(int device, const unsigned char* handle64, void** d_ptr);
+int limeb200_peer_close(int device, void* d_ptr);
+int limeb200_peer_free(int device, void* d_ptr);
+int limeb200_heom_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_y0, void* const* d_y1,
+                              void* const* d_flags, double* d_rho, double dt, int nsteps, unsigned epoch,
+                              void* stream);
+/* 1 when a bounded spin of the last sharded run timed out (a peer never arrived), else 0 */
+int limeb200_heom_sharded_error(limeb200_heom_t plan, void* stream);
+
 /* _heom_dl-exact propagator, lime/oqs.py:1802-1865: single Drude mode, in-place
  * Gauss-Seidel Euler sweep over a linear chain of `nado` tiers (tier 0 advanced twice per
  * step, last tier frozen).  d_ado[B][nado][n][n] (tier-major, unlike lime's (n,n,tier)),

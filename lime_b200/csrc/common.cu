@@ -38,4 +38,10 @@ int limeb200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor
     return LB_OK;
 }
 
+int limeb200_memcpy_d2d(void* d_dst, const void* d_src, long long bytes, void* stream) {
+    LB_REQUIRE(d_dst && d_src && bytes >= 0, "bad arguments");
+    LB_CUDA(cudaMemcpyAsync(d_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return LB_OK;
+}
+
 }  // extern "C"

@@ -142,6 +142,8 @@ struct HeomStageArgs {
     cplx* rho; const cplx* yin; cplx* ynext; cplx* acc;
     double dt;
     int apc;                // ADOs per CTA
+    int npeer;              // sharded persistent kernels: the new stage value is also stored into
+    cplx* peer_next[7];     // the same element of every peer GPU's stage vector (NVLink stores)
 };
 
 // L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
@@ -282,7 +284,9 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const size_t o = ((size_t)b * d.nhe + ado) * nn + idx;
     if (a.stage < 0) { a.ynext[o] = k; return; }
     if (rreg) {
-        a.ynext[o] = heom_rk_update(a.stage, k, *rreg, *areg, a.dt);
+        const cplx yn = heom_rk_update(a.stage, k, *rreg, *areg, a.dt);
+        a.ynext[o] = yn;
+        for (int r = 0; r < a.npeer; ++r) a.peer_next[r][o] = yn;
         if (a.stage == 3) a.rho[o] = *rreg;
         return;
     }
@@ -291,6 +295,7 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const cplx yn = heom_rk_update(a.stage, k, r, ac, a.dt);
     if (a.stage < 3) a.acc[o] = ac; else a.rho[o] = r;
     a.ynext[o] = yn;
+    for (int p = 0; p < a.npeer; ++p) a.peer_next[p][o] = yn;
 }
 
 // stage-wise kernel: grid ceil(items/apc); block >= apc*nn threads; dynamic smem (1 + 3*apc)*nn cplx
@@ -309,7 +314,13 @@ struct HeomPersistArgs {
     cplx* y0; cplx* y1;
     int nsteps, E, traj_every;
     const cplx* eT; cplx* obs; cplx* traj;
-    unsigned* barrier;      // zero-initialised counter
+    unsigned* barrier;      // zero-initialised: [0] arrival counter, [1] release word, [2] error word
+    // ADO-sharded run (one process per GPU): peers' stage vectors and flag arrays (CUDA IPC mappings)
+    int world, rank;
+    unsigned epoch;         // flags are monotonic across launches: stage x of this launch signals epoch + x + 1
+    cplx* y0p[7]; cplx* y1p[7];       // peers' y0 / y1 (order: every rank != this one)
+    unsigned* flagp[7];               // peers' flag arrays; peer q's slot for this rank is flagp[q][rank]
+    unsigned* flags;                  // this rank's flag array [world]
 };
 
 // grid-wide barrier on a monotonic counter (zeroed by the host before the launch): one release
@@ -326,6 +337,45 @@ __device__ __forceinline__ void heom_grid_barrier(unsigned* ctr, unsigned target
             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
         } while (v < target);
         asm volatile("fence.acq_rel.gpu;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// Barrier across every CTA of every rank of an ADO-sharded run.  Each CTA makes its (remote) stores
+// visible system-wide and arrives on the local counter; CTA 0 waits for the local arrivals, tells
+// every peer "my stage x is complete" with a release store into the peer's flag array, waits for
+// the peers' flags, and releases the local CTAs.  Spins are bounded (~ 5 s) so that a missing peer
+// produces an error instead of a hung GPU.
+__device__ __forceinline__ void heom_world_barrier(const HeomPersistArgs& p, unsigned target, unsigned xcount) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        const long long limit = 10000000000LL;
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier) : "memory");
+        unsigned v;
+        if (blockIdx.x == 0) {
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier) : "memory");
+            } while (v < target && clock64() - t0 < limit);
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int q = 0; q < p.world - 1; ++q)
+                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flagp[q] + p.rank), "r"(xcount) : "memory");
+            for (int q = 0; q < p.world; ++q) {
+                if (q == p.rank) continue;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags + q) : "memory");
+                } while ((int)(v - xcount) < 0 && clock64() - t0 < limit);
+                if ((int)(v - xcount) < 0) atomicExch(p.barrier + 2, 1u);
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.barrier + 1), "r"(xcount) : "memory");
+        } else {
+            do {
+                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier + 1) : "memory");
+            } while ((int)(v - xcount) < 0 && clock64() - t0 < limit);
+        }
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
     __syncthreads();
 }
@@ -372,6 +422,8 @@ heom_persist_kernel(HeomPersistArgs p) {
             a.stage = stage;
             a.yin = (stage & 1) ? p.y1 : p.y0;
             a.ynext = (stage & 1) ? p.y0 : p.y1;
+            a.npeer = p.world - 1;
+            for (int q = 0; q < p.world - 1; ++q) a.peer_next[q] = (stage & 1) ? p.y0p[q] : p.y1p[q];
             if (fixed) {
                 if (blockIdx.x < ntiles) heom_stage_tile(a, (long long)blockIdx.x * a.apc, smem, tabs, &rreg, &areg);
             } else {
@@ -381,7 +433,8 @@ heom_persist_kernel(HeomPersistArgs p) {
                 }
             }
             bar_target += gridDim.x;
-            heom_grid_barrier(p.barrier, bar_target);
+            if (p.world > 1) heom_world_barrier(p, bar_target, p.epoch + 4u * step + stage + 1u);
+            else heom_grid_barrier(p.barrier, bar_target);
         }
         // y0 == rho_{n+1}; tier-0 observables / trajectory: one warp per (hierarchy, observable)
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -489,10 +542,12 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
             const cplx yn = heom_rk_update(stage, k, rreg, areg, a.dt);
             if (act) {
                 yout[own] = yn;
+                for (int q = 0; q < p.world - 1; ++q) ((stage & 1) ? p.y0p[q] : p.y1p[q])[own] = yn;
                 if (stage == 3) a.rho[own] = rreg;
             }
             bar_target += gridDim.x;
-            heom_grid_barrier(p.barrier, bar_target);
+            if (p.world > 1) heom_world_barrier(p, bar_target, p.epoch + 4u * step + stage + 1u);
+            else heom_grid_barrier(p.barrier, bar_target);
         }
         // tier-0 observables / trajectory (a.rho was written before the barrier)
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -970,6 +1025,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     if (nown <= 0) return LB_OK;
     const int nn = p->n * p->n;
     HeomStageArgs a;
+    a.npeer = 0;
     a.d = p->dev();
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
@@ -980,6 +1036,60 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
         LB_CUDA(cudaFuncSetAttribute(heom_stage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     heom_stage_kernel<<<grid, ceil_div(a.apc * nn, 32) * 32, smem, st>>>(a);
     p->launches++;
+    return LB_OK;
+}
+
+// launch one of the persistent kernels over the plan's owned ADO range (pa: y0/y1, outputs and the
+// sharding fields filled by the caller; y0 must already hold the state)
+static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho, int B, double dt, int nsteps,
+                               cudaStream_t st) {
+    const int nn = p->n * p->n;
+    const long long total = p->nhe * nn;
+    const long long nown = p->row_hi - p->row_lo;
+    if (nown <= 0) return LB_ERR_UNSUPPORTED;
+    pa.s.d = p->dev();
+    pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = p->row_lo; pa.s.row_hi = p->row_hi;
+    pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
+    pa.s.dt = dt;
+    pa.s.npeer = 0;
+    pa.nsteps = nsteps;
+    int coop = 0;
+    LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    if (!coop) return LB_ERR_UNSUPPORTED;
+    // balanced tiles: one tile per CTA for the whole run when the items fit in (1 or 2 CTAs per SM) x
+    // at most (1024 or 576) threads; larger problems loop over tiles of up to 1024 threads
+    const long long nitems = nown * B;
+    void (*kern)(HeomPersistArgs) = heom_persist_kernel<1024, 1>;
+    int per_sm = 1;
+    {
+        long long apc1 = ceil_div(nitems, (long long)p->sm_count);
+        long long apc2 = ceil_div(nitems, 2LL * p->sm_count);
+        if (apc1 * nn <= 1024) pa.s.apc = (int)std::max<long long>(1, apc1);
+        else if (apc2 * nn <= 576) { pa.s.apc = (int)apc2; kern = heom_persist_kernel<576, 2>; per_sm = 2; }
+        else pa.s.apc = std::max(1, 1024 / nn);
+    }
+    const int threads = ceil_div(pa.s.apc * nn, 32) * 32;
+    size_t smem = (size_t)(1 + 3 * pa.s.apc) * nn * 16 + (size_t)3 * pa.s.apc * p->nmodes * 4;
+    const bool one_tile_per_cta = ceil_div(nitems, (long long)pa.s.apc) <= (long long)per_sm * p->sm_count;
+    const size_t smem_c = (size_t)(1 + pa.s.apc) * nn * 16 + (size_t)HEOM_PC_NE * threads * 20;
+    if (p->diagq && one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
+        (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
+        kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
+        smem = smem_c;
+    }
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    per_sm = std::min(per_sm, occ);
+    if (per_sm < 1) return LB_ERR_UNSUPPORTED;
+    const long long ntiles = ceil_div(nitems, (long long)pa.s.apc);
+    const int grid = (int)std::min<long long>(ntiles, (long long)per_sm * p->sm_count);
+    if (!p->dbar.p) LB_CUDA(p->dbar.alloc(64));
+    LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
+    pa.barrier = p->dbar.as<unsigned>();
+    void* kargs[] = {&pa};
+    LB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), kargs, smem, st));
+    p->launches += 1;
     return LB_OK;
 }
 
@@ -1060,53 +1170,15 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     if (path == 3) {
         // persistent cooperative kernel: all steps in one launch, one grid barrier per stage
         HeomPersistArgs pa;
-        pa.s.d = p->dev();
-        pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = 0; pa.s.row_hi = p->nhe;
-        pa.s.rho = (cplx*)d_ado; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
-        pa.s.dt = dt;
+        memset(&pa, 0, sizeof(pa));
+        pa.world = 1;
         pa.y0 = p->s_y.as<cplx>(); pa.y1 = p->s_y.as<cplx>() + (size_t)B * total;
-        pa.nsteps = nsteps; pa.E = E; pa.traj_every = traj_every;
         pa.eT = (const cplx*)d_eT; pa.obs = E > 0 ? (cplx*)d_obs : nullptr; pa.traj = (cplx*)d_traj;
-        int coop = 0;
-        LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
-        // balanced tiles: one tile per CTA for the whole run when the items fit in (1 or 2 CTAs per SM) x
-        // at most (1024 or 576) threads; larger problems loop over tiles of up to 1024 threads
-        const long long nitems = p->nhe * B;
-        const int nmodes_ = p->nmodes;
-        void (*kern)(HeomPersistArgs) = heom_persist_kernel<1024, 1>;
-        int per_sm = 1;
-        {
-            long long apc1 = ceil_div(nitems, (long long)p->sm_count);
-            long long apc2 = ceil_div(nitems, 2LL * p->sm_count);
-            if (apc1 * nn <= 1024) pa.s.apc = (int)std::max<long long>(1, apc1);
-            else if (apc2 * nn <= 576) { pa.s.apc = (int)apc2; kern = heom_persist_kernel<576, 2>; per_sm = 2; }
-            else pa.s.apc = std::max(1, 1024 / nn);
-        }
-        const int threads = ceil_div(pa.s.apc * nn, 32) * 32;
-        size_t smem = (size_t)(1 + 3 * pa.s.apc) * nn * 16 + (size_t)3 * pa.s.apc * nmodes_ * 4;
-        const bool one_tile_per_cta = ceil_div(nitems, (long long)pa.s.apc) <= (long long)per_sm * p->sm_count;
-        const size_t smem_c = (size_t)(1 + pa.s.apc) * nn * 16 + (size_t)HEOM_PC_NE * threads * 20;
-        if (p->diagq && one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
-            (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
-            kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
-            smem = smem_c;
-        }
-        LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int occ = 0;
-        LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
-        per_sm = std::min(per_sm, occ);
-        const long long ntiles = ceil_div(nitems, (long long)pa.s.apc);
-        if (per_sm >= 1 && coop) {
-            const int grid = (int)std::min<long long>(ntiles, (long long)per_sm * p->sm_count);
-            if (!p->dbar.p) LB_CUDA(p->dbar.alloc(64));
-            LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
-            pa.barrier = p->dbar.as<unsigned>();
-            LB_CUDA(cudaMemcpyAsync(pa.y0, d_ado, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
-            void* kargs[] = {&pa};
-            LB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), kargs, smem, st));
-            p->launches += 1;
-            return LB_OK;
-        }
+        pa.E = E; pa.traj_every = traj_every;
+        LB_CUDA(cudaMemcpyAsync(pa.y0, d_ado, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
+        int r = heom_launch_persist(p, pa, (cplx*)d_ado, B, dt, nsteps, st);
+        if (r == LB_OK) return LB_OK;
+        if (r != LB_ERR_UNSUPPORTED) return r;
         LB_REQUIRE(p->path_req != 3, "cooperative launch is not available on this device");
         p->path = 2;
     }
@@ -1130,6 +1202,81 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     }
     LB_CUDA(cudaGetLastError());
     return LB_OK;
+}
+
+// ---- peer memory (CUDA IPC) for the ADO-sharded propagator: one process per GPU, one box
+int limeb200_peer_alloc(int device, long long bytes, void** d_ptr, unsigned char* handle64) {
+    LB_REQUIRE(d_ptr && handle64 && bytes > 0, "bad arguments");
+    LB_CUDA(cudaSetDevice(device));
+    void* ptr = nullptr;
+    LB_CUDA(cudaMalloc(&ptr, (size_t)bytes));
+    LB_CUDA(cudaMemset(ptr, 0, (size_t)bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, ptr);
+    if (e != cudaSuccess) { cudaFree(ptr); LB_CUDA(e); }
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    memcpy(handle64, &h, 64);
+    *d_ptr = ptr;
+    return LB_OK;
+}
+int limeb200_peer_open(int device, const unsigned char* handle64, void** d_ptr) {
+    LB_REQUIRE(d_ptr && handle64, "bad arguments");
+    LB_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    LB_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return LB_OK;
+}
+int limeb200_peer_close(int device, void* d_ptr) {
+    LB_CUDA(cudaSetDevice(device));
+    LB_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return LB_OK;
+}
+int limeb200_peer_free(int device, void* d_ptr) {
+    LB_CUDA(cudaSetDevice(device));
+    LB_CUDA(cudaFree(d_ptr));
+    return LB_OK;
+}
+
+int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* const* d_y0, void* const* d_y1,
+                              void* const* d_flags, double* d_rho, double dt, int nsteps, unsigned epoch,
+                              void* stream) {
+    LB_REQUIRE(p && d_y0 && d_y1 && d_flags && d_rho, "null argument");
+    LB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8");
+    LB_REQUIRE(p->npar == 1, "sharded runs take one hierarchy (no parameter batch)");
+    LB_REQUIRE(nsteps >= 0, "bad nsteps");
+    LB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    p->launches = 0;
+    if (nsteps == 0) return LB_OK;
+    const long long total = p->nhe * p->n * p->n;
+    if (1 > p->scratch_B || !p->s_acc.p) {
+        LB_CUDA(p->s_acc.alloc((size_t)total * 16));
+        if (!p->s_y.p) LB_CUDA(p->s_y.alloc(16));
+        p->scratch_B = 1;
+    }
+    HeomPersistArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world; pa.rank = rank; pa.epoch = epoch;
+    pa.y0 = (cplx*)d_y0[rank]; pa.y1 = (cplx*)d_y1[rank]; pa.flags = (unsigned*)d_flags[rank];
+    int q = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        pa.y0p[q] = (cplx*)d_y0[r]; pa.y1p[q] = (cplx*)d_y1[r]; pa.flagp[q] = (unsigned*)d_flags[r];
+        ++q;
+    }
+    int r = heom_launch_persist(p, pa, (cplx*)d_rho, 1, dt, nsteps, st);
+    if (r == LB_ERR_UNSUPPORTED) { limeb200::set_error("persistent sharded kernel cannot be launched on this device"); return r; }
+    return r;
+}
+/* 1 when a bounded spin of the last sharded run timed out (a peer never arrived) */
+int limeb200_heom_sharded_error(limeb200_heom_t p, void* stream) {
+    LB_REQUIRE(p, "null plan");
+    if (!p->dbar.p) return 0;
+    unsigned w[3] = {0, 0, 0};
+    LB_CUDA(cudaMemcpyAsync(w, p->dbar.p, 12, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    return (int)w[2];
 }
 
 int limeb200_heom_dl_euler(const double* h_H, const double* h_sz, int n, int nado,

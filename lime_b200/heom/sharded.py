@@ -11,7 +11,12 @@ halo exchange would move about the same bytes.  rho and the RK4 accumulator are 
 touched on the owned rows, so they need no communication; after stage 3 the gathered stage vector
 IS rho_{n+1}.
 
-The data path is: CUDA stage kernel -> NCCL all-gather over NVLink, both on the current stream.
+Two data paths:
+  exchange='p2p'  (default on CUDA) fused compute + exchange: ONE persistent kernel per rank for the whole
+                  run (limeb200_heom_run_sharded); every new stage-vector element is stored locally and, through
+                  CUDA-IPC peer pointers, into every peer's stage vector over NVLink; a flag barrier across the
+                  GPUs separates the stages.  torch.distributed is used only to exchange the IPC handles.
+  exchange='nccl' CUDA stage kernel -> NCCL all-gather, 4 x per step, captured in a CUDA graph.
 `stage_fn` is a seam for the world_size-2 gloo tests of this host logic (they plug a CPU stage
 function built from the oracle); the product path always uses the CUDA plan.
 """
@@ -32,7 +37,8 @@ def partition(nhe, world):
 
 class ShardedHEOM:
     def __init__(self, H, Q, coup_strength, cut_freq, temperature, N_exp=2, N_cut=4,
-                 pref_dn=-1j, pref_up=-1j, group=None, stage_fn=None, device=None):
+                 pref_dn=-1j, pref_up=-1j, group=None, stage_fn=None, device=None, use_graph=True,
+                 exchange='p2p'):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -60,7 +66,10 @@ class ShardedHEOM:
         self.lo, self.hi = self.ranges[self.rank]
         self.last_launches = 0
         self._stage_fn = stage_fn
-        self._graph = None
+        self.use_graph = use_graph
+        self.exchange = exchange if stage_fn is None else 'collective'
+        self._peer = None
+        self._epoch = 0
         if stage_fn is None:
             self.dev = _dev.device() if device is None else device
             self.plan = engine.HeomPlan(self.H, self.Q, self.qmap, self.c, self.nu, self.states, self.dn, self.up,
@@ -92,10 +101,89 @@ class ShardedHEOM:
                 flat[r].copy_(chunks[r])
         self.last_launches += 1
 
+    # ---- fused compute + exchange over peer memory ---------------------------------------------
+    def _peer_setup(self):
+        import ctypes as C
+        from .._lib import lib, check
+        nbytes = self.nhe_pad * self.n * self.n * 16
+        mine, handles = [], []
+        for size in (nbytes, nbytes, 256):
+            ptr = C.c_void_p()
+            h = (C.c_ubyte * 64)()
+            check(lib().limeb200_peer_alloc(self.dev.index, size, C.byref(ptr), h))
+            mine.append(ptr.value)
+            handles.append(bytes(h))
+        allh = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(allh, handles, group=self.group)
+        else:
+            allh[0] = handles
+        ptrs = [[0] * self.world for _ in range(3)]
+        opened = []
+        for r in range(self.world):
+            for k in range(3):
+                if r == self.rank:
+                    ptrs[k][r] = mine[k]
+                else:
+                    q = C.c_void_p()
+                    hb = (C.c_ubyte * 64).from_buffer_copy(allh[r][k])
+                    check(lib().limeb200_peer_open(self.dev.index, hb, C.byref(q)))
+                    ptrs[k][r] = q.value
+                    opened.append(q.value)
+        arr = [(C.c_void_p * self.world)(*ptrs[k]) for k in range(3)]
+        self._peer = dict(mine=mine, ptrs=ptrs, arr=arr, opened=opened, nbytes=nbytes)
+
+    def close(self):
+        if self._peer is not None:
+            from .._lib import lib
+            torch.cuda.synchronize()
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            for q in self._peer['opened']:
+                lib().limeb200_peer_close(self.dev.index, q)
+            if self.world > 1:
+                dist.barrier(group=self.group)
+            for m in self._peer['mine']:
+                lib().limeb200_peer_free(self.dev.index, m)
+            self._peer = None
+
+    def _run_p2p(self, ado, dt, nsteps):
+        import ctypes as C
+        from .._lib import lib, check
+        if self._peer is None:
+            self._peer_setup()
+        pr = self._peer
+        rho = torch.zeros((1, self.nhe_pad, self.n, self.n), dtype=torch.complex128, device=ado.device)
+        rho[:, :self.nhe] = ado
+        st = torch.cuda.current_stream()
+        # every rank's y0 <- the full state; peers may only start storing into our buffers once we are ready
+        sp = C.c_void_p(st.cuda_stream)
+        check(lib().limeb200_memcpy_d2d(C.c_void_p(pr['mine'][0]), C.c_void_p(rho.data_ptr()), pr['nbytes'], sp))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        check(lib().limeb200_heom_run_sharded(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1],
+                                              pr['arr'][2], C.c_void_p(rho.data_ptr()), float(dt), int(nsteps),
+                                              C.c_uint(self._epoch), C.c_void_p(st.cuda_stream)))
+        self._epoch += 4 * nsteps
+        err = lib().limeb200_heom_sharded_error(self.plan._h, C.c_void_p(st.cuda_stream))
+        if err:
+            from .._lib import LimeB200Error
+            raise LimeB200Error('sharded HEOM run: a peer GPU never reached the stage barrier')
+        check(lib().limeb200_memcpy_d2d(C.c_void_p(rho.data_ptr()), C.c_void_p(pr['mine'][0]), pr['nbytes'], sp))
+        ado.copy_(rho[:, :self.nhe])
+        torch.cuda.synchronize()
+        self.last_launches = 1
+        if self.world > 1:
+            dist.barrier(group=self.group)       # nobody reuses the buffers before everyone has copied out
+        return ado
+
     def run_device(self, ado, dt, nsteps):
         """ado: [1, N_he, n, n] complex128 on self.dev, identical on every rank; advanced in place by
         nsteps RK4 steps (every rank ends up with the full hierarchy)."""
         assert ado.shape == (1, self.nhe, self.n, self.n) and ado.dtype == torch.complex128
+        if self.exchange == 'p2p' and self._stage_fn is None and nsteps > 0:
+            return self._run_p2p(ado, dt, nsteps)
         shape = (1, self.nhe_pad, self.n, self.n)
         y = [torch.zeros(shape, dtype=torch.complex128, device=ado.device) for _ in range(2)]
         acc = torch.zeros(shape, dtype=torch.complex128, device=ado.device)
@@ -103,11 +191,28 @@ class ShardedHEOM:
         rho[:, :self.nhe] = ado
         y[0].copy_(rho)
         self.last_launches = 0
-        for _ in range(nsteps):
+
+        def one_step():
             for stage in range(4):
                 yin, ynext = y[stage & 1], y[(stage + 1) & 1]
                 self._stage(stage, rho, yin, ynext, acc, dt)
                 self._exchange(ynext)
+
+        if self.use_graph and ado.is_cuda and nsteps > 2:
+            # one RK4 step (4 stage kernels + 4 all-gathers) captured once, replayed nsteps times: the
+            # per-stage host cost (ctypes call + collective launch) would otherwise dominate
+            one_step()                                   # warm-up outside capture (NCCL channel set-up)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                one_step()
+            per_step = self.last_launches // 2
+            for _ in range(nsteps - 1):
+                g.replay()
+            self.last_launches = per_step * nsteps
+        else:
+            for _ in range(nsteps):
+                one_step()
         ado.copy_(y[0][:, :self.nhe])        # after stage 3 the gathered stage vector is rho_{n+1}
         return ado
 

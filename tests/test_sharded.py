@@ -52,7 +52,7 @@ def _oracle_stage(sh, stage, rho, yin, ynext, acc, dt):
         out[sl] = r[sl]
 
 
-def _worker(rank, world, port, backend, q):
+def _worker(rank, world, port, backend, q, exchange='p2p'):
     os.environ['MASTER_ADDR'] = '127.0.0.1'
     os.environ['MASTER_PORT'] = str(port)
     dist.init_process_group(backend, rank=rank, world_size=world)
@@ -61,21 +61,24 @@ def _worker(rank, world, port, backend, q):
         H, Q, lam, gam, T, depth, rho0 = _problem()
         if backend == 'nccl':
             torch.cuda.set_device(rank)
-            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth)
+            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, exchange=exchange)
         else:
             sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, stage_fn=_oracle_stage)
         ado = torch.from_numpy(sh.initial(rho0)).to(sh.dev)
-        sh.run_device(ado, 0.01, 12)
+        sh.run_device(ado, 0.01, 5)
+        sh.run_device(ado, 0.01, 7)              # second call: flags / epochs continue
         q.put((rank, ado.cpu().numpy()[0], sh.ranges, sh.nhe))
+        if backend == 'nccl':
+            sh.close()
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, backend):
+def _run(world, backend, exchange='p2p'):
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, backend, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in range(world)]
@@ -123,10 +126,24 @@ def test_sharded_heom_gloo_world2():
 
 
 @pytest.mark.gpu
-def test_sharded_heom_nccl_world2():
+def test_sharded_heom_single_rank_persistent_kernel(cuda):
+    """world = 1: the sharded entry point (persistent kernel + peer-allocated buffers) on one GPU"""
+    from lime_b200.heom.sharded import ShardedHEOM
+    H, Q, lam, gam, T, depth, rho0 = _problem()
+    sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth)
+    ado = torch.from_numpy(sh.initial(rho0)).to(sh.dev)
+    sh.run_device(ado, 0.01, 5)
+    sh.run_device(ado, 0.01, 7)
+    assert relerr(ado.cpu().numpy()[0], _reference()) <= 1e-10
+    sh.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('exchange', ['p2p', 'nccl'])
+def test_sharded_heom_nccl_world2(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    res = _run(2, 'nccl')
+    res = _run(2, 'nccl', exchange)
     ref = _reference()
     for rank, ado, ranges, nhe in res:
         assert relerr(ado, ref) <= 1e-10, rank
