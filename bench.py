@@ -431,6 +431,7 @@ class Sos2DES:
         self.units_per_step = self.T * self.n * self.n
         self.launches = 0
         self.kernel = 'sos_outer_kernel'
+        self.grid = None
         if need_gpu:
             import torch
             self.torch = torch
@@ -443,8 +444,10 @@ class Sos2DES:
 
     def step(self):
         from lime_b200.signal import sos
-        E, dip, gamma, g, e, f = self.sys
-        self.out = sos._photon_echo(E, dip, -self.w, self.w, self.taus, g, e, f, gamma, return_device=True)
+        if self.grid is None:       # weights / grids resident in HBM; the step is the O(grid) device work
+            E, dip, gamma, g, e, f = self.sys
+            self.grid = sos.PhotonEchoGrid(E, dip, -self.w, self.w, self.taus, g, e, f, gamma)
+        self.out = self.grid.run()
         self.launches += 3          # pole factor, weighted factor, rank-R outer product
 
     def check(self):

@@ -604,7 +604,8 @@ __device__ __forceinline__ void heom_chip_outputs(const HeomChipArgs& a, const c
 
 // diagonal Q, one element per thread, at most NE/2 modes per element: neighbour offsets and
 // coefficients are computed ONCE and stay in registers for the whole launch
-template <int NE>
+// NS > 0: system dimension known at compile time (row i / column j of H in registers, -i[H, .] unrolled)
+template <int NE, int NS>
 __global__ void __launch_bounds__(1024, 1)
 heom_onchip_cached(HeomChipArgs a) {
     extern __shared__ double2 smem[];
@@ -650,13 +651,33 @@ heom_onchip_cached(HeomChipArgs a) {
         }
     }
     __syncthreads();
+    constexpr int NSS = NS > 0 ? NS : 1;
+    cplx hrow[NSS], hcol[NSS];
+#pragma unroll
+    for (int m = 0; m < NSS; ++m) {
+        hrow[m] = NS > 0 ? Hs[i * NS + m] : cmake(0, 0);
+        hcol[m] = NS > 0 ? Hs[m * NS + j] : cmake(0, 0);
+    }
     for (int step = 0; step < a.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
             const cplx* yin = (stage & 1) ? y1 : y0;
             cplx* yout = (stage & 1) ? y0 : y1;
             const cplx yv = yin[ok ? l : 0];
-            cplx k = heom_sys(Hs, n, yin + (size_t)ado * nn, i, j);
+            cplx k;
+            if (NS > 0) {
+                const cplx* ya = yin + (size_t)ado * nn;
+                cplx sacc = cmake(0, 0);
+#pragma unroll
+                for (int m = 0; m < NSS; ++m) {
+                    cfma(sacc, hrow[m], ya[m * NS + j]);
+                    const cplx t = cmul(ya[i * NS + m], hcol[m]);
+                    sacc.x -= t.x; sacc.y -= t.y;
+                }
+                k = cmake(sacc.y, -sacc.x);
+            } else {
+                k = heom_sys(Hs, n, yin + (size_t)ado * nn, i, j);
+            }
             k.x = fma(-damp, yv.x, k.x);
             k.y = fma(-damp, yv.y, k.y);
 #pragma unroll
@@ -1042,7 +1063,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
 // launch one of the persistent kernels over the plan's owned ADO range (pa: y0/y1, outputs and the
 // sharding fields filled by the caller; y0 must already hold the state)
 static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho, int B, double dt, int nsteps,
-                               cudaStream_t st) {
+                               cudaStream_t st, bool require_one_tile_per_cta = false) {
     const int nn = p->n * p->n;
     const long long total = p->nhe * nn;
     const long long nown = p->row_hi - p->row_lo;
@@ -1071,6 +1092,9 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     const int threads = ceil_div(pa.s.apc * nn, 32) * 32;
     size_t smem = (size_t)(1 + 3 * pa.s.apc) * nn * 16 + (size_t)3 * pa.s.apc * p->nmodes * 4;
     const bool one_tile_per_cta = ceil_div(nitems, (long long)pa.s.apc) <= (long long)per_sm * p->sm_count;
+    // larger problems gain nothing from persistence (the per-stage launches are already long) and
+    // run better with the smaller CTAs of the stage-wise kernel
+    if (require_one_tile_per_cta && !one_tile_per_cta) return LB_ERR_UNSUPPORTED;
     const size_t smem_c = (size_t)(1 + pa.s.apc) * nn * 16 + (size_t)HEOM_PC_NE * threads * 20;
     if (p->diagq && one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
         (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
@@ -1153,8 +1177,10 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         a.T = T;
         void (*kern)(HeomChipArgs) = EPT == 1 ? heom_onchip_kernel<1> : EPT == 2 ? heom_onchip_kernel<2>
                                    : EPT == 4 ? heom_onchip_kernel<4> : heom_onchip_kernel<8>;
-        if (p->diagq && EPT == 1 && p->max_modes_per_elem <= 4)       // register-cached neighbour lists
-            kern = p->max_modes_per_elem <= 2 ? heom_onchip_cached<4> : heom_onchip_cached<8>;
+        if (p->diagq && EPT == 1 && p->max_modes_per_elem <= 4) {     // register-cached neighbour lists
+            if (p->n == 2) kern = p->max_modes_per_elem <= 2 ? heom_onchip_cached<4, 2> : heom_onchip_cached<8, 2>;
+            else kern = p->max_modes_per_elem <= 2 ? heom_onchip_cached<4, 0> : heom_onchip_cached<8, 0>;
+        }
         LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_chip));
         kern<<<B, T, smem_chip, st>>>(a);
         LB_CUDA(cudaGetLastError());
@@ -1176,7 +1202,7 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         pa.eT = (const cplx*)d_eT; pa.obs = E > 0 ? (cplx*)d_obs : nullptr; pa.traj = (cplx*)d_traj;
         pa.E = E; pa.traj_every = traj_every;
         LB_CUDA(cudaMemcpyAsync(pa.y0, d_ado, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
-        int r = heom_launch_persist(p, pa, (cplx*)d_ado, B, dt, nsteps, st);
+        int r = heom_launch_persist(p, pa, (cplx*)d_ado, B, dt, nsteps, st, p->path_req == 0);
         if (r == LB_OK) return LB_OK;
         if (r != LB_ERR_UNSUPPORTED) return r;
         LB_REQUIRE(p->path_req != 3, "cooperative launch is not available on this device");

@@ -367,6 +367,17 @@ def sos_factor(z, W, p1, p2=None, dev=None):
     return F
 
 
+def sos_factor_dev(z, dW, dp1, dp2=None):
+    """same as sos_factor with the weights / poles already on the device: dW [T,R,D] complex128,
+    dp1/dp2 [R,D,2] float64 -> device [T,R,n]"""
+    T, R, D = dW.shape
+    n = z.shape[0]
+    F = _dev.empty((T, R, n), dev=z.device)
+    check(lib().limeb200_sos_factor(_dev.ptr(z), n, _dev.ptr(dW), _dev.ptr(dp1), _dev.ptr(dp2), T, R, D,
+                                    _dev.ptr(F), _dev.stream_ptr()))
+    return F
+
+
 def sos_outer(A, Bf, T, scale=1.0, out=None, accumulate=False):
     """out[t][r][c] (+)= scale * sum_q A[ta][q][r] * B[tb][q][c]  (device tensors)"""
     TA, R, nrow = A.shape

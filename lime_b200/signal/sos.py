@@ -129,6 +129,29 @@ def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts
     return _finish(out, single)
 
 
+class PhotonEchoGrid:
+    """[ext] device-resident photon-echo evaluation for repeated use on one system: the O(states^3) weights
+    (host set-up, `_pe_terms`) and the grids are uploaded once; `run()` is the O(grid) part only -- two factor
+    kernels and the rank-R outer product -- and returns the [T, n3, n1] signal on the device."""
+
+    def __init__(self, evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts=('GSB', 'SE', 'ESA')):
+        W, P, (eA, gA) = _pe_terms(evals, dip, np.atleast_1d(tau2), g_idx, e_idx, f_idx, gamma, parts)
+        self.T, R = W.shape[0], W.shape[1]
+        self.z1, self.z3 = _z(omega1), _z(omega3)
+        self.dW = _dev.to_dev(np.ascontiguousarray(W))
+        self.dP = _dev.to_dev(np.asarray(P, dtype=np.float64).reshape(R, W.shape[2], 2), np.float64)
+        self.dWa = _dev.to_dev(np.ones((1, R, 1), dtype=complex))
+        self.dPa = _dev.to_dev(np.stack([np.asarray(eA, dtype=float), np.asarray(gA, dtype=float)], axis=-1)
+                               .reshape(R, 1, 2), np.float64)
+        self.out = None
+
+    def run(self):
+        A = engine.sos_factor_dev(self.z1, self.dWa, self.dPa)       # [1,R,n1]  G_ab(omega1)
+        Bf = engine.sos_factor_dev(self.z3, self.dW, self.dP)        # [T,R,n3]
+        self.out = engine.sos_outer(Bf, A, self.T, out=self.out)     # [T,n3,n1]
+        return self.out
+
+
 def GSB(evals, dip, omega1, omega3, tau2, g_idx, e_idx, gamma):
     """ground-state bleach; lime/signal/sos.py:478-528"""
     return _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, [], gamma, ('GSB',))

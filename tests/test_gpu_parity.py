@@ -383,3 +383,7 @@ def test_sos_waiting_time_batch_and_ragged_grid(cuda):
     # linearity in the dipole scale: S ~ mu^4
     pe2 = sos._photon_echo(E, 2.0 * dip, -w, w, T[1], g_idx, e_idx, f_idx, gamma)
     assert relerr(pe2, 16.0 * pe[1]) <= 1e-12
+    # [ext] device-resident evaluation (what bench.py times) gives the same numbers, repeatedly
+    grid = sos.PhotonEchoGrid(E, dip, -w, w, T, g_idx, e_idx, f_idx, gamma)
+    assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
+    assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
