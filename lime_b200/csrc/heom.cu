@@ -14,6 +14,7 @@
 #include "../../include/lime_b200.h"
 #include "common.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 #include <cooperative_groups.h>
 
@@ -691,6 +692,150 @@ heom_onchip_cached(HeomChipArgs a) {
     if (ok) gado[l] = rho;
 }
 
+// Small systems (n = NS known at compile time, diagonal Q, at most NM modes): ONE THREAD PER ADO,
+// several hierarchies per CTA.  The thread keeps its ADO (NS x NS), rho, the RK4 accumulator, the
+// neighbour offsets and the per-mode coefficients in registers; -i[H, .] needs no shared memory
+// at all, and the stage vector is stored structure-of-arrays ([element][ADO]) so that the gather of
+// a neighbour ADO by consecutive threads is conflict-free.  Shared-memory traffic per element-stage
+// drops from ~10 to (1 + 2 NM + 1) accesses, index arithmetic from per-element to per-ADO.
+template <int NS, int NM>
+__global__ void __launch_bounds__(576, 1)
+heom_onchip_ado_kernel(HeomChipArgs a, int HP) {
+    extern __shared__ double2 smem[];
+    constexpr int NN = NS * NS;
+    const HeomDev& d = a.d;
+    const int nhe = (int)d.nhe;
+    const int hl = threadIdx.x / nhe;                  // hierarchy slot in this CTA
+    const int ado = threadIdx.x - hl * nhe;
+    const int b = blockIdx.x * HP + hl;
+    const bool ok = hl < HP && b < a.B;
+    const int par = d.npar > 1 ? (ok ? b : 0) : 0;
+    const int span = HP * nhe;                         // ADOs per buffer row
+    cplx* y0 = smem;                                   // [NN][span]
+    cplx* y1 = y0 + (size_t)NN * span;
+    const int me = hl * nhe + ado;                     // this ADO's column
+    cplx* gado = a.ado + ((size_t)(ok ? b : 0) * nhe + ado) * NN;
+    cplx H[NN];
+#pragma unroll
+    for (int e = 0; e < NN; ++e) H[e] = __ldg(d.H + e);
+    cplx rho[NN], acc[NN];
+#pragma unroll
+    for (int e = 0; e < NN; ++e) {
+        rho[e] = ok ? gado[e] : cmake(0, 0);
+        acc[e] = cmake(0, 0);
+        if (hl < HP) y0[e * span + me] = rho[e];
+    }
+    const double damp = ok ? heom_damp(d, par, ado) : 0.0;
+    int dno[NM], upo[NM];
+    cplx cl[NM], cr[NM];
+    double qd[NM][NS];
+    {
+        // diagonal of the coupling operator of each mode, recovered from the per-element lists
+#pragma unroll
+        for (int m = 0; m < NM; ++m) {
+            dno[m] = upo[m] = me;
+            cl[m] = cr[m] = cmake(0, 0);
+#pragma unroll
+            for (int i = 0; i < NS; ++i) qd[m][i] = 0.0;
+        }
+        for (int i = 0; i < NS; ++i) {
+            const int idx = i * NS + i;
+            for (int t = d.em_start[idx]; t < d.em_start[idx + 1]; ++t) {
+                const int m = d.em_mode[t];
+#pragma unroll
+                for (int mm = 0; mm < NM; ++mm)
+                    if (mm == m) {
+#pragma unroll
+                        for (int ii = 0; ii < NS; ++ii)
+                            if (ii == i) qd[mm][ii] = d.em_v[t].x;
+                    }
+            }
+        }
+        if (ok) {
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                if (m < d.nmodes) {
+                    const int id = d.dn[(size_t)ado * d.nmodes + m], iu = d.up[(size_t)ado * d.nmodes + m];
+                    const double nk = (double)d.states[(size_t)ado * d.nmodes + m];
+                    if (id >= 0) {
+                        dno[m] = hl * nhe + id;
+                        cl[m] = cscale(nk, d.cdn[(size_t)par * d.nmodes + m]);
+                        cr[m] = cscale(nk, d.cdnR[(size_t)par * d.nmodes + m]);
+                    }
+                    if (iu >= 0) upo[m] = hl * nhe + iu; else upo[m] = -1 - me;     // flag: no up neighbour
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const cplx pu = d.pref_up;
+    for (int step = 0; step < a.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            const cplx* yin = (stage & 1) ? y1 : y0;
+            cplx* yout = (stage & 1) ? y0 : y1;
+            cplx y[NN], k[NN];
+#pragma unroll
+            for (int e = 0; e < NN; ++e) y[e] = yin[e * span + me];
+            // -i [H, y] - damp y, all in registers
+#pragma unroll
+            for (int i = 0; i < NS; ++i)
+#pragma unroll
+                for (int j = 0; j < NS; ++j) {
+                    cplx sacc = cmake(0, 0);
+#pragma unroll
+                    for (int m = 0; m < NS; ++m) {
+                        cfma(sacc, H[i * NS + m], y[m * NS + j]);
+                        const cplx t = cmul(y[i * NS + m], H[m * NS + j]);
+                        sacc.x -= t.x; sacc.y -= t.y;
+                    }
+                    k[i * NS + j] = cmake(fma(-damp, y[i * NS + j].x, sacc.y), fma(-damp, y[i * NS + j].y, -sacc.x));
+                }
+#pragma unroll
+            for (int m = 0; m < NM; ++m) {
+                const bool has_up = upo[m] >= 0;
+                const int uo = has_up ? upo[m] : me;
+#pragma unroll
+                for (int i = 0; i < NS; ++i)
+#pragma unroll
+                    for (int j = 0; j < NS; ++j) {
+                        const int e = i * NS + j;
+                        const cplx yd = yin[e * span + dno[m]];
+                        const cplx yu = yin[e * span + uo];
+                        const double qi = qd[m][i], qj = qd[m][j];
+                        const cplx cdn = cmake(qi * cl[m].x - qj * cr[m].x, qi * cl[m].y - qj * cr[m].y);
+                        cfma(k[e], cdn, yd);
+                        if (has_up) cfma(k[e], cscale(qi - qj, pu), yu);
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < NN; ++e) {
+                const cplx yn = heom_rk_update(stage, k[e], rho[e], acc[e], a.dt);
+                if (hl < HP) yout[e * span + me] = yn;
+            }
+            __syncthreads();
+        }
+        if (ok && ado == 0) {          // tier 0 = reduced density matrix, in this thread's registers
+            if (a.obs)
+                for (int eo = 0; eo < a.E; ++eo) {
+                    cplx v = cmake(0, 0);
+#pragma unroll
+                    for (int e = 0; e < NN; ++e) cfma(v, __ldg(a.eT + (size_t)eo * NN + e), rho[e]);
+                    a.obs[((size_t)step * a.B + b) * a.E + eo] = v;
+                }
+            if (a.traj && ((step + 1) % a.traj_every) == 0) {
+                cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * NN;
+#pragma unroll
+                for (int e = 0; e < NN; ++e) dst[e] = rho[e];
+            }
+        }
+    }
+    if (ok) {
+#pragma unroll
+        for (int e = 0; e < NN; ++e) gado[e] = rho[e];
+    }
+}
+
 template <int EPT>
 __global__ void __launch_bounds__(1024, 1)
 heom_onchip_kernel(HeomChipArgs a) {
@@ -1171,6 +1316,20 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         a.B = B; a.nsteps = nsteps; a.traj_every = traj_every; a.E = E;
         a.ado = (cplx*)d_ado; a.eT = (const cplx*)d_eT; a.obs = E > 0 ? (cplx*)d_obs : nullptr; a.traj = (cplx*)d_traj;
         a.dt = dt;
+        a.T = 0;
+        if (p->diagq && p->n == 2 && p->nmodes <= 4 && p->nhe <= 576 && !getenv("LIMEB200_HEOM_NO_ADO_KERNEL")) {
+            // one thread per ADO, HP hierarchies per CTA
+            int HP = std::max(1, std::min(576 / (int)p->nhe, (int)((100 * 1024) / ((size_t)2 * p->nhe * nn * 16))));
+            HP = std::min(HP, std::max(1, ceil_div(B, 2 * p->sm_count)));
+            const size_t smem = (size_t)2 * nn * HP * p->nhe * 16;
+            const int threads = ceil_div(HP * (int)p->nhe, 32) * 32;
+            void (*k2)(HeomChipArgs, int) = p->nmodes <= 2 ? heom_onchip_ado_kernel<2, 2> : heom_onchip_ado_kernel<2, 4>;
+            LB_CUDA(cudaFuncSetAttribute(k2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            k2<<<ceil_div(B, HP), threads, smem, st>>>(a, HP);
+            LB_CUDA(cudaGetLastError());
+            p->launches++;
+            return LB_OK;
+        }
         int T = (int)std::min<long long>(1024, ceil_div(total, 32LL) * 32);
         int ept = (int)ceil_div(total, (long long)T);
         int EPT = ept <= 1 ? 1 : ept <= 2 ? 2 : ept <= 4 ? 4 : 8;
