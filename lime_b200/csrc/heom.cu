@@ -713,7 +713,7 @@ heom_onchip_ado_kernel(HeomChipArgs a, int HP) {
     const int span = HP * nhe;                         // ADOs per buffer row
     cplx* y0 = smem;                                   // [NN][span]
     cplx* y1 = y0 + (size_t)NN * span;
-    const int me = hl * nhe + ado;                     // this ADO's column
+    const int me = hl < HP ? hl * nhe + ado : 0;       // this ADO's column (idle threads: any valid one)
     cplx* gado = a.ado + ((size_t)(ok ? b : 0) * nhe + ado) * NN;
     cplx H[NN];
 #pragma unroll
