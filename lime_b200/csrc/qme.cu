@@ -53,7 +53,7 @@ struct limeb200_qme_s {
     DevBuf deptr, deidx, deval;
     // ---- band path (qme_band.cuh)
     DevBuf dbgd, dbgcol, dbgval, dbxcol[QME_BAND_MAXS], dbxval[QME_BAND_MAXS], dbzcol[QME_BAND_MAXS], dbzval[QME_BAND_MAXS];
-    int band_noff = 0, band_gt = 0, band_xt = 0, band_C = 0, band_R = 0;
+    int band_noff = 0, band_gt = 0, band_xt = 0, band_C = 0, band_R = 0, band_chain = 0;
     size_t band_smem = 0;
     // ---- scratch
     DevBuf s_y, s_acc, s_tmp, s_gk;
@@ -249,11 +249,61 @@ struct BandHost {
 };
 
 
+// If the off-diagonal graph of G is a disjoint union of P <= 4 simple paths of equal length, return the
+// interleaved ordering (new index = position * P + path) whose FULL pattern (G and all X_s, Z_s) has the
+// smallest bandwidth over the 2^P path orientations.  In that ordering G couples row i only to rows i -/+ P.
+bool chain_order(int N, const HostOp& G, const std::vector<std::vector<int>>& adj_all, std::vector<int>& order,
+                 int& RS, int& bw_out) {
+    std::vector<std::vector<int>> adj(N);
+    add_pattern(G, N, adj);
+    for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    for (int v = 0; v < N; ++v)
+        if (adj[v].size() > 2) return false;
+    std::vector<char> seen(N, 0);
+    std::vector<std::vector<int>> paths;
+    for (int v = 0; v < N; ++v) {
+        if (seen[v] || adj[v].size() > 1) continue;           // start at path ends (degree 0 or 1)
+        std::vector<int> path{v};
+        seen[v] = 1;
+        int cur = v;
+        for (;;) {
+            int nxt = -1;
+            for (int u : adj[cur])
+                if (!seen[u]) nxt = u;
+            if (nxt < 0) break;
+            seen[nxt] = 1;
+            path.push_back(nxt);
+            cur = nxt;
+        }
+        paths.push_back(path);
+    }
+    for (int v = 0; v < N; ++v)
+        if (!seen[v]) return false;                            // a cycle
+    const int P = (int)paths.size();
+    if (P < 1 || P > 4) return false;
+    const size_t L = paths[0].size();
+    for (auto& pth : paths)
+        if (pth.size() != L) return false;
+    int best = N + 1;
+    std::vector<int> cand(N), cinv(N);
+    for (int mask = 0; mask < (1 << P); ++mask) {
+        for (int k = 0; k < P; ++k)
+            for (size_t pos = 0; pos < L; ++pos)
+                cand[pos * P + k] = paths[k][(mask >> k) & 1 ? L - 1 - pos : pos];
+        for (int i = 0; i < N; ++i) cinv[cand[i]] = i;
+        const int bw = pattern_bandwidth(adj_all, cinv);
+        if (bw < best) { best = bw; order = cand; }
+    }
+    RS = P;
+    bw_out = best;
+    return true;
+}
+
 // split the (permuted) operators into the tables of qme_band.cuh; false when the structure is
 // outside what that kernel handles (more than 4 off-diagonal entries per row of G, more than
 // one entry per row of an X_s / Z_s, more than 2 sandwich terms)
 bool build_band_host(const HostOp& G, const std::vector<HostOp>& X, const std::vector<HostOp>& Z, int N, int nb,
-                     const std::vector<int>& perm, const std::vector<int>& inv, BandHost& o) {
+                     const std::vector<int>& perm, const std::vector<int>& inv, BandHost& o, int chain_rs = 0) {
     const int S = (int)X.size();
     if (S > QME_BAND_MAXS || N > 128) return false;
     EllHost eg;
@@ -285,7 +335,25 @@ bool build_band_host(const HostOp& G, const std::vector<HostOp>& X, const std::v
             }
             if (c != i) { o.gcol[(size_t)slot * N + i] = c; ++slot; }
         }
+        if (chain_rs > 0) {
+            // directional slots: slot 0 = row i - RS, slot 1 = row i + RS (absent neighbours: value 0)
+            int cols[2] = {o.gcol[i], o.gcol[(size_t)N + i]};
+            std::vector<hcplx> v0(nb), v1(nb);
+            for (int b = 0; b < nb; ++b) { v0[b] = o.gval[((size_t)b * 2 + 0) * N + i]; v1[b] = o.gval[((size_t)b * 2 + 1) * N + i]; }
+            for (int q = 0; q < 2; ++q) {
+                o.gcol[(size_t)q * N + i] = i;
+                for (int b = 0; b < nb; ++b) o.gval[((size_t)b * 2 + q) * N + i] = hcplx(0, 0);
+            }
+            for (int q = 0; q < 2; ++q) {
+                if (cols[q] == i) continue;
+                const int dst = cols[q] == i - chain_rs ? 0 : (cols[q] == i + chain_rs ? 1 : -1);
+                if (dst < 0) return false;
+                o.gcol[(size_t)dst * N + i] = cols[q];
+                for (int b = 0; b < nb; ++b) o.gval[((size_t)b * 2 + dst) * N + i] = q == 0 ? v0[b] : v1[b];
+            }
+        }
     }
+    if (chain_rs > 0 && (o.noff != 2 || !o.gt)) return false;
     for (int s = 0; s < S; ++s) {
         const HostOp* ops[2] = {&X[s], &Z[s]};
         std::vector<int>* cols[2] = {&o.xcol[s], &o.zcol[s]};
@@ -484,7 +552,25 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
                 int bw = pattern_bandwidth(adj, cinv);
                 if (bw < bw_best) { bw_best = bw; perm = cand; inv = cinv; p->permuted = true; }
             }
-            if (path == 5) {
+            p->band_chain = 0;
+            if (path == 5 && getenv("LIMEB200_BAND_CHAIN")) {     // opt-in: measured SLOWER (1.40e6 vs 2.0-2.2e6 rho-steps/s on config 2, spills at 128 registers)
+                // chain structure: interleaved path ordering + sliding-window kernel
+                std::vector<int> corder, cinv(N);
+                int rs = 0, cbw = 0;
+                if (chain_order(N, p->G, adj, corder, rs, cbw)) {
+                    for (int i = 0; i < N; ++i) cinv[corder[i]] = i;
+                    BandHost cb;
+                    int C = 0, R = 0;
+                    size_t sm = 0;
+                    if (build_band_host(p->G, p->X, p->Z, N, nb, corder, cinv, cb, rs) && cb.xt &&
+                        qme_band_geometry(N, p->E, cb.bw, cb.noff, S, p->smem_optin, &C, &R, &sm) &&
+                        C * R == N && R % (4 * rs) == 0 && N % 64 == 0) {
+                        band = cb; perm = corder; inv = cinv; p->permuted = true;
+                        p->band_C = C; p->band_R = R; p->band_smem = sm; p->band_chain = rs;
+                    }
+                }
+            }
+            if (path == 5 && !p->band_chain) {
                 bool ok5 = build_band_host(p->G, p->X, p->Z, N, nb, perm, inv, band) &&
                            qme_band_geometry(N, p->E, band.bw, band.noff, S, p->smem_optin, &p->band_C, &p->band_R, &p->band_smem);
                 if (!ok5) {
@@ -814,7 +900,10 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
         g.eptr = p->deptr.as<int>(); g.eidx = p->deidx.as<int>(); g.eval = p->deval.as<cplx>();
         g.rho = rho; g.obs = obs; g.traj = traj; g.dt = dt;
         { const char* dbg = getenv("LIMEB200_DEBUG_FLAGS"); g.debug_flags = dbg ? atoi(dbg) : 0; }
+        g.chain_rs = p->band_chain;
         int r;
+        if (p->band_chain) r = qme_band_launch_chain_tc2(g, S, p->band_smem, st);
+        else
         r = p->band_noff == 2 ? qme_band_launch_tc2_n2(g, S, p->band_gt, p->band_xt, p->band_smem, st)
                               : qme_band_launch_tc2_n4(g, S, p->band_gt, p->band_xt, p->band_smem, st);
         if (r != LB_OK) return r;

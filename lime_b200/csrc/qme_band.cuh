@@ -85,6 +85,7 @@ struct QmeBandArgs {
     cplx* traj;                  // [nsteps/traj_every][B][N][N] or null
     double dt;
     int debug_flags;             // bit 0: skip the halo exchange (timing experiments only; wrong results)
+    int chain_rs;                // CH kernels: G couples row i to rows i - chain_rs (slot 0) and i + chain_rs (slot 1) only
 };
 
 // GT: 0 complex off-diagonal G, 1 purely imaginary.  XT: 0 complex X/Z, 1 real.
@@ -93,7 +94,10 @@ struct QmeBandArgs {
 // a register base + immediate): two stage buffers of (R + 2h) rows x N (+128 pad: lanes whose
 // column l + 32u lies beyond N read into the next row and are never stored), the reduction
 // scratch, and the row-side coefficient tables of this CTA's rows.
-template <int TR, int TC, int NOFF, int S, int GT, int XT>
+// CH = 1 ("chain" structure, NOFF = 2): the off-diagonal part of G couples row i only to rows i -/+ RS, and a
+// thread's TR rows are RS apart, so the left-hand neighbours of a row are the thread's previous / next row: a
+// sliding window of three rows in registers replaces 3 of the 7 shared-memory loads per element by (TR + 2) / TR.
+template <int TR, int TC, int NOFF, int S, int GT, int XT, int CH>
 __global__ void __launch_bounds__(512, 1)
 qme_band_kernel(QmeBandArgs a) {
     extern __shared__ double2 smem[];
@@ -176,13 +180,15 @@ qme_band_kernel(QmeBandArgs a) {
     }
     __syncthreads();
     cplx rho[TR][TC], acc[TR][TC];
-    const int l0 = (warp / CB) * TR;                   // first own row, relative to row_lo
+    const int RS = CH ? a.chain_rs : 1;                // distance between a thread's consecutive rows
+    const int l0 = CH ? ((warp / CB) / RS) * (TR * RS) + (warp / CB) % RS
+                      : (warp / CB) * TR;              // first own row, relative to row_lo
 #pragma unroll
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
-            const int i = row_lo + l0 + r;
-            rho[r][u] = (i < row_hi && okc[u]) ? smem[(l0 + r + h) * N + jb + 32 * u] : cmake(0, 0);
+            const int i = row_lo + l0 + r * RS;
+            rho[r][u] = (i < row_hi && okc[u]) ? smem[(l0 + r * RS + h) * N + jb + 32 * u] : cmake(0, 0);
             acc[r][u] = cmake(0, 0);
         }
     // ---- neighbours: mapped shared-memory windows and mbarriers
@@ -215,18 +221,30 @@ qme_band_kernel(QmeBandArgs a) {
             if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * (stage & 1), halo_bytes);
             const char* yinb = reinterpret_cast<const char*>(smem + yin);          // stage input, row 0
             const char* yinl = yinb + jb * 16;                                      // ... at this thread's first column
+            cplx wlo[TC], wcur[TC], whi[TC];                  // CH: rows li - RS, li, li + RS of the stage vector
+            if (CH) {
+#pragma unroll
+                for (int u = 0; u < TC; ++u) {
+                    wlo[u] = *reinterpret_cast<const cplx*>(yinl + (l0 - RS + h) * N * 16 + 512 * u);
+                    wcur[u] = *reinterpret_cast<const cplx*>(yinl + (l0 + h) * N * 16 + 512 * u);
+                }
+            }
 #pragma unroll
             for (int r = 0; r < TR; ++r) {
-                const int li = l0 + r;                            // row relative to row_lo (warp-uniform)
+                const int li = l0 + r * RS;                       // row relative to row_lo (warp-uniform)
                 if (row_lo + li < row_hi) {
                     const int ownoff = (li + h) * N * 16;
                     const char* ownb = yinb + ownoff;             // y[i][0]
                     const char* ownl = yinl + ownoff;             // y[i][jb]
                     const cplx gdi = smem[o_lgd + li];
                     cplx k[TC];
+                    if (CH) {
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) whi[u] = *reinterpret_cast<const cplx*>(ownl + RS * N * 16 + 512 * u);
+                    }
 #pragma unroll
                     for (int u = 0; u < TC; ++u) {
-                        const cplx y = *reinterpret_cast<const cplx*>(ownl + 512 * u);
+                        const cplx y = CH ? wcur[u] : *reinterpret_cast<const cplx*>(ownl + 512 * u);
                         const double dr = gdi.x + gdj[u].x, di = gdi.y + gdj[u].y;
                         k[u].x = dr * y.x - di * y.y;
                         k[u].y = dr * y.y + di * y.x;
@@ -238,7 +256,7 @@ qme_band_kernel(QmeBandArgs a) {
                         const cplx v = smem[o_lgv + q * R + li];
 #pragma unroll
                         for (int u = 0; u < TC; ++u) {
-                            const cplx y = *reinterpret_cast<const cplx*>(lrow + 512 * u);
+                            const cplx y = CH ? (q == 0 ? wlo[u] : whi[u]) : *reinterpret_cast<const cplx*>(lrow + 512 * u);
                             if (GT == 1) {
                                 k[u].x = fma(-v.y, y.y, k[u].x);
                                 k[u].y = fma(v.y, y.x, k[u].y);
@@ -318,6 +336,10 @@ qme_band_kernel(QmeBandArgs a) {
                         if (TC > 2 && okc[TC > 2 ? 2 : 0]) st_async_c128<1024>(d, yn[TC > 2 ? 2 : 0], rb);
                         if (TC > 3 && okc[TC > 3 ? 3 : 0]) st_async_c128<1536>(d, yn[TC > 3 ? 3 : 0], rb);
                     }
+                    if (CH) {
+#pragma unroll
+                        for (int u = 0; u < TC; ++u) { wlo[u] = wcur[u]; wcur[u] = whi[u]; }
+                    }
                 }
             }
             // local writes visible / local reads of the old stage vector finished ...
@@ -370,7 +392,7 @@ qme_band_kernel(QmeBandArgs a) {
             for (int r = 0; r < TR; ++r)
 #pragma unroll
                 for (int u = 0; u < TC; ++u) {
-                    const int i = row_lo + l0 + r, j = jb + 32 * u;
+                    const int i = row_lo + l0 + r * RS, j = jb + 32 * u;
                     if (i < row_hi && okc[u]) {
                         int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                         dst[(size_t)gr * N + gc] = rho[r][u];
@@ -393,7 +415,7 @@ qme_band_kernel(QmeBandArgs a) {
     for (int r = 0; r < TR; ++r)
 #pragma unroll
         for (int u = 0; u < TC; ++u) {
-            const int i = row_lo + l0 + r, j = jb + 32 * u;
+            const int i = row_lo + l0 + r * RS, j = jb + 32 * u;
             if (i < row_hi && okc[u]) {
                 int gr = a.perm ? a.perm[i] : i, gc = a.perm ? a.perm[j] : j;
                 out[(size_t)gr * N + gc] = rho[r][u];
@@ -431,10 +453,10 @@ static inline bool qme_band_geometry(int N, int E, int bandwidth, int NOFF, int 
 int qme_band_launch_tc2_n2(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
 int qme_band_launch_tc2_n4(const QmeBandArgs& a, int S, int GT, int XT, size_t smem, cudaStream_t st);
 
-template <int TC, int NOFF, int S, int GT, int XT>
+template <int TC, int NOFF, int S, int GT, int XT, int CH = 0>
 static int qme_band_launch_one(const QmeBandArgs& a, size_t smem, cudaStream_t st) {
     constexpr int TR = 4;
-    auto kern = qme_band_kernel<TR, TC, NOFF, S, GT, XT>;
+    auto kern = qme_band_kernel<TR, TC, NOFF, S, GT, XT, CH>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int W = ((a.R + TR - 1) / TR) * ((a.N + 32 * TC - 1) / (32 * TC));
     cudaLaunchConfig_t cfg = {};
@@ -468,3 +490,12 @@ static int qme_band_launch_one(const QmeBandArgs& a, size_t smem, cudaStream_t s
         return XT ? qme_band_launch_one<TC, NOFF, 2, 0, 1>(a, smem, st)                               \
                   : qme_band_launch_one<TC, NOFF, 2, 0, 0>(a, smem, st);                              \
     }
+
+// chain-structured variants (NOFF = 2, purely imaginary off-diagonal G, real X/Z: the ladder-operator case)
+#define QME_BAND_DEFINE_LAUNCH_CHAIN(NAME, TC)                                                        \
+    int NAME(const QmeBandArgs& a, int S, size_t smem, cudaStream_t st) {                             \
+        if (S == 0) return qme_band_launch_one<TC, 2, 0, 1, 1, 1>(a, smem, st);                       \
+        if (S == 1) return qme_band_launch_one<TC, 2, 1, 1, 1, 1>(a, smem, st);                       \
+        return qme_band_launch_one<TC, 2, 2, 1, 1, 1>(a, smem, st);                                   \
+    }
+int qme_band_launch_chain_tc2(const QmeBandArgs& a, int S, size_t smem, cudaStream_t st);

@@ -65,7 +65,7 @@ def test_lindblad_drop_in_surface(cuda):
 
 
 @pytest.mark.parametrize('path', [1, 2, 3, 4, 5])
-@pytest.mark.parametrize('ncav', [8, 16, 37, 64])
+@pytest.mark.parametrize('ncav', [8, 16, 32, 37, 64])
 def test_lindblad_jc_every_kernel(cuda, path, ncav):
     """Jaynes-Cummings (config-2 shape, small cutoffs) through every kernel family"""
     from lime_b200 import oqs
@@ -135,6 +135,19 @@ def test_lindblad_non_hermitian_hamiltonian(cuda):
         assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
     res = oqs._lindblad(csr_matrix(H), rho0, [csr_matrix(c) for c in c_ops], e_ops=e_ops, Nt=30, dt=0.01)
     assert relerr(res.observables, o) <= TOL
+
+
+def test_lindblad_band_chain_variant(cuda, monkeypatch):
+    """opt-in sliding-window ("chain") variant of the register-tiled kernel: interleaved path ordering"""
+    from lime_b200 import oqs
+    monkeypatch.setenv('LIMEB200_BAND_CHAIN', '1')
+    for ncav in (32, 64):
+        H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav)
+        rho0 = rho0 + 0.01 * cases.rand_cplx(2 * ncav, 5)
+        o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=25, dt=0.01)
+        plan = oqs._lindblad_plan(csr_matrix(H), [csr_matrix(c) for c in c_ops], e_ops, path=5)
+        rf, ob, _ = plan.run(rho0, 0.01, 25)
+        assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
 
 
 def test_lindblad_band_variants_and_sparse_rhs(cuda):
