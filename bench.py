@@ -644,7 +644,7 @@ def run_ours(args):
             'gpu_launches': int(launches.item()),
             'clocks': clocks,
             'roofline': {'bound': w.bound, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': TRAFFIC.get(w.name),
+                         'frac': achieved / peak, 'traffic': TRAFFIC.get((w.name, int(w.units_per_step))),
                          'kernel': w.kernel, 'peak_source': peak_src,
                          'algorithmic_bytes_per_unit': w.alg_bytes_per_unit,
                          'units_per_launch': w.units_per_step,
@@ -666,7 +666,11 @@ def run_ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
 # `ncu --set full` capture summarised under profiles/ (same command, same sizes); None = not captured
-TRAFFIC = {}
+TRAFFIC = {
+    # profiles/r01_traffic_jc_lindblad_default.csv: 1 192 611 840 B read + 1 206 404 096 B written by ONE launch of the
+    # default config (4096 x 128^2 rho, 1000 RK4 steps): rho in, rho out, observables -- 0.11 % of the algorithmic bytes
+    ('jc_lindblad', 4096000): 2399015936,
+}
 
 
 def main():
