@@ -213,6 +213,10 @@ int limeb200_heom_dl_euler(const double* h_H, const double* h_sz, int n, int nad
  * d_F [T][R][n] complex out */
 int limeb200_sos_factor(const double* d_z, int n, const double* d_W, const double* d_p1,
                         const double* d_p2, int T, int R, int D, double* d_F, void* stream);
+/* time-domain factors for the response functions of lime/signal/2DES.py:37-247:
+ * F_t[q][n] = sum_d W_t[q][d] * (-i) theta(t_n) exp(-i e1[q][d] t_n - g1[q][d] t_n), theta(0) = 1 */
+int limeb200_sos_factor_time(const double* d_t, int n, const double* d_W, const double* d_p1,
+                             int T, int R, int D, double* d_F, void* stream);
 /* d_out[T][nrow][ncol] (+)= scale * sum_q A[ta][q][row] * B[tb][q][col];
  * TA, TB = 1 (factor shared by all t) or T.                                               */
 int limeb200_sos_outer(const double* d_A, int TA, const double* d_B, int TB, int T, int R,

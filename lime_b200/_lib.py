@@ -57,6 +57,7 @@ SIGNATURES = {
     'limeb200_heom_sharded_error': (c_int, [c_vp, c_vp]),
     'limeb200_heom_dl_euler': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),
     'limeb200_sos_factor': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
+    'limeb200_sos_factor_time': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'limeb200_sos_outer': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, c_vp, c_vp]),
     'limeb200_sos_tpa2d': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int,
                                    c_int, c_vp, c_vp]),

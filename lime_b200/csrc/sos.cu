@@ -35,6 +35,31 @@ sos_factor_kernel(const double* __restrict__ z, int n, const cplx* __restrict__ 
     F[((size_t)t * R + q) * n + i] = s;
 }
 
+// time-domain factors (lime/signal/2DES.py:37-60): F[t][q][n] = sum_d W[t][q][d] * G(t_n; e, g),
+// G(t) = -i theta(t) exp(-i e t - g t), theta(0) = 1
+__global__ void __launch_bounds__(256)
+sos_factor_time_kernel(const double* __restrict__ tt, int n, const cplx* __restrict__ W,
+                       const double2* __restrict__ p1, int R, int D, cplx* __restrict__ F) {
+    const int t = blockIdx.z, q = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ti = tt[i];
+    const cplx* w = W + ((size_t)t * R + q) * D;
+    const double2* a = p1 + (size_t)q * D;
+    cplx s = cmake(0, 0);
+    if (ti >= 0.0) {
+        for (int d = 0; d < D; ++d) {
+            const double2 pa = a[d];
+            double sn, cs;
+            sincos(-pa.x * ti, &sn, &cs);
+            const double m = exp(-pa.y * ti);
+            // -i * m (cs + i sn) = m (sn - i cs)
+            cfma(s, w[d], cmake(m * sn, -m * cs));
+        }
+    }
+    F[((size_t)t * R + q) * n + i] = s;
+}
+
 // out[t][r][c] (+)= scale * sum_q A[ta][q][r] B[tb][q][c];  32x32 tile per CTA of 256 threads,
 // each thread 4 consecutive columns -> one 64-byte store per thread
 __global__ void __launch_bounds__(256)
@@ -117,6 +142,18 @@ int limeb200_sos_factor(const double* d_z, int n, const double* d_W, const doubl
     dim3 grid(ceil_div(n, 256), R, T);
     sos_factor_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_z, n, (const cplx*)d_W, (const double2*)d_p1,
                                                              (const double2*)d_p2, R, D, (cplx*)d_F);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int limeb200_sos_factor_time(const double* d_t, int n, const double* d_W, const double* d_p1,
+                             int T, int R, int D, double* d_F, void* stream) {
+    LB_REQUIRE(d_t && d_W && d_p1 && d_F, "null argument");
+    LB_REQUIRE(n >= 1 && T >= 1 && R >= 1 && D >= 1, "bad sizes");
+    LB_REQUIRE(R <= 65535 && T <= 65535, "R/T too large");
+    dim3 grid(ceil_div(n, 256), R, T);
+    sos_factor_time_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_t, n, (const cplx*)d_W, (const double2*)d_p1,
+                                                                  R, D, (cplx*)d_F);
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }

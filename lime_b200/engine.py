@@ -378,6 +378,21 @@ def sos_factor_dev(z, dW, dp1, dp2=None):
     return F
 
 
+def sos_factor_time(t, W, p1, dev=None):
+    """F[T][q][n] = sum_d W[T][q][d] * (-i) theta(t_n) exp(-i e t_n - g t_n); t: device float64 [n];
+    W: host [T,R,D] complex; p1: host [R,D,2] (e, g).  -> device [T,R,n]"""
+    dev = _dev.device() if dev is None else dev
+    W = np.ascontiguousarray(np.asarray(W, dtype=np.complex128))
+    T, R, D = W.shape
+    dW = _dev.to_dev(W, dev=dev)
+    dp1 = _dev.to_dev(np.asarray(p1, dtype=np.float64).reshape(R, D, 2), np.float64, dev)
+    n = t.shape[0]
+    F = _dev.empty((T, R, n), dev=dev)
+    check(lib().limeb200_sos_factor_time(_dev.ptr(t), n, _dev.ptr(dW), _dev.ptr(dp1), T, R, D,
+                                         _dev.ptr(F), _dev.stream_ptr()))
+    return F
+
+
 def sos_outer(A, Bf, T, scale=1.0, out=None, accumulate=False):
     """out[t][r][c] (+)= scale * sum_q A[ta][q][r] * B[tb][q][c]  (device tensors)"""
     TA, R, nrow = A.shape

@@ -252,6 +252,26 @@ def main():
     note('sos', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'sos.npz'), w1=w1, w3=w3, w2=w2, w1b=w1b, t2=t2, **g)
 
+    # ---- time-domain response functions, lime/signal/2DES.py:37-247 (the module cannot be imported:
+    # it runs undefined names at :249-263; the function definitions themselves are exec'd verbatim here)
+    src = open('/root/reference/lime/signal/2DES.py').read().split('\n')
+    ns = {'np': np, 'au2mev': 27211.386, 'au2ev': 27.211386}       # lime/units.py:6,8 (imported at 2DES.py:24)
+    exec('\n'.join(src[36:247]), ns)
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    ns['en'] = E
+    ns['decay'] = gamma
+    t1 = np.linspace(0, 300, 9)[None, :]
+    t3 = np.linspace(0, 400, 7)[:, None]
+    tw = 50.0
+    g = {'ESA': ns['ESA'](E, dip, g_idx, e_idx, f_idx, gamma, t1, tw, t3),
+         'GSB': ns['GSB'](E, dip, g_idx, e_idx, gamma, t1, tw, t3),
+         'SE': ns['SE'](E, dip, g_idx, e_idx, t1, tw, t3)}
+    o = {'ESA': lo.td_ESA(E, gamma, dip, g_idx, e_idx, f_idx, t1, tw, t3),
+         'GSB': lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1, tw, t3),
+         'SE': lo.td_SE(E, gamma, dip, g_idx, e_idx, t1, tw, t3)}
+    note('twodes_time', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'twodes_time.npz'), t1=t1[0], t3=t3[:, 0], t2=tw, **g)
+
     with open(os.path.join(GOLD, 'PINNING.json'), 'w') as f:
         json.dump({'generated_by': 'oracle/gen_golden.py', 'reference': 'binggu56/lime @ /root/reference',
                    'numpy': np.__version__, 'oracle_vs_reference_max_rel_err': report}, f, indent=1)

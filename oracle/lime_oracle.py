@@ -795,6 +795,60 @@ def TPA2D_time_order(E, dip, omegaps, omega1s, g_idx, e_idx, f_idx, gamma):
 
 
 # --------------------------------------------------------------------------
+# time-domain third-order response functions              lime/signal/2DES.py
+# (the module itself is not importable -- it executes undefined names at :249-263 --
+#  but the functions :37-247 are; oracle/gen_golden.py execs exactly those lines of the
+#  reference source to pin this restatement)
+# --------------------------------------------------------------------------
+def td_G(en, decay, a, b, t):
+    """-i theta(t) exp(-i (E_a - E_b) t - (g_a + g_b)/2 t), lime/signal/2DES.py:37-60
+    (`en`, `decay` are module globals there)"""
+    return -1j * np.heaviside(t, 1) * np.exp(-1j * (en[a] - en[b]) * t - (decay[a] + decay[b]) / 2. * t)
+
+
+def td_ESA(en, decay, dip, g_idx, e_idx, f_idx, t1, t2, t3):
+    """lime/signal/2DES.py:99-155: gg -> ge -> e'e -> fe -> ee, sign -1"""
+    signal = 0
+    a = 0
+    for b in e_idx:
+        G_ab = td_G(en, decay, a, b, t1)
+        for c in e_idx:
+            G_cb = td_G(en, decay, c, b, t2)
+            for d in f_idx:
+                G_db = td_G(en, decay, d, b, t3)
+                signal += dip[b, a] * dip[c, a] * dip[d, c] * dip[b, d] * G_db * G_cb * G_ab
+    return -1 * signal
+
+
+def td_GSB(en, decay, dip, g_idx, e_idx, t1, t2, t3):
+    """lime/signal/2DES.py:158-203: gg -> ge -> gg' -> e'g' -> g'g'"""
+    signal = 0
+    a = 0
+    for b in e_idx:
+        G_ab = td_G(en, decay, a, b, t1)
+        for c in g_idx:
+            G_ac = td_G(en, decay, a, c, t2)
+            for d in e_idx:
+                G_dc = td_G(en, decay, d, c, t3)
+                signal += dip[a, b] * dip[b, c] * dip[c, d] * dip[d, a] * G_dc * G_ac * G_ab
+    return signal
+
+
+def td_SE(en, decay, dip, g_idx, e_idx, t1, t2, t3):
+    """lime/signal/2DES.py:207-247: gg -> ge -> e'e -> g'e -> g'g'"""
+    signal = 0.0
+    a = 0
+    for b in e_idx:
+        G_ab = td_G(en, decay, a, b, t1)
+        for c in e_idx:
+            G_cb = td_G(en, decay, c, b, t2)
+            for d in g_idx:
+                G_cd = td_G(en, decay, c, d, t3)
+                signal += dip[a, b] * dip[c, a] * dip[d, c] * dip[b, d] * G_cd * G_cb * G_ab
+    return signal
+
+
+# --------------------------------------------------------------------------
 # model builders used by the BASELINE configs (host-side in lime too)
 # --------------------------------------------------------------------------
 def jaynes_cummings(omega0, omegac, g, ncav, kappa, rwa=False):

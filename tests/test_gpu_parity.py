@@ -400,3 +400,33 @@ def test_sos_waiting_time_batch_and_ragged_grid(cuda):
     grid = sos.PhotonEchoGrid(E, dip, -w, w, T, g_idx, e_idx, f_idx, gamma)
     assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
     assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
+
+
+def test_time_domain_2des(cuda):
+    """lime/signal/2DES.py:37-247 (G, ESA, GSB, SE in the time domain) against the frozen outputs of the
+    reference functions themselves and against the oracle; scalars, vectors, waiting-time batch"""
+    from lime_b200.signal import twodes
+    g = golden('twodes_time')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    t1, t3, tw = g['t1'], g['t3'], float(g['t2'])
+    twodes.en, twodes.decay = None, None
+    assert relerr(twodes.ESA(E, dip, g_idx, e_idx, f_idx, gamma, t1[None, :], tw, t3[:, None]), g['ESA']) <= TOL
+    assert relerr(twodes.GSB(E, dip, g_idx, e_idx, gamma, t1, tw, t3), g['GSB']) <= TOL
+    assert relerr(twodes.SE(E, dip, g_idx, e_idx, t1, tw, t3, gamma=gamma), g['SE']) <= TOL
+    # module globals as in lime
+    twodes.en, twodes.decay = E, gamma
+    try:
+        assert relerr(twodes.SE(None, dip, g_idx, e_idx, t1, tw, t3), g['SE']) <= TOL
+        assert relerr(twodes.G(2, 0, t3), lo.td_G(E, gamma, 2, 0, t3)) <= 1e-13
+        assert abs(twodes.G(1, 0, 3.0) - lo.td_G(E, gamma, 1, 0, 3.0)) <= 1e-13
+        assert twodes.G(1, 0, -1.0) == 0
+    finally:
+        twodes.en, twodes.decay = None, None
+    # scalar delays and a batch of waiting times
+    s = twodes.ESA(E, dip, g_idx, e_idx, f_idx, gamma, 10.0, tw, 20.0)
+    assert abs(s - lo.td_ESA(E, gamma, dip, g_idx, e_idx, f_idx, 10.0, tw, 20.0)) <= TOL * abs(s)
+    tws = np.array([0.0, 25.0, 80.0])
+    b = twodes.GSB(E, dip, g_idx, e_idx, gamma, t1, tws, t3)
+    assert b.shape == (3, len(t3), len(t1))
+    for k, t2 in enumerate(tws):
+        assert relerr(b[k], lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1[None, :], t2, t3[:, None])) <= TOL

@@ -185,3 +185,13 @@ def test_sos():
     assert relerr(lo.DQC_R2(E, dip, omega2=w2, omega3=w1b, tau1=50.0, **kw), g['R2_t1']) <= TOL
     assert relerr(lo.TPA2D(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D']) <= TOL
     assert relerr(lo.TPA2D_time_order(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D_to']) <= TOL
+
+
+def test_time_domain_2des_oracle_matches_reference_functions():
+    """golden = the reference's own ESA/GSB/SE source (lime/signal/2DES.py:37-247) exec'd by oracle/gen_golden.py"""
+    g = golden('twodes_time')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    t1, t3, tw = g['t1'][None, :], g['t3'][:, None], float(g['t2'])
+    assert np.array_equal(lo.td_ESA(E, gamma, dip, g_idx, e_idx, f_idx, t1, tw, t3), g['ESA'])
+    assert np.array_equal(lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1, tw, t3), g['GSB'])
+    assert np.array_equal(lo.td_SE(E, gamma, dip, g_idx, e_idx, t1, tw, t3), g['SE'])
