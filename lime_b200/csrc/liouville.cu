@@ -8,6 +8,7 @@
 // all nsteps steps.
 #include "../../include/lime_b200.h"
 #include "common.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -118,6 +119,78 @@ liouville_rk4_kernel(LvArgs a) {
     }
 }
 
+// Small Liouville dimension (instantiated for D = 4, the two-level system): ONE THREAD PER VECTOR.  The vector, the RK4
+// accumulator and the stage vector live in registers; the densified generator and the observable rows sit in
+// shared memory and are read with warp-uniform (broadcast) loads; no barrier inside the time loop.
+template <int D>
+__global__ void __launch_bounds__(128)
+liouville_small_kernel(LvArgs a) {
+    extern __shared__ double2 smem[];
+    cplx* Rs = smem;                    // [D][D] dense, row-major
+    cplx* es = smem + D * D;            // [E][D]
+    for (int l = threadIdx.x; l < D * D; l += blockDim.x) Rs[l] = cmake(0, 0);
+    for (int l = threadIdx.x; l < a.E * D; l += blockDim.x) es[l] = a.e[l];
+    __syncthreads();
+    for (int r = threadIdx.x; r < D; r += blockDim.x)
+        for (int p = a.indptr[r]; p < a.indptr[r + 1]; ++p) {
+            cplx& d = Rs[r * D + a.indices[p]];
+            d = cadd(d, a.data[p]);
+        }
+    __syncthreads();
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    cplx v[D], acc[D], y[D];
+    const cplx* gv = a.v + (size_t)b * D;
+#pragma unroll
+    for (int r = 0; r < D; ++r) { v[r] = gv[r]; y[r] = v[r]; }
+    const double dt = a.dt, hdt = 0.5 * a.dt, w6 = a.dt / 6.0;
+    for (int step = 0; step < a.nsteps; ++step) {
+#pragma unroll
+        for (int stage = 0; stage < 4; ++stage) {
+            cplx k[D];
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                cplx s = cmake(0, 0);
+#pragma unroll
+                for (int c = 0; c < D; ++c) cfma(s, Rs[r * D + c], y[c]);
+                k[r] = s;
+            }
+#pragma unroll
+            for (int r = 0; r < D; ++r) {
+                if (stage == 0) {
+                    acc[r] = k[r];
+                    y[r] = cmake(fma(hdt, k[r].x, v[r].x), fma(hdt, k[r].y, v[r].y));
+                } else if (stage == 1) {
+                    rfma(acc[r], 2.0, k[r]);
+                    y[r] = cmake(fma(hdt, k[r].x, v[r].x), fma(hdt, k[r].y, v[r].y));
+                } else if (stage == 2) {
+                    rfma(acc[r], 2.0, k[r]);
+                    y[r] = cmake(fma(dt, k[r].x, v[r].x), fma(dt, k[r].y, v[r].y));
+                } else {
+                    v[r].x = fma(w6, acc[r].x + k[r].x, v[r].x);
+                    v[r].y = fma(w6, acc[r].y + k[r].y, v[r].y);
+                    y[r] = v[r];
+                }
+            }
+        }
+        if (a.obs)
+            for (int eo = 0; eo < a.E; ++eo) {
+                cplx s = cmake(0, 0);
+#pragma unroll
+                for (int r = 0; r < D; ++r) cfma(s, es[eo * D + r], v[r]);
+                a.obs[((size_t)step * a.B + b) * a.E + eo] = s;
+            }
+        if (a.traj && ((step + 1) % a.traj_every) == 0) {
+            cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * D;
+#pragma unroll
+            for (int r = 0; r < D; ++r) dst[r] = v[r];
+        }
+    }
+    cplx* out = a.v + (size_t)b * D;
+#pragma unroll
+    for (int r = 0; r < D; ++r) out[r] = v[r];
+}
+
 }  // namespace
 
 extern "C" int limeb200_liouville_rk4_csr(const int* d_indptr, const int* d_indices, const double* d_data,
@@ -139,6 +212,14 @@ extern "C" int limeb200_liouville_rk4_csr(const int* d_indptr, const int* d_indi
     a.D = D; a.B = B; a.E = E; a.nsteps = nsteps; a.traj_every = d_traj ? traj_every : 1;
     a.v = (cplx*)d_v; a.e = (const cplx*)d_e; a.obs = E > 0 ? (cplx*)d_obs : nullptr; a.traj = (cplx*)d_traj;
     a.dt = dt;
+    if (D == 4 && E <= 16 && B >= 4096 && !getenv("LIMEB200_LIOUVILLE_GENERIC")) {
+        // thread-per-vector kernel for batches of two-level systems (D = 9, 16 would spill: 8 D doubles of state)
+        const size_t smem = (size_t)(D * D + E * D) * 16;
+        void (*k)(LvArgs) = liouville_small_kernel<4>;
+        k<<<ceil_div(B, 128), 128, smem, (cudaStream_t)stream>>>(a);
+        LB_CUDA(cudaGetLastError());
+        return LB_OK;
+    }
     int ept = 1, tps;
     if (D <= 4) tps = 4;
     else if (D <= 8) tps = 8;

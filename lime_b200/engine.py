@@ -214,6 +214,34 @@ def liouville_rk4(R, v0, dt, nsteps, e_rows=None, traj_every=0, dev=None):
     return out, obs, traj
 
 
+class LiouvillePlan:
+    """device-resident form of liouville_rk4: R (CSR) and the observable rows are uploaded once;
+    run_device advances a device batch v [B, D] in place"""
+
+    def __init__(self, R, e_rows=None, dev=None):
+        self.dev = _dev.device() if dev is None else dev
+        m = csr_matrix(R).astype(np.complex128)
+        m.sum_duplicates()
+        m.sort_indices()
+        self.D = m.shape[0]
+        self.ip = _dev.to_dev(m.indptr, np.int32, self.dev)
+        self.ix = _dev.to_dev(m.indices, np.int32, self.dev)
+        self.da = _dev.to_dev(m.data, np.complex128, self.dev)
+        self.E = 0 if e_rows is None else len(e_rows)
+        self.e = _dev.to_dev(np.stack([np.asarray(e, dtype=np.complex128).reshape(self.D) for e in e_rows]),
+                             dev=self.dev) if self.E else None
+
+    def run_device(self, v, dt, nsteps, traj_every=0):
+        assert v.dtype == torch.complex128 and v.is_contiguous() and v.shape[1] == self.D
+        B = v.shape[0]
+        obs = _dev.empty((nsteps, B, self.E), dev=self.dev) if self.E else None
+        traj = _dev.empty((nsteps // traj_every, B, self.D), dev=self.dev) if traj_every else None
+        check(lib().limeb200_liouville_rk4_csr(_dev.ptr(self.ip), _dev.ptr(self.ix), _dev.ptr(self.da), self.D,
+                                               _dev.ptr(v), B, _dev.ptr(self.e), self.E, _dev.ptr(obs), _dev.ptr(traj),
+                                               int(traj_every), float(dt), int(nsteps), _dev.stream_ptr()))
+        return obs, traj
+
+
 # ---------------------------------------------------------------------------------------
 # HEOM
 # ---------------------------------------------------------------------------------------

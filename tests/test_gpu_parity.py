@@ -430,3 +430,19 @@ def test_time_domain_2des(cuda):
     assert b.shape == (3, len(t3), len(t1))
     for k, t2 in enumerate(tws):
         assert relerr(b[k], lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1[None, :], t2, t3[:, None])) <= TOL
+
+
+def test_redfield_two_level_batch_thread_per_vector_kernel(cuda):
+    """config-1 throughput variant: the Redfield tensor of examples/redfield.py on a batch large enough to
+    take the thread-per-vector kernel; checked against the oracle on a few members"""
+    from lime_b200.oqs import Redfield_solver
+    H, a_ops, spectra, rho0, dt, Nt, e_ops, tlist = cases.redfield_example()
+    s = Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = s.redfield_tensor()
+    batch = cases.rand_dm_batch(5000, 2, 9)
+    out, obs = s.evolve_batch(batch, dt, 40, e_ops=e_ops)
+    assert obs.shape == (40, 5000, 1)
+    for b in (0, 17, 4999):
+        o, rl = lo.redfield(R, batch[b], evecs=evecs, Nt=40, dt=dt, e_ops=e_ops)
+        assert relerr(obs[:, b], o) <= TOL
+        assert relerr(evecs @ out[b] @ evecs.conj().T, rl[-1]) <= TOL
