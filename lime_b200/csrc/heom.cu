@@ -239,7 +239,9 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const long long nown = a.row_hi - a.row_lo;
     const long long item = item0 + g;
     const bool act = g < a.apc && item < nown * a.B;
-    const int b = act ? (int)(item / nown) : 0;
+    int b = 0;
+    if (act && a.B > 1)         // 32-bit division whenever the flat index fits (a 64-bit one costs ~100 instructions)
+        b = (nown * a.B < (1LL << 31)) ? (int)((unsigned)item / (unsigned)nown) : (int)(item / nown);
     const long long ado = act ? a.row_lo + (item - (long long)b * nown) : a.row_lo;
     const int par = d.npar > 1 ? b : 0;
     const cplx* y = a.yin + (size_t)b * d.nhe * nn;

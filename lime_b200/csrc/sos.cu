@@ -61,7 +61,10 @@ sos_factor_time_kernel(const double* __restrict__ tt, int n, const cplx* __restr
 }
 
 // out[t][r][c] (+)= scale * sum_q A[ta][q][r] B[tb][q][c];  32x32 tile per CTA of 256 threads,
-// each thread 4 consecutive columns -> one 64-byte store per thread
+// each thread 4 columns 8 apart: the 8 lanes of a row read / write consecutive 16-byte elements, so
+// the shared-memory loads are conflict-free (4 consecutive columns per thread gave 4-way conflicts and
+// a shared-memory-bound kernel, profiles/r01_sos_outer_v1.txt) and every store instruction writes
+// full 128-byte row segments
 __global__ void __launch_bounds__(256)
 sos_outer_kernel(const cplx* __restrict__ A, int TA, const cplx* __restrict__ Bf, int TB, int R,
                  int nrow, int ncol, double scale, int accumulate, cplx* __restrict__ out) {
@@ -79,19 +82,19 @@ sos_outer_kernel(const cplx* __restrict__ A, int TA, const cplx* __restrict__ Bf
     }
     __syncthreads();
     const int tr = threadIdx.x >> 3;            // 0..31 row in tile
-    const int tc = (threadIdx.x & 7) * 4;       // 4 columns
+    const int tc = threadIdx.x & 7;             // columns tc + 8 u
     cplx acc[4] = {cmake(0, 0), cmake(0, 0), cmake(0, 0), cmake(0, 0)};
     for (int q = 0; q < R; ++q) {
         const cplx av = As[q * 32 + tr];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) cfma(acc[u], av, Bs[q * 32 + tc + u]);
+        for (int u = 0; u < 4; ++u) cfma(acc[u], av, Bs[q * 32 + tc + 8 * u]);
     }
     const int r = r0 + tr;
     if (r >= nrow) return;
     cplx* o = out + ((size_t)t * nrow + r) * ncol;
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-        const int c = c0 + tc + u;
+        const int c = c0 + tc + 8 * u;
         if (c < ncol) {
             cplx v = cscale(scale, acc[u]);
             if (accumulate) v = cadd(v, o[c]);
