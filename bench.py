@@ -287,6 +287,77 @@ class RedfieldBatch:
         return time.perf_counter() - t
 
 
+class LindbladDense:
+    """SURVEY.md 8d config 2': random dense Hermitian H (GUE), M = 2 random collapse operators, N = 256, batch 64 --
+    the regime where [H, rho] is a real dense contraction (FP64-bound, not HBM-bound)"""
+    name = 'lindblad_dense'
+    metric = 'lindblad_rho_steps_per_s'
+    unit = 'rho-steps/s'
+    dtype = 'complex128 (f64 arithmetic)'
+    scaling = 'weak'
+    bound = 'tensor'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        self.N = args.size or 256
+        self.B = args.batch or 64
+        self.rk = args.rk_steps or 10
+        self.M = 2
+        self.dt = 0.002
+        rng = np.random.default_rng(1)
+        N = self.N
+        a = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        self.H = (a + a.conj().T) / (2 * np.sqrt(N))
+        self.c_ops = [0.1 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))) / np.sqrt(N)
+                      for _ in range(self.M)]
+        self.e_ops = [self.H]
+        r = np.random.default_rng(10 + rank)
+        x = r.standard_normal((self.B, N, 8)) + 1j * r.standard_normal((self.B, N, 8))
+        rho = x @ x.conj().transpose(0, 2, 1)
+        self.rho0 = np.ascontiguousarray(rho / np.einsum('bii->b', rho)[:, None, None])
+        self.flops_per_unit = 4 * (2 + 2 * self.M) * 8 * N ** 3
+        self.alg_bytes_per_unit = 2 * 16 * N * N
+        self.units_per_step = self.B * self.rk
+        self.launches = 0
+        self.kernel = 'qme_dense_stage'
+        if need_gpu:
+            import torch
+            from lime_b200 import oqs
+            self.torch = torch
+            self.plan = oqs._lindblad_plan(self.H, self.c_ops, self.e_ops)
+            self.rho = torch.from_numpy(self.rho0).cuda()
+
+    def config(self):
+        return {'workload': 'lindblad_dense: GUE Hamiltonian N=%d, M=2 dense collapse operators, batch %d per GPU, dt=%g, '
+                            '%d RK4 steps per bench step' % (self.N, self.B, self.dt, self.rk),
+                'N': self.N, 'batch_per_gpu': self.B, 'flops_per_rho_step': self.flops_per_unit,
+                'l2_policy': 'L2 flushed between bench steps (state %.0f MiB)' % (self.B * self.N ** 2 * 16 / 2 ** 20),
+                'sharding': 'batch split across ranks, no collective'}
+
+    def step(self):
+        self.obs, _ = self.plan.run_device(self.rho, self.dt, self.rk)
+        self.launches += self.plan.last_launches
+
+    def check(self):
+        tr = self.torch.einsum('bii->b', self.rho).cpu().numpy()
+        return {'max_trace_error': float(np.max(np.abs(tr - 1.0)))}
+
+    def e2e_setup(self):
+        pass
+
+    def e2e_step(self):
+        from lime_b200.oqs import Lindblad_solver
+        s = Lindblad_solver(self.H, c_ops=self.c_ops)
+        rho_f, obs, _ = s.evolve_batch(self.rho0, self.dt, self.rk, e_ops=self.e_ops)
+        return self.rho0.nbytes, rho_f.nbytes + obs.nbytes
+
+    def cpu_point(self, idx, variant, nsteps):
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        t = time.perf_counter()
+        lo.lindblad(self.H, self.rho0[idx % self.B], self.c_ops, self.e_ops, Nt=nsteps, dt=self.dt)
+        return time.perf_counter() - t
+
+
 class HeomBase:
     metric = 'heom_ado_steps_per_s'
     unit = 'ADO-steps/s'
@@ -548,9 +619,9 @@ class Sos2DES:
         return time.perf_counter() - t
 
 
-WORKLOADS = {c.name: c for c in (JCLindblad, HeomFMO, HeomSpinBoson, Sos2DES, RedfieldBatch)}
+WORKLOADS = {c.name: c for c in (JCLindblad, HeomFMO, HeomSpinBoson, Sos2DES, RedfieldBatch, LindbladDense)}
 # units one cpu_point "step" stands for
-CPU_UNITS = {'jc_lindblad': lambda w: 1, 'redfield_batch': lambda w: 1, 'heom_sb': lambda w: 91, 'heom_fmo': lambda w: None,
+CPU_UNITS = {'jc_lindblad': lambda w: 1, 'lindblad_dense': lambda w: 1, 'redfield_batch': lambda w: 1, 'heom_sb': lambda w: 91, 'heom_fmo': lambda w: None,
              'sos_2des': lambda w: w.n * w.n}
 
 
@@ -693,6 +764,23 @@ def run_ours(args):
     peak, peak_src = measured_peaks()
     kernel_s = (sum(ms) / len(ms)) * 1e-3
     achieved = w.alg_bytes_per_unit * w.units_per_step / kernel_s / 1e9
+    roof_unit = 'GB/s'
+    if w.bound == 'tensor':
+        # FP64 roof measured in this run: cuBLAS ZGEMM 4096^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json has
+        # bf16 only); flops counted as 8 N^3 per complex product
+        n = 4096
+        xa = torch.randn(n, n, dtype=torch.complex128, device='cuda')
+        xb = torch.randn(n, n, dtype=torch.complex128, device='cuda')
+        best = 1e30
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); torch.matmul(xa, xb); e1.record(); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) * 1e-3)
+        peak = 8.0 * n ** 3 / best / 1e12
+        peak_src = 'measured in this run: cuBLAS ZGEMM 4096^3 (torch.matmul complex128), best of 10'
+        achieved = w.flops_per_unit * w.units_per_step / kernel_s / 1e12
+        roof_unit = 'TFLOP/s'
+        del xa, xb
 
     # ---- end to end through the public API with host buffers
     w.e2e_setup()
@@ -717,7 +805,7 @@ def run_ours(args):
                     'api': 'lime_b200 public API, pinned host buffers, %d steps, wall clock incl. plan set-up' % ne2e},
             'gpu_launches': int(launches.item()),
             'clocks': clocks,
-            'roofline': {'bound': w.bound, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+            'roofline': {'bound': w.bound, 'achieved': achieved, 'peak': peak, 'unit': roof_unit,
                          'frac': achieved / peak, 'traffic': TRAFFIC.get((w.name, int(w.units_per_step))),
                          'kernel': w.kernel, 'peak_source': peak_src,
                          'algorithmic_bytes_per_unit': w.alg_bytes_per_unit,
@@ -756,6 +844,7 @@ def main():
     ap.add_argument('--workload', default='jc_lindblad', choices=sorted(WORKLOADS))
     ap.add_argument('--rk-steps', type=int, default=0, help='RK4 steps per launch (0 = workload default)')
     ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
+    ap.add_argument('--size', type=int, default=0, help='Hilbert dimension for lindblad_dense (0 = 256)')
     ap.add_argument('--depth', type=int, default=0, help='HEOM depth for heom_fmo (0 = 4)')
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded heom_fmo: fused peer-memory kernel or stage kernel + NCCL all-gather')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')

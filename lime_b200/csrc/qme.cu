@@ -735,6 +735,17 @@ void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
     a.eptr = p->deptr.as<int>(); a.eidx = p->deidx.as<int>(); a.eval = p->deval.as<cplx>();
 }
 
+// 64x64 register-tiled kernel from N = 96 up, 32x32 tiles below
+void launch_dense_stage(const QmeStageArgs& a, cudaStream_t st) {
+    if (a.N >= 96) {
+        dim3 grid(ceil_div(a.N, 64), ceil_div(a.N, 64), a.B);
+        qme_dense_stage64<<<grid, 256, 0, st>>>(a);
+    } else {
+        dim3 grid(ceil_div(a.N, 32), ceil_div(a.N, 32), a.B);
+        qme_dense_stage<<<grid, 256, 0, st>>>(a);
+    }
+}
+
 int run_dense_onchip(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, const cplx* coef,
                      cplx* obs, cplx* traj, int traj_every, cudaStream_t st, bool* handled) {
     const int N = p->N, NN = N * N, S = (int)p->X.size(), nd = (int)p->D.size();
@@ -821,7 +832,7 @@ int run_dense_stage(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, c
                 a.A[0] = yin; a.sA[0] = (long long)NN;
                 a.Bm[0] = p->dZh.as<cplx>() + (size_t)s * NN; a.sB[0] = (p->nb > 1) ? (long long)S * NN : 0;
                 a.mode = 0; a.out = tmp + (size_t)s * B * NN; a.sOut = (long long)NN; a.dt = dt;
-                qme_dense_stage<<<grid, 256, 0, st>>>(a);
+                launch_dense_stage(a, st);
                 p->launches++;
             }
             QmeStageArgs a;
@@ -835,7 +846,7 @@ int run_dense_stage(limeb200_qme_t p, cplx* rho, int B, double dt, int nsteps, c
                 a.Bm[2 + s] = tmp + (size_t)s * B * NN; a.sB[2 + s] = (long long)NN;
             }
             a.mode = stage + 1; a.rho = rho; a.acc = acc; a.ynext = yout; a.dt = dt;
-            qme_dense_stage<<<grid, 256, 0, st>>>(a);
+            launch_dense_stage(a, st);
             p->launches++;
         }
         if (obs && p->E > 0) {
@@ -951,7 +962,7 @@ int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B,
             a.A[0] = yin; a.sA[0] = (long long)NN;
             a.Bm[0] = p->dZh.as<cplx>() + (size_t)s * NN; a.sB[0] = (p->nb > 1) ? (long long)S * NN : 0;
             a.mode = 0; a.out = tmp + (size_t)s * B * NN; a.sOut = (long long)NN;
-            qme_dense_stage<<<grid, 256, 0, st>>>(a);
+            launch_dense_stage(a, st);
             p->launches++;
         }
         QmeStageArgs a;
@@ -964,7 +975,7 @@ int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B,
             a.Bm[2 + s] = tmp + (size_t)s * B * NN; a.sB[2 + s] = (long long)NN;
         }
         a.mode = 0; a.out = (cplx*)d_out; a.sOut = (long long)NN;
-        qme_dense_stage<<<grid, 256, 0, st>>>(a);
+        launch_dense_stage(a, st);
         p->launches++;
     } else {
         QmeEllArgs a;

@@ -307,6 +307,104 @@ qme_dense_stage(QmeStageArgs a) {
 }
 
 // obs[b][e] = sum_idx eT[e][idx] * rho[b][idx]; one CTA per (e, b)
+// Same contract as qme_dense_stage with a 64x64 output tile and a 4x4 register tile per thread (rows
+// ty + 16 r, columns tx + 16 c): per k step a warp issues 4 broadcast loads of A and 4 conflict-free loads of B
+// for 16 complex FMAs per thread, which moves the kernel from shared-memory bound to FP64-pipe bound.
+// Global -> shared copies are software-pipelined through registers (next k-tile loaded while the current one
+// is consumed).
+__global__ void __launch_bounds__(256, 2)
+qme_dense_stage64(QmeStageArgs a) {
+    constexpr int KT = 8;
+    __shared__ cplx As[2][KT][64];       // [k][row]   (transposed: row index fastest)
+    __shared__ cplx Bs[2][KT][64];       // [k][col]
+    const int N = a.N;
+    const int b = blockIdx.z;
+    const int ti = blockIdx.y * 64, tj = blockIdx.x * 64;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    cplx c[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) c[r][q] = cmake(0, 0);
+    // loader mapping: A tile 64 rows x KT cols (2 elements per thread), B tile KT rows x 64 cols (2 per thread)
+    const int la_r = threadIdx.x >> 2, la_c = (threadIdx.x & 3) * 2;      // A: row, first of 2 consecutive k
+    const int lb_r = threadIdx.x >> 5, lb_c = (threadIdx.x & 31) * 2;     // B: k row, first of 2 consecutive cols
+    const int nk = (N + KT - 1) / KT;
+    const int total = a.nprod * nk;
+    cplx ra[2], rb[2];
+    auto fetch = [&](int it) {
+        const int p = it / nk, k0 = (it - p * nk) * KT;
+        const cplx* Ap = a.A[p] + (size_t)b * a.sA[p];
+        const cplx* Bp = a.Bm[p] + (size_t)b * a.sB[p];
+        const int gi = ti + la_r;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int gk = k0 + la_c + u;
+            ra[u] = (gi < N && gk < N) ? Ap[(size_t)gi * N + gk] : cmake(0, 0);
+            const int gkb = k0 + lb_r, gj = tj + lb_c + u;
+            rb[u] = (gkb < N && gj < N) ? Bp[(size_t)gkb * N + gj] : cmake(0, 0);
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            As[buf][la_c + u][la_r] = ra[u];
+            Bs[buf][lb_r][lb_c + u] = rb[u];
+        }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+        for (int q = 0; q < KT; ++q) {
+            cplx av[4], bv[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { av[r] = As[buf][q][ty + 16 * r]; bv[r] = Bs[buf][q][tx + 16 * r]; }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) cfma(c[r][cc], av[r], bv[cc]);
+        }
+        if (it + 1 < total) stash(buf ^ 1);
+        __syncthreads();
+    }
+    const double dt = a.dt, hdt = 0.5 * a.dt;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int gi = ti + ty + 16 * r, gj = tj + tx + 16 * cc;
+            if (gi >= N || gj >= N) continue;
+            const size_t idx = (size_t)gi * N + gj;
+            const cplx k = c[r][cc];
+            if (a.mode == 0) {
+                a.out[(size_t)b * a.sOut + idx] = k;
+            } else {
+                const size_t o = (size_t)b * N * N + idx;
+                cplx rr = a.rho[o];
+                if (a.mode == 1) {
+                    a.acc[o] = k;
+                    a.ynext[o] = cmake(fma(hdt, k.x, rr.x), fma(hdt, k.y, rr.y));
+                } else if (a.mode == 2) {
+                    cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                    a.ynext[o] = cmake(fma(hdt, k.x, rr.x), fma(hdt, k.y, rr.y));
+                } else if (a.mode == 3) {
+                    cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                    a.ynext[o] = cmake(fma(dt, k.x, rr.x), fma(dt, k.y, rr.y));
+                } else {
+                    const cplx tot = cadd(a.acc[o], k);
+                    rr.x += tot.x / 6.0 * dt;
+                    rr.y += tot.y / 6.0 * dt;
+                    a.rho[o] = rr;
+                    a.ynext[o] = rr;
+                }
+            }
+        }
+}
+
 __global__ void __launch_bounds__(256)
 qme_trace_obs(const cplx* __restrict__ eT, const cplx* __restrict__ rho, cplx* __restrict__ obs,
               int NN, int E, long long obs_stride_b) {

@@ -446,3 +446,15 @@ def test_redfield_two_level_batch_thread_per_vector_kernel(cuda):
         o, rl = lo.redfield(R, batch[b], evecs=evecs, Nt=40, dt=dt, e_ops=e_ops)
         assert relerr(obs[:, b], o) <= TOL
         assert relerr(evecs @ out[b] @ evecs.conj().T, rl[-1]) <= TOL
+
+
+def test_lindblad_dense_stage_64_tile_ragged(cuda):
+    """dense stage-wise path with the 64x64 register-tiled kernel at a size that is no multiple of the tile"""
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=101, M=2, E=1, seed=77)
+    H = H / 10.0
+    o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=6, dt=0.01)
+    plan = oqs._lindblad_plan(H, c_ops, e_ops, path=2)
+    rf, ob, _ = plan.run(rho0, 0.01, 6)
+    assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+    assert relerr(plan.rhs(rho0), lo.liouvillian(rho0, H, c_ops)) <= 1e-12
