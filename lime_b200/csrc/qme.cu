@@ -7,6 +7,7 @@
 #include "qme_cluster.cuh"
 #include "qme_band.cuh"
 #include <algorithm>
+#include <cstdlib>
 #include <memory>
 
 namespace {
@@ -735,9 +736,14 @@ void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
     a.eptr = p->deptr.as<int>(); a.eidx = p->deidx.as<int>(); a.eval = p->deval.as<cplx>();
 }
 
-// 64x64 register-tiled kernel from N = 96 up, 32x32 tiles below
+// N >= 96: FP64 tensor-core (DMMA) kernel, or the 64x64 register-tiled DFMA kernel when
+// LIMEB200_DENSE_NO_DMMA is set; 32x32 tiles below
 void launch_dense_stage(const QmeStageArgs& a, cudaStream_t st) {
-    if (a.N >= 96) {
+    static const bool no_dmma = getenv("LIMEB200_DENSE_NO_DMMA") != nullptr;
+    if (a.N >= 96 && !no_dmma) {
+        dim3 grid(ceil_div(a.N, 64), ceil_div(a.N, 64), a.B);
+        qme_dense_stage_dmma<<<grid, 128, 0, st>>>(a);
+    } else if (a.N >= 96) {
         dim3 grid(ceil_div(a.N, 64), ceil_div(a.N, 64), a.B);
         qme_dense_stage64<<<grid, 256, 0, st>>>(a);
     } else {

@@ -405,6 +405,125 @@ qme_dense_stage64(QmeStageArgs a) {
         }
 }
 
+// FP64 tensor-core variant (DMMA, mma.sync m8n8k4): same contract as qme_dense_stage.
+// CTA tile 64x64 complex, 4 warps, each warp a 32x32 complex sub-tile = 4x4 MMA tiles of 8x8, four real
+// MMAs per complex tile and k-step (C_re += A_re B_re + (-A_im) B_im, C_im += A_re B_im + A_im B_re).
+// Operand tiles are stored planar (re / im) in shared memory, k-major, so that the m8n8k4 fragments
+// (A: row = lane/4, k = lane%4; B: k = lane%4, col = lane/4) are single 8-byte loads.
+__device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+#define QDM_KT 8
+#define QDM_LD 72        // 64 + 8 doubles of padding per k row
+__global__ void __launch_bounds__(128, 2)
+qme_dense_stage_dmma(QmeStageArgs a) {
+    __shared__ double Ar[2][QDM_KT][QDM_LD], Ai[2][QDM_KT][QDM_LD];     // [buf][k][row]
+    __shared__ double Br[2][QDM_KT][QDM_LD], Bi[2][QDM_KT][QDM_LD];     // [buf][k][col]
+    const int N = a.N;
+    const int b = blockIdx.z;
+    const int ti = blockIdx.y * 64, tj = blockIdx.x * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wr = (warp >> 1) * 32, wc = (warp & 1) * 32;              // warp sub-tile origin
+    const int fr = lane >> 2, fk = lane & 3;                            // fragment row/col and k index
+    double cr[4][4][2], ci[4][4][2];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { cr[r][c][0] = cr[r][c][1] = 0.0; ci[r][c][0] = ci[r][c][1] = 0.0; }
+    // loaders: A tile 64 rows x 8 k (4 elements per thread), B tile 8 k x 64 cols (4 per thread)
+    const int la_r = threadIdx.x >> 1, la_k = (threadIdx.x & 1) * 4;     // A: row, 4 consecutive k
+    const int lb_k = threadIdx.x >> 4, lb_c = (threadIdx.x & 15) * 4;    // B: k row, 4 consecutive cols
+    const int nk = (N + QDM_KT - 1) / QDM_KT;
+    const int total = a.nprod * nk;
+    cplx ra[4], rb[4];
+    auto fetch = [&](int it) {
+        const int p = it / nk, k0 = (it - p * nk) * QDM_KT;
+        const cplx* Ap = a.A[p] + (size_t)b * a.sA[p];
+        const cplx* Bp = a.Bm[p] + (size_t)b * a.sB[p];
+        const int gi = ti + la_r, gkb = k0 + lb_k;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gk = k0 + la_k + u, gj = tj + lb_c + u;
+            ra[u] = (gi < N && gk < N) ? Ap[(size_t)gi * N + gk] : cmake(0, 0);
+            rb[u] = (gkb < N && gj < N) ? Bp[(size_t)gkb * N + gj] : cmake(0, 0);
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            Ar[buf][la_k + u][la_r] = ra[u].x; Ai[buf][la_k + u][la_r] = ra[u].y;
+            Br[buf][lb_k][lb_c + u] = rb[u].x; Bi[buf][lb_k][lb_c + u] = rb[u].y;
+        }
+    };
+    fetch(0);
+    stash(0);
+    __syncthreads();
+    for (int it = 0; it < total; ++it) {
+        const int buf = it & 1;
+        if (it + 1 < total) fetch(it + 1);
+#pragma unroll
+        for (int kb = 0; kb < QDM_KT / 4; ++kb) {
+            double are[4], aim[4], ain[4], bre[4], bim[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                are[t] = Ar[buf][kb * 4 + fk][wr + t * 8 + fr];
+                aim[t] = Ai[buf][kb * 4 + fk][wr + t * 8 + fr];
+                ain[t] = -aim[t];
+                bre[t] = Br[buf][kb * 4 + fk][wc + t * 8 + fr];
+                bim[t] = Bi[buf][kb * 4 + fk][wc + t * 8 + fr];
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    dmma8x8x4(cr[r][c][0], cr[r][c][1], are[r], bre[c]);
+                    dmma8x8x4(cr[r][c][0], cr[r][c][1], ain[r], bim[c]);
+                    dmma8x8x4(ci[r][c][0], ci[r][c][1], are[r], bim[c]);
+                    dmma8x8x4(ci[r][c][0], ci[r][c][1], aim[r], bre[c]);
+                }
+        }
+        if (it + 1 < total) stash(buf ^ 1);
+        __syncthreads();
+    }
+    // epilogue: C fragment element (row = lane/4, cols = 2*(lane%4) + {0,1}) of every 8x8 tile
+    const double dt = a.dt, hdt = 0.5 * a.dt;
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gi = ti + wr + r * 8 + fr, gj = tj + wc + c * 8 + fk * 2 + e;
+                if (gi >= N || gj >= N) continue;
+                const size_t idx = (size_t)gi * N + gj;
+                const cplx k = cmake(cr[r][c][e], ci[r][c][e]);
+                if (a.mode == 0) {
+                    a.out[(size_t)b * a.sOut + idx] = k;
+                } else {
+                    const size_t o = (size_t)b * N * N + idx;
+                    cplx rr = a.rho[o];
+                    if (a.mode == 1) {
+                        a.acc[o] = k;
+                        a.ynext[o] = cmake(fma(hdt, k.x, rr.x), fma(hdt, k.y, rr.y));
+                    } else if (a.mode == 2) {
+                        cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                        a.ynext[o] = cmake(fma(hdt, k.x, rr.x), fma(hdt, k.y, rr.y));
+                    } else if (a.mode == 3) {
+                        cplx ac = a.acc[o]; rfma(ac, 2.0, k); a.acc[o] = ac;
+                        a.ynext[o] = cmake(fma(dt, k.x, rr.x), fma(dt, k.y, rr.y));
+                    } else {
+                        const cplx tot = cadd(a.acc[o], k);
+                        rr.x += tot.x / 6.0 * dt;
+                        rr.y += tot.y / 6.0 * dt;
+                        a.rho[o] = rr;
+                        a.ynext[o] = rr;
+                    }
+                }
+            }
+}
+
 __global__ void __launch_bounds__(256)
 qme_trace_obs(const cplx* __restrict__ eT, const cplx* __restrict__ rho, cplx* __restrict__ obs,
               int NN, int E, long long obs_stride_b) {
