@@ -1319,7 +1319,10 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         a.ado = (cplx*)d_ado; a.eT = (const cplx*)d_eT; a.obs = E > 0 ? (cplx*)d_obs : nullptr; a.traj = (cplx*)d_traj;
         a.dt = dt;
         a.T = 0;
-        if (p->diagq && p->n == 2 && p->nmodes <= 4 && p->nhe <= 576 && !getenv("LIMEB200_HEOM_NO_ADO_KERNEL")) {
+        // (measured on config 3: below ~2 hierarchies per SM the thread-per-element kernel has 4x the parallelism and is
+        //  1.8x faster -- B = 1: 3.3e7 vs 1.8e7 ADO-steps/s; from B = 512 up the thread-per-ADO kernel wins)
+        if (p->diagq && p->n == 2 && p->nmodes <= 4 && p->nhe <= 576 && B >= 2 * p->sm_count &&
+            !getenv("LIMEB200_HEOM_NO_ADO_KERNEL")) {
             // one thread per ADO, HP hierarchies per CTA
             int HP = std::max(1, std::min(576 / (int)p->nhe, (int)((100 * 1024) / ((size_t)2 * p->nhe * nn * 16))));
             HP = std::min(HP, std::max(1, ceil_div(B, 2 * p->sm_count)));

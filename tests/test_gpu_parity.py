@@ -458,3 +458,44 @@ def test_lindblad_dense_stage_64_tile_ragged(cuda):
     rf, ob, _ = plan.run(rho0, 0.01, 6)
     assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
     assert relerr(plan.rhs(rho0), lo.liouvillian(rho0, H, c_ops)) <= 1e-12
+
+
+def test_heom_config3_long_run(cuda):
+    """config 3 (spin-boson, K = 2, depth 12, dt = 0.01): 4000 RK4 steps of the single hierarchy stay within
+    1e-10 of the oracle (thread-per-ADO kernel, one launch)"""
+    from lime_b200.heom.heom import HEOM
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=12)
+    h = HEOM(H, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    res = h.evolve(rho0, 0.01, 4000, e_ops=[sz], store_states=False)
+    st = h.states.astype(np.int64)
+    ado_o, obs_o, _ = lo.heom_rk4(h.initial(rho0), H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                  h.up.astype(np.int64), 0.01, 4000, e_ops=[sz])
+    assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
+    assert abs(np.trace(res.ado[0]) - 1) < 1e-11
+
+
+def test_heom_parameter_batch_thread_per_ado_kernel(cuda):
+    """batch large enough (>= 2 hierarchies per SM) to take the thread-per-ADO kernel; per-hierarchy bath parameters"""
+    from lime_b200 import engine
+    from lime_b200.heom.heom import _calc_matsubara_params
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=6)
+    states, dn, up = engine.heom_tables([depth + 1] * K, depth)
+    B = 600
+    lams = np.linspace(0.05, 0.4, B)
+    Ts = np.linspace(0.6, 2.0, B)
+    cs, nus = [], []
+    for lam_b, T_b in zip(lams, Ts):
+        c, nu = _calc_matsubara_params(K, lam_b, gam, T_b)
+        cs.append(c)
+        nus.append(nu)
+    plan = engine.HeomPlan(H, sz, [0] * K, np.array(cs), np.array(nus), states, dn, up)
+    ado0 = np.zeros((B, states.shape[0], 2, 2), dtype=complex)
+    ado0[:, 0] = rho0
+    sx = np.array([[0, 1.], [1, 0]])
+    out, obs, traj = plan.run(ado0, 0.01, 30, e_ops=[sz, sx], traj_every=10)
+    assert plan.path == 1
+    for b in (0, 299, 599):
+        ado_o, obs_o, tr_o = lo.heom_rk4(ado0[b], H, sz[None], [0] * K, cs[b], nus[b], states.astype(np.int64),
+                                         dn.astype(np.int64), up.astype(np.int64), 0.01, 30, e_ops=[sz, sx], store=True)
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+        assert relerr(traj[:, b], np.array([tr_o[9], tr_o[19], tr_o[29]])) <= TOL
