@@ -358,6 +358,92 @@ class LindbladDense:
         return time.perf_counter() - t
 
 
+class LiouvilleEig:
+    """two-time correlation function <A(t)B(t+tau)C(t)> from the eigen-decomposition of the
+    Liouvillian (lime/superoperator.py:703-754).  The decomposition (host LAPACK, as in lime) is set-up; a step is
+    everything after it: coeff = lhs @ rhs (k^3), cor = tmp1.T @ coeff @ tmp2 on the FP64 tensor cores."""
+    name = 'liouville_eig'
+    metric = 'two_time_correlation_points_per_s'
+    unit = 'points/s'
+    dtype = 'complex128 (f64 arithmetic)'
+    scaling = 'weak'
+    bound = 'tensor'
+
+    def __init__(self, args, rank, world, need_gpu=True):
+        self.N = args.size or 16
+        self.nt = args.batch or 256
+        N = self.N
+        rng = np.random.default_rng(5)
+        a = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        self.H = (a + a.conj().T) / 2
+        self.c_ops = [0.3 * (rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))) / np.sqrt(N)]
+        self.ops = [rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N)) for _ in range(3)]
+        x = rng.standard_normal((N, N)) + 1j * rng.standard_normal((N, N))
+        rho = x @ x.conj().T
+        self.rho0 = rho / np.trace(rho)
+        self.tl = np.linspace(0, 2.0, self.nt)
+        self.taul = np.linspace(0, 2.0, self.nt)
+        k = N * N
+        self.flops_per_unit = 8.0 * (k ** 3 + self.nt * k * k + self.nt * self.nt * k) / (self.nt * self.nt)
+        self.alg_bytes_per_unit = 16
+        self.units_per_step = self.nt * self.nt
+        self.launches = 0
+        self.kernel = 'qme_dense_stage_dmma (limeb200_zgemm)'
+        if need_gpu:
+            import torch
+            from lime_b200.superoperator import Lindblad_solver, left, right, operator_to_vector
+            from lime_b200 import _dev
+            self.torch = torch
+            self.solver = Lindblad_solver(self.H, self.c_ops)
+            self.solver.eigenstates()
+            s = self.solver
+            a_, b_, c_ = self.ops
+            alpha = (np.conj(s.idv) @ left(b_).dot(s.right_eigvecs)) / s.norm
+            beta = (s.left_eigvecs.conj().T @ operator_to_vector(self.rho0)) / s.norm
+            X = right(a_).dot(left(c_).dot(s.right_eigvecs))
+            self.d = [_dev.to_dev(np.ascontiguousarray(m)) for m in (
+                (s.left_eigvecs * np.conj(alpha)[None, :]).conj().T, np.asarray(X) * beta[None, :],
+                np.exp(np.outer(self.taul, s.eigvals)), np.exp(np.outer(s.eigvals, self.tl)))]
+
+    def config(self):
+        return {'workload': 'liouville_eig: <A(t)B(t+tau)C(t)> on a %d x %d (tau, t) grid from the eigen-decomposition of a '
+                            'random N=%d Lindblad generator (k = N^2 = %d); the decomposition itself (host LAPACK) is set-up'
+                            % (self.nt, self.nt, self.N, self.N ** 2),
+                'l2_policy': 'L2 flushed between bench steps', 'sharding': 'replicas only'}
+
+    def step(self):
+        from lime_b200 import engine
+        lhs, rhs, t1, t2 = self.d
+        coeff = engine.zgemm(lhs, rhs)
+        self.out = engine.zgemm(engine.zgemm(t1, coeff), t2)
+        self.launches += 3
+
+    def check(self):
+        return {}
+
+    def e2e_setup(self):
+        pass
+
+    def e2e_step(self):
+        out = self.solver.correlation_3op_2t(self.rho0, self.ops, self.tl, self.taul)
+        return 4 * self.N ** 4 * 16, out.nbytes
+
+    def cpu_point(self, idx, variant, nsteps):
+        """lime's O(k^2) Python loop is hours at k = 256; the CPU sample is the same function at N = 4 (k = 16),
+        reported per grid point of ITS grid and therefore only indicative"""
+        sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+        import lime_oracle as lo
+        n = 4
+        o = lo.SuperLindblad(self.H[:n, :n], [c[:n, :n] for c in self.c_ops])
+        o.eigenstates()
+        ops = [x[:n, :n] for x in self.ops]
+        r = self.rho0[:n, :n] / np.trace(self.rho0[:n, :n])
+        t = time.perf_counter()
+        for _ in range(nsteps):
+            o.correlation_3op_2t(r, ops, self.tl, self.taul)
+        return time.perf_counter() - t
+
+
 class HeomBase:
     metric = 'heom_ado_steps_per_s'
     unit = 'ADO-steps/s'
@@ -619,9 +705,9 @@ class Sos2DES:
         return time.perf_counter() - t
 
 
-WORKLOADS = {c.name: c for c in (JCLindblad, HeomFMO, HeomSpinBoson, Sos2DES, RedfieldBatch, LindbladDense)}
+WORKLOADS = {c.name: c for c in (JCLindblad, HeomFMO, HeomSpinBoson, Sos2DES, RedfieldBatch, LindbladDense, LiouvilleEig)}
 # units one cpu_point "step" stands for
-CPU_UNITS = {'jc_lindblad': lambda w: 1, 'lindblad_dense': lambda w: 1, 'redfield_batch': lambda w: 1, 'heom_sb': lambda w: 91, 'heom_fmo': lambda w: None,
+CPU_UNITS = {'jc_lindblad': lambda w: 1, 'liouville_eig': lambda w: w.nt * w.nt, 'lindblad_dense': lambda w: 1, 'redfield_batch': lambda w: 1, 'heom_sb': lambda w: 91, 'heom_fmo': lambda w: None,
              'sos_2des': lambda w: w.n * w.n}
 
 

@@ -99,6 +99,13 @@ int limeb200_qme_rhs(limeb200_qme_t plan, const double* d_in, double* d_out, int
 /* number of kernels the last run launched (bench.py's gpu_launches) */
 long long limeb200_qme_last_launches(limeb200_qme_t plan);
 
+/* plain batched complex GEMM on the FP64 tensor cores (DMMA): C[b] = A[b] * B[b], row-major,
+ * A [M][K], B [K][N], C [M][N]; strides in complex elements, 0 = shared by the batch.
+ * replaces the dense products of the Liouvillian eigen-decomposition solver,
+ * lime/superoperator.py:525-560 (evolve) and :703-754 (correlation_3op_2t: tmp1.T @ coeff @ tmp2) */
+int limeb200_zgemm(const double* d_A, const double* d_B, double* d_C, int M, int N, int K, int batch,
+                   long long sA, long long sB, long long sC, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Liouville-space linear ODE  dv/dt = R v,  R an arbitrary D x D CSR matrix (DEVICE arrays)
  * replaces: rhs + rk4 loop of _redfield  lime/oqs.py:453-472 (R from redfield_tensor),

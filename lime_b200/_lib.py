@@ -33,6 +33,7 @@ SIGNATURES = {
     'limeb200_qme_run': (c_int, [c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
     'limeb200_qme_rhs': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     'limeb200_qme_last_launches': (c_ll, [c_vp]),
+    'limeb200_zgemm': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_vp]),
     'limeb200_liouville_rk4_csr': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int,
                                            c_dbl, c_int, c_vp]),
     'limeb200_heom_count_states': (c_ll, [c_vp, c_int, c_int]),

@@ -1006,4 +1006,23 @@ int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B,
     return LB_OK;
 }
 
+/* plain batched complex GEMM on the FP64 tensor cores: C[b] = A[b] * B[b], row-major, A [M][K], B [K][N], C [M][N];
+ * strides in complex elements (0 = operand shared by the batch).  Used by the Liouvillian eigen-decomposition
+ * correlation functions (lime/superoperator.py:703-754: tmp1.T @ coeff @ tmp2). */
+int limeb200_zgemm(const double* d_A, const double* d_B, double* d_C, int M, int N, int K, int batch,
+                   long long sA, long long sB, long long sC, void* stream) {
+    LB_REQUIRE(d_A && d_B && d_C, "null argument");
+    LB_REQUIRE(M >= 1 && N >= 1 && K >= 1 && batch >= 1 && batch <= 65535, "bad sizes");
+    QmeStageArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N; a.B = batch; a.nprod = 1; a.Mr = M; a.Nc = N; a.Kd = K;
+    a.A[0] = (const cplx*)d_A; a.sA[0] = sA;
+    a.Bm[0] = (const cplx*)d_B; a.sB[0] = sB;
+    a.mode = 0; a.out = (cplx*)d_C; a.sOut = sC;
+    dim3 grid(ceil_div(N, 64), ceil_div(M, 64), batch);
+    qme_dense_stage_dmma<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
 }  // extern "C"

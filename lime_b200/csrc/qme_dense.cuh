@@ -223,6 +223,7 @@ qme_dense_onchip(QmeDenseArgs a) {
 #define QME_MAXPROD 18
 struct QmeStageArgs {
     int N, B, nprod;
+    int Mr, Nc, Kd;                  // DMMA kernel: products are [Mr x Kd] * [Kd x Nc] (0 = N: the square stage case)
     const cplx* A[QME_MAXPROD];      // left factors
     const cplx* Bm[QME_MAXPROD];     // right factors
     long long sA[QME_MAXPROD];       // batch strides (elements); 0 = shared
@@ -422,6 +423,7 @@ qme_dense_stage_dmma(QmeStageArgs a) {
     __shared__ double Ar[2][QDM_KT][QDM_LD], Ai[2][QDM_KT][QDM_LD];     // [buf][k][row]
     __shared__ double Br[2][QDM_KT][QDM_LD], Bi[2][QDM_KT][QDM_LD];     // [buf][k][col]
     const int N = a.N;
+    const int Mr = a.Mr ? a.Mr : N, Nc = a.Nc ? a.Nc : N, Kd = a.Kd ? a.Kd : N;
     const int b = blockIdx.z;
     const int ti = blockIdx.y * 64, tj = blockIdx.x * 64;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -435,7 +437,7 @@ qme_dense_stage_dmma(QmeStageArgs a) {
     // loaders: A tile 64 rows x 8 k (4 elements per thread), B tile 8 k x 64 cols (4 per thread)
     const int la_r = threadIdx.x >> 1, la_k = (threadIdx.x & 1) * 4;     // A: row, 4 consecutive k
     const int lb_k = threadIdx.x >> 4, lb_c = (threadIdx.x & 15) * 4;    // B: k row, 4 consecutive cols
-    const int nk = (N + QDM_KT - 1) / QDM_KT;
+    const int nk = (Kd + QDM_KT - 1) / QDM_KT;
     const int total = a.nprod * nk;
     cplx ra[4], rb[4];
     auto fetch = [&](int it) {
@@ -446,8 +448,8 @@ qme_dense_stage_dmma(QmeStageArgs a) {
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const int gk = k0 + la_k + u, gj = tj + lb_c + u;
-            ra[u] = (gi < N && gk < N) ? Ap[(size_t)gi * N + gk] : cmake(0, 0);
-            rb[u] = (gkb < N && gj < N) ? Bp[(size_t)gkb * N + gj] : cmake(0, 0);
+            ra[u] = (gi < Mr && gk < Kd) ? Ap[(size_t)gi * Kd + gk] : cmake(0, 0);
+            rb[u] = (gkb < Kd && gj < Nc) ? Bp[(size_t)gkb * Nc + gj] : cmake(0, 0);
         }
     };
     auto stash = [&](int buf) {
@@ -496,13 +498,13 @@ qme_dense_stage_dmma(QmeStageArgs a) {
 #pragma unroll
             for (int e = 0; e < 2; ++e) {
                 const int gi = ti + wr + r * 8 + fr, gj = tj + wc + c * 8 + fk * 2 + e;
-                if (gi >= N || gj >= N) continue;
-                const size_t idx = (size_t)gi * N + gj;
+                if (gi >= Mr || gj >= Nc) continue;
+                const size_t idx = (size_t)gi * Nc + gj;
                 const cplx k = cmake(cr[r][c][e], ci[r][c][e]);
                 if (a.mode == 0) {
                     a.out[(size_t)b * a.sOut + idx] = k;
                 } else {
-                    const size_t o = (size_t)b * N * N + idx;
+                    const size_t o = (size_t)b * Mr * Nc + idx;
                     cplx rr = a.rho[o];
                     if (a.mode == 1) {
                         a.acc[o] = k;

@@ -214,6 +214,27 @@ def liouville_rk4(R, v0, dt, nsteps, e_rows=None, traj_every=0, dev=None):
     return out, obs, traj
 
 
+def zgemm(A, Bm):
+    """C = A @ B on the FP64 tensor cores.  A [M,K] or [b,M,K], B [K,N] or [b,K,N]: numpy arrays (uploaded) or
+    device tensors; returns a device tensor [M,N] / [b,M,N]."""
+    dev = _dev.device()
+    ta = A if isinstance(A, torch.Tensor) else _dev.to_dev(np.asarray(A), dev=dev)
+    tb = Bm if isinstance(Bm, torch.Tensor) else _dev.to_dev(np.asarray(Bm), dev=dev)
+    assert ta.dtype == torch.complex128 and tb.dtype == torch.complex128
+    ta, tb = ta.contiguous(), tb.contiguous()
+    batch = max(ta.shape[0] if ta.dim() == 3 else 1, tb.shape[0] if tb.dim() == 3 else 1)
+    M, K = ta.shape[-2], ta.shape[-1]
+    K2, N = tb.shape[-2], tb.shape[-1]
+    if K != K2:
+        raise ValueError('zgemm: inner dimensions %d and %d differ' % (K, K2))
+    sA = M * K if ta.dim() == 3 else 0
+    sB = K * N if tb.dim() == 3 else 0
+    out = _dev.empty((batch, M, N), dev=dev)
+    check(lib().limeb200_zgemm(_dev.ptr(ta), _dev.ptr(tb), _dev.ptr(out), M, N, K, batch, sA, sB, M * N,
+                               _dev.stream_ptr()))
+    return out if (ta.dim() == 3 or tb.dim() == 3) else out[0]
+
+
 class LiouvillePlan:
     """device-resident form of liouville_rk4: R (CSR) and the observable rows are uploaded once;
     run_device advances a device batch v [B, D] in place"""

@@ -252,6 +252,30 @@ def main():
     note('sos', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'sos.npz'), w1=w1, w3=w3, w2=w2, w1b=w1b, t2=t2, **g)
 
+    # ---- Liouvillian eigen-decomposition solver, lime/superoperator.py:456-773
+    import lime.superoperator as lsup
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=3, M=2, E=2, seed=61)
+    ref = lsup.Lindblad_solver(H, c_ops)
+    ref.eigenstates()
+    osv = lo.SuperLindblad(H, c_ops)
+    osv.eigenstates()
+    tl = np.linspace(0, 2.0, 7)
+    taul = np.linspace(0, 1.5, 5)
+    wl = np.linspace(-2, 2, 6)
+    A3, B3, C3 = cases.rand_cplx(3, 71), cases.rand_cplx(3, 72), cases.rand_cplx(3, 73)
+    g = {'evolve': ref.evolve(rho0, tl, e_ops).observables,
+         'c2_1t': ref.correlation_2op_1t(rho0, [A3, B3], tl), 'c2_1w': ref.correlation_2op_1w(rho0, [A3, B3], wl),
+         'c3_1t': ref.correlation_3op_1t(rho0, [A3, B3, C3], tl), 'c3_1w': ref.correlation_3op_1w(rho0, [A3, B3, C3], wl),
+         'c3_2t': ref.correlation_3op_2t(rho0, [A3, B3, C3], tl, taul),
+         'c4_2t': ref.correlation_4op_2t(rho0, [A3, B3, C3, A3], tl, taul)}
+    o = {'evolve': osv.evolve(rho0, tl, e_ops),
+         'c2_1t': osv.correlation_2op_1t(rho0, [A3, B3], tl), 'c2_1w': osv.correlation_2op_1w(rho0, [A3, B3], wl),
+         'c3_1t': osv.correlation_3op_1t(rho0, [A3, B3, C3], tl), 'c3_1w': osv.correlation_3op_1w(rho0, [A3, B3, C3], wl),
+         'c3_2t': osv.correlation_3op_2t(rho0, [A3, B3, C3], tl, taul),
+         'c4_2t': osv.correlation_4op_2t(rho0, [A3, B3, C3, A3], tl, taul)}
+    note('super_lindblad', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'super_lindblad.npz'), tl=tl, taul=taul, wl=wl, A=A3, B=B3, C=C3, **g)
+
     # ---- time-domain response functions, lime/signal/2DES.py:37-247 (the module cannot be imported:
     # it runs undefined names at :249-263; the function definitions themselves are exec'd verbatim here)
     src = open('/root/reference/lime/signal/2DES.py').read().split('\n')

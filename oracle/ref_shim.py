@@ -12,9 +12,9 @@ The shim does not alter any arithmetic of the reference:
     are replaced by permissive stubs (lime/fft.py:6, lime/mol.py:25,
     lime/signal/sos.py:10,14, lime/superoperator.py:16, lime/style.py:1-7);
   * opt_einsum.contract -> numpy.einsum (lime/oqs.py:23,219,366);
-  * lime.mol.Result.__init__ gets the defaults nout=1, t0=0.0 because
-    lime/mol.py:92 does arithmetic on None for every density-matrix solver
-    (lime/oqs.py:449,1670,1780).
+  * lime.mol.Result.__init__ gets the defaults nout=1, t0=0.0 (and dt from `times` when only
+    `times` is given, lime/superoperator.py:527) because lime/mol.py:92 does arithmetic on None
+    for every density-matrix solver (lime/oqs.py:449,1670,1780).
 """
 import sys
 import types
@@ -99,6 +99,8 @@ def load():
                 t0 = 0.0
             if Nt is None and times is not None:
                 Nt = len(times)
+            if dt is None and times is not None:     # superoperator.Lindblad_solver.evolve: Result(times=tlist)
+                dt = (times[1] - times[0]) if len(times) > 1 else 0.0
             _orig_init(self, description=description, psi0=psi0, rho0=rho0,
                        dt=dt, Nt=Nt, times=times, t0=t0, nout=nout)
 

@@ -499,3 +499,45 @@ def test_heom_parameter_batch_thread_per_ado_kernel(cuda):
                                          dn.astype(np.int64), up.astype(np.int64), 0.01, 30, e_ops=[sz, sx], store=True)
         assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
         assert relerr(traj[:, b], np.array([tr_o[9], tr_o[19], tr_o[29]])) <= TOL
+
+
+def test_liouvillian_eigen_solver(cuda):
+    """superoperator.Lindblad_solver (lime/superoperator.py:456-773).  Frozen reference outputs
+    (another host may round the LAPACK eigenvectors differently: 1e-8) and the oracle on this host (1e-10);
+    the device part is the DMMA ZGEMM"""
+    from lime_b200.superoperator import Lindblad_solver
+    from lime_b200 import engine
+    g = golden('super_lindblad')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=3, M=2, E=2, seed=61)
+    A, B, C = g['A'], g['B'], g['C']
+    tl, taul, wl = g['tl'], g['taul'], g['wl']
+    s = Lindblad_solver(H, c_ops)
+    with pytest.raises(TypeError):
+        s.evolve(rho0, tl, e_ops)
+    s.eigenstates()
+    o = lo.SuperLindblad(H, c_ops)
+    o.eigenstates()
+    got = {'evolve': s.evolve(rho0, tl, e_ops).observables,
+           'c2_1t': s.correlation_2op_1t(rho0, [A, B], tl), 'c2_1w': s.correlation_2op_1w(rho0, [A, B], wl),
+           'c3_1t': s.correlation_3op_1t(rho0, [A, B, C], tl), 'c3_1w': s.correlation_3op_1w(rho0, [A, B, C], wl),
+           'c3_2t': s.correlation_3op_2t(rho0, [A, B, C], tl, taul),
+           'c4_2t': s.correlation_4op_2t(rho0, [A, B, C, A], tl, taul)}
+    want = {'evolve': o.evolve(rho0, tl, e_ops),
+            'c2_1t': o.correlation_2op_1t(rho0, [A, B], tl), 'c2_1w': o.correlation_2op_1w(rho0, [A, B], wl),
+            'c3_1t': o.correlation_3op_1t(rho0, [A, B, C], tl), 'c3_1w': o.correlation_3op_1w(rho0, [A, B, C], wl),
+            'c3_2t': o.correlation_3op_2t(rho0, [A, B, C], tl, taul),
+            'c4_2t': o.correlation_4op_2t(rho0, [A, B, C, A], tl, taul)}
+    for k in got:
+        assert got[k].shape == g[k].shape, k
+        assert relerr(got[k], want[k]) <= TOL, k
+        assert relerr(got[k], g[k]) <= 1e-8, k
+    assert got['c3_2t'].shape == (len(taul), len(tl))
+    with pytest.raises(ValueError):
+        s.correlation_4op_2t(rho0, [A, B, C], tl, taul)
+    # the GEMM primitive itself, ragged and batched shapes
+    rng = np.random.default_rng(3)
+    for (m, n, k, b) in [(1, 1, 1, 1), (70, 33, 129, 1), (64, 64, 64, 3), (5, 200, 17, 2)]:
+        a = rng.standard_normal((b, m, k)) + 1j * rng.standard_normal((b, m, k))
+        bb = rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n))
+        c = engine.zgemm(a, bb).cpu().numpy()
+        assert relerr(c, a @ bb) <= 1e-13

@@ -195,3 +195,17 @@ def test_time_domain_2des_oracle_matches_reference_functions():
     assert np.array_equal(lo.td_ESA(E, gamma, dip, g_idx, e_idx, f_idx, t1, tw, t3), g['ESA'])
     assert np.array_equal(lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1, tw, t3), g['GSB'])
     assert np.array_equal(lo.td_SE(E, gamma, dip, g_idx, e_idx, t1, tw, t3), g['SE'])
+
+
+def test_liouvillian_eigen_solver_oracle_matches_reference():
+    """tests/golden/super_lindblad.npz = outputs of lime.superoperator.Lindblad_solver itself (same host at
+    generation time: bit-identical there; another host's LAPACK may round the eigenvectors differently)"""
+    g = golden('super_lindblad')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=3, M=2, E=2, seed=61)
+    o = lo.SuperLindblad(H, c_ops)
+    o.eigenstates()
+    A, B, C = g['A'], g['B'], g['C']
+    assert relerr(o.evolve(rho0, g['tl'], e_ops), g['evolve']) <= 1e-9
+    assert relerr(o.correlation_2op_1t(rho0, [A, B], g['tl']), g['c2_1t']) <= 1e-9
+    assert relerr(o.correlation_3op_1w(rho0, [A, B, C], g['wl']), g['c3_1w']) <= 1e-9
+    assert relerr(o.correlation_3op_2t(rho0, [A, B, C], g['tl'], g['taul']), g['c3_2t']) <= 1e-9
