@@ -27,3 +27,100 @@ class Result:
 
     def expect(self):
         return self.observables
+
+
+# ---------------------------------------------------------------------------------------
+# wave-function solver
+# ---------------------------------------------------------------------------------------
+def _dag(a):
+    return a.conjugate().transpose()
+
+
+def _quantum_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=[], t0=0.0, nout=1, store_states=True, output='obs.dat'):
+    """RK4 propagation of i d psi/dt = H psi (rk4 + tdse, lime/phys.py:636-649,902-903) with lime's sampling:
+    entry 0 of `psilist` / `observables` is the INITIAL state, entry k the state after k*nout steps, for
+    k < Nt//nout (lime/mol.py:1304-1372).  psi0 may be [N] or [B, N] ([ext]: a batch in one launch; then the
+    states come back as [Nt//nout, B, N]).  The time loop is ONE launch of the Liouville-space RK4 kernel with
+    R = -iH (limeb200_liouville_rk4_csr); the bilinear observables <psi|e|psi> are taken from the stored states."""
+    from scipy.sparse import csr_matrix
+    from . import engine
+    psi0 = np.asarray(psi0, dtype=complex)
+    single = psi0.ndim == 1
+    v0 = psi0[None] if single else psi0
+    nblk = Nt // nout
+    R = csr_matrix(-1j * (H if hasattr(H, 'tocsr') else np.asarray(H, dtype=complex)))
+    nsteps = max(nblk - 1, 0) * nout
+    if nsteps > 0:
+        vf, _, traj = engine.liouville_rk4(R, v0, dt, nsteps, traj_every=nout)
+        states = np.concatenate([v0[None], traj], axis=0)          # [nblk, B, N]
+    else:
+        vf = v0.copy()
+        states = v0[None][:max(nblk, 0)]
+    e_ops = [] if e_ops is None else list(e_ops)
+    obs = np.zeros((states.shape[0], v0.shape[0], len(e_ops)), dtype=complex)
+    for j, e in enumerate(e_ops):
+        ed = e.toarray() if hasattr(e, 'toarray') else np.asarray(e)
+        obs[:, :, j] = np.einsum('kbi,ij,kbj->kb', states.conj(), ed, states)
+    if not store_states:
+        with open(output, 'w') as f:
+            fmt = '{} ' * (len(e_ops) + 1) + '\n'
+            for k in range(1, states.shape[0]):
+                f.write(fmt.format(t0 + k * dt * nout, *obs[k, 0]))
+        return vf[0] if single else vf
+    result = Result(dt=dt, Nt=Nt, psi0=psi0, t0=t0, nout=nout)
+    result.observables = obs[:, 0] if single else obs
+    result.psilist = [s[0] for s in states] if single else list(states)
+    return result
+
+
+class SESolver:
+    """time-dependent Schroedinger equation, lime/mol.py:1094-1277 (time-independent Hamiltonians; the laser-driven
+    branch `driven_dynamics` is not on the density-matrix path and raises NotImplementedError)"""
+
+    def __init__(self, H=None):
+        self.H = H
+        self.groundstate = None
+
+    def run(self, psi0=None, dt=0.01, Nt=1, e_ops=None, nout=1, t0=0.0, edip=None, pulse=None):
+        if psi0 is None:
+            psi0 = self.groundstate
+        if pulse is not None:
+            if edip is None:
+                raise ValueError('Electric dipole must be provided for laser-driven dynamics.')
+            raise NotImplementedError('laser-driven wave-function dynamics (lime.mol.driven_dynamics) is not built')
+        return _quantum_dynamics(self.H, psi0, dt=dt, Nt=Nt, e_ops=e_ops, nout=nout, t0=t0)
+
+    def propagator(self, dt, Nt):
+        """[U(0), U(dt), ...] with U(t) = exp(-iHt) by RK4 on the identity, lime/mol.py:1279-1301: the N columns are
+        one batched launch"""
+        N = self.H.shape[-1]
+        r = _quantum_dynamics(self.H, np.identity(N, dtype=complex), dt=dt, Nt=Nt)
+        return [np.ascontiguousarray(s.T) for s in r.psilist]          # batch member b = column b of U
+
+    def correlation_2op_1t(self):
+        pass
+
+    def correlation_3op_1t(self, psi0, oplist, dt, Nt):
+        """<A B(t) C>, lime/mol.py:1185-1211: ket and bra propagated together as a batch of two"""
+        a_op, b_op, c_op = oplist
+        batch = np.stack([c_op @ psi0, _dag(a_op) @ psi0])
+        st = np.array(_quantum_dynamics(self.H, batch, dt=dt, Nt=Nt).psilist)       # [Nt, 2, N]
+        return np.einsum('ki,ij,kj->k', st[:, 1].conj(), np.asarray(b_op), st[:, 0])
+
+    def correlation_3op_2t(self, psi0, oplist, dt, Nt, Ntau):
+        """<A(t) B(t+tau) C(t)>, lime/mol.py:1213-1246: lime runs 2 Nt propagations of Ntau steps in a Python loop;
+        here they are ONE batched launch"""
+        a_op, b_op, c_op = oplist
+        psi_t = np.array(_quantum_dynamics(self.H, psi0, dt=dt, Nt=Nt).psilist)     # [Nt, N]
+        batch = np.concatenate([psi_t @ np.asarray(c_op).T, psi_t @ _dag(np.asarray(a_op)).T], axis=0)
+        st = np.array(_quantum_dynamics(self.H, batch, dt=dt, Nt=Ntau).psilist)     # [Ntau, 2 Nt, N]
+        ket, bra = st[:, :Nt], st[:, Nt:]
+        return np.ascontiguousarray(np.einsum('jti,ik,jtk->tj', bra.conj(), np.asarray(b_op), ket))
+
+    def correlation_4op_1t(self, psi0, oplist, dt=0.005, Nt=1):
+        a_op, b_op, c_op, d_op = oplist
+        return self.correlation_3op_1t(psi0, [a_op, b_op @ c_op, d_op], dt, Nt)
+
+    def correlation_4op_2t(self, psi0, oplist, dt=0.005, Nt=1, Ntau=1):
+        a_op, b_op, c_op, d_op = oplist
+        return self.correlation_3op_2t(psi0, [a_op, b_op @ c_op, d_op], dt, Nt, Ntau)

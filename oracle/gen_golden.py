@@ -276,6 +276,26 @@ def main():
     note('super_lindblad', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'super_lindblad.npz'), tl=tl, taul=taul, wl=wl, A=A3, B=B3, C=C3, **g)
 
+    # ---- wave-function solver, lime/mol.py:1094-1391
+    import lime.mol as lmol
+    H = cases.rand_herm(5, 81)
+    psi0 = cases.rand_cplx(5, 82)[:, 0]
+    psi0 = psi0 / np.linalg.norm(psi0)
+    e_ops = [cases.rand_herm(5, 83), cases.rand_herm(5, 84)]
+    ops = [cases.rand_cplx(5, 85), cases.rand_cplx(5, 86), cases.rand_cplx(5, 87)]
+    ses = lmol.SESolver(H)
+    r = quiet(ses.run, psi0=psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
+    g = {'obs': r.observables, 'psilist': np.array(r.psilist),
+         'c3_1t': quiet(ses.correlation_3op_1t, psi0, ops, 0.01, 12),
+         'c3_2t': quiet(ses.correlation_3op_2t, psi0, ops, 0.01, 5, 6),
+         'c4_2t': quiet(ses.correlation_4op_2t, psi0, ops + [ops[0]], 0.01, 4, 3)}
+    oo, pl = lo.quantum_dynamics(H, psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
+    o = {'obs': oo, 'psilist': np.array(pl), 'c3_1t': lo.se_correlation_3op_1t(H, psi0, ops, 0.01, 12),
+         'c3_2t': lo.se_correlation_3op_2t(H, psi0, ops, 0.01, 5, 6),
+         'c4_2t': lo.se_correlation_3op_2t(H, psi0, [ops[0], ops[1] @ ops[2], ops[0]], 0.01, 4, 3)}
+    note('sesolver', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'sesolver.npz'), A=ops[0], B=ops[1], C=ops[2], **g)
+
     # ---- time-domain response functions, lime/signal/2DES.py:37-247 (the module cannot be imported:
     # it runs undefined names at :249-263; the function definitions themselves are exec'd verbatim here)
     src = open('/root/reference/lime/signal/2DES.py').read().split('\n')

@@ -890,6 +890,55 @@ class SuperLindblad:
 
 
 # --------------------------------------------------------------------------
+# wave-function solver                                lime/mol.py:1094-1391
+# 
+# --------------------------------------------------------------------------
+def tdse(wf, h):
+    """lime/phys.py:902-903"""
+    return -1j * h.dot(wf)
+
+
+def obs_psi(psi, a):
+    """<psi|a|psi>, lime/phys.py:846-862"""
+    return np.vdot(psi, a.dot(psi))
+
+
+def quantum_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=[], t0=0.0, nout=1):
+    """_quantum_dynamics with store_states=True, lime/mol.py:1304-1372: returns (observables
+    [Nt//nout, E], psilist [Nt//nout]); entry 0 is the initial state"""
+    psi = psi0.copy()
+    observables = np.zeros((Nt // nout, len(e_ops)), dtype=complex)
+    psilist = [psi0]
+    observables[0, :] = [obs_psi(psi, e) for e in e_ops]
+    for k1 in range(1, Nt // nout):
+        for k2 in range(nout):
+            psi = rk4(psi, tdse, dt, H)
+        observables[k1, :] = [obs_psi(psi, e) for e in e_ops]
+        psilist.append(psi.copy())
+    return observables, psilist
+
+
+def se_correlation_3op_1t(H, psi0, oplist, dt, Nt):
+    """<A B(t) C>, lime/mol.py:1185-1211"""
+    a_op, b_op, c_op = oplist
+    ket = quantum_dynamics(H, c_op @ psi0, dt=dt, Nt=Nt)[1]
+    bra = quantum_dynamics(H, dag(a_op) @ psi0, dt=dt, Nt=Nt)[1]
+    return np.array([np.vdot(bra[j], b_op @ ket[j]) for j in range(Nt)])
+
+
+def se_correlation_3op_2t(H, psi0, oplist, dt, Nt, Ntau):
+    """<A(t) B(t+tau) C(t)>, lime/mol.py:1213-1246"""
+    psi_t = quantum_dynamics(H, psi0, dt=dt, Nt=Nt)[1]
+    a_op, b_op, c_op = oplist
+    corr = np.zeros([Nt, Ntau], dtype=complex)
+    for i, psi in enumerate(psi_t):
+        ket = quantum_dynamics(H, c_op @ psi, dt=dt, Nt=Ntau)[1]
+        bra = quantum_dynamics(H, dag(a_op) @ psi, dt=dt, Nt=Ntau)[1]
+        corr[i, :] = [np.vdot(bra[j], b_op @ ket[j]) for j in range(Ntau)]
+    return corr
+
+
+# --------------------------------------------------------------------------
 # time-domain third-order response functions              lime/signal/2DES.py
 # (the module itself is not importable -- it executes undefined names at :249-263 --
 #  but the functions :37-247 are; oracle/gen_golden.py execs exactly those lines of the

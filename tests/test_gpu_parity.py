@@ -541,3 +541,27 @@ def test_liouvillian_eigen_solver(cuda):
         bb = rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n))
         c = engine.zgemm(a, bb).cpu().numpy()
         assert relerr(c, a @ bb) <= 1e-13
+
+
+def test_sesolver_wavefunction_path(cuda):
+    """lime.mol.SESolver (RK4 of the Schroedinger equation and its correlation functions)
+    against frozen outputs of the reference and the oracle"""
+    from lime_b200.mol import SESolver
+    g = golden('sesolver')
+    H = cases.rand_herm(5, 81)
+    psi0 = cases.rand_cplx(5, 82)[:, 0]
+    psi0 = psi0 / np.linalg.norm(psi0)
+    e_ops = [cases.rand_herm(5, 83), cases.rand_herm(5, 84)]
+    ops = [g['A'], g['B'], g['C']]
+    s = SESolver(H)
+    r = s.run(psi0=psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
+    assert r.observables.shape == (20, 2) and len(r.psilist) == 20
+    assert relerr(r.observables, g['obs']) <= TOL and relerr(np.array(r.psilist), g['psilist']) <= TOL
+    assert relerr(s.correlation_3op_1t(psi0, ops, 0.01, 12), g['c3_1t']) <= TOL
+    assert relerr(s.correlation_3op_2t(psi0, ops, 0.01, 5, 6), g['c3_2t']) <= TOL
+    assert relerr(s.correlation_4op_2t(psi0, ops + [ops[0]], 0.01, 4, 3), g['c4_2t']) <= TOL
+    U = s.propagator(0.01, 6)
+    import scipy.linalg
+    assert len(U) == 6 and relerr(U[5], scipy.linalg.expm(-1j * H * 0.05)) <= 1e-9      # RK4 truncation error
+    with pytest.raises(NotImplementedError):
+        s.run(psi0=psi0, pulse=object(), edip=H)

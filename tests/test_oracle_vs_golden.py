@@ -209,3 +209,14 @@ def test_liouvillian_eigen_solver_oracle_matches_reference():
     assert relerr(o.correlation_2op_1t(rho0, [A, B], g['tl']), g['c2_1t']) <= 1e-9
     assert relerr(o.correlation_3op_1w(rho0, [A, B, C], g['wl']), g['c3_1w']) <= 1e-9
     assert relerr(o.correlation_3op_2t(rho0, [A, B, C], g['tl'], g['taul']), g['c3_2t']) <= 1e-9
+
+
+def test_sesolver_oracle_matches_reference():
+    g = golden('sesolver')
+    H = cases.rand_herm(5, 81)
+    psi0 = cases.rand_cplx(5, 82)[:, 0]
+    psi0 = psi0 / np.linalg.norm(psi0)
+    e_ops = [cases.rand_herm(5, 83), cases.rand_herm(5, 84)]
+    o, pl = lo.quantum_dynamics(H, psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
+    assert np.array_equal(o, g['obs']) and np.array_equal(np.array(pl), g['psilist'])
+    assert np.array_equal(lo.se_correlation_3op_2t(H, psi0, [g['A'], g['B'], g['C']], 0.01, 5, 6), g['c3_2t'])
