@@ -553,7 +553,7 @@ class Redfield_solver:
 
     def correlation_4op_3t(self, rho0, oplist, signature, tau):
         """<<I|A G(t3) B G(t2) C G(t1) D|rho0>>; result[i,j,k] with axis 0 the LAST interval;
-        lime/oqs.py:277-366.  Host contraction of the (device- or eig-built) propagator."""
+        lime/oqs.py:277-366.  The O(Nt^2) / O(Nt^3) products run as complex GEMMs on the device."""
         if len(oplist) != 4:
             raise ValueError('Number of operators is not 4.')
         a, b, c, d = [operator_to_superoperator(o, s) for o, s in zip(oplist, signature)]
@@ -562,12 +562,17 @@ class Redfield_solver:
         G = self.G
         idm = self.idm(sp=False)
         rho = d.dot(dm2vec(rho0.toarray() if issparse(rho0) else rho0))
-        tmp = np.tensordot(G, rho, axes=((1), (0)))
-        tmp = c.dot(tmp)
-        tmp = np.tensordot(G, tmp, axes=([1], [0]))
-        tmp = np.tensordot(np.asarray(b.todense()), tmp, axes=([1], [0]))
-        tmp = np.tensordot(G, tmp, axes=([1], [0]))
-        return np.einsum('a, ab, bijk -> ijk', idm, np.asarray(a.todense()), tmp, optimize=True)
+        # lime's tensordot chain (lime/oqs.py:348-366), with every O(Nt^2) and O(Nt^3) product as a complex GEMM
+        # on the FP64 tensor cores; the D-vector steps stay on the host
+        D, Nt = G.shape[0], G.shape[2]
+        T2 = np.ascontiguousarray(c.dot(np.tensordot(G, rho, axes=((1), (0)))))          # [D, Nt_k]
+        Gm = np.ascontiguousarray(G.transpose(2, 0, 1)).reshape(Nt * D, D)               # rows (j, a)
+        T3 = engine.zgemm(Gm, T2).view(Nt, D, Nt)                                        # [j][b][k]
+        T4 = engine.zgemm(np.ascontiguousarray(np.asarray(b.todense(), dtype=complex)), T3)    # [j][a][k]
+        w = np.asarray(idm @ np.asarray(a.todense())).reshape(-1)                        # <<I| A
+        Gw = np.ascontiguousarray(np.einsum('a,abi->ib', w, G))                          # [Nt_i, D]
+        R = engine.zgemm(Gw, T4)                                                         # [j][i][k]
+        return np.ascontiguousarray(R.permute(1, 0, 2).cpu().numpy())
 
 
 # ---------------------------------------------------------------------------------------
