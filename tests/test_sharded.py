@@ -12,7 +12,7 @@ import torch.multiprocessing as mp
 
 import cases
 import lime_oracle as lo
-from conftest import relerr
+from conftest import relerr          # noqa: E402
 
 
 def _free_port():
@@ -123,6 +123,15 @@ def test_sharded_heom_gloo_world2():
         assert ranges == [(0, 18), (18, 35)]
         assert relerr(ado, ref) <= 1e-12, rank
     assert np.array_equal(res[0][1], res[1][1])          # every rank ends with the same full hierarchy
+
+
+def test_sharded_heom_gloo_world3_uneven():
+    """35 ADOs over 3 ranks: chunks of 12 with a short last one (padding rows are exchanged but never owned)"""
+    res = _run(3, 'gloo')
+    ref = _reference()
+    for rank, ado, ranges, nhe in res:
+        assert ranges == [(0, 12), (12, 24), (24, 35)]
+        assert relerr(ado, ref) <= 1e-12, rank
 
 
 @pytest.mark.gpu
