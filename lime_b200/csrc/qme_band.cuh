@@ -26,13 +26,6 @@ namespace cgb = cooperative_groups;
 
 #define QME_BAND_MAXS 2
 
-// cluster-wide barrier with release/acquire semantics at cluster scope (what cg::cluster_group::sync()
-// does, minus the GPU-scope MEMBAR and the L1 invalidate it adds): orders this CTA's local and
-// distributed-shared-memory stores before the neighbours' loads of the next stage
-__device__ __forceinline__ void cluster_barrier() {
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
 // ---- mbarrier / st.async plumbing for the halo exchange ------------------------------------
 // Halo rows are pushed into the neighbour CTA with st.async, which signals an mbarrier in the
 // DESTINATION CTA as the bytes land; the consumer waits on its own mbarrier for the expected
