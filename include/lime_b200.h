@@ -86,6 +86,11 @@ int limeb200_qme_set_path(limeb200_qme_t plan, int path);
 int limeb200_qme_finalize(limeb200_qme_t plan);
 /* which kernel finalize chose (same numbering as set_path) */
 int limeb200_qme_get_path(limeb200_qme_t plan);
+/* what finalize decided: info9 = {path, basis permuted?, bandwidth (halo rows), band kernel: off-diagonal slots,
+ * purely imaginary off-diagonal G?, real X/Z?, cluster size, rows per CTA, chain stride}; perm[N] = new -> old basis
+ * order (may be NULL).  limeb200_qme_create(.., device = -1) makes an ANALYSIS-ONLY plan (no GPU needed, assumes a
+ * B200: 148 SMs, 227 KB shared memory) on which this is the only useful call -- it cannot run.          */
+int limeb200_qme_get_info(limeb200_qme_t plan, int* info9, int* perm);
 
 /* nsteps RK4 steps of B density matrices, in place in d_rho[B][N][N].
  *   d_coef : [nsteps][ndrive] complex or NULL

@@ -30,6 +30,7 @@ SIGNATURES = {
     'limeb200_qme_set_path': (c_int, [c_vp, c_int]),
     'limeb200_qme_finalize': (c_int, [c_vp]),
     'limeb200_qme_get_path': (c_int, [c_vp]),
+    'limeb200_qme_get_info': (c_int, [c_vp, c_vp, c_vp]),
     'limeb200_qme_run': (c_int, [c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
     'limeb200_qme_rhs': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     'limeb200_qme_last_launches': (c_ll, [c_vp]),

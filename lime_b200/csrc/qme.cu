@@ -55,6 +55,7 @@ struct limeb200_qme_s {
     // ---- band path (qme_band.cuh)
     DevBuf dbgd, dbgcol, dbgval, dbxcol[QME_BAND_MAXS], dbxval[QME_BAND_MAXS], dbzcol[QME_BAND_MAXS], dbzval[QME_BAND_MAXS];
     int band_noff = 0, band_gt = 0, band_xt = 0, band_C = 0, band_R = 0, band_chain = 0;
+    std::vector<int> host_perm;                 // basis order chosen by finalize (new -> old)
     size_t band_smem = 0;
     // ---- scratch
     DevBuf s_y, s_acc, s_tmp, s_gk;
@@ -406,6 +407,14 @@ extern "C" {
 int limeb200_qme_create(limeb200_qme_t* plan, int N, int device) {
     LB_REQUIRE(plan, "null plan pointer");
     LB_REQUIRE(N >= 1 && N <= 8192, "N out of range (1..8192)");
+    if (device == -1) {
+        // analysis-only plan (host): kernel selection, basis ordering and cluster geometry for a B200 (148 SMs,
+        // 227 KB shared memory per block) can be inspected with limeb200_qme_get_info; it cannot run
+        auto* p = new limeb200_qme_s();
+        p->N = N; p->device = -1; p->sm_count = 148; p->smem_optin = 232448;
+        *plan = p;
+        return LB_OK;
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -426,7 +435,7 @@ int limeb200_qme_create(limeb200_qme_t* plan, int N, int device) {
 }
 
 int limeb200_qme_destroy(limeb200_qme_t plan) {
-    if (plan) { cudaSetDevice(plan->device); delete plan; }
+    if (plan) { if (plan->device >= 0) cudaSetDevice(plan->device); delete plan; }
     return LB_OK;
 }
 
@@ -498,13 +507,22 @@ int limeb200_qme_set_path(limeb200_qme_t p, int path) {
     return LB_OK;
 }
 int limeb200_qme_get_path(limeb200_qme_t p) { return p ? p->path : LB_ERR_ARG; }
+int limeb200_qme_get_info(limeb200_qme_t p, int* info9, int* perm) {
+    LB_REQUIRE(p && p->finalized && info9, "plan not finalized");
+    info9[0] = p->path; info9[1] = p->permuted ? 1 : 0; info9[2] = p->bandwidth;
+    info9[3] = p->band_noff; info9[4] = p->band_gt; info9[5] = p->band_xt;
+    info9[6] = p->band_C; info9[7] = p->band_R; info9[8] = p->band_chain;
+    if (perm)
+        for (int i = 0; i < p->N; ++i) perm[i] = i < (int)p->host_perm.size() ? p->host_perm[i] : i;
+    return LB_OK;
+}
 long long limeb200_qme_last_launches(limeb200_qme_t p) { return p ? p->launches : -1; }
 
 int limeb200_qme_finalize(limeb200_qme_t p) {
     LB_REQUIRE(p, "null plan");
     LB_REQUIRE(!p->finalized, "plan already finalized");
     LB_REQUIRE(p->G.given, "generator not set");
-    LB_CUDA(cudaSetDevice(p->device));
+    if (p->device >= 0) LB_CUDA(cudaSetDevice(p->device));
     const int N = p->N, S = (int)p->X.size(), nd = (int)p->D.size();
     const size_t NN = (size_t)N * N;
     // operator batch
@@ -601,6 +619,19 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     }
     if (path == 1 || path == 2) LB_REQUIRE(dense_mem_ok, "dense operator batch too large (nb=%d, N=%d)", nb, N);
     p->path = path;
+    p->host_perm = perm;
+    if (p->device < 0) {             // analysis-only plan: nothing to upload
+        if (path >= 3) {
+            int bw = 0;
+            EllHost e;
+            to_ell(p->G, N, e, bw, perm, inv);
+            for (int s2 = 0; s2 < S; ++s2) { to_ell(p->X[s2], N, e, bw, perm, inv); to_ell(p->Z[s2], N, e, bw, perm, inv); }
+            p->bandwidth = bw;
+        }
+        if (path == 5) { p->band_noff = band.noff; p->band_gt = band.gt; p->band_xt = band.xt; }
+        p->finalized = true;
+        return LB_OK;
+    }
 
     if (path == 1 || path == 2) {
         std::vector<hcplx> g, gh, x, zh;
@@ -877,6 +908,7 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
                      const double* d_coef, double* d_obs, double* d_traj, int traj_every,
                      void* stream) {
     LB_REQUIRE(p && p->finalized, "plan not finalized");
+    LB_REQUIRE(p->device >= 0, "analysis-only plan (device -1) cannot run: there is no CPU fallback");
     LB_REQUIRE(d_rho && B >= 1 && nsteps >= 0, "bad arguments");
     LB_REQUIRE(p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
     LB_REQUIRE(p->D.empty() || d_coef, "drive operators present but d_coef is NULL");
@@ -946,6 +978,7 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
 
 int limeb200_qme_rhs(limeb200_qme_t p, const double* d_in, double* d_out, int B, void* stream) {
     LB_REQUIRE(p && p->finalized, "plan not finalized");
+    LB_REQUIRE(p->device >= 0, "analysis-only plan (device -1) cannot run: there is no CPU fallback");
     LB_REQUIRE(d_in && d_out && B >= 1, "bad arguments");
     LB_REQUIRE(p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
     LB_REQUIRE(p->D.empty(), "rhs with drive operators is not supported");

@@ -214,6 +214,45 @@ def liouville_rk4(R, v0, dt, nsteps, e_rows=None, traj_every=0, dev=None):
     return out, obs, traj
 
 
+def analyze_qme(N, G, sandwiches=(), e_ops=None, path=None):
+    """What limeb200_qme_finalize would decide for these operators on a B200 -- host only, no GPU needed
+    (analysis-only plan, device = -1).  Returns dict(path, permuted, bandwidth, noff, imag_offdiag, real_xz,
+    cluster, rows_per_cta, chain, perm)."""
+    h = C.c_void_p()
+    check(lib().limeb200_qme_create(C.byref(h), int(N), -1))
+    try:
+        if issparse(G):
+            ip, ix, d, nnz, nb = _csr_parts(G)
+            check(lib().limeb200_qme_set_generator_csr(h, hptr(ip), hptr(ix), hptr(d), nnz, nb))
+        else:
+            a, nb = _dense_batch(G, N)
+            check(lib().limeb200_qme_set_generator_dense(h, hptr(a), nb))
+        for X, Z in sandwiches:
+            if issparse(X) and issparse(Z):
+                xp, zp = _csr_parts(X), _csr_parts(Z)
+                check(lib().limeb200_qme_add_sandwich_csr(h, hptr(xp[0]), hptr(xp[1]), hptr(xp[2]), xp[3],
+                                                          hptr(zp[0]), hptr(zp[1]), hptr(zp[2]), zp[3], 1))
+            else:
+                x, _ = _dense_batch(X, N)
+                z, _ = _dense_batch(Z, N)
+                check(lib().limeb200_qme_add_sandwich_dense(h, hptr(x), hptr(z), 1))
+        if e_ops:
+            e = np.ascontiguousarray(np.stack([_dev.as_c128(o) for o in e_ops]))
+            check(lib().limeb200_qme_set_observables(h, hptr(e), len(e_ops)))
+        if path is not None:
+            check(lib().limeb200_qme_set_path(h, int(path)))
+        check(lib().limeb200_qme_finalize(h))
+        info = np.zeros(9, dtype=np.int32)
+        perm = np.zeros(N, dtype=np.int32)
+        check(lib().limeb200_qme_get_info(h, hptr(info), hptr(perm)))
+    finally:
+        lib().limeb200_qme_destroy(h)
+    keys = ['path', 'permuted', 'bandwidth', 'noff', 'imag_offdiag', 'real_xz', 'cluster', 'rows_per_cta', 'chain']
+    out = {k: int(v) for k, v in zip(keys, info)}
+    out['perm'] = perm
+    return out
+
+
 def zgemm(A, Bm):
     """C = A @ B on the FP64 tensor cores.  A [M,K] or [b,M,K], B [K,N] or [b,K,N]: numpy arrays (uploaded) or
     device tensors; returns a device tensor [M,N] / [b,M,N]."""

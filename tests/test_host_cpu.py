@@ -112,3 +112,57 @@ def test_no_cpu_fallback():
     h = ctypes.c_void_p()
     rc = _lib.lib().limeb200_qme_create(ctypes.byref(h), 4, 0)
     assert rc < 0 and b'no CUDA device' in _lib.lib().limeb200_last_error()
+
+
+def test_qme_plan_analysis_host_logic(monkeypatch):
+    """kernel selection, bandwidth-reducing basis order and cluster geometry (limeb200_qme_finalize's host logic)
+    through an analysis-only plan -- no GPU involved"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import engine
+    from lime_b200.oqs import lindblad_generator
+    import cases
+
+    def jc(ncav, **kw):
+        H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav, **kw)
+        G, Gr, ls = lindblad_generator(csr_matrix(H), [csr_matrix(c) for c in c_ops])
+        return G, [(l, l) for l in ls], e_ops
+
+    G, sw, e_ops = jc(64)                                   # config 2: N = 128
+    a = engine.analyze_qme(128, G, sw, e_ops)
+    assert a['path'] == 5 and a['cluster'] == 4 and a['rows_per_cta'] == 32
+    assert a['noff'] == 2 and a['imag_offdiag'] == 1 and a['real_xz'] == 1 and a['chain'] == 0
+    assert sorted(a['perm']) == list(range(128)) and a['permuted'] == 1
+    assert 1 <= a['bandwidth'] <= 4
+    # every operator entry lies within the band in the chosen order
+    inv = np.argsort(a['perm'])
+    for op in [G] + [x for x, _ in sw]:
+        r, c = op.nonzero()
+        assert np.max(np.abs(inv[r] - inv[c])) <= a['bandwidth']
+    # opt-in chain variant: two interleaved parity chains, G couples rows 2 apart
+    monkeypatch.setenv('LIMEB200_BAND_CHAIN', '1')
+    b = engine.analyze_qme(128, G, sw, e_ops)
+    assert b['path'] == 5 and b['chain'] == 2 and b['bandwidth'] == 3
+    inv = np.argsort(b['perm'])
+    r, c = (G - csr_matrix(np.diag(G.diagonal()))).nonzero()
+    assert set(np.abs(inv[r] - inv[c])) == {2}
+    monkeypatch.delenv('LIMEB200_BAND_CHAIN')
+    # too large for a cluster: generic sparse kernel; small / dense operands: dense kernels
+    G2, sw2, e2 = jc(128)
+    assert engine.analyze_qme(256, G2, sw2, e2)['path'] in (3, 4)
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    Gd, _, ls = lindblad_generator(H, c_ops)
+    assert engine.analyze_qme(6, Gd, [(l, l) for l in ls])['path'] == 1
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=100, M=1)
+    Gd, _, ls = lindblad_generator(H, c_ops)
+    assert engine.analyze_qme(100, Gd, [(l, l) for l in ls])['path'] == 2
+    # an analysis-only plan refuses to run
+    import ctypes as C
+    from lime_b200._lib import lib
+    h = C.c_void_p()
+    assert lib().limeb200_qme_create(C.byref(h), 4, -1) == 0
+    g = np.zeros((4, 4), dtype=complex)
+    assert lib().limeb200_qme_set_generator_dense(h, g.ctypes.data_as(C.c_void_p), 1) == 0
+    assert lib().limeb200_qme_finalize(h) == 0
+    assert lib().limeb200_qme_run(h, None, 1, 0.1, 1, None, None, None, 1, None) < 0
+    assert b'no CPU fallback' in lib().limeb200_last_error()
+    lib().limeb200_qme_destroy(h)
