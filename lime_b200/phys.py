@@ -93,9 +93,19 @@ def lorentzian(x, width=1.):
 
 
 def rk4(rho, fun, dt, *args):
-    """lime/phys.py:636-649: generic RK4 driver for an arbitrary Python right-hand side;
-    updates `rho` in place and returns it.  (The solvers do not loop over this function:
-    their whole time loop runs inside one CUDA launch.)"""
+    """lime/phys.py:636-649: one classical RK4 step; updates `rho` IN PLACE and returns the same object.
+
+    When `fun` is this package's `liouvillian` (args = H, c_ops) -- the combination lime's `_lindblad` loops over,
+    lime/oqs.py:1676 -- the step is one launch of the fused CUDA propagator.  For any other Python right-hand side
+    this is lime's generic driver: the four evaluations are whatever `fun` does (e.g. `oqs.liouvillian` evaluates
+    on the device); only the axpy algebra of an arbitrary user callback is NumPy.  None of the solvers in this
+    package loops over this function: their whole time loop runs inside one CUDA launch."""
+    from . import oqs
+    if fun is oqs.liouvillian and len(args) == 2 and isinstance(rho, np.ndarray):
+        plan = oqs._lindblad_plan(args[0], args[1], None)
+        out, _, _ = plan.run(rho, dt, 1)
+        rho[...] = out
+        return rho
     dt2 = dt / 2.0
     k1 = fun(rho, *args)
     k2 = fun(rho + k1 * dt2, *args)

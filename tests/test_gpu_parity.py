@@ -58,6 +58,13 @@ def test_lindblad_drop_in_surface(cuda):
     assert relerr(oqs.lindbladian(c_ops[0], rho0), ref) <= 1e-13
     res2 = oqs.Lindblad_solver(H, c_ops).evolve(rho0, 0.01, 80, e_ops=e_ops)
     assert relerr(res2.observables, g['observables']) <= TOL
+    # rk4(rho, liouvillian, dt, H, c_ops): one fused device step, in place, same object returned (lime/phys.py:636-649)
+    from lime_b200 import phys
+    r = rho0.copy()
+    ref = lo.rk4(rho0.copy(), lo.liouvillian, 0.01, H, c_ops)
+    assert phys.rk4(r, oqs.liouvillian, 0.01, H, c_ops) is r and relerr(r, ref) <= 1e-13
+    r = rho0.copy()          # generic driver with a user callback whose evaluations run on the device
+    assert relerr(phys.rk4(r, lambda x, h, c: oqs.liouvillian(x, h, c), 0.01, H, c_ops), ref) <= 1e-13
     # no e_ops / no c_ops edge cases
     r3 = oqs._lindblad(H, rho0, [], e_ops=None, Nt=5, dt=0.01)
     o3, l3 = lo.lindblad(H, rho0, [], None, Nt=5, dt=0.01)
