@@ -192,6 +192,9 @@ long long limeb200_heom_last_launches(limeb200_heom_t plan);
  *   d_y0/d_y1[world]    : every rank's two stage vectors [nhe_pad][n][n] (index = rank; own entry local)
  *   d_flags[world]      : every rank's flag array (>= world unsigned, zero-initialised)
  *   d_rho               : local [nhe_pad][n][n]; only the owned rows are read and written
+ *   d_peer_mask         : [nhe] bytes or NULL.  Bit q of entry a = "peer slot q (the q-th rank != this one) reads
+ *                         ADO a" (it owns a neighbour of a): new values of a are stored only into those peers, except
+ *                         at the last stage of the run, which goes to every peer.  NULL: always every peer.
  *   epoch               : flags are monotonic; pass the number of stages run so far (4 * steps)
  * On entry every rank's d_y0[rank] holds the full state; on return it holds the full new state.  */
 int limeb200_memcpy_d2d(void* d_dst, const void* d_src, long long bytes, void* stream);   /* async, stream-ordered */
@@ -200,8 +203,8 @@ int limeb200_peer_open(int device, const unsigned char* handle64, void** d_ptr);
 int limeb200_peer_close(int device, void* d_ptr);
 int limeb200_peer_free(int device, void* d_ptr);
 int limeb200_heom_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_y0, void* const* d_y1,
-                              void* const* d_flags, double* d_rho, double dt, int nsteps, unsigned epoch,
-                              void* stream);
+                              void* const* d_flags, double* d_rho, const unsigned char* d_peer_mask,
+                              double dt, int nsteps, unsigned epoch, void* stream);
 /* 1 when a bounded spin of the last sharded run timed out (a peer never arrived), else 0 */
 int limeb200_heom_sharded_error(limeb200_heom_t plan, void* stream);
 

@@ -145,6 +145,8 @@ struct HeomStageArgs {
     int apc;                // ADOs per CTA
     int npeer;              // sharded persistent kernels: the new stage value is also stored into
     cplx* peer_next[7];     // the same element of every peer GPU's stage vector (NVLink stores)
+    const unsigned char* peer_mask;   // [nhe] bit q set: peer slot q reads this ADO (null or send_all: every peer)
+    int send_all;
 };
 
 // L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
@@ -289,7 +291,11 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     if (rreg) {
         const cplx yn = heom_rk_update(a.stage, k, *rreg, *areg, a.dt);
         a.ynext[o] = yn;
-        for (int r = 0; r < a.npeer; ++r) a.peer_next[r][o] = yn;
+        if (a.npeer) {
+            const unsigned m = (a.send_all || !a.peer_mask) ? 0xffu : a.peer_mask[ado];
+            for (int r = 0; r < a.npeer; ++r)
+                if ((m >> r) & 1u) a.peer_next[r][o] = yn;
+        }
         if (a.stage == 3) a.rho[o] = *rreg;
         return;
     }
@@ -298,7 +304,11 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const cplx yn = heom_rk_update(a.stage, k, r, ac, a.dt);
     if (a.stage < 3) a.acc[o] = ac; else a.rho[o] = r;
     a.ynext[o] = yn;
-    for (int p = 0; p < a.npeer; ++p) a.peer_next[p][o] = yn;
+    if (a.npeer) {
+        const unsigned m = (a.send_all || !a.peer_mask) ? 0xffu : a.peer_mask[ado];
+        for (int p = 0; p < a.npeer; ++p)
+            if ((m >> p) & 1u) a.peer_next[p][o] = yn;
+    }
 }
 
 // stage-wise kernel: grid ceil(items/apc); block >= apc*nn threads; dynamic smem (1 + 3*apc)*nn cplx
@@ -324,6 +334,8 @@ struct HeomPersistArgs {
     cplx* y0p[7]; cplx* y1p[7];       // peers' y0 / y1 (order: every rank != this one)
     unsigned* flagp[7];               // peers' flag arrays; peer q's slot for this rank is flagp[q][rank]
     unsigned* flags;                  // this rank's flag array [world]
+    const unsigned char* peer_mask;   // [nhe] which peer slots need each owned ADO (null: all); the last stage of the
+                                      // run always goes to every peer so that each rank ends with the full state
 };
 
 // grid-wide barrier on a monotonic counter (zeroed by the host before the launch): one release
@@ -426,6 +438,8 @@ heom_persist_kernel(HeomPersistArgs p) {
             a.yin = (stage & 1) ? p.y1 : p.y0;
             a.ynext = (stage & 1) ? p.y0 : p.y1;
             a.npeer = p.world - 1;
+            a.peer_mask = p.peer_mask;
+            a.send_all = (step == p.nsteps - 1 && stage == 3) ? 1 : 0;
             for (int q = 0; q < p.world - 1; ++q) a.peer_next[q] = (stage & 1) ? p.y0p[q] : p.y1p[q];
             if (fixed) {
                 if (blockIdx.x < ntiles) heom_stage_tile(a, (long long)blockIdx.x * a.apc, smem, tabs, &rreg, &areg);
@@ -497,6 +511,7 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
     const size_t own = hb + (size_t)ado * nn + idx;
     cplx rreg = act ? a.rho[own] : cmake(0, 0), areg = cmake(0, 0);
     const double damp = act ? heom_damp(d, par, ado) : 0.0;
+    const unsigned pmask = (p.peer_mask && act) ? p.peer_mask[ado] : 0xffu;
     {
         int ne = 0;
         if (act) {
@@ -545,7 +560,9 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
             const cplx yn = heom_rk_update(stage, k, rreg, areg, a.dt);
             if (act) {
                 yout[own] = yn;
-                for (int q = 0; q < p.world - 1; ++q) ((stage & 1) ? p.y0p[q] : p.y1p[q])[own] = yn;
+                const unsigned m = (step == p.nsteps - 1 && stage == 3) ? 0xffu : pmask;
+                for (int q = 0; q < p.world - 1; ++q)
+                    if ((m >> q) & 1u) ((stage & 1) ? p.y0p[q] : p.y1p[q])[own] = yn;
                 if (stage == 3) a.rho[own] = rreg;
             }
             bar_target += gridDim.x;
@@ -1193,7 +1210,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     if (nown <= 0) return LB_OK;
     const int nn = p->n * p->n;
     HeomStageArgs a;
-    a.npeer = 0;
+    a.npeer = 0; a.peer_mask = nullptr; a.send_all = 1;
     a.d = p->dev();
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
@@ -1219,7 +1236,7 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = p->row_lo; pa.s.row_hi = p->row_hi;
     pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
     pa.s.dt = dt;
-    pa.s.npeer = 0;
+    pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
     pa.nsteps = nsteps;
     int coop = 0;
     LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
@@ -1429,8 +1446,8 @@ int limeb200_peer_free(int device, void* d_ptr) {
 }
 
 int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* const* d_y0, void* const* d_y1,
-                              void* const* d_flags, double* d_rho, double dt, int nsteps, unsigned epoch,
-                              void* stream) {
+                              void* const* d_flags, double* d_rho, const unsigned char* d_peer_mask,
+                              double dt, int nsteps, unsigned epoch, void* stream) {
     LB_REQUIRE(p && d_y0 && d_y1 && d_flags && d_rho, "null argument");
     LB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8");
     LB_REQUIRE(p->npar == 1, "sharded runs take one hierarchy (no parameter batch)");
@@ -1448,6 +1465,7 @@ int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* cons
     HeomPersistArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.world = world; pa.rank = rank; pa.epoch = epoch;
+    pa.peer_mask = d_peer_mask;
     pa.y0 = (cplx*)d_y0[rank]; pa.y1 = (cplx*)d_y1[rank]; pa.flags = (unsigned*)d_flags[rank];
     int q = 0;
     for (int r = 0; r < world; ++r) {

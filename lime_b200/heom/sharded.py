@@ -29,6 +29,23 @@ from .. import _dev
 from .heom import _calc_matsubara_params
 
 
+def peer_masks(dn, up, ranges, rank):
+    """uint8 [N_he]: bit q of entry a is set when peer slot q (the q-th rank other than `rank`) owns an ADO that
+    couples to ADO a, i.e. that peer reads a in every stage.  Only entries of the ADOs `rank` owns are non-zero."""
+    nhe = dn.shape[0]
+    mask = np.zeros(nhe, dtype=np.uint8)
+    lo, hi = ranges[rank]
+    q = 0
+    for r, (rlo, rhi) in enumerate(ranges):
+        if r == rank:
+            continue
+        nb = np.concatenate([dn[rlo:rhi].reshape(-1), up[rlo:rhi].reshape(-1)])
+        nb = np.unique(nb[(nb >= lo) & (nb < hi)])
+        mask[nb] |= np.uint8(1 << q)
+        q += 1
+    return mask
+
+
 def partition(nhe, world):
     """(chunk, [(lo, hi)] per rank): contiguous, equal chunks (the last one may be short or empty)"""
     chunk = -(-nhe // world)
@@ -38,7 +55,7 @@ def partition(nhe, world):
 class ShardedHEOM:
     def __init__(self, H, Q, coup_strength, cut_freq, temperature, N_exp=2, N_cut=4,
                  pref_dn=-1j, pref_up=-1j, group=None, stage_fn=None, device=None, use_graph=True,
-                 exchange='p2p'):
+                 exchange='p2p', halo_only=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -70,6 +87,10 @@ class ShardedHEOM:
         self.exchange = exchange if stage_fn is None else 'collective'
         self._peer = None
         self._epoch = 0
+        # fused path: new stage values travel only to the peers that own a neighbour of the ADO (plus one full
+        # broadcast at the end of a run); halo_only=False stores every value into every peer
+        self.peer_mask = peer_masks(self.dn, self.up, self.ranges, self.rank) if halo_only else None
+        self._d_mask = None
         if stage_fn is None:
             self.dev = _dev.device() if device is None else device
             self.plan = engine.HeomPlan(self.H, self.Q, self.qmap, self.c, self.nu, self.states, self.dn, self.up,
@@ -162,8 +183,11 @@ class ShardedHEOM:
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)
+        if self.peer_mask is not None and self._d_mask is None:
+            self._d_mask = torch.from_numpy(self.peer_mask).to(ado.device)
+        mptr = C.c_void_p(self._d_mask.data_ptr()) if self._d_mask is not None else None
         check(lib().limeb200_heom_run_sharded(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1],
-                                              pr['arr'][2], C.c_void_p(rho.data_ptr()), float(dt), int(nsteps),
+                                              pr['arr'][2], C.c_void_p(rho.data_ptr()), mptr, float(dt), int(nsteps),
                                               C.c_uint(self._epoch), C.c_void_p(st.cuda_stream)))
         self._epoch += 4 * nsteps
         err = lib().limeb200_heom_sharded_error(self.plan._h, C.c_void_p(st.cuda_stream))

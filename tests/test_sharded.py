@@ -61,7 +61,8 @@ def _worker(rank, world, port, backend, q, exchange='p2p'):
         H, Q, lam, gam, T, depth, rho0 = _problem()
         if backend == 'nccl':
             torch.cuda.set_device(rank)
-            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, exchange=exchange)
+            sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, exchange=exchange.replace('_all', ''),
+                             halo_only=(exchange != 'p2p_all'))
         else:
             sh = ShardedHEOM(H, Q, lam, gam, T, N_exp=2, N_cut=depth, stage_fn=_oracle_stage)
         ado = torch.from_numpy(sh.initial(rho0)).to(sh.dev)
@@ -115,6 +116,30 @@ def test_partition():
     assert chunk == 1 and r[3] == (3, 3)
 
 
+def test_peer_masks_cover_exactly_the_remote_neighbours():
+    from lime_b200 import engine
+    from lime_b200.heom.sharded import partition, peer_masks
+    states, dn, up = engine.heom_tables([5] * 4, 4)
+    nhe = states.shape[0]
+    for world in (2, 3, 8):
+        chunk, ranges = partition(nhe, world)
+        masks = [peer_masks(dn, up, ranges, r) for r in range(world)]
+        for me in range(world):
+            lo, hi = ranges[me]
+            assert not masks[me][:lo].any() and not masks[me][hi:].any()        # only owned ADOs are sent
+            others = [r for r in range(world) if r != me]
+            for q, r in enumerate(others):
+                rlo, rhi = ranges[r]
+                need = set(np.concatenate([dn[rlo:rhi].ravel(), up[rlo:rhi].ravel()]).tolist()) - {-1}
+                need = {a for a in need if lo <= a < hi}
+                got = set(np.nonzero((masks[me] >> q) & 1)[0].tolist())
+                assert got == need, (world, me, r)
+    # the point of the exercise: far fewer stores than "everything to everyone" at 8 ranks
+    chunk, ranges = partition(nhe, 8)
+    sent = sum(int(np.unpackbits(peer_masks(dn, up, ranges, r)).sum()) for r in range(8))
+    assert sent < 0.6 * 7 * nhe
+
+
 def test_sharded_heom_gloo_world2():
     res = _run(2, 'gloo')
     ref = _reference()
@@ -148,7 +173,7 @@ def test_sharded_heom_single_rank_persistent_kernel(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('exchange', ['p2p', 'nccl'])
+@pytest.mark.parametrize('exchange', ['p2p', 'p2p_all', 'nccl'])
 def test_sharded_heom_nccl_world2(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
