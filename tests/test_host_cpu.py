@@ -166,3 +166,29 @@ def test_qme_plan_analysis_host_logic(monkeypatch):
     assert lib().limeb200_qme_run(h, None, 1, 0.1, 1, None, None, None, 1, None) < 0
     assert b'no CPU fallback' in lib().limeb200_last_error()
     lib().limeb200_qme_destroy(h)
+
+
+def test_bench_input_builders_match_the_oracle_builders():
+    """the synthetic inputs the GPU arm propagates (lime_b200/models.py) are the operators the CPU arm builds
+    (oracle jaynes_cummings = lime's Composite.getH layout, lime/cavity.py:57-97)"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import models
+    import lime_oracle as lo
+    omega0, kappa, ncav = 1.0, 0.05, 12
+    g = np.array([0.01, 0.1, 0.2])
+    det = np.array([-0.2, 0.0, 0.15])
+    pat, vals, c_ops, e_ops, rho0 = models.jaynes_cummings_batch(omega0, omega0 + det, g, ncav, kappa)
+    pat = csr_matrix(pat)
+    rows = np.repeat(np.arange(2 * ncav), np.diff(pat.indptr))
+    for b in range(3):
+        H, c_o, e_o = lo.jaynes_cummings(omega0, omega0 + det[b], g[b], ncav, kappa)
+        Hb = csr_matrix((vals[b], (rows, pat.indices)), shape=pat.shape).toarray()
+        assert np.allclose(Hb, H.toarray(), atol=0, rtol=1e-15)
+        assert np.array_equal(c_ops[0].toarray(), c_o[0].toarray())
+        for x, y in zip(e_ops, e_o):
+            assert np.array_equal(x.toarray(), y.toarray())
+    assert rho0[ncav, ncav] == 1 and np.count_nonzero(rho0) == 1            # |e,0><e,0|, index = i_mol*ncav + n
+    Hf, Q, lam, gam, kT = models.fmo_heom_inputs()
+    assert Hf.shape == (7, 7) and np.allclose(Hf, Hf.conj().T) and len(Q) == 7
+    assert all(np.array_equal(q, np.diag(np.diag(q))) and np.trace(q) == 1 for q in Q)
+    assert abs(lam * 219474.6305 - 35.0) < 1e-9 and abs(kT * 315775.13 - 300.0) < 1e-9
