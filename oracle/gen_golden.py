@@ -252,6 +252,24 @@ def main():
     note('sos', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'sos.npz'), w1=w1, w3=w3, w2=w2, w1b=w1b, t2=t2, **g)
 
+    # ---- Mol-based wrappers and the single-frequency TPA, lime/signal/sos.py:199-228, 731-902
+    import tempfile
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    mol = cases.DuckMol(E, dip, gamma, dephasing=0.01 / au2ev)
+    tmpd = tempfile.mkdtemp()
+    wp = np.linspace(1.4, 2.1, 9) / au2ev
+    g = {'PE': quiet(sos.photon_echo, mol, wp, wp, t2=30.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx,
+                     fname=os.path.join(tmpd, 's')),
+         'PE_t3': quiet(sos.photon_echo_t3, mol, wp, wp, 20.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx,
+                        fname=os.path.join(tmpd, 't')),
+         'TPA': np.array([sos.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in np.linspace(3.0, 4.0, 7) / au2ev])}
+    o = {'PE': lo.photon_echo_core(E, dip, -wp, wp, 30.0, g_idx, e_idx, f_idx, gamma),
+         'PE_t3': lo.SE_t3(E, dip, -wp, wp, 20.0, g_idx, e_idx, gamma, dephasing=0.01 / au2ev) +
+         lo.ESA_t3(E, dip, -wp, wp, 20.0, g_idx, e_idx, f_idx, gamma, dephasing=0.01 / au2ev),
+         'TPA': np.array([lo.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in np.linspace(3.0, 4.0, 7) / au2ev])}
+    note('sos_mol', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'sos_mol.npz'), wp=wp, wtpa=np.linspace(3.0, 4.0, 7) / au2ev, **g)
+
     # ---- Liouvillian eigen-decomposition solver, lime/superoperator.py:456-773
     import lime.superoperator as lsup
     H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=3, M=2, E=2, seed=61)

@@ -762,6 +762,23 @@ def lorentzian(x, width=1.):
     return 1. / np.pi * width / (width ** 2 + (x) ** 2)
 
 
+def TPA(E, dip, omegap, g_idx, e_idx, f_idx, gamma, degenerate=True):
+    """TPA signal with classical light (degenerate pump), lime/signal/sos.py:199-228"""
+    if degenerate:
+        omega1 = omegap * 0.5
+        omega2 = omegap - omega1
+    i = 0
+    signal = 0
+    for f in f_idx:
+        tmp = 0.0
+        for m in e_idx:
+            p1 = dip[f, m] * dip[m, i] / (omega1 - (E[m] - E[i]) + 1j * gamma[m])
+            p2 = dip[f, m] * dip[m, i] / (omega2 - (E[m] - E[i]) + 1j * gamma[m])
+            tmp += (p1 + p2)
+        signal += np.abs(tmp) ** 2 * lorentzian(omegap - E[f] + E[i], width=gamma[f])
+    return signal
+
+
 def TPA2D(E, dip, omegaps, omega1s, g_idx, e_idx, f_idx, gamma):
     """lime/signal/sos.py:230-256 (real output)"""
     g = 0

@@ -152,3 +152,15 @@ def sos_system(N=8, ne=3, seed=0):
     e_idx = list(range(1, 1 + ne))
     f_idx = list(range(1 + ne, N))
     return E, dip, gamma, g_idx, e_idx, f_idx
+
+
+class DuckMol:
+    """the attributes lime's Mol-based wrappers read (lime/signal/sos.py:731-902): eigvals(), edip_rms, gamma,
+    dephasing, nstates"""
+
+    def __init__(self, E, dip, gamma, dephasing=0.0):
+        self._E, self.edip_rms, self.gamma, self.dephasing = E, dip, gamma, dephasing
+        self.nstates = len(E)
+
+    def eigvals(self):
+        return self._E

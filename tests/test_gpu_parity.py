@@ -572,3 +572,26 @@ def test_sesolver_wavefunction_path(cuda):
     assert len(U) == 6 and relerr(U[5], scipy.linalg.expm(-1j * H * 0.05)) <= 1e-9      # RK4 truncation error
     with pytest.raises(NotImplementedError):
         s.run(psi0=psi0, pulse=object(), edip=H)
+
+
+def test_sos_mol_wrappers_and_tpa(cuda, tmp_path):
+    """photon_echo / photon_echo_t3 (Mol-based wrappers with their np.savez side effect) and the single-frequency
+    TPA, lime/signal/sos.py:199-228, 731-902, against frozen reference outputs"""
+    from lime_b200.signal import sos
+    g = golden('sos_mol')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    mol = cases.DuckMol(E, dip, gamma, dephasing=0.01 / 27.211386)
+    wp = g['wp']
+    pe = sos.photon_echo(mol, wp, wp, t2=30.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=str(tmp_path / 's'))
+    assert relerr(pe, g['PE']) <= TOL
+    saved = np.load(str(tmp_path / 's.npz'))
+    assert np.array_equal(saved['arr_2'], pe)
+    t3 = sos.photon_echo_t3(mol, wp, wp, 20.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=str(tmp_path / 't'))
+    assert relerr(t3, g['PE_t3']) <= TOL
+    se, esa = sos.photon_echo_t3(mol, wp, wp, 20.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=None, separate=True)
+    assert relerr(se + esa, g['PE_t3']) <= TOL
+    tpa = np.array([sos.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in g['wtpa']])
+    assert relerr(tpa, g['TPA']) <= TOL
+    mol.gamma = None
+    with pytest.raises(ValueError):
+        sos.photon_echo(mol, wp, wp)

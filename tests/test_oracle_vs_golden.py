@@ -220,3 +220,10 @@ def test_sesolver_oracle_matches_reference():
     o, pl = lo.quantum_dynamics(H, psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
     assert np.array_equal(o, g['obs']) and np.array_equal(np.array(pl), g['psilist'])
     assert np.array_equal(lo.se_correlation_3op_2t(H, psi0, [g['A'], g['B'], g['C']], 0.01, 5, 6), g['c3_2t'])
+
+
+def test_tpa_oracle_matches_reference():
+    g = golden('sos_mol')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    assert np.array_equal(np.array([lo.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in g['wtpa']]), g['TPA'])
+    assert np.array_equal(lo.photon_echo_core(E, dip, -g['wp'], g['wp'], 30.0, g_idx, e_idx, f_idx, gamma), g['PE'])
