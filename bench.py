@@ -117,7 +117,7 @@ class JCLindblad:
     name = 'jc_lindblad'
     metric = 'lindblad_rho_steps_per_s'
     unit = 'rho-steps/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     scaling = 'weak'
     bound = 'hbm'
 
@@ -218,7 +218,7 @@ class RedfieldBatch:
     name = 'redfield_batch'
     metric = 'redfield_rho_steps_per_s'
     unit = 'rho-steps/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     scaling = 'weak'
     bound = 'hbm'
 
@@ -293,7 +293,7 @@ class LindbladDense:
     name = 'lindblad_dense'
     metric = 'lindblad_rho_steps_per_s'
     unit = 'rho-steps/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     scaling = 'weak'
     bound = 'tensor'
 
@@ -365,7 +365,7 @@ class LiouvilleEig:
     name = 'liouville_eig'
     metric = 'two_time_correlation_points_per_s'
     unit = 'points/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     scaling = 'weak'
     bound = 'tensor'
 
@@ -447,7 +447,7 @@ class LiouvilleEig:
 class HeomBase:
     metric = 'heom_ado_steps_per_s'
     unit = 'ADO-steps/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     bound = 'hbm'
 
 
@@ -635,7 +635,7 @@ class Sos2DES:
     name = 'sos_2des'
     metric = 'sos_grid_points_per_s'
     unit = 'grid-points/s'
-    dtype = 'complex128 (f64 arithmetic)'
+    dtype = 'f64'                      # complex128 = interleaved f64 pairs
     scaling = 'weak'
     bound = 'hbm'
 
