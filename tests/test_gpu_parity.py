@@ -110,6 +110,10 @@ def test_lindblad_batch_parameter_scan(cuda, path):
     s = Lindblad_solver(None, c_ops=cs)
     rho_f, obs, _ = s.evolve_batch(rho0, 0.02, 40, e_ops=e_ops, H_batch=Hs, path=path)
     assert obs.shape == (40, len(pts), 2)
+    # same operator objects again: the cached plan is reused and gives the same numbers
+    plan_id = id(s._batch_plan[1])
+    rho_f2, obs2, _ = s.evolve_batch(rho0, 0.02, 40, e_ops=e_ops, H_batch=Hs, path=path)
+    assert id(s._batch_plan[1]) == plan_id and np.array_equal(obs2, obs) and np.array_equal(rho_f2, rho_f)
     for b, (o, rl) in enumerate(refs):
         assert relerr(obs[:, b], o) <= TOL
         assert relerr(rho_f[b], rl[-1]) <= TOL
