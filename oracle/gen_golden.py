@@ -294,6 +294,33 @@ def main():
     note('super_lindblad', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'super_lindblad.npz'), tl=tl, taul=taul, wl=wl, A=A3, B=B3, C=C3, **g)
 
+    # ---- spectral post-processing, lime/fft.py
+    import lime.fft as lfft
+    rng = np.random.default_rng(91)
+    xg = np.linspace(-3.0, 4.0, 48)
+    f1 = rng.standard_normal((5, 48)) + 1j * rng.standard_normal((5, 48))
+    f2 = rng.standard_normal((24, 24)) + 1j * rng.standard_normal((24, 24))
+    xs, ys = np.linspace(0, 2, 11), np.linspace(-1, 1, 9)
+    fxy = rng.standard_normal((9, 11)) + 1j * rng.standard_normal((9, 11))
+    kxs, kys = np.linspace(-3, 3, 7), np.linspace(-2, 2, 5)
+    # lime's dft opens a figure (lime/fft.py:122-123), which the plotting stub cannot unpack: exec its source
+    # without the two plotting lines
+    import inspect
+    dsrc = [l for l in inspect.getsource(lfft.dft).split('\n') if 'plt.' not in l and 'ax.' not in l]
+    dns = {'np': np}
+    exec('\n'.join(dsrc), dns)
+    ref_dft = dns['dft']
+    g = {'fft': lfft.fft(f1, xg)[0], 'fft_freq': lfft.fft(f1, xg)[1],
+         'ifft': lfft.ifft(f1[0], xg)[0], 'ifft_freq': lfft.ifft(f1[0], xg)[1],
+         'fft2': lfft.fft2(f2, 0.1, 0.2)[2], 'fft2_fy': lfft.fft2(f2, 0.1, 0.2)[1],
+         'dft': ref_dft(xg, f1[1], kxs), 'dft2': lfft.dft2(xs, ys, fxy, kxs, kys)}
+    o = {'fft': lo.fft(f1, xg)[0], 'fft_freq': lo.fft(f1, xg)[1],
+         'ifft': lo.ifft(f1[0], xg)[0], 'ifft_freq': lo.ifft(f1[0], xg)[1],
+         'fft2': lo.fft2(f2, 0.1, 0.2)[2], 'fft2_fy': lo.fft2(f2, 0.1, 0.2)[1],
+         'dft': lo.dft(xg, f1[1], kxs), 'dft2': lo.dft2(xs, ys, fxy, kxs, kys)}
+    note('fft', **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'fft.npz'), xg=xg, f1=f1, f2=f2, xs=xs, ys=ys, fxy=fxy, kxs=kxs, kys=kys, **g)
+
     # ---- wave-function solver, lime/mol.py:1094-1391
     import lime.mol as lmol
     H = cases.rand_herm(5, 81)

@@ -907,6 +907,69 @@ class SuperLindblad:
 
 
 # --------------------------------------------------------------------------
+# spectral post-processing                                   lime/fft.py
+# 
+# --------------------------------------------------------------------------
+def fft(f, x=None, axis=-1, **kwargs):
+    """lime/fft.py:15-58"""
+    nx = np.asarray(f).shape[axis]
+    if x is None:
+        x = np.arange(nx)
+    dx = x[1] - x[0]
+    g = np.fft.fft(f, axis=axis, **kwargs)
+    g = np.fft.fftshift(g, axes=(axis, ))
+    g *= dx
+    freq = 2. * np.pi * np.fft.fftshift(np.fft.fftfreq(nx, d=dx))
+    g *= np.exp(-1j * freq * x[0])
+    return g, freq
+
+
+def ifft(f, x=None, axis=-1):
+    """lime/fft.py:61-86"""
+    nx = np.asarray(f).shape[axis]
+    if x is None:
+        x = np.arange(nx)
+    dx = x[1] - x[0]
+    g = np.fft.ifft(f, axis=axis)
+    g = np.fft.ifftshift(g)
+    g = g * dx / 2. / np.pi * len(x)
+    freq = 2. * np.pi * np.fft.ifftshift(np.fft.fftfreq(nx, d=dx))
+    return g * np.exp(1j * freq * x[0]), freq
+
+
+def fft2(f, dx=1, dy=1):
+    """lime/fft.py:88-110"""
+    nx, ny = f.shape
+    g = np.fft.fft2(f)
+    g = np.fft.fftshift(g)
+    g = g * dx * dy
+    freqx = 2. * np.pi * np.fft.fftshift(np.fft.fftfreq(nx, d=dx))
+    freqy = 2. * np.pi * np.fft.fftshift(np.fft.fftfreq(nx, d=dy))
+    return freqx, freqy, g
+
+
+def dft(x, f, k):
+    """lime/fft.py:112-124 (without the figure)"""
+    dx = (x[1] - x[0]).real
+    g = np.zeros(len(k), dtype=np.complex128)
+    for i in range(len(k)):
+        g[i] = np.sum(f * np.exp(-1j * k[i] * x)) * dx
+    return g
+
+
+def dft2(x, y, f, kx, ky):
+    """lime/fft.py:126-137"""
+    dx = x[1] - x[0]
+    dy = y[1] - y[0]
+    X, Y = np.meshgrid(x, y)
+    g = np.zeros((len(kx), len(ky)), dtype=complex)
+    for i in range(len(kx)):
+        for j in range(len(ky)):
+            g[i, j] = np.sum(f * np.exp(-1j * kx[i] * X - 1j * ky[j] * Y)) * dx * dy
+    return g
+
+
+# --------------------------------------------------------------------------
 # wave-function solver                                lime/mol.py:1094-1391
 # (SURVEY.md 8f item 3)
 # --------------------------------------------------------------------------

@@ -599,3 +599,21 @@ def test_sos_mol_wrappers_and_tpa(cuda, tmp_path):
     mol.gamma = None
     with pytest.raises(ValueError):
         sos.photon_echo(mol, wp, wp)
+
+
+def test_fft_module(cuda):
+    """lime/fft.py (fft, ifft, fft2 = library FFT + lime's shift/scale/phase epilogue on the
+    device; dft, dft2 = separable sums as tensor-core GEMMs) against frozen reference outputs"""
+    from lime_b200 import fft as lfft
+    g = golden('fft')
+    xg, f1, f2 = g['xg'], g['f1'], g['f2']
+    out, freq = lfft.fft(f1, xg)
+    assert relerr(out, g['fft']) <= 1e-12 and np.array_equal(freq, g['fft_freq'])
+    out0, _ = lfft.fft(f1.T.copy(), xg, axis=0)
+    assert relerr(out0, g['fft'].T) <= 1e-12
+    out, freq = lfft.ifft(f1[0], xg)
+    assert relerr(out, g['ifft']) <= 1e-12 and np.array_equal(freq, g['ifft_freq'])
+    fx, fy, out = lfft.fft2(f2, 0.1, 0.2)
+    assert relerr(out, g['fft2']) <= 1e-12 and np.array_equal(fy, g['fft2_fy'])
+    assert relerr(lfft.dft(xg, f1[1], g['kxs']), g['dft']) <= 1e-12
+    assert relerr(lfft.dft2(g['xs'], g['ys'], g['fxy'], g['kxs'], g['kys']), g['dft2']) <= 1e-12

@@ -227,3 +227,10 @@ def test_tpa_oracle_matches_reference():
     E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
     assert np.array_equal(np.array([lo.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in g['wtpa']]), g['TPA'])
     assert np.array_equal(lo.photon_echo_core(E, dip, -g['wp'], g['wp'], 30.0, g_idx, e_idx, f_idx, gamma), g['PE'])
+
+
+def test_fft_oracle_matches_reference():
+    g = golden('fft')
+    assert np.array_equal(lo.fft(g['f1'], g['xg'])[0], g['fft'])
+    assert np.array_equal(lo.fft2(g['f2'], 0.1, 0.2)[2], g['fft2'])
+    assert np.array_equal(lo.dft2(g['xs'], g['ys'], g['fxy'], g['kxs'], g['kys']), g['dft2'])
