@@ -122,7 +122,7 @@ class JCLindblad:
     bound = 'hbm'
 
     def __init__(self, args, rank, world, need_gpu=True):
-        from lime_b200 import models
+        from lime_b200 import builders as models
         self.ncav, self.ng, self.ndet = 64, 64, 64
         if args.batch:
             self.ng = max(1, args.batch // self.ndet) if args.batch >= self.ndet else 1
@@ -542,7 +542,7 @@ class HeomFMO(HeomBase):
     scaling = 'strong'
 
     def __init__(self, args, rank, world, need_gpu=True):
-        from lime_b200 import models
+        from lime_b200 import builders as models
         from lime_b200.units import au2fs
         self.B = args.batch or 1
         self.rk = args.rk_steps or 200

@@ -169,10 +169,10 @@ def test_qme_plan_analysis_host_logic(monkeypatch):
 
 
 def test_bench_input_builders_match_the_oracle_builders():
-    """the synthetic inputs the GPU arm propagates (lime_b200/models.py) are the operators the CPU arm builds
+    """the synthetic inputs the GPU arm propagates (lime_b200/builders.py) are the operators the CPU arm builds
     (oracle jaynes_cummings = lime's Composite.getH layout, lime/cavity.py:57-97)"""
     from scipy.sparse import csr_matrix
-    from lime_b200 import models
+    from lime_b200 import builders as models
     import lime_oracle as lo
     omega0, kappa, ncav = 1.0, 0.05, 12
     g = np.array([0.01, 0.1, 0.2])
