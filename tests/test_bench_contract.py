@@ -30,3 +30,14 @@ def test_reference_arm_json_line():
 
 def test_reference_arm_other_ranks_exit_quietly():
     assert _run(['--workload', 'redfield_batch'], env={'RANK': '1', 'WORLD_SIZE': '2'}) == ''
+
+
+def test_gpu_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip('a GPU is visible')
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'bench.py'), '--steps', '1', '--warmup', '0'],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode != 0 and 'no CPU fallback' in (out.stderr + out.stdout)
+    assert out.stdout.strip() == ''          # no JSON line, no number
