@@ -149,7 +149,7 @@ class JCLindblad:
             self.plan, _ = oqs._lindblad_plan_batch((self.pat, self.vals), self.c_ops, self.e_ops)
             self.rho = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(self.rho0, (self.B, self.N, self.N)))).cuda()
             self.kernel = {1: 'qme_dense_onchip', 2: 'qme_dense_stage', 3: 'qme_ell_global',
-                           4: 'qme_ell_cluster', 5: 'qme_band_kernel'}[self.plan.path]
+                           4: 'qme_ell_cluster', 5: 'qme_band_kernel', 6: 'qme_tile_kernel'}[self.plan.path]
 
     def config(self):
         return {'workload': 'jc_lindblad: Jaynes-Cummings (no RWA) Fock cutoff 64 -> N=128, '

@@ -6,6 +6,7 @@
 #include "qme_sparse.cuh"
 #include "qme_cluster.cuh"
 #include "qme_band.cuh"
+#include "qme_tile.cuh"
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
@@ -57,6 +58,10 @@ struct limeb200_qme_s {
     int band_noff = 0, band_gt = 0, band_xt = 0, band_C = 0, band_R = 0, band_chain = 0;
     std::vector<int> host_perm;                 // basis order chosen by finalize (new -> old)
     size_t band_smem = 0;
+    // ---- register-patch path (qme_tile.cuh)
+    DevBuf dtbrow, dtcolold, dtcolpos, dtcolc, dtrowc, dtxs0, dteptr, dterank, dteoff, dteval;
+    int tile_NP = 0, tile_P = 0, tile_chunk = 0, tile_C = 0;
+    size_t tile_smem = 0;
     // ---- scratch
     DevBuf s_y, s_acc, s_tmp, s_gk;
     int scratch_B = 0;
@@ -374,6 +379,229 @@ bool build_band_host(const HostOp& G, const std::vector<HostOp>& X, const std::v
     return true;
 }
 
+
+// ---- register-patch path (qme_tile.cuh): structure analysis and tables -------------------------------------------
+struct TileHost {
+    int NP = 0, P = 0, L = 0, Lp = 0, C = 0, chunk = 0;
+    size_t smem = 0;
+    std::vector<int> order;                 // chain order (unpadded) q -> old index, for get_info
+    std::vector<int> brow, colold, colpos, xs0, eptr, erank, eoff;
+    std::vector<double> colc, rowc;
+    std::vector<hcplx> eval;
+};
+
+// Does the problem have the structure qme_tile_kernel needs?  G: off-diagonal graph = P simple paths of equal
+// length L (tridiagonal in chain order) with purely imaginary off-diagonal values; every X_s, Z_s: one real entry
+// per row, and in chain order the source rows of TR consecutive rows are consecutive rows that the owning CTA holds
+// (own or halo rows).  Paths are padded to a multiple of C*TR rows with empty rows.
+bool build_tile_host(const HostOp& G, const std::vector<HostOp>& X, const std::vector<HostOp>& Z, int N, int nb, int E,
+                     const std::vector<hcplx>& eops, long long smem_optin, TileHost& o) {
+    constexpr int TR = 4;
+    const int S = (int)X.size();
+    if (S > QME_TILE_MAXS || N < 4 || N > 128) return false;
+    std::vector<int> id(N);
+    for (int i = 0; i < N; ++i) id[i] = i;
+    EllHost eg;
+    int bw = 0;
+    to_ell(G, N, eg, bw, id, id);
+    if (G.nb < nb) replicate(eg.val, (size_t)N * eg.w, nb);
+    // dense views of the (few) coefficients: gdiag[b][i], goff[b][i][j] through a per-row lookup
+    auto gval = [&](int b, int i, int j) -> hcplx {
+        hcplx v(0, 0);
+        for (int q = 0; q < eg.w; ++q)
+            if (eg.col[(size_t)i * eg.w + q] == j) v += eg.val[((size_t)b * N + i) * eg.w + q];
+        return v;
+    };
+    std::vector<std::vector<int>> adj(N);
+    for (int i = 0; i < N; ++i)
+        for (int q = 0; q < eg.w; ++q) {
+            const int j = eg.col[(size_t)i * eg.w + q];
+            if (j == i) continue;
+            bool nz = false;
+            for (int b = 0; b < nb; ++b) {
+                const hcplx v = eg.val[((size_t)b * N + i) * eg.w + q];
+                if (v != hcplx(0, 0)) nz = true;
+                if (v.real() != 0.0) return false;            // off-diagonal G must be purely imaginary
+            }
+            if (nz) { adj[i].push_back(j); adj[j].push_back(i); }
+        }
+    for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+    for (int v = 0; v < N; ++v)
+        if (adj[v].size() > 2) return false;
+    std::vector<char> seen(N, 0);
+    std::vector<std::vector<int>> paths;
+    for (int v = 0; v < N; ++v) {
+        if (seen[v] || adj[v].size() > 1) continue;
+        std::vector<int> path{v};
+        seen[v] = 1;
+        for (int cur = v;;) {
+            int nxt = -1;
+            for (int u : adj[cur])
+                if (!seen[u]) nxt = u;
+            if (nxt < 0) break;
+            seen[nxt] = 1;
+            path.push_back(nxt);
+            cur = nxt;
+        }
+        paths.push_back(path);
+    }
+    for (int v = 0; v < N; ++v)
+        if (!seen[v]) return false;                            // a cycle
+    const int P = (int)paths.size();
+    if (P < 1 || P > 4) return false;
+    const int L = (int)paths[0].size();
+    for (auto& pth : paths)
+        if ((int)pth.size() != L) return false;
+    // sandwich operators: one real entry per row
+    std::vector<EllHost> ex(S), ez(S);
+    for (int s = 0; s < S; ++s) {
+        int bws = 0;
+        to_ell(X[s], N, ex[s], bws, id, id);
+        to_ell(Z[s], N, ez[s], bws, id, id);
+        if (ex[s].w != 1 || ez[s].w != 1) return false;
+        if (X[s].nb < nb) replicate(ex[s].val, (size_t)N, nb);
+        if (Z[s].nb < nb) replicate(ez[s].val, (size_t)N, nb);
+        for (const hcplx& v : ex[s].val) if (v.imag() != 0.0) return false;
+        for (const hcplx& v : ez[s].val) if (v.imag() != 0.0) return false;
+    }
+    auto has_entry = [&](const EllHost& e, int i) {
+        for (int b = 0; b < nb; ++b)
+            if (e.val[(size_t)b * N + i] != hcplx(0, 0)) return true;
+        return false;
+    };
+    // geometry: smallest cluster whose CTAs fit (<= 16 warps, shared memory)
+    for (int C = 1; C <= 8; C *= 2) {
+        const int Lp = ceil_div(L, C * TR) * C * TR;
+        const int chunk = Lp / C;
+        const int Np = P * Lp;
+        if (Np > 128) continue;
+        const int NP = Np <= 64 ? 64 : 128;
+        const int warps = (P * chunk / TR) * (NP / 64);
+        if (warps > 16) continue;
+        const size_t smem = qme_tile_smem(NP, P, chunk, C, E);
+        if (smem > (size_t)smem_optin) continue;
+        const int NBR = P * (chunk + 2), R = P * chunk;
+        // orientation of the paths
+        for (int mask = 0; mask < (1 << P); ++mask) {
+            std::vector<int> qold((size_t)Np, -1), inv(N, -1);      // padded chain index q = p*Lp + n
+            for (int pth = 0; pth < P; ++pth)
+                for (int n = 0; n < L; ++n) {
+                    const int old = paths[pth][(mask >> pth) & 1 ? L - 1 - n : n];
+                    qold[(size_t)pth * Lp + n] = old;
+                    inv[old] = pth * Lp + n;
+                }
+            // buffer row of chain row q in CTA c (own or halo), -1 if the CTA does not hold it
+            auto bufrow = [&](int c, int q) {
+                const int pth = q / Lp, t = q % Lp - c * chunk + 1;
+                return (t >= 0 && t <= chunk + 1) ? pth * (chunk + 2) + t : -1;
+            };
+            std::vector<int> xs0((size_t)C * (R / TR) * QME_TILE_MAXS, 0);
+            bool ok = true;
+            for (int c = 0; c < C && ok; ++c)
+                for (int g = 0; g < R / TR && ok; ++g) {
+                    const int own0 = g * TR, pth = own0 / chunk, t0 = 1 + own0 % chunk;
+                    const int q0 = pth * Lp + c * chunk + t0 - 1;
+                    for (int s = 0; s < S && ok; ++s) {
+                        int base = pth * (chunk + 2) + t0;                 // default: the patch's own rows (coefficient 0)
+                        bool have = false;
+                        for (int r = 0; r < TR && ok; ++r) {
+                            const int old = qold[q0 + r];
+                            if (old < 0 || !has_entry(ex[s], old)) continue;
+                            const int br = bufrow(c, inv[ex[s].col[old]]);
+                            if (br < 0) { ok = false; break; }
+                            if (have && br - r != base) ok = false;
+                            base = br - r; have = true;
+                        }
+                        if (!ok) break;
+                        if (base < 0 || base + TR - 1 >= NBR) { ok = false; break; }
+                        // rows read from a halo row must belong to a patch that pushes in that direction (see qme_tile.cuh)
+                        for (int r = 0; r < TR; ++r) {
+                            const int t = (base + r) % (chunk + 2);
+                            if (t == 0 && t0 != 1 && have) ok = false;
+                            if (t == chunk + 1 && t0 + TR - 1 != chunk && have) ok = false;
+                        }
+                        xs0[((size_t)c * (R / TR) + g) * QME_TILE_MAXS + s] = base;
+                    }
+                }
+            if (!ok) continue;
+            // ---- tables
+            o.NP = NP; o.P = P; o.L = L; o.Lp = Lp; o.C = C; o.chunk = chunk; o.smem = smem;
+            o.xs0 = xs0;
+            o.order.clear();
+            for (int q = 0; q < Np; ++q)
+                if (qold[q] >= 0) o.order.push_back(qold[q]);
+            auto posof = [&](int q) { return 64 * (q / 64) + 32 * (q % 2) + (q % 64) / 2; };
+            auto same_path = [&](int q1, int q2) {
+                return q1 >= 0 && q2 >= 0 && q1 < Np && q2 < Np && q1 / Lp == q2 / Lp && qold[q1] >= 0 && qold[q2] >= 0;
+            };
+            o.brow.assign((size_t)C * NBR, -1);
+            for (int c = 0; c < C; ++c)
+                for (int pth = 0; pth < P; ++pth)
+                    for (int t = 0; t <= chunk + 1; ++t) {
+                        const int n = c * chunk + t - 1;
+                        if (n >= 0 && n < Lp) o.brow[(size_t)c * NBR + pth * (chunk + 2) + t] = qold[(size_t)pth * Lp + n];
+                    }
+            o.colold.assign(NP, -1);
+            o.colpos.assign((size_t)NP * 4, 0);
+            o.colc.assign((size_t)nb * NP * QME_TILE_COLC, 0.0);
+            for (int pos = 0; pos < NP; ++pos) {
+                const int q = 64 * (pos / 64) + 2 * (pos % 32) + (pos % 64) / 32;
+                for (int k = 0; k < 4; ++k) o.colpos[(size_t)pos * 4 + k] = pos * 16;
+                if (q >= Np || qold[q] < 0) continue;
+                const int old = qold[q];
+                o.colold[pos] = old;
+                const bool hl = same_path(q, q - 1), hr = same_path(q, q + 1);
+                if (hl) o.colpos[(size_t)pos * 4 + 0] = posof(q - 1) * 16;
+                if (hr) o.colpos[(size_t)pos * 4 + 1] = posof(q + 1) * 16;
+                for (int s = 0; s < S; ++s)
+                    if (has_entry(ez[s], old)) o.colpos[(size_t)pos * 4 + 2 + s] = posof(inv[ez[s].col[old]]) * 16;
+                for (int b = 0; b < nb; ++b) {
+                    double* cc = &o.colc[((size_t)b * NP + pos) * QME_TILE_COLC];
+                    const hcplx gd = gval(b, old, old);
+                    cc[0] = gd.real(); cc[1] = -gd.imag();                         // conj(G_jj)
+                    cc[2] = hl ? -gval(b, old, qold[q - 1]).imag() : 0.0;         // conj(G[j][j-1]) = i cL
+                    cc[3] = hr ? -gval(b, old, qold[q + 1]).imag() : 0.0;
+                    for (int s = 0; s < S; ++s) cc[4 + s] = ez[s].val[(size_t)b * N + old].real();
+                }
+            }
+            o.rowc.assign((size_t)nb * C * R * QME_TILE_ROWC, 0.0);
+            for (int b = 0; b < nb; ++b)
+                for (int c = 0; c < C; ++c)
+                    for (int ow = 0; ow < R; ++ow) {
+                        const int pth = ow / chunk, q = pth * Lp + c * chunk + ow % chunk;
+                        const int old = qold[q];
+                        if (old < 0) continue;
+                        double* rcp = &o.rowc[(((size_t)b * C + c) * R + ow) * QME_TILE_ROWC];
+                        const hcplx gd = gval(b, old, old);
+                        rcp[0] = gd.real(); rcp[1] = gd.imag();
+                        rcp[2] = same_path(q, q - 1) ? gval(b, old, qold[q - 1]).imag() : 0.0;
+                        rcp[3] = same_path(q, q + 1) ? gval(b, old, qold[q + 1]).imag() : 0.0;
+                        for (int s = 0; s < S; ++s) rcp[4 + s] = ex[s].val[(size_t)b * N + old].real();
+                    }
+            // observables: Tr(e rho) = sum_ij e[j][i] rho[i][j]
+            const size_t NN = (size_t)N * N;
+            o.eptr.assign(E + 1, 0);
+            o.erank.clear(); o.eoff.clear(); o.eval.clear();
+            for (int e = 0; e < E; ++e) {
+                for (int qi = 0; qi < Np; ++qi)
+                    for (int qj = 0; qj < Np; ++qj) {
+                        if (qold[qi] < 0 || qold[qj] < 0) continue;
+                        const hcplx v = eops[e * NN + (size_t)qold[qj] * N + qold[qi]];
+                        if (v == hcplx(0, 0)) continue;
+                        const int n = qi % Lp, c = n / chunk;
+                        o.erank.push_back(c);
+                        o.eoff.push_back(((qi / Lp) * (chunk + 2) + n - c * chunk + 1) * NP + posof(qj));
+                        o.eval.push_back(v);
+                    }
+                o.eptr[e + 1] = (int)o.erank.size();
+            }
+            if (o.erank.empty()) { o.erank.push_back(-1); o.eoff.push_back(0); o.eval.push_back(hcplx(0, 0)); }
+            return true;
+        }
+    }
+    return false;
+}
+
 int set_op_dense(limeb200_qme_t p, HostOp& op, const double* h, int nb) {
     LB_REQUIRE(p && h, "null argument");
     LB_REQUIRE(!p->finalized, "plan already finalized");
@@ -502,7 +730,7 @@ int limeb200_qme_set_observables(limeb200_qme_t p, const double* h_e, int E) {
 int limeb200_qme_set_path(limeb200_qme_t p, int path) {
     LB_REQUIRE(p, "null plan");
     LB_REQUIRE(!p->finalized, "plan already finalized");
-    LB_REQUIRE(path >= 0 && path <= 5, "path must be 0..5");
+    LB_REQUIRE(path >= 0 && path <= 6, "path must be 0..6");
     p->path_req = path;
     return LB_OK;
 }
@@ -512,6 +740,7 @@ int limeb200_qme_get_info(limeb200_qme_t p, int* info9, int* perm) {
     info9[0] = p->path; info9[1] = p->permuted ? 1 : 0; info9[2] = p->bandwidth;
     info9[3] = p->band_noff; info9[4] = p->band_gt; info9[5] = p->band_xt;
     info9[6] = p->band_C; info9[7] = p->band_R; info9[8] = p->band_chain;
+    if (p->path == 6) { info9[6] = p->tile_C; info9[7] = p->tile_P * p->tile_chunk; info9[8] = p->tile_P; }
     if (perm)
         for (int i = 0; i < p->N; ++i) perm[i] = i < (int)p->host_perm.size() ? p->host_perm[i] : i;
     return LB_OK;
@@ -550,6 +779,13 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     std::vector<int> perm(N), inv(N);
     for (int i = 0; i < N; ++i) perm[i] = inv[i] = i;
     BandHost band;
+    TileHost tile;
+    if (path == 6 || (path == 5 && p->path_req == 0 && N >= 64 && !getenv("LIMEB200_NO_TILE"))) {
+        // register-patch kernel for chain-structured operators; anything else goes to the band kernel
+        const bool ok6 = sparse_ok && build_tile_host(p->G, p->X, p->Z, N, nb, p->E, p->eops, p->smem_optin, tile);
+        LB_REQUIRE(ok6 || p->path_req != 6, "register-patch path does not fit this problem (N=%d)", N);
+        path = ok6 ? 6 : 5;
+    }
     if (path == 4 || path == 5) {
         bool fits = sparse_ok;
         if (fits) {
@@ -620,6 +856,11 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     if (path == 1 || path == 2) LB_REQUIRE(dense_mem_ok, "dense operator batch too large (nb=%d, N=%d)", nb, N);
     p->path = path;
     p->host_perm = perm;
+    if (path == 6) {
+        p->host_perm = tile.order;
+        p->tile_NP = tile.NP; p->tile_P = tile.P; p->tile_chunk = tile.chunk; p->tile_C = tile.C;
+        p->tile_smem = std::max(tile.smem, (size_t)120 * 1024);     // > half of the SM's shared memory: one CTA (and its tensor memory) per SM
+    }
     if (p->device < 0) {             // analysis-only plan: nothing to upload
         if (path >= 3) {
             int bw = 0;
@@ -705,6 +946,18 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
                 LB_CUDA(p->dbzcol[s].upload(band.zcol[s].data(), band.zcol[s].size() * sizeof(int)));
                 LB_CUDA(p->dbzval[s].upload(band.zval[s].data(), band.zval[s].size() * 16));
             }
+        }
+        if (path == 6) {
+            LB_CUDA(p->dtbrow.upload(tile.brow.data(), tile.brow.size() * sizeof(int)));
+            LB_CUDA(p->dtcolold.upload(tile.colold.data(), tile.colold.size() * sizeof(int)));
+            LB_CUDA(p->dtcolpos.upload(tile.colpos.data(), tile.colpos.size() * sizeof(int)));
+            LB_CUDA(p->dtcolc.upload(tile.colc.data(), tile.colc.size() * sizeof(double)));
+            LB_CUDA(p->dtrowc.upload(tile.rowc.data(), tile.rowc.size() * sizeof(double)));
+            LB_CUDA(p->dtxs0.upload(tile.xs0.data(), tile.xs0.size() * sizeof(int)));
+            LB_CUDA(p->dteptr.upload(tile.eptr.data(), tile.eptr.size() * sizeof(int)));
+            LB_CUDA(p->dterank.upload(tile.erank.data(), tile.erank.size() * sizeof(int)));
+            LB_CUDA(p->dteoff.upload(tile.eoff.data(), tile.eoff.size() * sizeof(int)));
+            LB_CUDA(p->dteval.upload(tile.eval.data(), tile.eval.size() * 16));
         }
         if (p->permuted) LB_CUDA(p->dperm.upload(perm.data(), N * sizeof(int)));
         // observables as COO over rho's (permuted) linear index:
@@ -934,6 +1187,21 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
     memset(&a, 0, sizeof(a));
     fill_ell_args(p, a, B);
     a.nsteps = nsteps; a.traj_every = traj_every; a.rho = rho; a.obs = obs; a.traj = traj; a.dt = dt;
+    if (p->path == 6) {
+        QmeTileArgs t;
+        memset(&t, 0, sizeof(t));
+        t.N = p->N; t.E = p->E; t.B = B; t.nsteps = nsteps; t.traj_every = traj_every; t.nb = p->nb;
+        t.C = p->tile_C; t.P = p->tile_P; t.chunk = p->tile_chunk;
+        t.brow = p->dtbrow.as<int>(); t.colold = p->dtcolold.as<int>(); t.colpos = p->dtcolpos.as<int>();
+        t.colc = p->dtcolc.as<double>(); t.rowc = p->dtrowc.as<double>(); t.xs0 = p->dtxs0.as<int>();
+        t.eptr = p->dteptr.as<int>(); t.erank = p->dterank.as<int>(); t.eoff = p->dteoff.as<int>();
+        t.eval = p->dteval.as<cplx>();
+        t.rho = rho; t.obs = obs; t.traj = traj; t.dt = dt;
+        int r = qme_tile_launch(t, p->tile_NP, (int)p->X.size(), p->tile_smem, st);
+        if (r != LB_OK) return r;
+        p->launches += 1;
+        return LB_OK;
+    }
     if (p->path == 5) {
         QmeBandArgs g;
         memset(&g, 0, sizeof(g));

@@ -1,0 +1,455 @@
+// Register-patch cluster propagator for chain-structured operators (Jaynes-Cummings / Rabi
+// ladders, tight-binding chains with ladder-type collapse operators):
+//
+//     d rho/dt = G rho + rho G^H + sum_s X_s rho Z_s^H        (lime/oqs.py:706-723 in generator
+//     form; RK4 of lime/phys.py:636-649, all nsteps of a launch fused)
+//
+// Structure exploited (checked on the host, qme.cu:build_tile_host; anything else runs on
+// qme_band_kernel): in a suitable basis order ("chain order": the off-diagonal graph of G is a
+// union of P simple paths) G is tridiagonal with purely imaginary off-diagonals and every X_s /
+// Z_s has one real entry per row.  The propagation is then a 5-point stencil on rho plus one
+// shifted pick-up per sandwich term, and the kernel is organised like a stencil code:
+//
+//   * one thread-block cluster per density matrix; CTA c owns, from each path, the chunk of
+//     `chunk` consecutive chain rows [c*chunk, (c+1)*chunk) and keeps them together with one halo
+//     row on either side of every chunk: buffer row (p, t), t = 0 .. chunk+1;
+//   * a thread owns a PATCH of TR chain-consecutive rows x 2 chain-consecutive columns.  Columns
+//     are stored in a lane-interleaved order (chain column q = 64 cb + 2 lane + u sits at position
+//     64 cb + 32 u + lane) so that the patch, its left and its right neighbour columns are each one
+//     conflict-free 512-byte warp access; the TR + 2 rows of the patch's row window slide through
+//     registers.  Per element and stage that is 4.5 shared-memory accesses of 16 B (window
+//     (TR+2)/TR, left/right 1, sandwich source 1, store 1) against 8 in qme_band_kernel, and no
+//     address arithmetic: every access is base register + immediate;
+//   * rho lives in TENSOR MEMORY (tcgen05.ld / tcgen05.st, 32x32b shape: TMEM lane = thread,
+//     columns = the thread's private words), used as a second register file -- it is read three
+//     times and written once per RK4 step, which keeps 4 TR registers per thread free for the
+//     sliding window; the RK4 accumulator stays in registers;
+//   * the two stage vectors ping-pong in shared memory; halo rows are pushed into the neighbour
+//     CTAs with st.async (complete_tx on the consumer's mbarrier), one __syncthreads + one
+//     mbarrier wait per stage, no cluster barrier in the time loop;
+//   * the four RK4 stages are unrolled with compile-time buffer addresses and stage algebra.
+#pragma once
+#include "common.cuh"
+#include "qme_band.cuh"          // mbarrier / st.async helpers
+#include <cooperative_groups.h>
+
+#define QME_TILE_MAXS 2
+#define QME_TILE_ROWC 6           // doubles per row-coefficient record: gd.x gd.y gup gdn xv0 xv1
+#define QME_TILE_COLC 6           // doubles per column-coefficient record: conj(gd).x conj(gd).y cL cR zv0 zv1
+
+struct QmeTileArgs {
+    int N, E, B, nsteps, traj_every, nb;
+    int C, P, chunk;             // CTAs per cluster, paths, chain rows of one path owned by one CTA
+    const int* brow;             // [C][P*(chunk+2)]  old basis index of buffer row (p, t), -1 = zero row
+    const int* colold;           // [NP]              old basis index of column position, -1 = padding
+    const int* colpos;           // [NP][4]           byte offsets inside a row: left nbr, right nbr, sandwich source 0, 1
+    const double* colc;          // [nb][NP][QME_TILE_COLC]
+    const double* rowc;          // [nb][C][R][QME_TILE_ROWC],  R = P*chunk own rows per CTA
+    const int* xs0;              // [C][R/TR][QME_TILE_MAXS]  buffer row of the sandwich source of a patch's first row
+    const int* eptr;             // observables as COO: entries [eptr[e], eptr[e+1])
+    const int* erank;            //   owner CTA of the entry's row
+    const int* eoff;             //   element offset (buffer row * NP + position) in the owner's buffer
+    const cplx* eval;
+    cplx* rho;                   // [B][N][N] in/out (caller's basis order)
+    cplx* obs;                   // [nsteps][B][E] or null
+    cplx* traj;                  // [nsteps/traj_every][B][N][N] or null
+    double dt;
+};
+
+// ---- tensor memory as a per-thread scratch file ------------------------------------------------
+struct TmemWords { unsigned r[8]; };
+// issue the load (asynchronous) ...
+__device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, TmemWords& w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(w.r[0]), "=r"(w.r[1]), "=r"(w.r[2]), "=r"(w.r[3]), "=r"(w.r[4]), "=r"(w.r[5]), "=r"(w.r[6]), "=r"(w.r[7])
+                 : "r"(taddr));
+}
+// ... and wait for it; the words are operands of the wait so that no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_ld8_wait(TmemWords& w, double (&d)[4]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7])
+                 :: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
+}
+__device__ __forceinline__ void tmem_st8(unsigned taddr, const double (&d)[4]) {
+    unsigned r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r[2 * i] = (unsigned)__double2loint(d[i]); r[2 * i + 1] = (unsigned)__double2hiint(d[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
+template <int NP, int TR, int S>
+struct QmeTileCtx {
+    static constexpr int ROWB = NP * 16;
+    // per-thread constants of the launch
+    unsigned own, nl, nr;              // byte offset (buffer 0, from the start of shared memory) of window row 0 at: own column 0, left nbr, right nbr
+    unsigned xs[S > 0 ? S : 1][2];     // ... of the sandwich source of patch row 0 at the source columns of u = 0, 1
+    unsigned rc;                       // ... of the row-coefficient records of the patch's rows
+    unsigned up_dst, dn_dst, up_bar, dn_bar;   // remote (shared::cluster) addresses, buffer 0, of the pushed rows; 0 = no push
+    unsigned trho;                     // tensor-memory address of this thread's rho words
+    double cdr[2], cdi[2], cL[2], cR[2], zv[S > 0 ? S : 1][2];
+    double hdt, dt, w6;
+};
+
+// One RK4 stage of one thread's patch.  STAGE is compile time: input buffer = STAGE & 1, output = the other one.
+template <int NP, int TR, int S, int STAGE>
+__device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, char* smem_gen, cplx (&acc)[TR][2],
+                                                unsigned bufb) {
+    constexpr int ROWB = NP * 16;
+    // ordinary shared-memory accesses (base register + immediate) that the compiler is free to schedule
+    const unsigned in_off = (STAGE & 1) ? bufb : 0u;
+    const unsigned out_off = (STAGE & 1) ? 0u : bufb;
+    const char* pown = smem_gen + (c.own + in_off);
+    const char* pl = smem_gen + (c.nl + in_off);
+    const char* pr = smem_gen + (c.nr + in_off);
+    const char* prc = smem_gen + c.rc;
+    char* pout = smem_gen + (c.own + out_off);
+    const double cy = (STAGE == 2) ? c.dt : c.hdt;
+
+    cplx wp[2], wc[2], wn[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        wp[u] = *reinterpret_cast<const cplx*>(pown + 512 * u);
+        wc[u] = *reinterpret_cast<const cplx*>(pown + ROWB + 512 * u);
+    }
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) wn[u] = *reinterpret_cast<const cplx*>(pown + (r + 2) * ROWB + 512 * u);
+        const cplx yl = *reinterpret_cast<const cplx*>(pl + (r + 1) * ROWB);
+        const cplx yr = *reinterpret_cast<const cplx*>(pr + (r + 1) * ROWB);
+        const double2 gd = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8));          // G_ii
+        const double2 gud = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8) + 16);    // Im G[i][i-1], Im G[i][i+1]
+        TmemWords tw;
+        if (STAGE > 0) tmem_ld8_issue(c.trho + 8 * r, tw);
+        cplx k[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            // diagonal: (G_ii + conj G_jj) y_ij
+            const double dr = gd.x + c.cdr[u], di = gd.y + c.cdi[u];
+            k[u].x = dr * wc[u].x - di * wc[u].y;
+            k[u].y = dr * wc[u].y + di * wc[u].x;
+            // left multiplication: i gup y[i-1][j] + i gdn y[i+1][j]
+            k[u].x = fma(-gud.x, wp[u].y, k[u].x);
+            k[u].y = fma(gud.x, wp[u].x, k[u].y);
+            k[u].x = fma(-gud.y, wn[u].y, k[u].x);
+            k[u].y = fma(gud.y, wn[u].x, k[u].y);
+            // right multiplication: y[i][j-1] conj(G[j][j-1]) + y[i][j+1] conj(G[j][j+1]), coefficients i cL, i cR
+            const cplx a = (u == 0) ? yl : wc[0];
+            const cplx b = (u == 0) ? wc[1] : yr;
+            k[u].x = fma(-c.cL[u], a.y, k[u].x);
+            k[u].y = fma(c.cL[u], a.x, k[u].y);
+            k[u].x = fma(-c.cR[u], b.y, k[u].x);
+            k[u].y = fma(c.cR[u], b.x, k[u].y);
+        }
+        if (S > 0) {
+            const double2 xv = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8) + 32);
+#pragma unroll
+            for (int s = 0; s < S; ++s) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const cplx ys = *reinterpret_cast<const cplx*>(smem_gen + (c.xs[s][u] + in_off) + r * ROWB);
+                    const double cf = (s == 0 ? xv.x : xv.y) * c.zv[s][u];
+                    k[u].x = fma(cf, ys.x, k[u].x);
+                    k[u].y = fma(cf, ys.y, k[u].y);
+                }
+            }
+        }
+        // RK4 stage algebra (lime/phys.py:636-649)
+        cplx yn[2];
+        if (STAGE == 0) {                     // the stage input IS rho
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                acc[r][u] = k[u];
+                yn[u] = cmake(fma(cy, k[u].x, wc[u].x), fma(cy, k[u].y, wc[u].y));
+            }
+        } else {
+            double rh[4];
+            tmem_ld8_wait(tw, rh);
+            if (STAGE < 3) {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    acc[r][u].x = fma(2.0, k[u].x, acc[r][u].x);
+                    acc[r][u].y = fma(2.0, k[u].y, acc[r][u].y);
+                    yn[u] = cmake(fma(cy, k[u].x, rh[2 * u]), fma(cy, k[u].y, rh[2 * u + 1]));
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    yn[u].x = fma(c.w6, acc[r][u].x + k[u].x, rh[2 * u]);
+                    yn[u].y = fma(c.w6, acc[r][u].y + k[u].y, rh[2 * u + 1]);
+                }
+                const double nr4[4] = {yn[0].x, yn[0].y, yn[1].x, yn[1].y};
+                tmem_st8(c.trho + 8 * r, nr4);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
+        // boundary rows of a chunk also go into the neighbour CTA's halo row; the bytes are counted on its mbarrier
+        if (r == 0 && c.up_dst) {
+            st_async_c128<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
+            st_async_c128<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
+        }
+        if (r == TR - 1 && c.dn_dst) {
+            st_async_c128<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
+            st_async_c128<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
+    }
+}
+
+// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][row coefficients R*6 doubles][tmem base]
+static inline size_t qme_tile_smem(int NP, int P, int chunk, int C, int E) {
+    const size_t nbr = (size_t)P * (chunk + 2);
+    const size_t e = E > 0 ? E : 1;
+    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + (size_t)P * chunk * QME_TILE_ROWC * 8 + 16;
+}
+
+template <int NP, int TR, int S>
+__global__ void __launch_bounds__(512, 1)
+qme_tile_kernel(QmeTileArgs a) {
+    extern __shared__ __align__(16) char smem_raw[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    constexpr int ROWB = NP * 16;
+    constexpr int CB = NP / 64;
+    constexpr int SS = S > 0 ? S : 1;
+    const int C = a.C, P = a.P, chunk = a.chunk;
+    const int rank = (C > 1) ? (int)cluster.block_rank() : 0;
+    const int b = blockIdx.x / C;
+    const size_t vb = (a.nb > 1) ? (size_t)b : 0;
+    const int NBR = P * (chunk + 2);                  // buffer rows
+    const int R = P * chunk;                          // own rows
+    const int T = blockDim.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int cb = warp % CB, g = warp / CB;          // column block, row group (patch rows g*TR .. g*TR+TR-1 of the own rows)
+    const int Ee = max(a.E, 1);
+
+    const unsigned bufb = (unsigned)NBR * ROWB;
+    const unsigned o_bar = 2 * bufb;                  // 4 mbarriers: halo[2], partial sums[2]
+    const unsigned o_red = o_bar + 64;                // [E][32] cplx
+    const unsigned o_part = o_red + Ee * 32 * 16;     // [2][C][E] cplx (rank 0)
+    const unsigned o_rc = o_part + 2 * C * Ee * 16;   // [R][6] doubles
+    const unsigned o_tm = o_rc + R * QME_TILE_ROWC * 8;
+    cplx* buf0 = reinterpret_cast<cplx*>(smem_raw);
+    cplx* red = reinterpret_cast<cplx*>(smem_raw + o_red);
+    cplx* part = reinterpret_cast<cplx*>(smem_raw + o_part);
+    double* rc = reinterpret_cast<double*>(smem_raw + o_rc);
+    unsigned* tmbase = reinterpret_cast<unsigned*>(smem_raw + o_tm);
+
+    // ---- tensor memory: 8 TR words per thread; warps sharing a lane quadrant take consecutive column ranges
+    constexpr int TM_PER_WARP = 8 * TR;
+    constexpr int TM_COLS = 256;      // 16 warps = 4 per lane quadrant; the launch requests > half of the shared memory, so one CTA per SM
+    static_assert(TM_PER_WARP * 4 <= TM_COLS, "tensor memory budget: 16 warps");
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmbase)), "n"(TM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+
+    // ---- load rho (own + halo rows, chain order / lane-interleaved columns) into buffer 0, zero buffer 1
+    const cplx* grho = a.rho + (size_t)b * a.N * a.N;
+    const int* brow = a.brow + rank * NBR;
+    for (int l = threadIdx.x; l < NBR * NP; l += T) {
+        const int br = l / NP, pos = l - br * NP;
+        const int orow = brow[br], ocol = a.colold[pos];
+        cplx v = cmake(0, 0);
+        if (orow >= 0 && ocol >= 0) v = grho[(size_t)orow * a.N + ocol];
+        buf0[l] = v;
+        buf0[NBR * NP + l] = cmake(0, 0);
+    }
+    for (int l = threadIdx.x; l < R * QME_TILE_ROWC; l += T)
+        rc[l] = a.rowc[(vb * C + rank) * R * QME_TILE_ROWC + l];
+
+    QmeTileCtx<NP, TR, S> c;
+    const int own0 = g * TR;                           // first own row of the patch
+    const int p = own0 / chunk, t0 = 1 + own0 % chunk; // path, buffer row inside the chunk block
+    const int wb = p * (chunk + 2) + t0 - 1;           // window row 0
+    const int pos0 = 64 * cb + lane;                   // column position of u = 0 (u = 1: + 32)
+    const unsigned sbase = smem_u32(smem_raw);
+    c.own = wb * ROWB + pos0 * 16;
+    c.nl = wb * ROWB + a.colpos[pos0 * 4 + 0];
+    c.nr = wb * ROWB + a.colpos[(pos0 + 32) * 4 + 1];
+    c.rc = o_rc + own0 * QME_TILE_ROWC * 8;
+#pragma unroll
+    for (int s = 0; s < SS; ++s) {
+        const int xr = (S > 0) ? a.xs0[(rank * (R / TR) + g) * QME_TILE_MAXS + s] : 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            c.xs[s][u] = (S > 0) ? (unsigned)(xr * ROWB + a.colpos[(pos0 + 32 * u) * 4 + 2 + s]) : 0u;
+            c.zv[s][u] = (S > 0) ? a.colc[(vb * NP + pos0 + 32 * u) * QME_TILE_COLC + 4 + s] : 0.0;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const double* cc = a.colc + (vb * NP + pos0 + 32 * u) * QME_TILE_COLC;
+        c.cdr[u] = cc[0]; c.cdi[u] = cc[1]; c.cL[u] = cc[2]; c.cR[u] = cc[3];
+    }
+    c.hdt = 0.5 * a.dt; c.dt = a.dt; c.w6 = a.dt / 6.0;
+    char* smem_gen = smem_raw;
+
+    // ---- neighbours: mapped shared-memory windows and mbarriers
+    const unsigned bar0 = sbase + o_bar;
+    const bool first_tile = (t0 == 1), last_tile = (t0 + TR - 1 == chunk);
+    c.up_dst = c.dn_dst = c.up_bar = c.dn_bar = 0;
+    unsigned r0_part = 0, r0_bar = 0, halo_bytes = 0;
+    if (C > 1) {
+        if (threadIdx.x == 0) {
+            for (int m = 0; m < 4; ++m) mbar_init(bar0 + 8 * m, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if (rank > 0) {
+            halo_bytes += P * ROWB;
+            if (first_tile) {       // own row t = 1 is the neighbour's halo row t = chunk + 1 of the same path
+                c.up_dst = mapa_u32(sbase + (p * (chunk + 2) + chunk + 1) * ROWB + pos0 * 16, rank - 1);
+                c.up_bar = mapa_u32(bar0, rank - 1);
+            }
+        }
+        if (rank < C - 1) {
+            halo_bytes += P * ROWB;
+            if (last_tile) {        // own row t = chunk is the neighbour's halo row t = 0
+                c.dn_dst = mapa_u32(sbase + (p * (chunk + 2)) * ROWB + pos0 * 16, rank + 1);
+                c.dn_bar = mapa_u32(bar0, rank + 1);
+            }
+        }
+        r0_part = mapa_u32(sbase + o_part, 0);
+        r0_bar = mapa_u32(bar0 + 16, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    c.trho = *tmbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(warp >> 2) * TM_PER_WARP;
+
+    cplx acc[TR][2];
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+        double rh[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const cplx v = *reinterpret_cast<const cplx*>(smem_raw + c.own + (r + 1) * ROWB + 512 * u);
+            rh[2 * u] = v.x; rh[2 * u + 1] = v.y;
+            acc[r][u] = cmake(0, 0);
+        }
+        tmem_st8(c.trho + 8 * r, rh);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (C > 1) cluster.sync();
+
+    for (int step = 0; step < a.nsteps; ++step) {
+#define QME_TILE_STAGE(ST)                                                                           \
+        if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * ((ST) & 1), halo_bytes);      \
+        qme_tile_stage<NP, TR, S, ST>(c, smem_gen, acc, bufb);                                        \
+        if ((ST) == 3) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                  \
+        __syncthreads();                                                                              \
+        if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));
+        QME_TILE_STAGE(0)
+        if (C > 1 && a.obs && step > 0 && rank == 0) {
+            // partial sums of the previous step (pushed by the other CTAs with st.async) are complete
+            const int sp = step - 1;
+            for (int e = threadIdx.x; e < a.E; e += T) {
+                mbar_wait(bar0 + 16 + 8 * (sp & 1), (unsigned)((sp >> 1) & 1));
+                const cplx* pp = part + (size_t)(sp & 1) * C * a.E;
+                cplx sum = cmake(0, 0);
+                for (int q = 0; q < C; ++q) sum = cadd(sum, pp[q * a.E + e]);
+                a.obs[((size_t)sp * a.B + b) * a.E + e] = sum;
+            }
+        }
+        QME_TILE_STAGE(1)
+        QME_TILE_STAGE(2)
+        QME_TILE_STAGE(3)
+#undef QME_TILE_STAGE
+        // buffer 0 now holds rho_{n+1} (own + halo rows)
+        if (a.obs) {
+            for (int e = 0; e < a.E; ++e) {
+                cplx v = cmake(0, 0);
+                for (int n = a.eptr[e] + threadIdx.x; n < a.eptr[e + 1]; n += T)
+                    if (a.erank[n] == rank) cfma(v, a.eval[n], buf0[a.eoff[n]]);
+                for (int off = 16; off > 0; off >>= 1) {
+                    v.x += __shfl_down_sync(0xffffffffu, v.x, off);
+                    v.y += __shfl_down_sync(0xffffffffu, v.y, off);
+                }
+                if (lane == 0) red[e * 32 + warp] = v;
+            }
+            __syncthreads();
+            if (C > 1 && rank == 0 && threadIdx.x == 0)
+                mbar_arrive_expect_tx(bar0 + 16 + 8 * (step & 1), (unsigned)((C - 1) * a.E * 16));
+            for (int e = threadIdx.x; e < a.E; e += T) {
+                cplx sum = cmake(0, 0);
+                for (int w = 0; w < (T + 31) / 32; ++w) sum = cadd(sum, red[e * 32 + w]);
+                if (C == 1) a.obs[((size_t)step * a.B + b) * a.E + e] = sum;
+                else if (rank == 0) part[(size_t)(step & 1) * C * a.E + e] = sum;
+                else st_async_c128<0>(r0_part + (unsigned)(((step & 1) * C + rank) * a.E + e) * 16u, sum,
+                                      r0_bar + 8 * (step & 1));
+            }
+            __syncthreads();          // red[] is reused by the next step
+        }
+        if (a.traj && ((step + 1) % a.traj_every) == 0) {
+            cplx* dst = a.traj + ((size_t)(step / a.traj_every) * a.B + b) * a.N * a.N;
+#pragma unroll
+            for (int r = 0; r < TR; ++r) {
+                const int orow = brow[wb + 1 + r];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ocol = a.colold[pos0 + 32 * u];
+                    if (orow >= 0 && ocol >= 0) dst[(size_t)orow * a.N + ocol] = *reinterpret_cast<const cplx*>(smem_raw + c.own + (r + 1) * ROWB + 512 * u);
+                }
+            }
+        }
+    }
+    if (C > 1 && a.obs && a.nsteps > 0 && rank == 0) {
+        const int sp = a.nsteps - 1;
+        for (int e = threadIdx.x; e < a.E; e += T) {
+            mbar_wait(bar0 + 16 + 8 * (sp & 1), (unsigned)((sp >> 1) & 1));
+            const cplx* pp = part + (size_t)(sp & 1) * C * a.E;
+            cplx sum = cmake(0, 0);
+            for (int q = 0; q < C; ++q) sum = cadd(sum, pp[q * a.E + e]);
+            a.obs[((size_t)sp * a.B + b) * a.E + e] = sum;
+        }
+    }
+    cplx* out = a.rho + (size_t)b * a.N * a.N;
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+        const int orow = brow[wb + 1 + r];
+        double rh[4];
+        TmemWords tw;
+        tmem_ld8_issue(c.trho + 8 * r, tw);
+        tmem_ld8_wait(tw, rh);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int ocol = a.colold[pos0 + 32 * u];
+            if (orow >= 0 && ocol >= 0) out[(size_t)orow * a.N + ocol] = cmake(rh[2 * u], rh[2 * u + 1]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmbase), "n"(TM_COLS));
+    if (C > 1) cluster.sync();      // keep shared memory alive until the neighbours' remote stores are done
+}
+
+template <int NP, int TR, int S>
+static int qme_tile_launch_one(const QmeTileArgs& a, size_t smem, cudaStream_t st) {
+    auto kern = qme_tile_kernel<NP, TR, S>;
+    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int W = (a.P * a.chunk / TR) * (NP / 64);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)a.B * a.C);
+    cfg.blockDim = dim3(32 * W);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = a.C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    LB_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+    return LB_OK;
+}
+
+// implemented in qme_tile_inst.cu
+int qme_tile_launch(const QmeTileArgs& a, int NP, int S, size_t smem, cudaStream_t st);

@@ -10,7 +10,8 @@ from scipy.sparse import issparse, csr_matrix
 from ._lib import lib, check, hptr, LimeB200Error
 from . import _dev
 
-PATH_AUTO, PATH_DENSE_ONCHIP, PATH_DENSE_STAGE, PATH_SPARSE_GLOBAL, PATH_SPARSE_CLUSTER, PATH_SPARSE_BAND = range(6)
+(PATH_AUTO, PATH_DENSE_ONCHIP, PATH_DENSE_STAGE, PATH_SPARSE_GLOBAL, PATH_SPARSE_CLUSTER, PATH_SPARSE_BAND,
+ PATH_SPARSE_TILE) = range(7)
 
 
 def _dense_batch(op, N):

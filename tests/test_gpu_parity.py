@@ -71,7 +71,7 @@ def test_lindblad_drop_in_surface(cuda):
     assert r3.observables.shape == (5, 0) and relerr(r3.rholist[-1], l3[-1]) <= TOL
 
 
-@pytest.mark.parametrize('path', [1, 2, 3, 4, 5])
+@pytest.mark.parametrize('path', [1, 2, 3, 4, 5, 6])
 @pytest.mark.parametrize('ncav', [8, 16, 32, 37, 64])
 def test_lindblad_jc_every_kernel(cuda, path, ncav):
     """Jaynes-Cummings (config-2 shape, small cutoffs) through every kernel family"""
@@ -80,7 +80,7 @@ def test_lindblad_jc_every_kernel(cuda, path, ncav):
     obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=60, dt=0.01)
     if path == 1 and 2 * ncav > 64:
         pytest.skip('dense on-chip path is N <= 64')
-    sp = path in (3, 4, 5)
+    sp = path in (3, 4, 5, 6)
     Hs = csr_matrix(H) if sp else H
     cs = [csr_matrix(c) for c in c_ops] if sp else c_ops
     plan = oqs._lindblad_plan(Hs, cs, e_ops, path=path)
