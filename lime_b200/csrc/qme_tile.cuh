@@ -20,10 +20,12 @@
 //     registers.  Per element and stage that is 4.5 shared-memory accesses of 16 B (window
 //     (TR+2)/TR, left/right 1, sandwich source 1, store 1) against 8 in qme_band_kernel, and no
 //     address arithmetic: every access is base register + immediate;
-//   * rho lives in TENSOR MEMORY (tcgen05.ld / tcgen05.st, 32x32b shape: TMEM lane = thread,
-//     columns = the thread's private words), used as a second register file -- it is read three
-//     times and written once per RK4 step, which keeps 4 TR registers per thread free for the
-//     sliding window; the RK4 accumulator stays in registers;
+//   * rho, the RK4 accumulator and the row-side coefficients live in TENSOR MEMORY (tcgen05.ld /
+//     tcgen05.st, 32x32b shape: TMEM lane = thread, columns = the thread's private words), used
+//     as a second register file: 32 words per patch row = [rho 8][acc 8][G_ii, Im G_i,i-1,
+//     Im G_i,i+1, X_0, X_1: 12][pad 4], fetched with one tcgen05.ld.x32 per row and stage.  That
+//     frees 8 TR registers per thread for the sliding window and takes the 3 coefficient loads
+//     per row (LDS.128 broadcasts, 2 wavefronts each) off the shared-memory pipe;
 //   * the two stage vectors ping-pong in shared memory; halo rows are pushed into the neighbour
 //     CTAs with st.async (complete_tx on the consumer's mbarrier), one __syncthreads + one
 //     mbarrier wait per stage, no cluster barrier in the time loop;
@@ -57,20 +59,30 @@ struct QmeTileArgs {
 };
 
 // ---- tensor memory as a per-thread scratch file ------------------------------------------------
-struct TmemWords { unsigned r[8]; };
-// issue the load (asynchronous) ...
-__device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, TmemWords& w) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                 : "=r"(w.r[0]), "=r"(w.r[1]), "=r"(w.r[2]), "=r"(w.r[3]), "=r"(w.r[4]), "=r"(w.r[5]), "=r"(w.r[6]), "=r"(w.r[7])
-                 : "r"(taddr));
+#define QME_TILE_TMW 32           // tensor-memory words per patch row: [rho 8][acc 8][coefficients 12][pad 4]
+struct TmemRow { unsigned r[32]; };
+// issue the load of a patch row's 32 words (asynchronous) ...
+__device__ __forceinline__ void tmem_ld32_issue(unsigned taddr, TmemRow& w) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(w.r[0]), "=r"(w.r[1]), "=r"(w.r[2]), "=r"(w.r[3]), "=r"(w.r[4]), "=r"(w.r[5]), "=r"(w.r[6]), "=r"(w.r[7]),
+          "=r"(w.r[8]), "=r"(w.r[9]), "=r"(w.r[10]), "=r"(w.r[11]), "=r"(w.r[12]), "=r"(w.r[13]), "=r"(w.r[14]), "=r"(w.r[15]),
+          "=r"(w.r[16]), "=r"(w.r[17]), "=r"(w.r[18]), "=r"(w.r[19]), "=r"(w.r[20]), "=r"(w.r[21]), "=r"(w.r[22]), "=r"(w.r[23]),
+          "=r"(w.r[24]), "=r"(w.r[25]), "=r"(w.r[26]), "=r"(w.r[27]), "=r"(w.r[28]), "=r"(w.r[29]), "=r"(w.r[30]), "=r"(w.r[31])
+        : "r"(taddr));
 }
 // ... and wait for it; the words are operands of the wait so that no consumer can be scheduled above it
-__device__ __forceinline__ void tmem_ld8_wait(TmemWords& w, double (&d)[4]) {
+__device__ __forceinline__ void tmem_ld32_wait(TmemRow& w) {
     asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7])
-                 :: "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
+        : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7]),
+          "+r"(w.r[8]), "+r"(w.r[9]), "+r"(w.r[10]), "+r"(w.r[11]), "+r"(w.r[12]), "+r"(w.r[13]), "+r"(w.r[14]), "+r"(w.r[15]),
+          "+r"(w.r[16]), "+r"(w.r[17]), "+r"(w.r[18]), "+r"(w.r[19]), "+r"(w.r[20]), "+r"(w.r[21]), "+r"(w.r[22]), "+r"(w.r[23]),
+          "+r"(w.r[24]), "+r"(w.r[25]), "+r"(w.r[26]), "+r"(w.r[27])
+        :: "memory");
+}
+__device__ __forceinline__ double tmem_dbl(const TmemRow& w, int i) {      // i-th double of the row record
+    return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
 }
 __device__ __forceinline__ void tmem_st8(unsigned taddr, const double (&d)[4]) {
     unsigned r[8];
@@ -87,26 +99,23 @@ struct QmeTileCtx {
     // per-thread constants of the launch
     unsigned own, nl, nr;              // byte offset (buffer 0, from the start of shared memory) of window row 0 at: own column 0, left nbr, right nbr
     unsigned xs[S > 0 ? S : 1][2];     // ... of the sandwich source of patch row 0 at the source columns of u = 0, 1
-    unsigned rc;                       // ... of the row-coefficient records of the patch's rows
     unsigned up_dst, dn_dst, up_bar, dn_bar;   // remote (shared::cluster) addresses, buffer 0, of the pushed rows; 0 = no push
-    unsigned trho;                     // tensor-memory address of this thread's rho words
+    unsigned trho;                     // tensor-memory address of this thread's row records
     double cdr[2], cdi[2], cL[2], cR[2], zv[S > 0 ? S : 1][2];
     double hdt, dt, w6;
 };
 
 // One RK4 stage of one thread's patch.  STAGE is compile time: input buffer = STAGE & 1, output = the other one.
 template <int NP, int TR, int S, int STAGE>
-__device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, char* smem_gen, cplx (&acc)[TR][2],
-                                                unsigned bufb) {
+__device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
     constexpr int ROWB = NP * 16;
     // ordinary shared-memory accesses (base register + immediate) that the compiler is free to schedule
     const unsigned in_off = (STAGE & 1) ? bufb : 0u;
     const unsigned out_off = (STAGE & 1) ? 0u : bufb;
-    const char* pown = smem_gen + (c.own + in_off);
-    const char* pl = smem_gen + (c.nl + in_off);
-    const char* pr = smem_gen + (c.nr + in_off);
-    const char* prc = smem_gen + c.rc;
-    char* pout = smem_gen + (c.own + out_off);
+    const char* pown = smem + (c.own + in_off);
+    const char* pl = smem + (c.nl + in_off);
+    const char* pr = smem + (c.nr + in_off);
+    char* pout = smem + (c.own + out_off);
     const double cy = (STAGE == 2) ? c.dt : c.hdt;
 
     cplx wp[2], wc[2], wn[2];
@@ -117,75 +126,70 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
     }
 #pragma unroll
     for (int r = 0; r < TR; ++r) {
+        TmemRow tw;
+        tmem_ld32_issue(c.trho + QME_TILE_TMW * r, tw);
 #pragma unroll
         for (int u = 0; u < 2; ++u) wn[u] = *reinterpret_cast<const cplx*>(pown + (r + 2) * ROWB + 512 * u);
         const cplx yl = *reinterpret_cast<const cplx*>(pl + (r + 1) * ROWB);
         const cplx yr = *reinterpret_cast<const cplx*>(pr + (r + 1) * ROWB);
-        const double2 gd = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8));          // G_ii
-        const double2 gud = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8) + 16);    // Im G[i][i-1], Im G[i][i+1]
-        TmemWords tw;
-        if (STAGE > 0) tmem_ld8_issue(c.trho + 8 * r, tw);
         cplx k[2];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            // diagonal: (G_ii + conj G_jj) y_ij
-            const double dr = gd.x + c.cdr[u], di = gd.y + c.cdi[u];
-            k[u].x = dr * wc[u].x - di * wc[u].y;
-            k[u].y = dr * wc[u].y + di * wc[u].x;
-            // left multiplication: i gup y[i-1][j] + i gdn y[i+1][j]
-            k[u].x = fma(-gud.x, wp[u].y, k[u].x);
-            k[u].y = fma(gud.x, wp[u].x, k[u].y);
-            k[u].x = fma(-gud.y, wn[u].y, k[u].x);
-            k[u].y = fma(gud.y, wn[u].x, k[u].y);
             // right multiplication: y[i][j-1] conj(G[j][j-1]) + y[i][j+1] conj(G[j][j+1]), coefficients i cL, i cR
             const cplx a = (u == 0) ? yl : wc[0];
             const cplx b = (u == 0) ? wc[1] : yr;
-            k[u].x = fma(-c.cL[u], a.y, k[u].x);
-            k[u].y = fma(c.cL[u], a.x, k[u].y);
+            k[u].x = -c.cL[u] * a.y;
+            k[u].y = c.cL[u] * a.x;
             k[u].x = fma(-c.cR[u], b.y, k[u].x);
             k[u].y = fma(c.cR[u], b.x, k[u].y);
         }
-        if (S > 0) {
-            const double2 xv = *reinterpret_cast<const double2*>(prc + r * (QME_TILE_ROWC * 8) + 32);
+        tmem_ld32_wait(tw);
+        const double gdx = tmem_dbl(tw, 8), gdy = tmem_dbl(tw, 9), gup = tmem_dbl(tw, 10), gdn = tmem_dbl(tw, 11);
 #pragma unroll
-            for (int s = 0; s < S; ++s) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const cplx ys = *reinterpret_cast<const cplx*>(smem_gen + (c.xs[s][u] + in_off) + r * ROWB);
-                    const double cf = (s == 0 ? xv.x : xv.y) * c.zv[s][u];
-                    k[u].x = fma(cf, ys.x, k[u].x);
-                    k[u].y = fma(cf, ys.y, k[u].y);
-                }
-            }
+        for (int u = 0; u < 2; ++u) {
+            // diagonal: (G_ii + conj G_jj) y_ij
+            const double dr = gdx + c.cdr[u], di = gdy + c.cdi[u];
+            k[u].x = fma(dr, wc[u].x, k[u].x);
+            k[u].x = fma(-di, wc[u].y, k[u].x);
+            k[u].y = fma(dr, wc[u].y, k[u].y);
+            k[u].y = fma(di, wc[u].x, k[u].y);
+            // left multiplication: i gup y[i-1][j] + i gdn y[i+1][j]
+            k[u].x = fma(-gup, wp[u].y, k[u].x);
+            k[u].y = fma(gup, wp[u].x, k[u].y);
+            k[u].x = fma(-gdn, wn[u].y, k[u].x);
+            k[u].y = fma(gdn, wn[u].x, k[u].y);
         }
-        // RK4 stage algebra (lime/phys.py:636-649)
-        cplx yn[2];
-        if (STAGE == 0) {                     // the stage input IS rho
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double xv = tmem_dbl(tw, 12 + s);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                acc[r][u] = k[u];
-                yn[u] = cmake(fma(cy, k[u].x, wc[u].x), fma(cy, k[u].y, wc[u].y));
-            }
-        } else {
-            double rh[4];
-            tmem_ld8_wait(tw, rh);
-            if (STAGE < 3) {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    acc[r][u].x = fma(2.0, k[u].x, acc[r][u].x);
-                    acc[r][u].y = fma(2.0, k[u].y, acc[r][u].y);
-                    yn[u] = cmake(fma(cy, k[u].x, rh[2 * u]), fma(cy, k[u].y, rh[2 * u + 1]));
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    yn[u].x = fma(c.w6, acc[r][u].x + k[u].x, rh[2 * u]);
-                    yn[u].y = fma(c.w6, acc[r][u].y + k[u].y, rh[2 * u + 1]);
-                }
-                const double nr4[4] = {yn[0].x, yn[0].y, yn[1].x, yn[1].y};
-                tmem_st8(c.trho + 8 * r, nr4);
+                const cplx ys = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
+                const double cf = xv * c.zv[s][u];
+                k[u].x = fma(cf, ys.x, k[u].x);
+                k[u].y = fma(cf, ys.y, k[u].y);
             }
         }
+        // RK4 stage algebra (lime/phys.py:636-649); record words 0-3 = rho, 4-7 = accumulator
+        cplx yn[2];
+        double st4[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const double kx = k[u].x, ky = k[u].y;
+            if (STAGE == 0) {                     // the stage input IS rho
+                st4[2 * u] = kx; st4[2 * u + 1] = ky;
+                yn[u] = cmake(fma(cy, kx, wc[u].x), fma(cy, ky, wc[u].y));
+            } else if (STAGE < 3) {
+                st4[2 * u] = fma(2.0, kx, tmem_dbl(tw, 4 + 2 * u));
+                st4[2 * u + 1] = fma(2.0, ky, tmem_dbl(tw, 5 + 2 * u));
+                yn[u] = cmake(fma(cy, kx, tmem_dbl(tw, 2 * u)), fma(cy, ky, tmem_dbl(tw, 2 * u + 1)));
+            } else {
+                yn[u].x = fma(c.w6, tmem_dbl(tw, 4 + 2 * u) + kx, tmem_dbl(tw, 2 * u));
+                yn[u].y = fma(c.w6, tmem_dbl(tw, 5 + 2 * u) + ky, tmem_dbl(tw, 2 * u + 1));
+                st4[2 * u] = yn[u].x; st4[2 * u + 1] = yn[u].y;
+            }
+        }
+        tmem_st8(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
 #pragma unroll
         for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
         // boundary rows of a chunk also go into the neighbour CTA's halo row; the bytes are counted on its mbarrier
@@ -200,13 +204,14 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
 #pragma unroll
         for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
     }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][row coefficients R*6 doubles][tmem base]
+// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base]
 static inline size_t qme_tile_smem(int NP, int P, int chunk, int C, int E) {
     const size_t nbr = (size_t)P * (chunk + 2);
     const size_t e = E > 0 ? E : 1;
-    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + (size_t)P * chunk * QME_TILE_ROWC * 8 + 16;
+    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + 16;
 }
 
 template <int NP, int TR, int S>
@@ -233,17 +238,16 @@ qme_tile_kernel(QmeTileArgs a) {
     const unsigned o_bar = 2 * bufb;                  // 4 mbarriers: halo[2], partial sums[2]
     const unsigned o_red = o_bar + 64;                // [E][32] cplx
     const unsigned o_part = o_red + Ee * 32 * 16;     // [2][C][E] cplx (rank 0)
-    const unsigned o_rc = o_part + 2 * C * Ee * 16;   // [R][6] doubles
-    const unsigned o_tm = o_rc + R * QME_TILE_ROWC * 8;
+    const unsigned o_tm = o_part + 2 * C * Ee * 16;
     cplx* buf0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* red = reinterpret_cast<cplx*>(smem_raw + o_red);
     cplx* part = reinterpret_cast<cplx*>(smem_raw + o_part);
-    double* rc = reinterpret_cast<double*>(smem_raw + o_rc);
     unsigned* tmbase = reinterpret_cast<unsigned*>(smem_raw + o_tm);
 
-    // ---- tensor memory: 8 TR words per thread; warps sharing a lane quadrant take consecutive column ranges
-    constexpr int TM_PER_WARP = 8 * TR;
-    constexpr int TM_COLS = 256;      // 16 warps = 4 per lane quadrant; the launch requests > half of the shared memory, so one CTA per SM
+    // ---- tensor memory: QME_TILE_TMW * TR words per thread; warps sharing a lane quadrant take consecutive column
+    // ranges.  All 512 columns are taken: the launch requests > half of the shared memory, so one CTA per SM.
+    constexpr int TM_PER_WARP = QME_TILE_TMW * TR;
+    constexpr int TM_COLS = 512;
     static_assert(TM_PER_WARP * 4 <= TM_COLS, "tensor memory budget: 16 warps");
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
@@ -262,8 +266,6 @@ qme_tile_kernel(QmeTileArgs a) {
         buf0[l] = v;
         buf0[NBR * NP + l] = cmake(0, 0);
     }
-    for (int l = threadIdx.x; l < R * QME_TILE_ROWC; l += T)
-        rc[l] = a.rowc[(vb * C + rank) * R * QME_TILE_ROWC + l];
 
     QmeTileCtx<NP, TR, S> c;
     const int own0 = g * TR;                           // first own row of the patch
@@ -274,7 +276,6 @@ qme_tile_kernel(QmeTileArgs a) {
     c.own = wb * ROWB + pos0 * 16;
     c.nl = wb * ROWB + a.colpos[pos0 * 4 + 0];
     c.nr = wb * ROWB + a.colpos[(pos0 + 32) * 4 + 1];
-    c.rc = o_rc + own0 * QME_TILE_ROWC * 8;
 #pragma unroll
     for (int s = 0; s < SS; ++s) {
         const int xr = (S > 0) ? a.xs0[(rank * (R / TR) + g) * QME_TILE_MAXS + s] : 0;
@@ -290,7 +291,6 @@ qme_tile_kernel(QmeTileArgs a) {
         c.cdr[u] = cc[0]; c.cdi[u] = cc[1]; c.cL[u] = cc[2]; c.cR[u] = cc[3];
     }
     c.hdt = 0.5 * a.dt; c.dt = a.dt; c.w6 = a.dt / 6.0;
-    char* smem_gen = smem_raw;
 
     // ---- neighbours: mapped shared-memory windows and mbarriers
     const unsigned bar0 = sbase + o_bar;
@@ -324,17 +324,21 @@ qme_tile_kernel(QmeTileArgs a) {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     c.trho = *tmbase + ((unsigned)(32 * (warp & 3)) << 16) + (unsigned)(warp >> 2) * TM_PER_WARP;
 
-    cplx acc[TR][2];
 #pragma unroll
     for (int r = 0; r < TR; ++r) {
-        double rh[4];
+        double rh[4], z4[4] = {0.0, 0.0, 0.0, 0.0}, c4[4];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const cplx v = *reinterpret_cast<const cplx*>(smem_raw + c.own + (r + 1) * ROWB + 512 * u);
             rh[2 * u] = v.x; rh[2 * u + 1] = v.y;
-            acc[r][u] = cmake(0, 0);
         }
-        tmem_st8(c.trho + 8 * r, rh);
+        const double* rcp = a.rowc + (((size_t)vb * C + rank) * R + own0 + r) * QME_TILE_ROWC;
+        tmem_st8(c.trho + QME_TILE_TMW * r, rh);
+        tmem_st8(c.trho + QME_TILE_TMW * r + 8, z4);
+        c4[0] = rcp[0]; c4[1] = rcp[1]; c4[2] = rcp[2]; c4[3] = rcp[3];
+        tmem_st8(c.trho + QME_TILE_TMW * r + 16, c4);
+        c4[0] = rcp[4]; c4[1] = rcp[5]; c4[2] = 0.0; c4[3] = 0.0;
+        tmem_st8(c.trho + QME_TILE_TMW * r + 24, c4);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
     if (C > 1) cluster.sync();
@@ -342,8 +346,7 @@ qme_tile_kernel(QmeTileArgs a) {
     for (int step = 0; step < a.nsteps; ++step) {
 #define QME_TILE_STAGE(ST)                                                                           \
         if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * ((ST) & 1), halo_bytes);      \
-        qme_tile_stage<NP, TR, S, ST>(c, smem_gen, acc, bufb);                                        \
-        if ((ST) == 3) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");                  \
+        qme_tile_stage<NP, TR, S, ST>(c, smem_raw, bufb);                                             \
         __syncthreads();                                                                              \
         if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));
         QME_TILE_STAGE(0)
@@ -414,14 +417,13 @@ qme_tile_kernel(QmeTileArgs a) {
 #pragma unroll
     for (int r = 0; r < TR; ++r) {
         const int orow = brow[wb + 1 + r];
-        double rh[4];
-        TmemWords tw;
-        tmem_ld8_issue(c.trho + 8 * r, tw);
-        tmem_ld8_wait(tw, rh);
+        TmemRow tw;
+        tmem_ld32_issue(c.trho + QME_TILE_TMW * r, tw);
+        tmem_ld32_wait(tw);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int ocol = a.colold[pos0 + 32 * u];
-            if (orow >= 0 && ocol >= 0) out[(size_t)orow * a.N + ocol] = cmake(rh[2 * u], rh[2 * u + 1]);
+            if (orow >= 0 && ocol >= 0) out[(size_t)orow * a.N + ocol] = cmake(tmem_dbl(tw, 2 * u), tmem_dbl(tw, 2 * u + 1));
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
