@@ -129,6 +129,10 @@ def test_qme_plan_analysis_host_logic(monkeypatch):
 
     G, sw, e_ops = jc(64)                                   # config 2: N = 128
     a = engine.analyze_qme(128, G, sw, e_ops)
+    # chain-structured operators: register-patch kernel, two parity paths, cluster of 4, 32 own rows per CTA
+    assert a['path'] == 6 and a['cluster'] == 4 and a['rows_per_cta'] == 32 and a['chain'] == 2
+    monkeypatch.setenv('LIMEB200_NO_TILE', '1')             # the band kernel it replaced stays selectable
+    a = engine.analyze_qme(128, G, sw, e_ops)
     assert a['path'] == 5 and a['cluster'] == 4 and a['rows_per_cta'] == 32
     assert a['noff'] == 2 and a['imag_offdiag'] == 1 and a['real_xz'] == 1 and a['chain'] == 0
     assert sorted(a['perm']) == list(range(128)) and a['permuted'] == 1
@@ -146,6 +150,7 @@ def test_qme_plan_analysis_host_logic(monkeypatch):
     r, c = (G - csr_matrix(np.diag(G.diagonal()))).nonzero()
     assert set(np.abs(inv[r] - inv[c])) == {2}
     monkeypatch.delenv('LIMEB200_BAND_CHAIN')
+    monkeypatch.delenv('LIMEB200_NO_TILE')
     # too large for a cluster: generic sparse kernel; small / dense operands: dense kernels
     G2, sw2, e2 = jc(128)
     assert engine.analyze_qme(256, G2, sw2, e2)['path'] in (3, 4)
