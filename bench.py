@@ -112,6 +112,24 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # workloads
 # ---------------------------------------------------------------------------------------
+def _jc_oracle_point(job):
+    """(final rho, observables[steps, 2]) of one Jaynes-Cummings point with lime's algorithm (checker of JCLindblad.check)"""
+    omega0, omegac, g, ncav, kappa, dt, nsteps = job
+    sys.path.insert(0, os.path.join(ROOT, 'oracle'))
+    import lime_oracle as lo
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(4)
+    except Exception:
+        pass
+    H, c_ops, e_ops = lo.jaynes_cummings(omega0, omegac, g, ncav, kappa)
+    N = 2 * ncav
+    rho0 = np.zeros((N, N), dtype=complex)
+    rho0[ncav, ncav] = 1.0
+    obs, rl = lo.lindblad(H.toarray(), rho0, [c.toarray() for c in c_ops], [e.toarray() for e in e_ops], Nt=nsteps, dt=dt)
+    return rl[-1], obs
+
+
 class JCLindblad:
     """config 2: batched Jaynes-Cummings Lindblad RK4, N = 2 x 64."""
     name = 'jc_lindblad'
@@ -142,6 +160,7 @@ class JCLindblad:
         self.alg_bytes_per_unit = 2 * 16 * self.N * self.N          # read rho_n, write rho_{n+1}
         self.units_per_step = self.B * self.rk
         self.launches = 0
+        self.spot_check = not getattr(args, 'no_spot_check', False)
         if need_gpu:
             import torch
             from lime_b200 import oqs
@@ -169,7 +188,29 @@ class JCLindblad:
         tr = self.torch.einsum('bii->b', self.rho).cpu().numpy()
         err = float(np.max(np.abs(tr - 1.0)))
         assert err < 1e-9, 'trace drifted: %g' % err
-        return {'max_trace_error': err}
+        out = {'max_trace_error': err}
+        if self.spot_check:
+            # oracle spot check of the launch the bench times: the FULL batch from rho0 for `rk` RK4 steps in one launch,
+            # three of its points against lime's algorithm (oracle port, dense np.dot route) on the host
+            import multiprocessing as mp
+            t = self.torch
+            rho = t.from_numpy(np.ascontiguousarray(np.broadcast_to(self.rho0, (self.B, self.N, self.N)))).cuda()
+            obs, _ = self.plan.run_device(rho, self.dt, self.rk)
+            pts = sorted({0, self.B // 2, self.B - 1})
+            got = [(rho[i].cpu().numpy(), obs[:, i].cpu().numpy()) for i in pts]
+            with mp.get_context('spawn').Pool(len(pts)) as pool:
+                ref = pool.map(_jc_oracle_point, [(self.omega0, self.omega0 + self.det_pts[i], self.g_pts[i], self.ncav,
+                                                   self.kappa, self.dt, self.rk) for i in pts])
+            worst = 0.0
+            for (r_g, o_g), (r_o, o_o) in zip(got, ref):
+                worst = max(worst, float(np.max(np.abs(r_g - r_o)) / np.max(np.abs(r_o))),
+                            float(np.max(np.abs(o_g - o_o)) / np.max(np.abs(o_o))))
+            assert worst <= 1e-10, 'bench launch differs from the oracle: %g' % worst
+            out.update(oracle_spot_check_relerr=worst, oracle_spot_check_points=pts, oracle_spot_check_rk4_steps=self.rk,
+                       oracle_spot_check_what='final rho and the (steps, 2) observables of these batch points, '
+                                              'max|a-b|/max|b|, vs oracle/lime_oracle.lindblad on the host')
+            del rho, obs
+        return out
 
     def e2e_setup(self):
         from lime_b200.oqs import Lindblad_solver
@@ -570,7 +611,7 @@ class HeomFMO(HeomBase):
             else:
                 self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
                 self.nhe = self.h.nhe
-                self.kernel = {1: 'heom_onchip', 2: 'heom_stage_kernel', 3: 'heom_persist_kernel'}
+                self.kernel = None
             rho0 = np.zeros((7, 7), dtype=complex)
             rho0[0, 0] = 1.0
             ado = np.zeros((self.B, self.nhe, 7, 7), dtype=complex)
@@ -598,11 +639,43 @@ class HeomFMO(HeomBase):
             self.obs, _ = self.h.plan.run_device(self.ado, self.dt, self.rk, eT=self.eT)
             self.launches += self.h.plan.last_launches
 
+    def kernel_name(self):
+        if self.kernel:
+            return self.kernel
+        return {1: 'heom_onchip_kernel', 2: 'heom_stage_kernel (one launch per RK4 stage)',
+                3: 'heom_persist_cached_kernel / heom_persist_kernel (one cooperative launch per run)'
+                }.get(self.h.plan.path, 'path %d' % self.h.plan.path)
+
     def check(self):
         tr = self.torch.einsum('bii->b', self.ado[:, 0]).cpu().numpy()
         err = float(np.max(np.abs(tr - 1.0)))
         assert err < 1e-9, 'trace drifted: %g' % err
-        return {'max_trace_error': err}
+        out = {'max_trace_error': err}
+        if self.world > 1:
+            # sharded vs single-GPU parity, executed in the run: the FULL hierarchy, nchk RK4 steps from rho0, the
+            # ADO-sharded propagator over all ranks against the one-GPU propagator of the same library on this rank
+            import torch.distributed as dist
+            from lime_b200.heom.heom import HEOM
+            t = self.torch
+            nchk = 200
+            a_sh = t.from_numpy(self.h_ado[:1].copy()).cuda()
+            self.h.run_device(a_sh, self.dt, nchk)
+            single = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
+            a_1 = t.from_numpy(self.h_ado[:1].copy()).cuda()
+            single.plan.run_device(a_1, self.dt, nchk)
+            rel = t.max(t.abs(a_sh - a_1)) / t.max(t.abs(a_1))
+            rel = rel.to(t.float64).reshape(1)
+            dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+            rel = float(rel.item())
+            assert rel <= 1e-12, 'sharded hierarchy differs from the single-GPU one: %g' % rel
+            out.update(sharded_vs_single_relerr=rel, sharded_vs_single_steps=nchk, sharded_vs_single_ados=self.nhe,
+                       sharded_vs_single_norm='max|a-b|/max|b| over the full hierarchy, max over ranks')
+            del single, a_sh, a_1
+        return out
+
+    def close(self):
+        if self.world > 1:
+            self.h.close()
 
     def e2e_setup(self):
         pass
@@ -767,6 +840,7 @@ def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return 0
+    args.workload = args.workload or 'jc_lindblad'
     w = WORKLOADS[args.workload](args, 0, 1, need_gpu=False)
     cores = os.cpu_count() or 1
     vals = []
@@ -795,30 +869,37 @@ def run_reference(args):
     return 0
 
 
-def run_ours(args):
+def _fp64_tensor_roof(torch):
+    """FP64 roof measured in this run: cuBLAS ZGEMM 4096^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json has
+    bf16 only); flops counted as 8 N^3 per complex product"""
+    n = 4096
+    xa = torch.randn(n, n, dtype=torch.complex128, device='cuda')
+    xb = torch.randn(n, n, dtype=torch.complex128, device='cuda')
+    best = 1e30
+    for _ in range(10):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(xa, xb); e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    return 8.0 * n ** 3 / best / 1e12, 'measured in this run: cuBLAS ZGEMM 4096^3 (torch.matmul complex128), best of 10'
+
+
+def measure(w, args, steps, warmup, rank, world, local, with_cpu):
+    """W warm-up steps, K timed steps (CUDA events on the launching stream, barrier + synchronize on both sides, max
+    over ranks), the workload's own check, the end-to-end leg through the public API and, on request, the CPU sample.
+    Returns the JSON line of workload `w` as a dict (identical on every rank up to rank-local clocks)."""
     import torch
     import torch.distributed as dist
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local = int(os.environ.get('LOCAL_RANK', '0'))
-    if not torch.cuda.is_available():
-        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
-    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    w = WORKLOADS[args.workload](args, rank, world)
     flush = None
     if 'flushed' in json.dumps(w.config()):
         flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device='cuda')
     st = torch.cuda.current_stream()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         w.step()
     barrier()
     w.launches = 0
@@ -828,10 +909,10 @@ def run_ours(args):
         gpu_id = local
     sampler = ClockSampler(gpu_id)
     sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     barrier()
     t_wall = time.perf_counter()
-    for k in range(args.steps):
+    for k in range(steps):
         if flush is not None:
             flush.fill_(k & 0xff)
         ev[k][0].record(st)
@@ -848,34 +929,23 @@ def run_ours(args):
         dist.all_reduce(launches, op=dist.ReduceOp.SUM)
     total_ms = float(total_ms.item())
     chk = w.check()
-    units_all = w.units_per_step * world * args.steps
+    units_all = w.units_per_step * world * steps
     value = units_all / (total_ms * 1e-3)
     peak, peak_src = measured_peaks()
-    kernel_s = (sum(ms) / len(ms)) * 1e-3
+    kernel_s = (total_ms / steps) * 1e-3
+    # per-launch figures of the rank's own launch: units_per_step units of alg_bytes_per_unit each
     achieved = w.alg_bytes_per_unit * w.units_per_step / kernel_s / 1e9
     roof_unit = 'GB/s'
     if w.bound == 'tensor':
-        # FP64 roof measured in this run: cuBLAS ZGEMM 4096^3 through torch.matmul, best of 10 (MEASURED_PEAKS.json has
-        # bf16 only); flops counted as 8 N^3 per complex product
-        n = 4096
-        xa = torch.randn(n, n, dtype=torch.complex128, device='cuda')
-        xb = torch.randn(n, n, dtype=torch.complex128, device='cuda')
-        best = 1e30
-        for _ in range(10):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(); torch.matmul(xa, xb); e1.record(); torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1) * 1e-3)
-        peak = 8.0 * n ** 3 / best / 1e12
-        peak_src = 'measured in this run: cuBLAS ZGEMM 4096^3 (torch.matmul complex128), best of 10'
+        peak, peak_src = _fp64_tensor_roof(torch)
         achieved = w.flops_per_unit * w.units_per_step / kernel_s / 1e12
         roof_unit = 'TFLOP/s'
-        del xa, xb
 
     # ---- end to end through the public API with host buffers
     w.e2e_setup()
     w.e2e_step()                                  # warm (pinned pools, plan caches)
     barrier()
-    ne2e = max(1, min(args.steps, 3))
+    ne2e = max(1, min(steps, 3))
     t0 = time.perf_counter()
     for _ in range(ne2e):
         h2d, d2h = w.e2e_step()
@@ -886,8 +956,10 @@ def run_ours(args):
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = w.units_per_step * world * ne2e / float(e2e_t.item())
 
-    line = {'metric': w.metric, 'value': value, 'unit': w.unit, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+    traffic = TRAFFIC.get((w.name, int(w.units_per_step)), {})
+    kernel = w.kernel_name() if hasattr(w, 'kernel_name') else w.kernel
+    line = {'metric': w.metric, 'value': value, 'unit': w.unit, 'n_gpus': world, 'steps': steps,
+            'warmup': warmup, 'ms_per_step': total_ms / steps, 'higher_is_better': True,
             'scaling': w.scaling, 'vs_baseline': None, 'dtype': w.dtype, 'data': 'synthetic',
             'config': w.config(),
             'e2e': {'value': e2e_val, 'unit': w.unit, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
@@ -896,32 +968,103 @@ def run_ours(args):
             'gpu_launches': int(launches.item()),
             'clocks': clocks,
             'roofline': {'bound': w.bound, 'achieved': achieved, 'peak': peak, 'unit': roof_unit,
-                         'frac': achieved / peak, 'traffic': TRAFFIC.get((w.name, int(w.units_per_step))),
-                         'kernel': w.kernel, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': traffic.get('bytes'),
+                         'traffic_source': traffic.get('source', 'not captured for this workload/size'),
+                         'kernel': kernel, 'peak_source': peak_src,
                          'algorithmic_bytes_per_unit': w.alg_bytes_per_unit,
                          'units_per_launch': w.units_per_step,
-                         'note': 'state stays on chip for all %s RK4 steps of a launch; achieved = algorithmic bytes '
+                         'note': getattr(w, 'roof_note', None) or
+                                 'state stays on chip for all %s RK4 steps of a launch; achieved = algorithmic bytes '
                                  '(one read + one write of every rho/ADO per RK4 step) / CUDA-event time, so it is a '
                                  'throughput normalised to the HBM roof, not measured DRAM traffic (see traffic)'
                                  % getattr(w, 'rk', 1)},
             'wall_s_timed_region': t_wall, 'check': chk}
+    if rank == 0 and world == 1 and with_cpu:
+        cores = os.cpu_count() or 1
+        v, desc, variant = cpu_throughput(w, args, with_cpu, cores)
+        line['cpu_baseline'] = {'value': v, 'unit': w.unit, 'cores': cores, 'kind': 'port', 'sample': desc}
+    del flush
+    return line
+
+
+# The HEOM half of the BASELINE metric, measured in the same invocation as the Lindblad headline (default run only).
+# (workload, overrides, label).  At N > 1 heom_fmo is ONE hierarchy ADO-sharded over the ranks (strong scaling, fused
+# peer-memory kernel), with a sharded-vs-single-GPU parity check executed in the run.
+def heom_suite(world):
+    if world == 1:
+        return [('heom_fmo', dict(depth=4, batch=1, rk_steps=400), 'config 4 on one GPU (persistent kernel)'),
+                ('heom_fmo', dict(depth=6, batch=1, rk_steps=50), 'config 4 deepened to N_c = 6 (38 760 ADOs)'),
+                ('heom_fmo', dict(depth=4, batch=64, rk_steps=8), 'config 4, batch of 64 hierarchies (HBM-resident)'),
+                ('heom_sb', dict(batch=32768, rk_steps=200), 'config 3 throughput variant')]
+    return [('heom_fmo', dict(depth=4, batch=1, rk_steps=400), 'config 4, ADO-sharded over %d GPUs' % world),
+            ('heom_fmo', dict(depth=6, batch=1, rk_steps=50), 'config 4 deepened to N_c = 6, ADO-sharded over %d GPUs' % world),
+            ('heom_sb', dict(batch=32768, rk_steps=200), 'config 3 throughput variant, hierarchies split over the ranks')]
+
+
+def run_ours(args):
+    import copy
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device (no CPU fallback)')
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    assert world == args.gpus or world == 1, 'launch with torchrun --nproc-per-node %d' % args.gpus
+
+    suite = args.workload is None and not args.no_suite
+    args.workload = args.workload or 'jc_lindblad'
+    w = WORKLOADS[args.workload](args, rank, world)
+    line = measure(w, args, args.steps, args.warmup, rank, world, local, 0 if args.no_cpu else args.cpu_seconds)
+    del w
+    torch.cuda.empty_cache()
+    if suite:
+        subs = []
+        for name, over, label in heom_suite(world):
+            a2 = copy.copy(args)
+            a2.workload = name
+            for k, v in over.items():
+                setattr(a2, k, v)
+            t0 = time.perf_counter()
+            try:
+                w2 = WORKLOADS[name](a2, rank, world)
+                # CPU sample only where one RK4 step of the port takes well under a second (not the 38 760-ADO hierarchy;
+                # the batch-of-64 line shares the per-unit CPU figure of the single hierarchy)
+                cpu = 0 if (args.no_cpu or over.get('depth', 4) > 4 or over.get('batch', 1) == 64) else min(args.cpu_seconds, 2.0)
+                sub = measure(w2, a2, min(args.steps, 5), 3, rank, world, local, cpu)
+                if hasattr(w2, 'close'):
+                    w2.close()
+                del w2
+            except Exception as exc:                       # a failed sub-workload must not lose the headline line
+                if world > 1:
+                    raise
+                sub = {'error': '%s: %s' % (type(exc).__name__, exc)}
+            torch.cuda.empty_cache()
+            sub['label'] = label
+            sub['wall_s_total'] = time.perf_counter() - t0
+            for k in ('clocks', 'higher_is_better', 'vs_baseline', 'data'):
+                sub.pop(k, None)
+            subs.append(sub)
+        line['heom'] = subs
+        line['gpu_launches_heom'] = sum(int(x.get('gpu_launches', 0)) for x in subs)
     if rank == 0:
-        if world == 1 and not args.no_cpu:
-            cores = os.cpu_count() or 1
-            v, desc, variant = cpu_throughput(w, args, args.cpu_seconds, cores)
-            line['cpu_baseline'] = {'value': v, 'unit': w.unit, 'cores': cores, 'kind': 'port', 'sample': desc}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     return 0
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
-# `ncu --set full` capture summarised under profiles/ (same command, same sizes); None = not captured
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from an ncu capture of the SAME command
+# and sizes (not measured in the bench run itself: ncu replays kernels, so it cannot share a run with the timed region);
+# key = (workload, units per launch); workloads / sizes without a capture report null
 TRAFFIC = {
-    # profiles/r01_traffic_jc_lindblad_default.csv: 1 192 611 840 B read + 1 206 404 096 B written by ONE launch of the
-    # default config (4096 x 128^2 rho, 1000 RK4 steps): rho in, rho out, observables -- 0.11 % of the algorithmic bytes
-    ('jc_lindblad', 4096000): 2399015936,
+    ('jc_lindblad', 4096000): {'bytes': 1178027008 + 1183905280,
+                               'source': 'profiles/r02_traffic_jc_lindblad_default.csv (ncu --metrics dram__bytes_read.sum,'
+                                         'dram__bytes_write.sum on one qme_tile_kernel launch of `python bench.py`: rho in, rho '
+                                         'out, observables = 0.11 % of the algorithmic bytes; the state is on chip for 1000 steps)'},
 }
 
 
@@ -931,7 +1074,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='jc_lindblad', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default=None, choices=sorted(WORKLOADS),
+                    help='one workload only; default: jc_lindblad as the headline line plus the HEOM suite under "heom"')
+    ap.add_argument('--no-suite', action='store_true', help='default run without the HEOM sub-lines')
     ap.add_argument('--rk-steps', type=int, default=0, help='RK4 steps per launch (0 = workload default)')
     ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
     ap.add_argument('--size', type=int, default=0, help='Hilbert dimension for lindblad_dense (0 = 256)')
@@ -939,6 +1084,7 @@ def main():
     ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded heom_fmo: fused peer-memory kernel or stage kernel + NCCL all-gather')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu', action='store_true')
+    ap.add_argument('--no-spot-check', action='store_true', help='skip the in-run oracle spot check of jc_lindblad')
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == 'ours':
         log('note: fewer than 3 warm-up steps requested')

@@ -51,7 +51,7 @@ def d2h(t, pinned=False):
         buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         _pinned_pool[key] = buf
     buf.copy_(t, non_blocking=True)
-    torch.cuda.current_stream().synchronize()
+    torch.cuda.current_stream(t.device).synchronize()      # the copy runs on the SOURCE device's current stream
     return buf.numpy()
 
 
@@ -67,8 +67,9 @@ def ptr(t):
     return C.c_void_p(t.data_ptr())
 
 
-def stream_ptr():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream_ptr(dev=None):
+    """the current stream of device `dev` (default: the current device) as a cudaStream_t"""
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
 
 def as_c128(a):

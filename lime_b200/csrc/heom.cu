@@ -1061,7 +1061,6 @@ struct limeb200_heom_s {
     DevBuf dH, dQ, dqstart, dqmodes, dems, demm, demv, ddamp, dcdn, dcdnR, dnu, dstates, ddn, dup;
     int max_modes_per_elem = 0;
     DevBuf s_y, s_acc, dbar;
-    int scratch_B = 0;
     long long launches = 0;
     long long smem_optin = 0;
     int sm_count = 148;
@@ -1369,11 +1368,9 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
         return LB_OK;
     }
     // ---- scratch shared by the persistent and the stage-wise paths
-    if (B > p->scratch_B || !p->s_y.p) {
-        LB_CUDA(p->s_y.alloc((size_t)2 * B * total * 16));
-        LB_CUDA(p->s_acc.alloc((size_t)B * total * 16));
-        p->scratch_B = B;
-    }
+    // (capacities are tracked in bytes: the sharded entry point allocates s_acc only)
+    if (p->s_y.bytes < (size_t)2 * B * total * 16) LB_CUDA(p->s_y.alloc((size_t)2 * B * total * 16));
+    if (p->s_acc.bytes < (size_t)B * total * 16) LB_CUDA(p->s_acc.alloc((size_t)B * total * 16));
     if (path == 3) {
         // persistent cooperative kernel: all steps in one launch, one grid barrier per stage
         HeomPersistArgs pa;
@@ -1457,11 +1454,7 @@ int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* cons
     p->launches = 0;
     if (nsteps == 0) return LB_OK;
     const long long total = p->nhe * p->n * p->n;
-    if (1 > p->scratch_B || !p->s_acc.p) {
-        LB_CUDA(p->s_acc.alloc((size_t)total * 16));
-        if (!p->s_y.p) LB_CUDA(p->s_y.alloc(16));
-        p->scratch_B = 1;
-    }
+    if (p->s_acc.bytes < (size_t)total * 16) LB_CUDA(p->s_acc.alloc((size_t)total * 16));
     HeomPersistArgs pa;
     memset(&pa, 0, sizeof(pa));
     pa.world = world; pa.rank = rank; pa.epoch = epoch;

@@ -143,7 +143,7 @@ class QmePlan:
         obs = _dev.empty((nsteps, B, self.E), dev=self.dev) if (want_obs and self.E) else None
         traj = _dev.empty((nsteps // traj_every, B, self.N, self.N), dev=self.dev) if traj_every else None
         check(lib().limeb200_qme_run(self._h, _dev.ptr(rho), B, float(dt), int(nsteps), _dev.ptr(coef),
-                                     _dev.ptr(obs), _dev.ptr(traj), int(traj_every), _dev.stream_ptr()))
+                                     _dev.ptr(obs), _dev.ptr(traj), int(traj_every), _dev.stream_ptr(self.dev)))
         return obs, traj
 
     def run(self, rho0, dt, nsteps, coef=None, traj_every=0, pinned=False):
@@ -176,7 +176,7 @@ class QmePlan:
             r = r[None]
         d = _dev.to_dev(r, dev=self.dev)
         o = torch.empty_like(d)
-        check(lib().limeb200_qme_rhs(self._h, _dev.ptr(d), _dev.ptr(o), d.shape[0], _dev.stream_ptr()))
+        check(lib().limeb200_qme_rhs(self._h, _dev.ptr(d), _dev.ptr(o), d.shape[0], _dev.stream_ptr(self.dev)))
         out = o.cpu().numpy()
         return out[0] if single else out
 
@@ -204,7 +204,7 @@ def liouville_rk4(R, v0, dt, nsteps, e_rows=None, traj_every=0, dev=None):
     traj = _dev.empty((nsteps // traj_every, B, D), dev=dev) if traj_every else None
     check(lib().limeb200_liouville_rk4_csr(_dev.ptr(d_ip), _dev.ptr(d_ix), _dev.ptr(d_da), D, _dev.ptr(d_v), B,
                                            _dev.ptr(d_e), E, _dev.ptr(obs), _dev.ptr(traj), int(traj_every),
-                                           float(dt), int(nsteps), _dev.stream_ptr()))
+                                           float(dt), int(nsteps), _dev.stream_ptr(dev)))
     out = d_v.cpu().numpy()
     obs = None if obs is None else obs.cpu().numpy()
     traj = None if traj is None else traj.cpu().numpy()
@@ -271,7 +271,7 @@ def zgemm(A, Bm):
     sB = K * N if tb.dim() == 3 else 0
     out = _dev.empty((batch, M, N), dev=dev)
     check(lib().limeb200_zgemm(_dev.ptr(ta), _dev.ptr(tb), _dev.ptr(out), M, N, K, batch, sA, sB, M * N,
-                               _dev.stream_ptr()))
+                               _dev.stream_ptr(dev)))
     return out if (ta.dim() == 3 or tb.dim() == 3) else out[0]
 
 
@@ -299,7 +299,7 @@ class LiouvillePlan:
         traj = _dev.empty((nsteps // traj_every, B, self.D), dev=self.dev) if traj_every else None
         check(lib().limeb200_liouville_rk4_csr(_dev.ptr(self.ip), _dev.ptr(self.ix), _dev.ptr(self.da), self.D,
                                                _dev.ptr(v), B, _dev.ptr(self.e), self.E, _dev.ptr(obs), _dev.ptr(traj),
-                                               int(traj_every), float(dt), int(nsteps), _dev.stream_ptr()))
+                                               int(traj_every), float(dt), int(nsteps), _dev.stream_ptr(self.dev)))
         return obs, traj
 
 
@@ -381,7 +381,7 @@ class HeomPlan:
         obs = _dev.empty((nsteps, B, E), dev=self.dev) if E else None
         traj = _dev.empty((nsteps // traj_every, B, self.n, self.n), dev=self.dev) if traj_every else None
         check(lib().limeb200_heom_run(self._h, _dev.ptr(ado), B, float(dt), int(nsteps), _dev.ptr(eT), E,
-                                      _dev.ptr(obs), _dev.ptr(traj), int(traj_every), _dev.stream_ptr()))
+                                      _dev.ptr(obs), _dev.ptr(traj), int(traj_every), _dev.stream_ptr(self.dev)))
         return obs, traj
 
     def run(self, ado0, dt, nsteps, e_ops=None, traj_every=0):
@@ -410,14 +410,14 @@ class HeomPlan:
             a = a[None]
         d = _dev.to_dev(a, dev=self.dev)
         o = torch.zeros_like(d)
-        check(lib().limeb200_heom_rhs(self._h, _dev.ptr(d), _dev.ptr(o), d.shape[0], _dev.stream_ptr()))
+        check(lib().limeb200_heom_rhs(self._h, _dev.ptr(d), _dev.ptr(o), d.shape[0], _dev.stream_ptr(self.dev)))
         out = o.cpu().numpy()
         return out[0] if single else out
 
     def stage(self, stage, rho, yin, ynext, acc, dt):
         """one RK4 stage over the owned ADO range (device tensors [B,N_he,n,n])"""
         check(lib().limeb200_heom_stage(self._h, int(stage), _dev.ptr(rho), _dev.ptr(yin), _dev.ptr(ynext),
-                                        _dev.ptr(acc), rho.shape[0], float(dt), _dev.stream_ptr()))
+                                        _dev.ptr(acc), rho.shape[0], float(dt), _dev.stream_ptr(self.dev)))
 
 
 def heom_dl_euler(H, sz, ado0, par, dt, nt, want_traj=True, dev=None):
@@ -433,7 +433,7 @@ def heom_dl_euler(H, sz, ado0, par, dt, nt, want_traj=True, dev=None):
     p = _dev.to_dev(np.asarray(par, dtype=np.float64).reshape(B, 3), np.float64, dev)
     traj = _dev.empty((nt, B, n, n), dev=dev) if want_traj else None
     check(lib().limeb200_heom_dl_euler(hptr(H), hptr(sz), n, nado, _dev.ptr(d), _dev.ptr(p), B, float(dt), int(nt),
-                                       _dev.ptr(traj), _dev.stream_ptr()))
+                                       _dev.ptr(traj), _dev.stream_ptr(dev)))
     return d.cpu().numpy(), (None if traj is None else traj.cpu().numpy())
 
 
@@ -452,7 +452,7 @@ def sos_factor(z, W, p1, p2=None, dev=None):
     n = z.shape[0]
     F = _dev.empty((T, R, n), dev=dev)
     check(lib().limeb200_sos_factor(_dev.ptr(z), n, _dev.ptr(dW), _dev.ptr(dp1), _dev.ptr(dp2), T, R, D,
-                                    _dev.ptr(F), _dev.stream_ptr()))
+                                    _dev.ptr(F), _dev.stream_ptr(dev)))
     return F
 
 
@@ -463,7 +463,7 @@ def sos_factor_dev(z, dW, dp1, dp2=None):
     n = z.shape[0]
     F = _dev.empty((T, R, n), dev=z.device)
     check(lib().limeb200_sos_factor(_dev.ptr(z), n, _dev.ptr(dW), _dev.ptr(dp1), _dev.ptr(dp2), T, R, D,
-                                    _dev.ptr(F), _dev.stream_ptr()))
+                                    _dev.ptr(F), _dev.stream_ptr(z.device)))
     return F
 
 
@@ -478,7 +478,7 @@ def sos_factor_time(t, W, p1, dev=None):
     n = t.shape[0]
     F = _dev.empty((T, R, n), dev=dev)
     check(lib().limeb200_sos_factor_time(_dev.ptr(t), n, _dev.ptr(dW), _dev.ptr(dp1), T, R, D,
-                                         _dev.ptr(F), _dev.stream_ptr()))
+                                         _dev.ptr(F), _dev.stream_ptr(dev)))
     return F
 
 
@@ -491,5 +491,5 @@ def sos_outer(A, Bf, T, scale=1.0, out=None, accumulate=False):
         out = _dev.empty((T, nrow, ncol), dev=A.device)
         accumulate = False
     check(lib().limeb200_sos_outer(_dev.ptr(A), TA, _dev.ptr(Bf), TB, T, R, nrow, ncol, float(scale),
-                                   1 if accumulate else 0, _dev.ptr(out), _dev.stream_ptr()))
+                                   1 if accumulate else 0, _dev.ptr(out), _dev.stream_ptr(A.device)))
     return out

@@ -79,6 +79,13 @@ class ShardedHEOM:
         self.states, self.dn, self.up = engine.heom_tables([N_cut + 1] * self.nmodes, N_cut)
         self.nhe = self.states.shape[0]
         self.chunk, self.ranges = partition(self.nhe, self.world)
+        if exchange == 'p2p' and stage_fn is None:
+            # checked identically on every rank BEFORE any IPC set-up, so that all ranks raise together
+            if self.world > 8:
+                raise ValueError('exchange="p2p" supports at most 8 ranks (one NVSwitch box); use exchange="nccl"')
+            if any(hi <= lo for lo, hi in self.ranges):
+                raise ValueError('exchange="p2p": %d ADOs leave a rank of %d without rows; use fewer ranks or '
+                                 'exchange="nccl"' % (self.nhe, self.world))
         self.nhe_pad = self.chunk * self.world
         self.lo, self.hi = self.ranges[self.rank]
         self.last_launches = 0

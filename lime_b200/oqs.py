@@ -66,6 +66,46 @@ def lindblad_generator(H, c_ops):
     return -1j * Hd + diss, (None if herm else 1j * Hd + diss), ls
 
 
+def _fingerprint(a):
+    """(shape, dtype, digest of the bytes) of an operator -- sparse or dense; None for None"""
+    import hashlib
+    if a is None:
+        return None
+    if issparse(a):
+        m = a if a.format == 'csr' else csr_matrix(a)
+        h = hashlib.blake2b(digest_size=16)
+        for part in (m.indptr, m.indices, m.data):
+            h.update(np.ascontiguousarray(part).view(np.uint8))
+        return ('csr', m.shape, str(m.dtype), h.hexdigest())
+    arr = np.ascontiguousarray(np.asarray(a))
+    return ('dense', arr.shape, str(arr.dtype), hashlib.blake2b(arr.view(np.uint8).reshape(-1), digest_size=16).hexdigest())
+
+
+_PLAN_CACHE = {}
+_PLAN_CACHE_MAX = 8
+
+
+def _lindblad_plan_cached(H, c_ops, e_ops, path=None, device_index=None):
+    """operator plans (analysis + upload) are cached on the CONTENT of (H, c_ops, e_ops): lime-style user loops such as
+    `rk4(rho, liouvillian, dt, H, c_ops)` (lime/phys.py:100-105) or repeated `_lindblad` calls then upload the
+    operators once; in-place edits of an operator change its fingerprint and build a new plan"""
+    c_ops = [] if c_ops is None else list(c_ops)
+    e_list = [] if e_ops is None else list(e_ops)
+    key = (_fingerprint(H), tuple(_fingerprint(c) for c in c_ops), tuple(_fingerprint(e) for e in e_list),
+           path, device_index if device_index is not None else torch.cuda.current_device() if torch.cuda.is_available() else None)
+    plan = _PLAN_CACHE.pop(key, None)
+    if plan is None:
+        plan = _lindblad_plan(H, c_ops, e_ops, path=path, device_index=device_index)
+        while len(_PLAN_CACHE) >= _PLAN_CACHE_MAX:
+            _PLAN_CACHE.pop(next(iter(_PLAN_CACHE)))
+    _PLAN_CACHE[key] = plan                      # re-inserted last = most recently used
+    return plan
+
+
+def clear_plan_cache():
+    _PLAN_CACHE.clear()
+
+
 def _lindblad_plan(H, c_ops, e_ops, path=None, device_index=None):
     N = H.shape[-1]
     G, Gr, ls = lindblad_generator(H, c_ops)
@@ -83,19 +123,15 @@ def _lindblad_plan(H, c_ops, e_ops, path=None, device_index=None):
 
 def liouvillian(rho, H, c_ops):
     """-i[H,rho] + sum_m (l rho l^dag - 1/2 {l^dag l, rho}); lime/oqs.py:706-713.
-    One device right-hand side; returns an ndarray."""
-    plan = _lindblad_plan(H, c_ops, None)
+    One device right-hand side; returns an ndarray.  The operator plan is cached on the operators' content."""
+    plan = _lindblad_plan_cached(H, c_ops, None)
     return plan.rhs(rho)
 
 
 def lindbladian(l, rho):
     """l rho l^dag - 1/2 {l^dag l, rho}; lime/oqs.py:716-723"""
-    N = l.shape[-1]
     ld = _dev.as_c128(l)
-    plan = engine.QmePlan(N)
-    plan.set_generator(-0.5 * (ld.conj().T @ ld))
-    plan.add_sandwich(ld, ld)
-    plan.finalize()
+    plan = _lindblad_plan_cached(np.zeros_like(ld), [ld], None)
     return plan.rhs(rho)
 
 
@@ -119,7 +155,7 @@ def _lindblad(H, rho0, c_ops, e_ops=None, Nt=1, dt=0.005, return_result=True):
     if e_ops is None:
         e_ops = []
     rho = _dev.as_c128(rho0)
-    plan = _lindblad_plan(H, c_ops, e_ops)
+    plan = _lindblad_plan_cached(H, c_ops, e_ops)
     if return_result:
         rho_f, obs, traj = plan.run(rho, dt, Nt, traj_every=1)
         result = Result(dt=dt, Nt=Nt, rho0=rho0)
@@ -184,6 +220,31 @@ def _lindblad_driven(H, rho0, c_ops=None, e_ops=None, Nt=1, dt=0.005, t0=0.,
         return result
     _write_obs_file('obs.dat', times, obs if obs is not None else np.zeros((Nt, 0), dtype=complex))
     return rho_f
+
+
+def _correlation_2p_1t(H, rho0, ops, c_ops, dt, Nt, method='lindblad', output='cor.dat'):
+    """<A(t) B> = Tr[A U(t) (B rho0) U^dag(t)] by quantum regression; lime/oqs.py:726-800.
+    Writes `t cor` per step to `output` (t accumulated with `t += dt`, as lime does) and returns cor[Nt].
+    lime propagates a CSR rho through rk4/liouvillian in a Python loop; here the Nt steps are one launch
+    from the (non-Hermitian) initial state B rho0 with A as the only observable."""
+    A, B = ops
+    if method != 'lindblad':
+        sys.exit('The method {} has not been implemented yet! Please \
+                 try lindblad.'.format(method))
+    rho = B.dot(rho0)
+    rho = _dev.as_c128(rho)
+    c_ops = [] if c_ops is None else list(c_ops)
+    plan = _lindblad_plan_cached(H, c_ops, [A])
+    _, obs, _ = plan.run(rho, dt, Nt)
+    cor = np.zeros(Nt, dtype=complex)
+    if Nt > 0:
+        cor[:] = obs[:, 0]
+    with open(output, 'w') as f:
+        t = 0.0
+        for k in range(Nt):
+            t += dt
+            f.write('{} {} \n'.format(t, cor[k]))
+    return cor
 
 
 class Lindblad_solver():
@@ -255,6 +316,10 @@ class Lindblad_solver():
         return plan.run(r, dt, Nt, traj_every=store_every, pinned=pinned)
 
     # ---- correlation functions (quantum regression), lime/oqs.py:1196-1331 ---------
+    def correlation_2op_1t(self, rho0, a_op, b_op, dt, Nt, output='cor.dat'):
+        """<A(t) B>, lime/oqs.py:1196-1225"""
+        return _correlation_2p_1t(self.H, rho0, ops=[a_op, b_op], c_ops=self.c_ops, dt=dt, Nt=Nt, output=output)
+
     def correlation_3op_1t(self, rho0, oplist, dt=0.005, Nt=1):
         """<A B(t) C>, lime/oqs.py:1227-1246"""
         a_op, b_op, c_op = oplist
@@ -309,7 +374,8 @@ def _lindblad_plan_batch(H_batch, c_ops, e_ops, path=None, device_index=None):
         for l in ls:
             diss = diss - 0.5 * (l.conj().T @ l)
         if isinstance(H_batch, tuple):
-            hpat = pat.copy()
+            hpat = abs(pat.astype(complex))
+            hpat.data[:] = 1.0          # stored zeros of the pattern must survive the sparse sum below
         else:
             hpat = csr_matrix((N, N))
             for h in Hs:
@@ -330,6 +396,10 @@ def _lindblad_plan_batch(H_batch, c_ops, e_ops, path=None, device_index=None):
             key_u = rows.astype(np.int64) * N + cols
             key_p = prow.astype(np.int64) * N + pat.indices
             pos = np.searchsorted(key_u, key_p)
+            if not (np.all(pos < key_u.size) and np.array_equal(key_u[np.minimum(pos, key_u.size - 1)], key_p)):
+                raise ValueError('Hamiltonian pattern is not contained in the union pattern')
+            if np.unique(key_p).size != key_p.size:
+                raise ValueError('Hamiltonian pattern holds duplicate entries')
             data[:] = dvals[None, :]
             data[:, pos] += -1j * hvals
         else:
@@ -421,6 +491,35 @@ def _redfield(R, rho0, evecs=None, Nt=1, dt=0.005, t0=0, e_ops=[], return_result
     return v
 
 
+def getG(L, t, w=None, k=6, domain='time'):
+    """Green's function of (i d/dt - L); lime/oqs.py:474-526.
+        time:  G[a,b,k] = sum_j U1[a,j] (-i e^{-i lambda_j t_k}) U2[j,b],   U2 = U1^{-1}
+        freq:  lime's einsum 'an, nk, bn -> abk' over W = 1/(w[:,None] - lambda[None,:]) -- it contracts the FIRST
+               axis of W (the frequency axis) with the eigen index, so it only runs for len(w) == dim(L) and returns
+               G[a,b,k] = sum_n U1[a,n] conj(U2[b,n]) / (w_n - lambda_k); reproduced as written.
+    The eigen-decomposition is host LAPACK as in lime; the O(D^2 K D) contraction is ONE complex GEMM on the FP64
+    tensor cores: G[(a,b),k] = P[(a,b),j] X[j,k] with P[(a,b),j] = U1[a,j] U2[j,b] (time) / U1[a,j] conj(U2[b,j]) (freq)."""
+    Ld = np.asarray(L.todense() if issparse(L) else L, dtype=complex)
+    evals1, U1 = scipy.linalg.eig(Ld)
+    U2 = scipy.linalg.inv(U1)
+    D = Ld.shape[0]
+    if domain == 'time':
+        t = np.asarray(t)
+        X = -1j * np.exp(-1j * evals1[:, np.newaxis] * t[np.newaxis, :])
+        P = (U1[:, None, :] * U2.T[None, :, :]).reshape(D * D, D)
+    elif domain == 'freq':
+        w = np.asarray(w)
+        X = 1. / (w[:, np.newaxis] - evals1[np.newaxis, :])
+        if X.shape[0] != D:
+            raise ValueError("operands could not be broadcast together: lime's einsum 'an, nk, bn -> abk' needs "
+                             "len(w) == %d" % D)
+        P = (U1[:, None, :] * U2.conj()[None, :, :]).reshape(D * D, D)
+    else:
+        return None                       # lime falls through to an UnboundLocalError; nothing to compute
+    G = engine.zgemm(np.ascontiguousarray(P), np.ascontiguousarray(X))
+    return G.cpu().numpy().reshape(D, D, X.shape[1])
+
+
 class Redfield_solver:
     """lime/oqs.py:40-371"""
 
@@ -507,6 +606,23 @@ class Redfield_solver:
         e_rows = [e.T.reshape(-1) for e in e_eb]
         out, obs, _ = engine.liouville_rk4(self.R, r_eb.reshape(-1, N * N), dt, Nt, e_rows=e_rows)
         return out.reshape(-1, N, N), obs
+
+    def gf(self, t, w=None, secular=False, k=1, domain='time', method='EOM'):
+        """Liouville-space Green's function with Redfield dissipation; lime/oqs.py:145-167.
+        'EOM': -i * expm(R, t) with lime.phys.expm = RK4 on the identity (lime/phys.py:1384-1401), returned as lime
+        MEANS to return it: lime multiplies the Python list expm returns by -1j, which always raises TypeError (and a
+        second call raises UnboundLocalError because R is only bound when self.R is None); here the intended value is
+        returned, a list of len(t) csr matrices -i U(t_k).
+        'eseries'/'diag'/'diagonalization': getG(1j * R, t)."""
+        if method == 'EOM':
+            if self.R is None:
+                self.redfield_tensor(secular=secular)
+            U = self.propagator(np.asarray(t), method='EOM')          # [a,b,k]
+            return [csr_matrix(-1j * U[:, :, i]) for i in range(U.shape[2])]
+        elif method in ['eseries', 'diag', 'diagonalization']:
+            if self.R is None:
+                self.redfield_tensor(secular=secular)
+            return getG(1j * self.R, t)
 
     def propagator(self, t, method='SOS'):
         """U[a,b,k] = (e^{R t_k})_{ab}; lime/oqs.py:169-223.
@@ -653,6 +769,10 @@ class HEOMSolverDL():
             Q = Q[0]
         h = HEOM(self.H, Q, coup_strength, cut_freq, temperature, N_exp=N_exp, N_cut=N_cut)
         return h.evolve(rho0, dt, Nt, e_ops=self.e_ops if e_ops is None else e_ops)
+
+    def correlation_2op_1t(self, rho0, a_op, b_op, dt, Nt, output='cor.dat'):
+        """<A(t) B>, lime/oqs.py:1368-1396 (Lindblad regression, as in lime)"""
+        return _correlation_2p_1t(self.H, rho0, ops=[a_op, b_op], c_ops=self.c_ops, dt=dt, Nt=Nt, output=output)
 
     def correlation_3op_2t(self, rho0, ops, dt, Nt, Ntau):
         """lime/oqs.py:1399-1431 (Lindblad regression, as in lime)"""

@@ -385,7 +385,7 @@ def _tpa2d(E, dip, omegaps, omega1s, e_idx, f_idx, gamma, time_order):
     out = torch.empty((wp.shape[0], w1.shape[0]), dtype=torch.float64, device=dev)
     check(lib().limeb200_sos_tpa2d(_dev.ptr(dE), _dev.ptr(dd), _dev.ptr(dg), N, _dev.ptr(ei), ei.shape[0],
                                    _dev.ptr(fi), fi.shape[0], _dev.ptr(wp), wp.shape[0], _dev.ptr(w1), w1.shape[0],
-                                   1 if time_order else 0, _dev.ptr(out), _dev.stream_ptr()))
+                                   1 if time_order else 0, _dev.ptr(out), _dev.stream_ptr(dev)))
     return out.cpu().numpy()
 
 

@@ -361,6 +361,124 @@ def main():
     note('twodes_time', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'twodes_time.npz'), t1=t1[0], t3=t3[:, 0], t2=tw, **g)
 
+
+    # ---- multi-index HEOM coupling rules, lime/heom/heom.py:156-216.  The excerpt sits in a dead __main__ block that
+    # uses names lime never defines (cut from QuTiP 4.5's HSolverDL._configure); the loop itself (:156-216) is exec'd
+    # VERBATIM here with those names supplied: cy_pad_csr places a superoperator block at (row ADO, column ADO) of the
+    # hierarchy Liouvillian, spreQ / spostQ / commQ are the left / right / commutator superoperators of Q (row-major
+    # vec, lime/superoperator.py:131-151 convention), mol.idm the identity superoperator, renorm False.  What comes out
+    # is the REFERENCE's own matrix L_helems; the oracle's heom_rhs (without the system term) must equal L_helems . vec.
+    hsrc = open('/root/reference/lime/heom/heom.py').read().split('\n')
+    loop = '\n'.join(l[4:] if l.startswith('    ') else l for l in hsrc[155:216])     # lines 156-216, un-indented once
+    assert loop.startswith('for he_idx in range(N_he):') and 'L_he = cy_pad_csr(op, N_he, N_he, he_idx, he_idx_neigh)' in loop
+
+    def heom_rules_reference(n, N_m, N_c, Qs, qmap, cnu, lam, gam, T):
+        """run lime/heom/heom.py:156-216; Qs/qmap: coupling operator of mode k (lime: one Q); cnu: the (c, nu) lists
+        `_calc_matsubara_params` returns inside the loop (lime's own function unless a multi-bath list is supplied)"""
+        import copy as _copy
+        N_he, he2idx, idx2he = heom.enr_state_dictionaries([N_c + 1] * N_m, N_c)
+        nn = n * n
+        I = np.eye(n)
+
+        def pad(op, nr, nc, i, j):
+            out = np.zeros((nr * nn, nc * nn), dtype=complex)
+            out[i * nn:(i + 1) * nn, j * nn:(j + 1) * nn] = op
+            return out
+
+        class Names(dict):
+            # spreQ / spostQ / commQ are looked up inside `for k in range(N_m)`: resolve them for the CURRENT mode k,
+            # which is how a bath-dependent coupling operator enters rules that are written for a single Q
+            def __missing__(self, key):
+                q = Qs[qmap[self['k']]] if 'k' in self else Qs[0]
+                if key == 'spreQ':
+                    return np.kron(q, I)
+                if key == 'spostQ':
+                    return np.kron(I, q.T)
+                if key == 'commQ':
+                    return np.kron(q, I) - np.kron(I, q.T)
+                raise KeyError(key)
+
+        class _Mol:
+            idm = np.eye(nn)
+        ns = Names(np=np, copy=_copy.copy, N_he=N_he, he2idx=he2idx, idx2he=idx2he, N_m=N_m, N_c=N_c,
+                   coup_strength=lam, cut_freq=gam, temperature=T, mol=_Mol(), cy_pad_csr=pad, renorm=False,
+                   L_helems=np.zeros((N_he * nn, N_he * nn), dtype=complex), N_he_interact=0,
+                   _calc_matsubara_params=(heom._calc_matsubara_params if cnu is None else (lambda *a: cnu)))
+        quiet(exec, loop, {'__builtins__': __builtins__}, ns)
+        return ns['L_helems'], ns['N_he_interact'], N_he
+
+    rng = np.random.default_rng(11)
+
+    def rherm(n):
+        a = rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))
+        return a + a.conj().T
+
+    hr_cases = {}
+    worst = 0.0
+    # (name, n, N_m, N_c, coupling operators, mode -> operator, (c, nu) override)
+    lam, gam, T = 0.3, 0.7, 1.3
+    c2a, nu2a = heom._calc_matsubara_params(2, lam, gam, T)
+    c2b, nu2b = heom._calc_matsubara_params(2, 0.5 * lam, 1.4 * gam, T)
+    Q2 = rherm(2)
+    Q3a, Q3b = rherm(3), rherm(3)
+    for name, n, N_m, N_c, Qs, qmap, cnu in [
+            ('k2_d3_n2', 2, 2, 3, [Q2], [0, 0], None),                                  # lime's case: one bath, one Q
+            ('k4_d2_n3', 3, 4, 2, [Q3a], [0, 0, 0, 0], None),
+            ('b2k2_d3_n3', 3, 4, 3, [Q3a, Q3b], [0, 0, 1, 1], (c2a + c2b, nu2a + nu2b)),  # two baths, bath-major modes
+            ('b2k2_d2_proj', 3, 4, 2, [np.diag([1.0, 0, 0]).astype(complex), np.diag([0, 1.0, 0]).astype(complex)],
+             [0, 0, 1, 1], (c2a + c2b, nu2a + nu2b))]:                                   # projector couplings (FMO-like)
+        L, ncoup, N_he = heom_rules_reference(n, N_m, N_c, Qs, qmap, cnu, lam, gam, T)
+        c, nu = (heom._calc_matsubara_params(N_m, lam, gam, T) if cnu is None else cnu)
+        st, dn, up = lo.heom_tables([N_c + 1] * N_m, N_c)
+        assert st.shape[0] == N_he
+        ado = rng.standard_normal((N_he, n, n)) + 1j * rng.standard_normal((N_he, n, n))
+        rhs_o = lo.heom_rhs(ado, np.zeros((n, n), dtype=complex), np.stack(Qs), qmap, c, nu, st, dn, up)
+        rhs_r = (L @ ado.reshape(-1)).reshape(N_he, n, n)
+        e = relerr(rhs_o, rhs_r)
+        worst = max(worst, e)
+        assert ncoup == int((dn >= 0).sum() + (up >= 0).sum())
+        hr_cases[name + '_L'] = L
+        hr_cases[name + '_Q'] = np.stack(Qs)
+        hr_cases[name + '_meta'] = np.array([n, N_m, N_c, ncoup])
+        hr_cases[name + '_qmap'] = np.array(qmap)
+        hr_cases[name + '_c'] = np.array(c, dtype=complex)
+        hr_cases[name + '_nu'] = np.array(nu, dtype=float)
+    note('heom_rules', oracle_rhs_vs_reference_L=worst, cases=len(hr_cases) // 6)
+    np.savez_compressed(os.path.join(GOLD, 'heom_rules.npz'), **hr_cases)
+
+
+    # ---- round-2 API rows: _correlation_2p_1t (lime/oqs.py:726-800), getG / Redfield_solver.gf (:145-167, 474-526)
+    import tempfile
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    A, B = e_ops[0], cases.rand_cplx(6, 77, 0.5)
+    fn = os.path.join(tempfile.mkdtemp(), 'cor.dat')
+    cor_ref = quiet(oqs.Lindblad_solver(H, c_ops).correlation_2op_1t, rho0, A, B, 0.01, 30, output=fn)
+    cor_txt = open(fn).read()
+    fn2 = os.path.join(tempfile.mkdtemp(), 'cor.dat')
+    cor_o = lo.correlation_2p_1t(H, rho0, [A, B], c_ops, 0.01, 30, output=fn2)
+    Hj, cj, ej, rj = cases.jc_point(ncav=8)
+    corj_ref = quiet(oqs._correlation_2p_1t, csr_matrix(Hj), rj, [ej[0], cj[0] / np.sqrt(0.05)], [csr_matrix(c) for c in cj], 0.01, 25,
+                     output=os.path.join(tempfile.mkdtemp(), 'cor.dat'))
+    corj_o = lo.correlation_2p_1t(Hj, rj, [ej[0], cj[0] / np.sqrt(0.05)], cj, 0.01, 25)
+    Hr, a_ops, spectra, rr = cases.redfield_multilevel()
+    sol = oqs.Redfield_solver(Hr, c_ops=a_ops, spectra=spectra)
+    quiet(sol.redfield_tensor)
+    tg = np.linspace(0, 3.0, 7)
+    D = Hr.shape[0] ** 2
+    wg = np.linspace(-2.0, 2.0, D)                      # lime's frequency-domain einsum needs len(w) == dim(L)
+    g = {'cor2': cor_ref, 'cor2_jc': corj_ref,
+         'G_time': quiet(sol.gf, tg, method='diag'),
+         'G_freq': quiet(oqs.getG, 1j * sol.R, tg, w=wg, domain='freq')}
+    o = {'cor2': cor_o, 'cor2_jc': corj_o, 'G_time': lo.getG(1j * sol.R, tg), 'G_freq': lo.getG(1j * sol.R, tg, w=wg, domain='freq')}
+    gf_eom = 'ok'
+    try:
+        quiet(oqs.Redfield_solver(Hr, c_ops=a_ops, spectra=spectra).gf, tg, method='EOM')
+    except Exception as exc:                            # lime multiplies a Python list by -1j: always TypeError
+        gf_eom = type(exc).__name__
+    note('api_r2', cor_file_identical=float(cor_txt != open(fn2).read()), gf_eom_raises_TypeError=float(gf_eom != 'TypeError'),
+         **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'api_r2.npz'), A=A, B=B, tg=tg, wg=wg, cor_txt=np.array(cor_txt), **g)
+
     with open(os.path.join(GOLD, 'PINNING.json'), 'w') as f:
         json.dump({'generated_by': 'oracle/gen_golden.py', 'reference': 'binggu56/lime @ /root/reference',
                    'numpy': np.__version__, 'oracle_vs_reference_max_rel_err': report}, f, indent=1)

@@ -18,12 +18,18 @@ Tr(d rho) forms the full product) so that (i) results agree with it to the last
 bit where NumPy is deterministic and (ii) timing the oracle is a fair stand-in
 for timing lime's CPU path.
 
-PARITY UNPINNED (no reference implementation exists):
-  * heom_rhs / heom_rk4 -- the multi-index hierarchy.  lime only ships the
-    index tables, the Matsubara coefficients and an un-runnable excerpt stating
-    the coupling rules (lime/heom/heom.py:156-216); the restatement follows those
-    rules literally, adds -i[H, rho_n] as in lime/oqs.py:1854 and integrates with
-    lime/phys.py:636-649.
+The multi-index hierarchy (heom_rhs / heom_rk4): lime ships the index tables, the
+Matsubara coefficients and an excerpt stating the coupling rules inside a dead
+__main__ block (lime/heom/heom.py:142-216) that uses names lime never defines.
+oracle/gen_golden.py exec's that rule loop (:156-216) VERBATIM with those names
+supplied and freezes the hierarchy Liouvillian it builds
+(tests/golden/heom_rules.npz); heom_rhs minus the system term equals that matrix
+applied to vec(ADOs) to 2e-16 -- PINNED on the reference's own rules for lime's
+single-Q case and for bath-dependent coupling operators.  The system term
+-i[H, rho_n] is lime/oqs.py:1854 and the integrator lime/phys.py:636-649 (both
+pinned through _heom_dl / rk4 elsewhere).
+PARITY UNPINNED: rkf45 (lime ships only examples/rkf45_test.py, which imports a
+module that is not in the tree) -- accuracy pinned on that file's analytic problems.
 All citations are file:line in /root/reference.
 """
 import numpy as np
@@ -224,6 +230,40 @@ def correlation_3p_1t(H, rho0, ops, c_ops, tlist):
         ts.append(t)
         rhos.append(rho.toarray() if issparse(rho) else np.array(rho))
     return np.array(ts), np.array(cors), np.array(rhos)
+
+
+def correlation_2p_1t(H, rho0, ops, c_ops, dt, Nt, output=None):
+    """<A(t) B> by quantum regression with CSR operands and a CSR rho, lime/oqs.py:726-800;
+    returns cor[Nt] and writes `t cor` lines to `output` when given"""
+    A, B = ops
+    rho = csr_matrix(B.dot(rho0))
+    H = csr_matrix(H)
+    A = csr_matrix(A)
+    c_sp = [csr_matrix(c) for c in c_ops]
+    t = 0.0
+    cor = np.zeros(Nt, dtype=complex)
+    lines = []
+    for k in range(Nt):
+        t += dt
+        rho = rk4(rho, liouvillian_sp, dt, H, c_sp)
+        tmp = A.dot(rho).diagonal().sum()                     # obs_dm on sparse operands, lime/phys.py:837-844
+        cor[k] = tmp
+        lines.append('{} {} \n'.format(t, tmp))
+    if output is not None:
+        with open(output, 'w') as f:
+            f.writelines(lines)
+    return cor
+
+
+def getG(L, t, w=None, domain='time'):
+    """lime/oqs.py:474-526 (dense eig of L, U2 = inv(U1), the two einsums as written)"""
+    evals1, U1 = scipy.linalg.eig(L.todense() if issparse(L) else L)
+    U2 = scipy.linalg.inv(U1)
+    if domain == 'time':
+        U = -1j * np.exp(-1j * evals1[:, np.newaxis] * t[np.newaxis, :])
+        return np.einsum('aj, jk, jb -> abk', U1, U, U2)
+    W = 1. / ((w[:, np.newaxis] - evals1[np.newaxis, :]))
+    return np.einsum('an, nk, bn ->abk', U1, W, U2.conj())
 
 
 def lindblad_correlation_3op_1t(H, c_ops, rho0, oplist, dt, Nt):
@@ -551,7 +591,7 @@ def heom_tables(dims, excitations):
 
 
 def heom_rhs(ado, H, Q, qmap, c, nu, states, dn, up, pref_dn=-1j, pref_up=-1j):
-    """PARITY UNPINNED restatement of the multi-index HEOM right-hand side.
+    """Multi-index HEOM right-hand side (pinned on the reference's rule loop, tests/golden/heom_rules.npz).
     ado: (N_he, n, n).  Q: (N_q, n, n) coupling operators, qmap[k] -> which Q mode
     k uses (lime has a single Q: qmap = 0).  Rules, lime/heom/heom.py:156-216:
       diagonal   -sum_k n_k nu_k rho_n                                   :167-173

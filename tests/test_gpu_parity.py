@@ -321,6 +321,135 @@ def test_heom_dense_q_and_multibath(cuda, path):
     assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
 
 
+@pytest.mark.parametrize('name', ['k2_d3_n2', 'k4_d2_n3', 'b2k2_d3_n3', 'b2k2_d2_proj'])
+def test_heom_rhs_against_reference_rule_matrix(cuda, name):
+    """device RHS of every HEOM kernel family against the REFERENCE's own hierarchy Liouvillian
+    (lime/heom/heom.py:156-216 exec'd in oracle/gen_golden.py, frozen in heom_rules.npz) plus -i[H, rho_n]"""
+    from lime_b200 import engine
+    from test_oracle_vs_golden import heom_rule_case
+    k = heom_rule_case(name)
+    n, nhe = k['n'], k['st'].shape[0]
+    H = cases.rand_herm(n, 31)
+    rng = np.random.default_rng(8)
+    ado = rng.standard_normal((nhe, n, n)) + 1j * rng.standard_normal((nhe, n, n))
+    ref = (k['L'] @ ado.reshape(-1)).reshape(nhe, n, n) - 1j * (H @ ado - ado @ H)
+    plan = engine.HeomPlan(H, k['Q'], k['qmap'], k['c'], k['nu'], k['st'], k['dn'], k['up'])
+    assert relerr(plan.rhs(ado), ref) <= 1e-12
+    # and one propagated trajectory per run path against RK4 of the reference matrix
+    Lfull = k['L'].copy()
+    nn = n * n
+    for a in range(nhe):
+        Lfull[a * nn:(a + 1) * nn, a * nn:(a + 1) * nn] += -1j * (np.kron(H, np.eye(n)) - np.kron(np.eye(n), H.T))
+    y = ado.reshape(-1).copy() * 0.1
+    y0 = y.copy()
+    for _ in range(20):
+        y = lo.rk4(y, lambda v: Lfull @ v, 0.01)
+    for path in (1, 2, 3):
+        pl = engine.HeomPlan(H, k['Q'], k['qmap'], k['c'], k['nu'], k['st'], k['dn'], k['up'])
+        pl.set_path(path)
+        out, _, _ = pl.run(y0.reshape(nhe, n, n), 0.01, 20)
+        assert relerr(out.reshape(-1), y) <= TOL, path
+
+
+@pytest.mark.parametrize('path', [2, 3])
+def test_heom_config4_full_size(cuda, path):
+    """config 4 at its real size: FMO, 7 baths x K = 2, depth 4 -> 3060 ADOs of 7x7, 19 040 couplings; 50 RK4 steps
+    of the stage-wise (2) and persistent (3) kernels against the oracle"""
+    from lime_b200 import builders
+    from lime_b200.heom.heom import HEOM
+    from lime_b200.units import au2fs
+    Hm, Q, lam, gam, kT = builders.fmo_heom_inputs()
+    h = HEOM(Hm, Q, lam, gam, kT, N_exp=2, N_cut=4)
+    assert h.nhe == 3060 and int((h.dn >= 0).sum() + (h.up >= 0).sum()) == 19040
+    h.plan.set_path(path)
+    rho0 = np.zeros((7, 7), dtype=complex)
+    rho0[0, 0] = 1.0
+    dt = 0.5 / au2fs
+    res = h.evolve(rho0, dt, 50, e_ops=[Q[0], Q[1]], store_states=False)
+    assert h.plan.path == path
+    st = h.states.astype(np.int64)
+    ado_o, obs_o, _ = lo.heom_rk4(h.initial(rho0), Hm, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                  h.up.astype(np.int64), dt, 50, e_ops=[Q[0], Q[1]])
+    assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
+
+
+def test_heom_solver_dl_class(cuda, tmp_path):
+    """HEOMSolverDL (lime/oqs.py:1335-1431): `solve` runs the Lindblad propagator exactly as lime's does (:1364-1366),
+    the regression correlation functions, and the [ext] hierarchy entry point solve_heom"""
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    s = oqs.HEOMSolverDL(H=H, c_ops=c_ops, e_ops=e_ops)
+    res = s.solve(rho0, 0.01, 30, True)
+    obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops, Nt=30, dt=0.01)
+    assert relerr(res.observables, obs_o) <= TOL and relerr(np.array(res.rholist), np.array(rl_o)) <= TOL
+    s.set_e_ops(e_ops[:1]); s.set_c_ops(c_ops); s.setH(H); s.configure(c_ops, e_ops)
+    g = golden('api_r2')
+    cor = s.correlation_2op_1t(rho0, g['A'], g['B'], 0.01, 30, output=str(tmp_path / 'c.dat'))
+    assert relerr(cor, g['cor2']) <= TOL
+    ops = [e_ops[0], e_ops[1], c_ops[0]]
+    assert relerr(s.correlation_3op_2t(rho0, ops, 0.01, 5, 7),
+                  lo.lindblad_correlation_3op_2t(H, c_ops, rho0, ops, 0.01, 5, 7)) <= TOL
+    Hs, sz, r0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=5)
+    hs = oqs.HEOMSolverDL(H=Hs, c_ops=[sz], e_ops=[sz])
+    r = hs.solve_heom(r0, 0.01, 40, lam, gam, T, N_exp=K, N_cut=depth)
+    st, dn, up = lo.heom_tables([depth + 1] * K, depth)
+    c, nu = lo.calc_matsubara_params(K, lam, gam, T)
+    ado0 = np.zeros((st.shape[0], 2, 2), dtype=complex)
+    ado0[0] = r0
+    ado_o, obs_o, tr_o = lo.heom_rk4(ado0, Hs, sz[None], [0] * K, c, nu, st, dn, up, 0.01, 40, e_ops=[sz], store=True)
+    assert relerr(r.ado, ado_o) <= TOL and relerr(r.observables, obs_o) <= TOL
+    assert relerr(np.array(r.rholist), np.array(tr_o)) <= TOL
+
+
+def test_lindblad_correlation_2op_1t(cuda, tmp_path):
+    """<A(t)B>, lime/oqs.py:726-800, 1196-1225: values and the cor.dat side effect, dense and CSR operands"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import oqs
+    g = golden('api_r2')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    fn = str(tmp_path / 'cor.dat')
+    cor = oqs.Lindblad_solver(H, c_ops).correlation_2op_1t(rho0, g['A'], g['B'], 0.01, 30, output=fn)
+    assert relerr(cor, g['cor2']) <= TOL
+    got = np.array([complex(l.split()[1]) for l in open(fn)])
+    ref = np.array([complex(l.split()[1]) for l in str(g['cor_txt']).splitlines()])
+    tt = np.array([float(l.split()[0]) for l in open(fn)])
+    tr = np.array([float(l.split()[0]) for l in str(g['cor_txt']).splitlines()])
+    assert np.array_equal(tt, tr) and relerr(got, ref) <= TOL          # same file layout, times bit-identical
+    Hj, cj, ej, rj = cases.jc_point(ncav=8)
+    corj = oqs._correlation_2p_1t(csr_matrix(Hj), rj, [ej[0], cj[0] / np.sqrt(0.05)], [csr_matrix(c) for c in cj], 0.01, 25,
+                                  output=str(tmp_path / 'c2.dat'))
+    assert relerr(corj, g['cor2_jc']) <= TOL
+    with pytest.raises(SystemExit):
+        oqs._correlation_2p_1t(H, rho0, [g['A'], g['B']], c_ops, 0.01, 3, method='redfield', output=str(tmp_path / 'c3.dat'))
+
+
+def test_redfield_green_functions(cuda):
+    """Redfield_solver.gf / getG (lime/oqs.py:145-167, 474-526) and correlation_2op_1t (:254-275)"""
+    from lime_b200 import oqs
+    g = golden('api_r2')
+    Hr, a_ops, spectra, rr = cases.redfield_multilevel()
+    sol = oqs.Redfield_solver(Hr, c_ops=a_ops, spectra=spectra)
+    assert relerr(sol.gf(g['tg'], method='diag'), g['G_time']) <= 1e-11       # redfield_tensor is built on demand
+    assert relerr(oqs.getG(1j * sol.R, g['tg'], w=g['wg'], domain='freq'), g['G_freq']) <= 1e-11
+    with pytest.raises(ValueError):
+        oqs.getG(1j * sol.R, g['tg'], w=g['wg'][:-1], domain='freq')           # lime's einsum needs len(w) == dim(L)
+    # 'EOM': lime multiplies a Python list by -1j (always TypeError); here: the list lime meant to return
+    t = np.linspace(0, 0.5, 6)
+    Gl = sol.gf(t, method='EOM')
+    U = lo.redfield_propagator(sol.R, t, method='EOM')
+    assert len(Gl) == 6 and relerr(np.stack([x.toarray() for x in Gl], axis=-1), -1j * np.asarray(U)) <= TOL
+    # two-point function through the propagator
+    sol2 = oqs.Redfield_solver(Hr, c_ops=a_ops, spectra=spectra)
+    sol2.redfield_tensor()
+    from lime_b200.superoperator import operator_to_superoperator
+    a = operator_to_superoperator(a_ops[0], 'left')
+    b = operator_to_superoperator(a_ops[1], 'left')
+    c2 = sol2.correlation_2op_1t(rr, a, b, t)
+    Uo = np.asarray(lo.redfield_propagator(sol2.R, t, method='SOS'))
+    ref = lo.dm2vec(np.identity(5)) @ (a @ np.tensordot(-1j * Uo, b @ lo.dm2vec(rr), axes=([1], [0])))
+    assert relerr(c2, ref) <= 1e-11
+
+
 @pytest.mark.parametrize('path', [0, 2, 3])
 def test_heom_fmo_shape_stagewise_and_batch(cuda, path):
     """config-4 shape at reduced depth: 7 sites, 7 baths x K=2, depth 2 (120 ADOs of 7x7);

@@ -19,9 +19,9 @@ def test_pinning_report_is_clean():
     rep = json.load(open(os.path.join(GOLD, 'PINNING.json')))['oracle_vs_reference_max_rel_err']
     for case, errs in rep.items():
         for k, v in errs.items():
-            if k in ('fixed_vs_strict', 'fmo_nhe', 'none_raises_TypeError'):
+            if k in ('fixed_vs_strict', 'fmo_nhe', 'none_raises_TypeError', 'cases'):
                 continue
-            assert v <= 1e-14, (case, k, v)
+            assert v <= (1e-14 if case != 'heom_rules' else 1e-15 * 4), (case, k, v)
     assert rep['heom_tables']['none_raises_TypeError'] == 1
     assert rep['heom_tables']['fmo_nhe'] == 3060
 
@@ -150,9 +150,48 @@ def test_heom_connectivity_counts():
                 assert up[dn[a, k], k] == a
 
 
+HEOM_RULE_CASES = ['k2_d3_n2', 'k4_d2_n3', 'b2k2_d3_n3', 'b2k2_d2_proj']
+
+
+def heom_rule_case(name):
+    """inputs of one frozen case of tests/golden/heom_rules.npz: the reference's own hierarchy Liouvillian L_helems
+    (lime/heom/heom.py:156-216 exec'd by oracle/gen_golden.py) and the bath data it was built from"""
+    g = golden('heom_rules')
+    n, N_m, N_c, ncoup = [int(x) for x in g[name + '_meta']]
+    st, dn, up = lo.heom_tables([N_c + 1] * N_m, N_c)
+    return dict(L=g[name + '_L'], Q=g[name + '_Q'], qmap=[int(x) for x in g[name + '_qmap']], c=g[name + '_c'],
+                nu=g[name + '_nu'], n=n, N_m=N_m, N_c=N_c, ncoup=ncoup, st=st, dn=dn, up=up)
+
+
+@pytest.mark.parametrize('name', HEOM_RULE_CASES)
+def test_heom_rhs_pinned_on_reference_coupling_rules(name):
+    """PINS the multi-index HEOM right-hand side: bath part of lo.heom_rhs == (the matrix the reference's own rule
+    loop builds) . vec, for lime's single-Q case and for bath-dependent coupling operators"""
+    k = heom_rule_case(name)
+    assert k['ncoup'] == int((k['dn'] >= 0).sum() + (k['up'] >= 0).sum())       # ADO connectivity, bit-exact
+    rng = np.random.default_rng(3)
+    nhe, n = k['st'].shape[0], k['n']
+    for _ in range(3):
+        ado = rng.standard_normal((nhe, n, n)) + 1j * rng.standard_normal((nhe, n, n))
+        ref = (k['L'] @ ado.reshape(-1)).reshape(nhe, n, n)
+        got = lo.heom_rhs(ado, np.zeros((n, n), dtype=complex), k['Q'], k['qmap'], k['c'], k['nu'],
+                          k['st'], k['dn'], k['up'])
+        assert relerr(got, ref) <= TOL
+    # block structure: L couples ADO a to b only along table edges (and the diagonal)
+    nn = n * n
+    blocks = np.abs(k['L']).reshape(nhe, nn, nhe, nn).max(axis=(1, 3)) > 0
+    allowed = np.eye(nhe, dtype=bool)
+    for a in range(nhe):
+        for m in range(k['N_m']):
+            for t in (k['dn'][a, m], k['up'][a, m]):
+                if t >= 0:
+                    allowed[a, t] = True
+    assert not np.any(blocks & ~allowed)
+
+
 def test_heom_rhs_matches_heom_dl_structure():
     """the multi-index RHS with one mode, pref_dn=1, pref_up=-1, c=a+ib reduces to the tier
-    equations _heom_dl integrates (lime/oqs.py:1853-1857) -- ties the unpinned restatement
+    equations _heom_dl integrates (lime/oqs.py:1853-1857) -- ties the multi-index restatement
     to the pinned one."""
     H, sz, rho0 = cases.spin_boson_heom()[:3]
     nado = 6
@@ -165,6 +204,22 @@ def test_heom_rhs_matches_heom_dl_structure():
         ref = -1j * lo.commutator(H, ado[n]) - lo.commutator(sz, ado[n + 1]) - n * gamma * ado[n] \
             + n * a * lo.commutator(sz, ado[n - 1])
         assert relerr(k[n], ref) < 1e-14
+
+
+def test_round2_api_rows(tmp_path):
+    """_correlation_2p_1t (lime/oqs.py:726-800, incl. the cor.dat text) and getG time / frequency (lime/oqs.py:474-526)"""
+    g = golden('api_r2')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    fn = str(tmp_path / 'cor.dat')
+    cor = lo.correlation_2p_1t(H, rho0, [g['A'], g['B']], c_ops, 0.01, 30, output=fn)
+    assert relerr(cor, g['cor2']) <= TOL
+    assert open(fn).read() == str(g['cor_txt'])
+    Hj, cj, ej, rj = cases.jc_point(ncav=8)
+    assert relerr(lo.correlation_2p_1t(Hj, rj, [ej[0], cj[0] / np.sqrt(0.05)], cj, 0.01, 25), g['cor2_jc']) <= TOL
+    Hr, a_ops, spectra, rr = cases.redfield_multilevel()
+    R, _ = lo.redfield_tensor(Hr, a_ops, spectra)
+    assert relerr(lo.getG(1j * R, g['tg']), g['G_time']) <= 1e-12
+    assert relerr(lo.getG(1j * R, g['tg'], w=g['wg'], domain='freq'), g['G_freq']) <= 1e-12
 
 
 def test_sos():
