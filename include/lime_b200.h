@@ -112,6 +112,31 @@ int limeb200_zgemm(const double* d_A, const double* d_B, double* d_C, int M, int
                    long long sA, long long sB, long long sC, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Runge-Kutta-Fehlberg 4(5): fused stage updates on device-resident real vectors of n doubles
+ * (a complex128 state is 2 x its element count).
+ * replaces: the stage arithmetic of r8_rkf45 / r8_fehl, the integrator lime's examples/rkf45_test.py:7,115
+ *           drives (`from lime.rkf45 import *`; the module itself is not in the lime tree).  Step-size control
+ *           is host logic (lime_b200/rkf45.py); the right-hand side is any device function, e.g.
+ *           limeb200_qme_rhs / limeb200_heom_rhs.
+ *   stage 1..5 : d_out = y + h * (Fehlberg combination of yp, f1..f(stage-1)) -- the argument of slope `stage`
+ *                (stage 5 yields the argument of the sixth function evaluation); unused slopes may be NULL
+ *   error      : d_s = 5th-order-pair solution; d_result2[0] = max_k ee_k/et_k, d_result2[1] = min_k et_k with
+ *                et = |y| + |s| + ae, ee = |-2090 yp + 21970 f3 - 15048 f4 + 22528 f2 - 27360 f5|
+ *   hinit      : d_result2[0] = max_k tol_k, d_result2[1] = min(h0, min_k (tol_k/|yp_k|)^(1/5) where tol_k < |yp_k| h0^5),
+ *                tol_k = relerr |y_k| + abserr  (the start-up step size rule)
+ *   axpy       : y += a x
+ * ------------------------------------------------------------------------------------ */
+int limeb200_rkf45_stage(int stage, long long n, const double* d_y, const double* d_yp, const double* d_f1,
+                         const double* d_f2, const double* d_f3, const double* d_f4, const double* d_f5, double h,
+                         double* d_out, void* stream);
+int limeb200_rkf45_error(long long n, const double* d_y, const double* d_yp, const double* d_f2, const double* d_f3,
+                         const double* d_f4, const double* d_f5, double h, double ae, double* d_s,
+                         double* d_result2, void* stream);
+int limeb200_rkf45_hinit(long long n, const double* d_y, const double* d_yp, double relerr, double abserr, double h0,
+                         double* d_result2, void* stream);
+int limeb200_rkf45_axpy(long long n, double a, const double* d_x, double* d_y, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Liouville-space linear ODE  dv/dt = R v,  R an arbitrary D x D CSR matrix (DEVICE arrays)
  * replaces: rhs + rk4 loop of _redfield  lime/oqs.py:453-472 (R from redfield_tensor),
  *           expm(method='EOM')            lime/phys.py:1384-1401 (B = D unit vectors)

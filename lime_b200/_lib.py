@@ -35,6 +35,10 @@ SIGNATURES = {
     'limeb200_qme_rhs': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp]),
     'limeb200_qme_last_launches': (c_ll, [c_vp]),
     'limeb200_zgemm': (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_vp]),
+    'limeb200_rkf45_stage': (c_int, [c_int, c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp, c_vp]),
+    'limeb200_rkf45_error': (c_int, [c_ll, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_dbl, c_vp, c_vp, c_vp]),
+    'limeb200_rkf45_hinit': (c_int, [c_ll, c_vp, c_vp, c_dbl, c_dbl, c_dbl, c_vp, c_vp]),
+    'limeb200_rkf45_axpy': (c_int, [c_ll, c_dbl, c_vp, c_vp, c_vp]),
     'limeb200_liouville_rk4_csr': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp, c_int,
                                            c_dbl, c_int, c_vp]),
     'limeb200_heom_count_states': (c_ll, [c_vp, c_int, c_int]),

@@ -1023,7 +1023,7 @@ void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
 // N >= 96: FP64 tensor-core (DMMA) kernel, or the 64x64 register-tiled DFMA kernel when
 // LIMEB200_DENSE_NO_DMMA is set; 32x32 tiles below
 void launch_dense_stage(const QmeStageArgs& a, cudaStream_t st) {
-    static const bool no_dmma = getenv("LIMEB200_DENSE_NO_DMMA") != nullptr;
+    const bool no_dmma = getenv("LIMEB200_DENSE_NO_DMMA") != nullptr;     // read per launch so that tests can switch it
     if (a.N >= 96 && !no_dmma) {
         dim3 grid(ceil_div(a.N, 64), ceil_div(a.N, 64), a.B);
         qme_dense_stage_dmma<<<grid, 128, 0, st>>>(a);

@@ -588,9 +588,13 @@ def test_redfield_two_level_batch_thread_per_vector_kernel(cuda):
         assert relerr(evecs @ out[b] @ evecs.conj().T, rl[-1]) <= TOL
 
 
-def test_lindblad_dense_stage_64_tile_ragged(cuda):
-    """dense stage-wise path with the 64x64 register-tiled kernel at a size that is no multiple of the tile"""
+@pytest.mark.parametrize('no_dmma', [False, True])
+def test_lindblad_dense_stage_64_tile_ragged(cuda, monkeypatch, no_dmma):
+    """dense stage-wise path at a size that is no multiple of the 64x64 tile: the FP64 tensor-core kernel
+    (qme_dense_stage_dmma, N >= 96) and, with LIMEB200_DENSE_NO_DMMA, the register-tiled DFMA kernel it replaced"""
     from lime_b200 import oqs
+    if no_dmma:
+        monkeypatch.setenv('LIMEB200_DENSE_NO_DMMA', '1')
     H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=101, M=2, E=1, seed=77)
     H = H / 10.0
     o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=6, dt=0.01)
@@ -598,6 +602,51 @@ def test_lindblad_dense_stage_64_tile_ragged(cuda):
     rf, ob, _ = plan.run(rho0, 0.01, 6)
     assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
     assert relerr(plan.rhs(rho0), lo.liouvillian(rho0, H, c_ops)) <= 1e-12
+
+
+@pytest.mark.parametrize('no_dmma', [False, True])
+def test_lindblad_dense_config2prime_full_size(cuda, monkeypatch, no_dmma):
+    """config 2' at its named size: N = 256, M = 2 dense operators, a batch of 3, 4 RK4 steps (DMMA and DFMA kernels);
+    and the 32x32-tile kernel below N = 96 with the DMMA path disabled"""
+    from lime_b200 import oqs
+    if no_dmma:
+        monkeypatch.setenv('LIMEB200_DENSE_NO_DMMA', '1')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=256, M=2, E=2, seed=123)
+    H = H / 20.0
+    c_ops = [c / 4.0 for c in c_ops]
+    plan = oqs._lindblad_plan(H, c_ops, e_ops, path=2)
+    r0 = np.stack([rho0, cases.rand_dm(256, 5), cases.rand_dm(256, 6)])
+    rf, ob, _ = plan.run(r0, 0.01, 4)
+    for b in (0, 2):
+        o, rl = lo.lindblad(H, r0[b], c_ops, e_ops=e_ops, Nt=4, dt=0.01)
+        assert relerr(ob[:, b], o) <= TOL and relerr(rf[b], rl[-1]) <= TOL
+    if no_dmma:
+        H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=80, M=1, E=1, seed=9)
+        o, rl = lo.lindblad(H / 8.0, rho0, c_ops, e_ops=e_ops, Nt=5, dt=0.01)
+        plan = oqs._lindblad_plan(H / 8.0, c_ops, e_ops, path=2)
+        rf, ob, _ = plan.run(rho0, 0.01, 5)
+        assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+
+
+def test_lindblad_config2_full_batch(cuda):
+    """config 2 at its real batch: 4096 coupling x detuning points of N = 128 in ONE launch (the launch bench.py
+    times), 12 RK4 steps; three of the points against the oracle, Tr rho = 1 on all of them"""
+    import torch
+    from lime_b200 import builders, oqs
+    pat, vals, c_ops, e_ops, rho0 = builders.jc_grid()
+    assert vals.shape[0] == 4096
+    plan, B = oqs._lindblad_plan_batch((pat, vals), c_ops, e_ops)
+    assert plan.path == 6
+    rho = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(rho0, (4096, 128, 128)))).cuda()
+    obs, _ = plan.run_device(rho, 0.01, 12)
+    tr = torch.einsum('bii->b', rho).cpu().numpy()
+    assert np.max(np.abs(tr - 1)) < 1e-12
+    gs = np.linspace(0.01, 0.2, 64)
+    dets = np.linspace(-0.2, 0.2, 64)
+    for b in (0, 2077, 4095):
+        Ho, co, eo = lo.jaynes_cummings(1.0, 1.0 + dets[b % 64], gs[b // 64], 64, 0.05)
+        o, rl = lo.lindblad(Ho.toarray(), rho0, [c.toarray() for c in co], [e.toarray() for e in eo], Nt=12, dt=0.01)
+        assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
 
 
 def test_heom_config3_long_run(cuda):
@@ -612,6 +661,23 @@ def test_heom_config3_long_run(cuda):
                                   h.up.astype(np.int64), 0.01, 4000, e_ops=[sz])
     assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
     assert abs(np.trace(res.ado[0]) - 1) < 1e-11
+
+
+def test_heom_config3_1e5_steps_one_launch(cuda):
+    """config 3 at its named length: 1e5 RK4 steps of the 91-ADO hierarchy in ONE launch.  The oracle needs minutes for
+    that, so the full length is checked through properties: splitting the run into 25 launches of 4000 steps (whose
+    first segment IS checked against the oracle above) gives the bit-identical state, the trace stays 1, tier 0 stays
+    Hermitian and the populations approach a stationary value"""
+    from lime_b200.heom.heom import HEOM
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=12)
+    h = HEOM(H, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    one, obs1, _ = h.plan.run(h.initial(rho0), 0.01, 100000, e_ops=[sz])
+    seg = h.initial(rho0)
+    for _ in range(25):
+        seg, _, _ = h.plan.run(seg, 0.01, 4000)
+    assert np.array_equal(one, seg)
+    assert abs(np.trace(one[0]) - 1) < 1e-10 and relerr(one[0], one[0].conj().T) < 1e-12
+    assert abs(obs1[-1, 0] - obs1[-2000, 0]) < 1e-6 and np.all(np.isfinite(one))
 
 
 def test_heom_parameter_batch_thread_per_ado_kernel(cuda):
@@ -746,3 +812,78 @@ def test_fft_module(cuda):
     assert relerr(out, g['fft2']) <= 1e-12 and np.array_equal(fy, g['fft2_fy'])
     assert relerr(lfft.dft(xg, f1[1], g['kxs']), g['dft']) <= 1e-12
     assert relerr(lfft.dft2(g['xs'], g['ys'], g['fxy'], g['kxs'], g['kys']), g['dft2']) <= 1e-12
+
+
+# ---------------------------------------------------------------- RKF45 (north_star; lime ships only examples/rkf45_test.py)
+def test_rkf45_lime_example_problems(cuda):
+    """examples/rkf45_test.py:72-119 (test04), :153-202 (test05), :283-330 (test06, single-step mode) through the
+    device stage kernels; tolerances sqrt(eps) as in the example, errors against the analytic solutions"""
+    from lime_b200 import rkf45 as rk
+    tol = float(np.sqrt(np.finfo(np.double).eps))
+
+    def f1(t, y):
+        return np.array([0.25 * y[0] * (1.0 - y[0] / 20.0)])
+
+    def exact1(t):
+        return 20.0 / (1.0 + 19.0 * np.exp(-0.25 * t))
+
+    y, flag, t = np.array([1.0]), 1, 0.0
+    yp = f1(t, y)
+    for i in range(1, 6):
+        t, tout = (i - 1) * 4.0, i * 4.0
+        y, yp, t, flag = rk.r8_rkf45(f1, 1, y, yp, t, tout, tol, tol, flag)
+        assert flag == 2 and t == tout and abs(y[0] - exact1(t)) < 2e-6
+
+    def f2(t, y):
+        return np.array([y[1], -y[0]])
+    y, flag = np.array([1.0, 0.0]), 1
+    yp = f2(0.0, y)
+    for i in range(1, 13):
+        t, tout = (i - 1) * 2 * 3.14159265 / 12, i * 2 * 3.14159265 / 12
+        y, yp, t, flag = rk.r8_rkf45(f2, 2, y, yp, t, tout, tol, tol, flag)
+        assert flag == 2 and abs(y[0] - np.cos(t)) < 1e-6 and abs(y[1] + np.sin(t)) < 1e-6
+
+    y, flag, t = np.array([1.0]), -1, 0.0
+    yp = f1(t, y)
+    for i in range(1, 6):
+        tout = i * 4.0
+        while flag < 0:
+            y, yp, t, flag = rk.r8_rkf45(f1, 1, y, yp, t, tout, tol, tol, flag)
+        assert flag == 2 and t == tout and abs(y[0] - exact1(t)) < 2e-6
+        flag = -2
+    # one uncontrolled Fehlberg step: fifth-order-pair solution of y' = y over h = 0.1
+    fs = rk.r8_fehl(lambda t, y: y, 1, np.array([1.0]), 0.0, 0.1, np.array([1.0]))
+    assert abs(fs[5][0] - np.exp(0.1)) < 1e-9
+
+
+def test_rkf45_device_resident_lindblad_and_heom(cuda):
+    """adaptive propagation with rho resident on the device: the right-hand side is limeb200_qme_rhs /
+    limeb200_heom_rhs, the stage arithmetic limeb200_rkf45_*; compared with the exact propagator e^{Lt} (Lindblad,
+    lime's superoperator) and with fine-step RK4 of the oracle (HEOM)"""
+    import torch
+    import scipy.linalg
+    from lime_b200 import rkf45 as rk, oqs, engine
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    plan = oqs._lindblad_plan(H, c_ops, None)
+    B = 3
+    r0 = np.stack([rho0, cases.rand_dm(6, 91), cases.rand_dm(6, 92)])
+    d = torch.from_numpy(r0).cuda()
+    tl = np.linspace(0.0, 2.0, 5)
+    states, S = rk.integrate(rk.QmeRHS(plan), d, tl, relerr=1e-10, abserr=1e-12)
+    Lsup = lo.liouvillian_super(H, c_ops).toarray()
+    for t, s in zip(tl, states):
+        U = scipy.linalg.expm(Lsup * t)
+        for b in range(B):
+            ref = (U @ r0[b].reshape(-1)).reshape(6, 6)
+            assert relerr(s[b].cpu().numpy(), ref) < 1e-8
+    assert S.steps_accepted > 4 and S.nfe > 0
+    # HEOM hierarchy, adaptive, against the oracle's RK4 with a small step
+    Hs, sz, rr, depth, K, lam, gam, T = cases.spin_boson_heom(depth=4)
+    from lime_b200.heom.heom import HEOM
+    h = HEOM(Hs, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    a0 = torch.from_numpy(h.initial(rr)[None]).cuda()
+    out, S = rk.integrate(rk.HeomRHS(h.plan), a0, [0.0, 0.5, 1.0], relerr=1e-10, abserr=1e-13)
+    st = h.states.astype(np.int64)
+    ado_o, _, _ = lo.heom_rk4(h.initial(rr), Hs, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64), h.up.astype(np.int64),
+                              0.0005, 2000)
+    assert relerr(out[-1][0].cpu().numpy(), ado_o) < 1e-8

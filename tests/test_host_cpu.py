@@ -197,3 +197,143 @@ def test_bench_input_builders_match_the_oracle_builders():
     assert Hf.shape == (7, 7) and np.allclose(Hf, Hf.conj().T) and len(Q) == 7
     assert all(np.array_equal(q, np.diag(np.diag(q))) and np.trace(q) == 1 for q in Q)
     assert abs(lam * 219474.6305 - 35.0) < 1e-9 and abs(kT * 315775.13 - 300.0) < 1e-9
+
+
+class _FakeRkf45Lib:
+    """NumPy stand-ins for the four limeb200_rkf45_* kernels (same argument lists), operating on CPU torch storage
+    through raw pointers -- a seam for testing the HOST step controller of lime_b200/rkf45.py without a GPU."""
+
+    @staticmethod
+    def _a(ptr, n):
+        import ctypes as C
+        v = ptr.value if hasattr(ptr, 'value') else ptr
+        return None if not v else np.ctypeslib.as_array(C.cast(v, C.POINTER(C.c_double)), shape=(n,))
+
+    def limeb200_rkf45_stage(self, stage, n, y, yp, f1, f2, f3, f4, f5, h, out, st):
+        a = self._a
+        y, p, f1, f2, f3, f4, out = a(y, n), a(yp, n), a(f1, n), a(f2, n), a(f3, n), a(f4, n), a(out, n)
+        if stage == 1:
+            out[:] = y + (h / 4.0) * p
+        elif stage == 2:
+            out[:] = y + (3.0 * h / 32.0) * (p + 3.0 * f1)
+        elif stage == 3:
+            out[:] = y + (h / 2197.0) * (1932.0 * p + (7296.0 * f2 - 7200.0 * f1))
+        elif stage == 4:
+            out[:] = y + (h / 4104.0) * ((8341.0 * p - 845.0 * f3) + (29440.0 * f2 - 32832.0 * f1))
+        else:
+            out[:] = y + (h / 20520.0) * ((-6080.0 * p + (9295.0 * f3 - 5643.0 * f4)) + (41040.0 * f1 - 28352.0 * f2))
+        return 0
+
+    def limeb200_rkf45_error(self, n, y, yp, f2, f3, f4, f5, h, ae, s, res, st):
+        a = self._a
+        y, p, f2, f3, f4, f5, s, res = a(y, n), a(yp, n), a(f2, n), a(f3, n), a(f4, n), a(f5, n), a(s, n), a(res, 2)
+        s[:] = y + (h / 7618050.0) * ((902880.0 * p + (3855735.0 * f3 - 1371249.0 * f4)) + (3953664.0 * f2 + 277020.0 * f5))
+        et = np.abs(y) + np.abs(s) + ae
+        ee = np.abs((-2090.0 * p + (21970.0 * f3 - 15048.0 * f4)) + (22528.0 * f2 - 27360.0 * f5))
+        res[0] = np.max(np.where(et > 0, ee / np.where(et > 0, et, 1.0), 0.0))
+        res[1] = np.min(et)
+        return 0
+
+    def limeb200_rkf45_hinit(self, n, y, yp, relerr, abserr, h0, res, st):
+        y, p, res = self._a(y, n), self._a(yp, n), self._a(res, 2)
+        tol = relerr * np.abs(y) + abserr
+        res[0] = np.max(np.where(tol > 0, tol, 0.0))
+        h = h0
+        for k in range(n):
+            if tol[k] > 0 and tol[k] < abs(p[k]) * h0 ** 5:
+                h = min(h, (tol[k] / abs(p[k])) ** 0.2)
+        res[1] = h
+        return 0
+
+    def limeb200_rkf45_axpy(self, n, a, x, y, st):
+        x, y = self._a(x, n), self._a(y, n)
+        y[:] = y + a * x
+        return 0
+
+
+@pytest.fixture
+def rkf45_on_host(monkeypatch):
+    import torch
+    from lime_b200 import rkf45, _dev
+    fake = _FakeRkf45Lib()
+    cpu = torch.device('cpu')
+    monkeypatch.setattr(rkf45, 'lib', lambda: fake)
+    monkeypatch.setattr(_dev, 'device', lambda index=None: cpu)
+    monkeypatch.setattr(_dev, 'stream_ptr', lambda dev=None: None)
+    monkeypatch.setattr(_dev, 'to_dev', lambda a, dtype=np.complex128, dev=None, pinned=False:
+                        torch.from_numpy(np.array(a, dtype=dtype, copy=True)))
+    monkeypatch.setattr(rkf45._Vec, '__init__', _vec_init_cpu)
+    return rkf45
+
+
+def _vec_init_cpu(self, y, dev):
+    import torch
+    self.host = True
+    a = np.asarray(y)
+    self.cplx = np.iscomplexobj(a)
+    self.shape = a.shape
+    self.t = torch.from_numpy(np.array(a, dtype=np.complex128 if self.cplx else np.float64, copy=True))
+    self.real = torch.view_as_real(self.t).reshape(-1) if self.cplx else self.t.reshape(-1)
+    self.n = self.real.numel()
+
+
+def test_rkf45_step_controller_host_logic(rkf45_on_host):
+    """the Shampine-Watts controller of lime_b200/rkf45.py on lime's own test problems (examples/rkf45_test.py:72-119,
+    153-202, 283-330) with the device kernels replaced by NumPy through a seam: flags, output times, accuracy"""
+    rk = rkf45_on_host
+    tol = float(np.sqrt(np.finfo(np.double).eps))
+
+    def f1(t, y):
+        return np.array([0.25 * y[0] * (1.0 - y[0] / 20.0)])
+
+    def exact1(t):
+        return 20.0 / (1.0 + 19.0 * np.exp(-0.25 * t))
+
+    # test04: scalar logistic equation, 5 output intervals on [0, 20]
+    S = rk.RKF45State()
+    y, flag, t = np.array([1.0]), 1, 0.0
+    yp = f1(t, y)
+    for i in range(1, 6):
+        t, tout = (i - 1) * 4.0, i * 4.0
+        y, yp, t, flag = rk.r8_rkf45(f1, 1, y, yp, t, tout, tol, tol, flag, state=S)
+        assert flag == 2 and t == tout
+        assert abs(y[0] - exact1(t)) < 2e-6
+        assert abs(yp[0] - f1(t, y)[0]) < 1e-14
+    # test05: harmonic oscillator, 12 intervals on [0, 2 pi]
+    def f2(t, y):
+        return np.array([y[1], -y[0]])
+    S = rk.RKF45State()
+    y, flag = np.array([1.0, 0.0]), 1
+    yp = f2(0.0, y)
+    for i in range(1, 13):
+        t, tout = (i - 1) * 2 * np.pi / 12, i * 2 * np.pi / 12
+        y, yp, t, flag = rk.r8_rkf45(f2, 2, y, yp, t, tout, tol, tol, flag, state=S)
+        assert flag == 2
+        assert abs(y[0] - np.cos(t)) < 1e-6 and abs(y[1] + np.sin(t)) < 1e-6
+    # test06: single-step mode, flag -1 / -2 until the output point answers +2
+    S = rk.RKF45State()
+    y, flag, t = np.array([1.0]), -1, 0.0
+    yp = f1(t, y)
+    nsteps = 0
+    for i in range(1, 6):
+        tout = i * 4.0
+        while flag < 0:
+            y, yp, t, flag = rk.r8_rkf45(f1, 1, y, yp, t, tout, tol, tol, flag, state=S)
+            nsteps += 1
+            assert flag in (-2, 2) and t <= tout
+        assert t == tout and abs(y[0] - exact1(t)) < 2e-6
+        flag = -2
+    assert nsteps > 5 and S.steps_accepted == nsteps
+    # input validation and the "relerr too small" answer
+    assert rk.r8_rkf45(f1, 0, y, yp, 0.0, 1.0, tol, tol, 1)[3] == 8
+    assert rk.r8_rkf45(f1, 1, y, yp, 0.0, 1.0, -1.0, tol, 1)[3] == 8
+    assert rk.r8_rkf45(f1, 1, y, yp, 0.0, 1.0, tol, tol, 0)[3] == 8
+    assert rk.r8_rkf45(f1, 1, y, yp, 0.0, 1.0, 1e-20, tol, 1, state=rk.RKF45State())[3] == 3
+    # complex state: d rho/dt = -i [H, rho] for a two-level system against the exact propagator
+    H = np.array([[0.3, 0.2 - 0.1j], [0.2 + 0.1j, -0.4]])
+    rho0 = np.array([[0.7, 0.2j], [-0.2j, 0.3]], dtype=complex)
+    states, S = rk.integrate(lambda t, r: -1j * (H @ r - r @ H), rho0, np.linspace(0, 3.0, 4), relerr=1e-10, abserr=1e-12)
+    w, v = np.linalg.eigh(H)
+    for t, r in zip(np.linspace(0, 3.0, 4), states):
+        U = v @ np.diag(np.exp(-1j * w * t)) @ v.conj().T
+        assert np.max(np.abs(r - U @ rho0 @ U.conj().T)) < 1e-8
