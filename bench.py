@@ -687,6 +687,9 @@ class HeomFMO(HeomBase):
         if self.world > 1:
             res = self.h.evolve(rho0, self.dt, self.rk)
             return rho0.nbytes, res.ado.nbytes
+        if self.B > 1:          # batch of hierarchies: HeomPlan.run (host batch in, final hierarchies + observables out)
+            out, obs, _ = self.h.plan.run(self.h_ado, self.dt, self.rk, e_ops=self.Q)
+            return self.h_ado.nbytes, out.nbytes + obs.nbytes
         res = self.h.evolve(rho0, self.dt, self.rk, e_ops=self.Q, store_states=False)
         return self.nhe * 49 * 16, res.ado.nbytes + res.observables.nbytes
 

@@ -209,13 +209,15 @@ long long limeb200_heom_last_launches(limeb200_heom_t plan);
 /* ADO-sharded propagation of ONE hierarchy over the GPUs of one box (one process per GPU): the
  * fused compute + exchange path.  Every rank runs a persistent kernel over the ADO range its plan
  * owns; each new stage-vector element is stored into the local stage vector AND, through peer
- * (CUDA IPC / NVLink) pointers, into the same element of every peer's stage vector; a flag
- * barrier across the GPUs separates the RK4 stages.  No host round trip and no collective library
+ * (CUDA IPC / NVLink) pointers, into the same element of every peer's stage vector; the RK4 stages are
+ * separated by a one-hop barrier: every CTA counts itself on every peer with one remote reduction and waits, in its
+ * OWN memory, for all CTAs of all ranks.  No host round trip and no collective library
  * call inside the time loop (the alternative is limeb200_heom_stage + an all-gather per stage).
  *   limeb200_peer_alloc : cudaMalloc + zero + export (handle64 = cudaIpcMemHandle_t bytes)
  *   limeb200_peer_open  : map a peer's allocation into this process
  *   d_y0/d_y1[world]    : every rank's two stage vectors [nhe_pad][n][n] (index = rank; own entry local)
- *   d_flags[world]      : every rank's flag array (>= world unsigned, zero-initialised)
+ *   d_flags[world]      : every rank's flag array (>= world unsigned, zero-initialised): word q counts arrivals of rank q
+ *   h_grids[world]      : HOST array, limeb200_heom_persist_grid(plan_r, 1) of every rank r (arrivals per stage)
  *   d_rho               : local [nhe_pad][n][n]; only the owned rows are read and written
  *   d_peer_mask         : [nhe] bytes or NULL.  Bit q of entry a = "peer slot q (the q-th rank != this one) reads
  *                         ADO a" (it owns a neighbour of a): new values of a are stored only into those peers, except
@@ -227,8 +229,9 @@ int limeb200_peer_alloc(int device, long long bytes, void** d_ptr, unsigned char
 int limeb200_peer_open(int device, const unsigned char* handle64, void** d_ptr);
 int limeb200_peer_close(int device, void* d_ptr);
 int limeb200_peer_free(int device, void* d_ptr);
+int limeb200_heom_persist_grid(limeb200_heom_t plan, int B);   /* CTAs the persistent kernel uses for B hierarchies (>= 1), <0 = error */
 int limeb200_heom_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_y0, void* const* d_y1,
-                              void* const* d_flags, double* d_rho, const unsigned char* d_peer_mask,
+                              void* const* d_flags, const int* h_grids, double* d_rho, const unsigned char* d_peer_mask,
                               double dt, int nsteps, unsigned epoch, void* stream);
 /* 1 when a bounded spin of the last sharded run timed out (a peer never arrived), else 0 */
 int limeb200_heom_sharded_error(limeb200_heom_t plan, void* stream);

@@ -59,7 +59,8 @@ SIGNATURES = {
     'limeb200_peer_open': (c_int, [c_int, c_vp, P(c_vp)]),
     'limeb200_peer_close': (c_int, [c_int, c_vp]),
     'limeb200_peer_free': (c_int, [c_int, c_vp]),
-    'limeb200_heom_run_sharded': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_uint, c_vp]),
+    'limeb200_heom_persist_grid': (c_int, [c_vp, c_int]),
+    'limeb200_heom_run_sharded': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_uint, c_vp]),
     'limeb200_heom_sharded_error': (c_int, [c_vp, c_vp]),
     'limeb200_heom_dl_euler': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),
     'limeb200_sos_factor': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),

@@ -333,7 +333,8 @@ struct HeomPersistArgs {
     unsigned epoch;         // flags are monotonic across launches: stage x of this launch signals epoch + x + 1
     cplx* y0p[7]; cplx* y1p[7];       // peers' y0 / y1 (order: every rank != this one)
     unsigned* flagp[7];               // peers' flag arrays; peer q's slot for this rank is flagp[q][rank]
-    unsigned* flags;                  // this rank's flag array [world]
+    unsigned* flags;                  // this rank's flag array [world]: flags[q] counts the CTA arrivals of rank q
+    unsigned peer_grid[7];            // CTAs of the persistent kernel on peer slot q (its arrivals per stage)
     const unsigned char* peer_mask;   // [nhe] which peer slots need each owned ADO (null: all); the last stage of the
                                       // run always goes to every peer so that each rank ends with the full state
 };
@@ -356,39 +357,36 @@ __device__ __forceinline__ void heom_grid_barrier(unsigned* ctr, unsigned target
     __syncthreads();
 }
 
-// Barrier across every CTA of every rank of an ADO-sharded run.  Each CTA makes its (remote) stores
-// visible system-wide and arrives on the local counter; CTA 0 waits for the local arrivals, tells
-// every peer "my stage x is complete" with a release store into the peer's flag array, waits for
-// the peers' flags, and releases the local CTAs.  Spins are bounded (~ 5 s) so that a missing peer
-// produces an error instead of a hung GPU.
+// Barrier across every CTA of every rank of an ADO-sharded run, one hop and no funnel: after its stores (local and
+// peer) a CTA (1) arrives on the local counter (gpu-scope release: covers its local stores), (2) makes its peer stores
+// visible system-wide and counts itself on EVERY peer with one remote reduction into that peer's flag word for this
+// rank, (3) waits until the local counter and the flag word of every peer have reached the value that says "all CTAs
+// of that rank have finished this stage" (flags are monotonic: peer_grid[q] arrivals per stage), (4) one system-scope
+// acquire fence.  Remote signalling therefore overlaps the local collection, nobody polls over NVLink (every flag a
+// rank polls lives in its own memory), and no stage is relayed through one CTA.  WAR on the ping-pong buffers is
+// covered by the same counts: a peer's arrival for stage s implies it has finished READING the buffer that stage
+// s + 1 overwrites.  Spins are bounded (~ 5 s) so that a missing peer produces an error instead of a hung GPU.
 __device__ __forceinline__ void heom_world_barrier(const HeomPersistArgs& p, unsigned target, unsigned xcount) {
     __syncthreads();
     if (threadIdx.x == 0) {
         const long long t0 = clock64();
         const long long limit = 10000000000LL;
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier) : "memory");
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        for (int q = 0; q < p.world - 1; ++q)
+            asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.flagp[q] + p.rank) : "memory");
         unsigned v;
-        if (blockIdx.x == 0) {
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier) : "memory");
+        } while (v < target && clock64() - t0 < limit);
+        int slot = 0;
+        for (int q = 0; q < p.world; ++q) {
+            if (q == p.rank) continue;
+            const unsigned want = p.peer_grid[slot++] * xcount;
             do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier) : "memory");
-            } while (v < target && clock64() - t0 < limit);
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-            for (int q = 0; q < p.world - 1; ++q)
-                asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.flagp[q] + p.rank), "r"(xcount) : "memory");
-            for (int q = 0; q < p.world; ++q) {
-                if (q == p.rank) continue;
-                do {
-                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags + q) : "memory");
-                } while ((int)(v - xcount) < 0 && clock64() - t0 < limit);
-                if ((int)(v - xcount) < 0) atomicExch(p.barrier + 2, 1u);
-            }
-            asm volatile("fence.acq_rel.sys;" ::: "memory");
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p.barrier + 1), "r"(xcount) : "memory");
-        } else {
-            do {
-                asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier + 1) : "memory");
-            } while ((int)(v - xcount) < 0 && clock64() - t0 < limit);
+                asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags + q) : "memory");
+            } while ((int)(v - want) < 0 && clock64() - t0 < limit);
+            if ((int)(v - want) < 0) atomicExch(p.barrier + 2, 1u);
         }
         asm volatile("fence.acq_rel.sys;" ::: "memory");
     }
@@ -1223,59 +1221,74 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     return LB_OK;
 }
 
-// launch one of the persistent kernels over the plan's owned ADO range (pa: y0/y1, outputs and the
-// sharding fields filled by the caller; y0 must already hold the state)
-static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho, int B, double dt, int nsteps,
-                               cudaStream_t st, bool require_one_tile_per_cta = false) {
+// launch geometry of the persistent kernels for B hierarchies over the plan's owned ADO range
+struct HeomPersistCfg {
+    void (*kern)(HeomPersistArgs) = nullptr;
+    int apc = 1, threads = 32, grid = 1;
+    size_t smem = 0;
+    bool one_tile_per_cta = false;
+};
+static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c) {
     const int nn = p->n * p->n;
     const long long total = p->nhe * nn;
     const long long nown = p->row_hi - p->row_lo;
     if (nown <= 0) return LB_ERR_UNSUPPORTED;
-    pa.s.d = p->dev();
-    pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = p->row_lo; pa.s.row_hi = p->row_hi;
-    pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
-    pa.s.dt = dt;
-    pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
-    pa.nsteps = nsteps;
     int coop = 0;
     LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
     if (!coop) return LB_ERR_UNSUPPORTED;
     // balanced tiles: one tile per CTA for the whole run when the items fit in (1 or 2 CTAs per SM) x
     // at most (1024 or 576) threads; larger problems loop over tiles of up to 1024 threads
     const long long nitems = nown * B;
-    void (*kern)(HeomPersistArgs) = heom_persist_kernel<1024, 1>;
+    c.kern = heom_persist_kernel<1024, 1>;
     int per_sm = 1;
     {
         long long apc1 = ceil_div(nitems, (long long)p->sm_count);
         long long apc2 = ceil_div(nitems, 2LL * p->sm_count);
-        if (apc1 * nn <= 1024) pa.s.apc = (int)std::max<long long>(1, apc1);
-        else if (apc2 * nn <= 576) { pa.s.apc = (int)apc2; kern = heom_persist_kernel<576, 2>; per_sm = 2; }
-        else pa.s.apc = std::max(1, 1024 / nn);
+        if (apc1 * nn <= 1024) c.apc = (int)std::max<long long>(1, apc1);
+        else if (apc2 * nn <= 576) { c.apc = (int)apc2; c.kern = heom_persist_kernel<576, 2>; per_sm = 2; }
+        else c.apc = std::max(1, 1024 / nn);
     }
-    const int threads = ceil_div(pa.s.apc * nn, 32) * 32;
-    size_t smem = (size_t)(1 + 3 * pa.s.apc) * nn * 16 + (size_t)3 * pa.s.apc * p->nmodes * 4;
-    const bool one_tile_per_cta = ceil_div(nitems, (long long)pa.s.apc) <= (long long)per_sm * p->sm_count;
-    // larger problems gain nothing from persistence (the per-stage launches are already long) and
-    // run better with the smaller CTAs of the stage-wise kernel
-    if (require_one_tile_per_cta && !one_tile_per_cta) return LB_ERR_UNSUPPORTED;
-    const size_t smem_c = (size_t)(1 + pa.s.apc) * nn * 16 + (size_t)HEOM_PC_NE * threads * 20;
-    if (p->diagq && one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
+    c.threads = ceil_div(c.apc * nn, 32) * 32;
+    c.smem = (size_t)(1 + 3 * c.apc) * nn * 16 + (size_t)3 * c.apc * p->nmodes * 4;
+    c.one_tile_per_cta = ceil_div(nitems, (long long)c.apc) <= (long long)per_sm * p->sm_count;
+    const size_t smem_c = (size_t)(1 + c.apc) * nn * 16 + (size_t)HEOM_PC_NE * c.threads * 20;
+    if (p->diagq && c.one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
         (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
-        kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
-        smem = smem_c;
+        c.kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
+        c.smem = smem_c;
     }
-    LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LB_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
     int occ = 0;
-    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem));
+    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.kern, c.threads, c.smem));
     per_sm = std::min(per_sm, occ);
     if (per_sm < 1) return LB_ERR_UNSUPPORTED;
-    const long long ntiles = ceil_div(nitems, (long long)pa.s.apc);
-    const int grid = (int)std::min<long long>(ntiles, (long long)per_sm * p->sm_count);
+    const long long ntiles = ceil_div(nitems, (long long)c.apc);
+    c.grid = (int)std::min<long long>(ntiles, (long long)per_sm * p->sm_count);
+    return LB_OK;
+}
+
+// launch one of the persistent kernels over the plan's owned ADO range (pa: y0/y1, outputs and the
+// sharding fields filled by the caller; y0 must already hold the state)
+static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho, int B, double dt, int nsteps,
+                               cudaStream_t st, bool require_one_tile_per_cta = false) {
+    HeomPersistCfg c;
+    int r = heom_persist_config(p, B, c);
+    if (r != LB_OK) return r;
+    // larger problems gain nothing from persistence (the per-stage launches are already long) and
+    // run better with the smaller CTAs of the stage-wise kernel
+    if (require_one_tile_per_cta && !c.one_tile_per_cta) return LB_ERR_UNSUPPORTED;
+    pa.s.d = p->dev();
+    pa.s.B = B; pa.s.stage = 0; pa.s.row_lo = p->row_lo; pa.s.row_hi = p->row_hi;
+    pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
+    pa.s.dt = dt;
+    pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
+    pa.s.apc = c.apc;
+    pa.nsteps = nsteps;
     if (!p->dbar.p) LB_CUDA(p->dbar.alloc(64));
     LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
     pa.barrier = p->dbar.as<unsigned>();
     void* kargs[] = {&pa};
-    LB_CUDA(cudaLaunchCooperativeKernel((void*)kern, dim3(grid), dim3(threads), kargs, smem, st));
+    LB_CUDA(cudaLaunchCooperativeKernel((void*)c.kern, dim3(c.grid), dim3(c.threads), kargs, c.smem, st));
     p->launches += 1;
     return LB_OK;
 }
@@ -1442,10 +1455,19 @@ int limeb200_peer_free(int device, void* d_ptr) {
     return LB_OK;
 }
 
+int limeb200_heom_persist_grid(limeb200_heom_t p, int B) {
+    LB_REQUIRE(p && B >= 1, "bad arguments");
+    LB_CUDA(cudaSetDevice(p->device));
+    HeomPersistCfg c;
+    int r = heom_persist_config(p, B, c);
+    if (r != LB_OK) { limeb200::set_error("persistent kernel cannot be launched for this plan"); return r; }
+    return c.grid;
+}
+
 int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* const* d_y0, void* const* d_y1,
-                              void* const* d_flags, double* d_rho, const unsigned char* d_peer_mask,
-                              double dt, int nsteps, unsigned epoch, void* stream) {
-    LB_REQUIRE(p && d_y0 && d_y1 && d_flags && d_rho, "null argument");
+                              void* const* d_flags, const int* h_grids, double* d_rho,
+                              const unsigned char* d_peer_mask, double dt, int nsteps, unsigned epoch, void* stream) {
+    LB_REQUIRE(p && d_y0 && d_y1 && d_flags && d_rho && h_grids, "null argument");
     LB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8");
     LB_REQUIRE(p->npar == 1, "sharded runs take one hierarchy (no parameter batch)");
     LB_REQUIRE(nsteps >= 0, "bad nsteps");
@@ -1464,6 +1486,8 @@ int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* cons
     for (int r = 0; r < world; ++r) {
         if (r == rank) continue;
         pa.y0p[q] = (cplx*)d_y0[r]; pa.y1p[q] = (cplx*)d_y1[r]; pa.flagp[q] = (unsigned*)d_flags[r];
+        LB_REQUIRE(h_grids[r] >= 1, "h_grids[%d] must be the peer's limeb200_heom_persist_grid", r);
+        pa.peer_grid[q] = (unsigned)h_grids[r];
         ++q;
     }
     int r = heom_launch_persist(p, pa, (cplx*)d_rho, 1, dt, nsteps, st);

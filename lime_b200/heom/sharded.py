@@ -14,8 +14,9 @@ IS rho_{n+1}.
 Two data paths:
   exchange='p2p'  (default on CUDA) fused compute + exchange: ONE persistent kernel per rank for the whole
                   run (limeb200_heom_run_sharded); every new stage-vector element is stored locally and, through
-                  CUDA-IPC peer pointers, into every peer's stage vector over NVLink; a flag barrier across the
-                  GPUs separates the stages.  torch.distributed is used only to exchange the IPC handles.
+                  CUDA-IPC peer pointers, into the stage vectors of the peers that read it over NVLink; the stages are
+                  separated by a one-hop barrier (every CTA counts itself on every peer with one remote reduction and
+                  polls only its own memory).  torch.distributed is used only to exchange the IPC handles.
   exchange='nccl' CUDA stage kernel -> NCCL all-gather, 4 x per step, captured in a CUDA graph.
 `stage_fn` is a seam for the world_size-2 gloo tests of this host logic (they plug a CPU stage
 function built from the oracle); the product path always uses the CUDA plan.
@@ -159,7 +160,15 @@ class ShardedHEOM:
                     ptrs[k][r] = q.value
                     opened.append(q.value)
         arr = [(C.c_void_p * self.world)(*ptrs[k]) for k in range(3)]
-        self._peer = dict(mine=mine, ptrs=ptrs, arr=arr, opened=opened, nbytes=nbytes)
+        # arrivals per stage of every rank = CTAs of its persistent kernel (the one-hop barrier counts them)
+        g = check(lib().limeb200_heom_persist_grid(self.plan._h, 1))
+        grids = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(grids, int(g), group=self.group)
+        else:
+            grids[0] = int(g)
+        self._peer = dict(mine=mine, ptrs=ptrs, arr=arr, opened=opened, nbytes=nbytes,
+                          grids=(C.c_int * self.world)(*grids))
 
     def close(self):
         if self._peer is not None:
@@ -194,7 +203,7 @@ class ShardedHEOM:
             self._d_mask = torch.from_numpy(self.peer_mask).to(ado.device)
         mptr = C.c_void_p(self._d_mask.data_ptr()) if self._d_mask is not None else None
         check(lib().limeb200_heom_run_sharded(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1],
-                                              pr['arr'][2], C.c_void_p(rho.data_ptr()), mptr, float(dt), int(nsteps),
+                                              pr['arr'][2], pr['grids'], C.c_void_p(rho.data_ptr()), mptr, float(dt), int(nsteps),
                                               C.c_uint(self._epoch), C.c_void_p(st.cuda_stream)))
         self._epoch += 4 * nsteps
         err = lib().limeb200_heom_sharded_error(self.plan._h, C.c_void_p(st.cuda_stream))

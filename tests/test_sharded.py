@@ -182,3 +182,88 @@ def test_sharded_heom_nccl_world2(exchange):
     for rank, ado, ranges, nhe in res:
         assert relerr(ado, ref) <= 1e-10, rank
     assert np.array_equal(res[0][1], res[1][1])
+
+
+def _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, dt, runs, halo_only=True):
+    """`world` ranks of the fused sharded kernel as `world` plans + streams on ONE GPU in one process: every rank's
+    persistent kernel is resident at the same time (the grids are small), "peer" stores and the one-hop barrier go
+    through ordinary device pointers instead of CUDA-IPC mappings.  Exercises limeb200_heom_run_sharded's cross-rank
+    protocol (peer stores, remote arrival counts, epochs across launches) on a single-GPU box."""
+    import ctypes as C
+    from lime_b200 import engine
+    from lime_b200._lib import lib, check
+    from lime_b200.heom.heom import _calc_matsubara_params
+    from lime_b200.heom.sharded import partition, peer_masks
+    dev = torch.device('cuda', 0)
+    n = H.shape[0]
+    c, nu, qmap = [], [], []
+    for b in range(len(Q)):
+        cb, nub = _calc_matsubara_params(2, np.broadcast_to(lam, (len(Q),))[b], np.broadcast_to(gam, (len(Q),))[b], T)
+        c += cb
+        nu += nub
+        qmap += [b, b]
+    states, dn, up = engine.heom_tables([depth + 1] * len(qmap), depth)
+    nhe = states.shape[0]
+    chunk, ranges = partition(nhe, world)
+    nhe_pad = chunk * world
+    plans = [engine.HeomPlan(H, np.stack(Q).astype(complex), qmap, np.array(c), np.array(nu), states, dn, up,
+                             row_range=ranges[r], device_index=0) for r in range(world)]
+    full = torch.zeros((1, nhe_pad, n, n), dtype=torch.complex128, device=dev)
+    full[0, :nhe] = torch.from_numpy(ado0).to(dev)
+    y0 = [full.clone() for _ in range(world)]
+    y1 = [torch.zeros_like(full) for _ in range(world)]
+    rho = [full.clone() for _ in range(world)]
+    flags = [torch.zeros(64, dtype=torch.int32, device=dev) for _ in range(world)]
+    masks = [torch.from_numpy(peer_masks(dn, up, ranges, r)).to(dev) if halo_only else None for r in range(world)]
+    grids = (C.c_int * world)(*[check(lib().limeb200_heom_persist_grid(p._h, 1)) for p in plans])
+    arr = [(C.c_void_p * world)(*[t.data_ptr() for t in ts]) for ts in (y0, y1, flags)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(world)]
+    torch.cuda.synchronize()
+    epoch = 0
+    for nsteps in runs:
+        for r in range(world):
+            check(lib().limeb200_heom_run_sharded(plans[r]._h, r, world, arr[0], arr[1], arr[2], grids,
+                                                  C.c_void_p(rho[r].data_ptr()),
+                                                  C.c_void_p(masks[r].data_ptr()) if halo_only else None,
+                                                  float(dt), int(nsteps), C.c_uint(epoch),
+                                                  C.c_void_p(streams[r].cuda_stream)))
+        torch.cuda.synchronize()
+        for r in range(world):
+            assert lib().limeb200_heom_sharded_error(plans[r]._h, C.c_void_p(streams[r].cuda_stream)) == 0, \
+                'rank %d: a peer never reached the stage barrier' % r
+        epoch += 4 * nsteps
+    return [y[0, :nhe].cpu().numpy() for y in y0], ranges
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 3, 4])
+@pytest.mark.parametrize('halo_only', [True, False])
+def test_sharded_virtual_ranks_on_one_gpu(cuda, world, halo_only):
+    """the cross-rank protocol of the fused sharded kernel (peer stores, one-hop barrier with remote arrival counts,
+    epochs continuing over two launches), 2-4 ranks resident together on a single GPU"""
+    H, Q, lam, gam, T, depth, rho0 = _problem()
+    ref = _reference()
+    ado0 = np.zeros_like(ref)
+    ado0[0] = rho0
+    outs, ranges = _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, 0.01, [5, 7], halo_only=halo_only)
+    for r, o in enumerate(outs):
+        assert relerr(o, ref) <= 1e-10, r
+        assert np.array_equal(o, outs[0])            # every rank ends with the same full hierarchy
+
+
+@pytest.mark.gpu
+def test_sharded_virtual_ranks_fmo_depth3_long(cuda):
+    """a larger hierarchy (FMO, depth 3: 680 ADOs of 7x7) over 4 virtual ranks for 200 steps against the one-GPU
+    propagator of the same library: the barrier protocol over 800 stages"""
+    from lime_b200 import builders
+    from lime_b200.heom.heom import HEOM
+    from lime_b200.units import au2fs
+    Hm, Q, lam, gam, kT = builders.fmo_heom_inputs()
+    h = HEOM(Hm, Q, lam, gam, kT, N_exp=2, N_cut=3)
+    rho0 = np.zeros((7, 7), dtype=complex)
+    rho0[0, 0] = 1.0
+    dt = 0.5 / au2fs
+    one, _, _ = h.plan.run(h.initial(rho0), dt, 200)
+    outs, _ = _virtual_ranks_one_gpu(4, Hm, Q, lam, gam, kT, 3, h.initial(rho0), dt, [200])
+    for o in outs:
+        assert relerr(o, one) <= 1e-12
