@@ -606,7 +606,9 @@ class HeomFMO(HeomBase):
                 self.h = ShardedHEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth,
                                      exchange=args.exchange)
                 self.nhe = self.h.nhe
-                self.kernel = ('heom_persist_cached_kernel (fused peer stores + flag barrier)' if args.exchange == 'p2p'
+                self.exchange = self.h.exchange
+                self.kernel = ('heom_flow_kernel (dataflow: tagged stage vectors, peer stores, no barrier)' if self.h.exchange == 'flow'
+                               else 'heom_persist_cached_kernel (fused peer stores + one-hop barrier)' if self.h.exchange == 'p2p'
                                else 'heom_stage_kernel + NCCL all_gather (CUDA graph)')
             else:
                 self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
@@ -643,7 +645,8 @@ class HeomFMO(HeomBase):
         if self.kernel:
             return self.kernel
         return {1: 'heom_onchip_kernel', 2: 'heom_stage_kernel (one launch per RK4 stage)',
-                3: 'heom_persist_cached_kernel / heom_persist_kernel (one cooperative launch per run)'
+                3: 'heom_persist_cached_kernel / heom_persist_kernel (one cooperative launch per run)',
+                4: 'heom_flow_kernel (dataflow: tagged stage vectors, no barrier; one cooperative launch per run)'
                 }.get(self.h.plan.path, 'path %d' % self.h.plan.path)
 
     def check(self):
@@ -1084,7 +1087,8 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
     ap.add_argument('--size', type=int, default=0, help='Hilbert dimension for lindblad_dense (0 = 256)')
     ap.add_argument('--depth', type=int, default=0, help='HEOM depth for heom_fmo (0 = 4)')
-    ap.add_argument('--exchange', default='p2p', choices=['p2p', 'nccl'], help='sharded heom_fmo: fused peer-memory kernel or stage kernel + NCCL all-gather')
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'flow', 'p2p', 'nccl'],
+                    help='sharded heom_fmo: dataflow kernel (auto/flow), barrier kernel with peer stores (p2p) or stage kernel + NCCL all-gather')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu', action='store_true')
     ap.add_argument('--no-spot-check', action='store_true', help='skip the in-run oracle spot check of jc_lindblad')

@@ -188,7 +188,9 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
                                  long long row_lo, long long row_hi);
 int limeb200_heom_destroy(limeb200_heom_t plan);
 /* 0 auto, 1 on-chip (one CTA per hierarchy, all steps fused), 2 one launch per RK4 stage,
- * 3 persistent cooperative kernel (all steps in one launch, one grid barrier per stage)   */
+ * 3 persistent cooperative kernel (all steps in one launch, one grid barrier per stage),
+ * 4 dataflow-synchronised persistent kernel (one hierarchy, diagonal coupling operators: tagged stage
+ *   vectors, no barrier; the default for a single large hierarchy when it applies)              */
 int limeb200_heom_set_path(limeb200_heom_t plan, int path);
 int limeb200_heom_get_path(limeb200_heom_t plan);
 /* nsteps RK4 steps (lime/phys.py:636-649) of B hierarchies d_ado[B][nhe][n][n], in place.
@@ -233,6 +235,23 @@ int limeb200_heom_persist_grid(limeb200_heom_t plan, int B);   /* CTAs the persi
 int limeb200_heom_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_y0, void* const* d_y1,
                               void* const* d_flags, const int* h_grids, double* d_rho, const unsigned char* d_peer_mask,
                               double dt, int nsteps, unsigned epoch, void* stream);
+/* Dataflow variant of the sharded propagator (csrc/heom_flow.cuh): no barrier between the stages.  Stage vectors
+ * are TAGGED -- entry e of d_T0 / d_T1 is two 16-byte words {value bits, 64-bit stage tag} -- and a consumer polls, in
+ * its own memory, exactly the entries it reads; producers store new entries locally and into the buffers of the ranks
+ * that read them (d_peer_mask as above; the last stage of a run goes to every rank).
+ *   d_T0 / d_T1[world] : every rank's two tagged buffers, 32 * nhe * n * n bytes each, zero-initialised (peer_alloc)
+ *   flow_pack          : d_T0 <- full state d_y [nhe][n][n] tagged `tag` (every rank, BEFORE the ranks synchronise
+ *                        on the host and launch flow_run_sharded with tag0 = tag)
+ *   flow_run_sharded   : nsteps RK4 steps; d_rho [nhe][n][n] local, owned rows read and written; tags used are
+ *                        tag0 .. tag0 + 4 nsteps: the next run must use a larger tag0
+ *   flow_unpack        : d_y <- values of d_T0 (after the ranks have synchronised on the host), checking every tag
+ *   limeb200_heom_sharded_error reports bit 0 = a wait timed out, bit 1 = unpack met a stale tag               */
+int limeb200_heom_flow_supported(limeb200_heom_t plan);
+int limeb200_heom_flow_pack(limeb200_heom_t plan, const double* d_y, void* d_T0, unsigned long long tag, void* stream);
+int limeb200_heom_flow_unpack(limeb200_heom_t plan, const void* d_T0, unsigned long long tag, double* d_y, void* stream);
+int limeb200_heom_flow_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_T0, void* const* d_T1,
+                                   double* d_rho, const unsigned char* d_peer_mask, double dt, int nsteps,
+                                   unsigned long long tag0, void* stream);
 /* 1 when a bounded spin of the last sharded run timed out (a peer never arrived), else 0 */
 int limeb200_heom_sharded_error(limeb200_heom_t plan, void* stream);
 

@@ -55,6 +55,18 @@ def d2h(t, pinned=False):
     return buf.numpy()
 
 
+def d2h_owned(t):
+    """device -> host numpy array that the CALLER owns: staged through a page-locked buffer from torch's caching host
+    allocator (a block is recycled only after the returned array -- which keeps the buffer alive -- is dropped), so the
+    copy runs at pinned PCIe speed without the aliasing of d2h(pinned=True)'s shape-keyed pool"""
+    if t is None:
+        return None
+    buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    buf.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return buf.numpy()
+
+
 def empty(shape, dtype=torch.complex128, dev=None):
     return torch.empty(shape, dtype=dtype, device=device() if dev is None else dev)
 

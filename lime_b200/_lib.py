@@ -61,6 +61,10 @@ SIGNATURES = {
     'limeb200_peer_free': (c_int, [c_int, c_vp]),
     'limeb200_heom_persist_grid': (c_int, [c_vp, c_int]),
     'limeb200_heom_run_sharded': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_uint, c_vp]),
+    'limeb200_heom_flow_supported': (c_int, [c_vp]),
+    'limeb200_heom_flow_pack': (c_int, [c_vp, c_vp, c_vp, C.c_ulonglong, c_vp]),
+    'limeb200_heom_flow_unpack': (c_int, [c_vp, c_vp, C.c_ulonglong, c_vp, c_vp]),
+    'limeb200_heom_flow_run_sharded': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_ulonglong, c_vp]),
     'limeb200_heom_sharded_error': (c_int, [c_vp, c_vp]),
     'limeb200_heom_dl_euler': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),
     'limeb200_sos_factor': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),

@@ -215,6 +215,30 @@ __device__ __forceinline__ cplx heom_sys(const cplx* Hs, int n, const cplx* ya, 
     return cmake(s.y, -s.x);          // -i * s
 }
 
+// same with the dimension known at compile time (fully unrolled, strength-reduced addressing)
+template <int NN_>
+__device__ __forceinline__ cplx heom_sys_t(const cplx* Hs, const cplx* ya, int i, int j) {
+    cplx s = cmake(0, 0);
+    const cplx* hrow = Hs + i * NN_;
+    const cplx* yrow = ya + i * NN_;
+#pragma unroll
+    for (int m = 0; m < NN_; ++m) {
+        cfma(s, hrow[m], ya[m * NN_ + j]);
+        const cplx a = yrow[m], h = Hs[m * NN_ + j];
+        s.x = fma(-a.x, h.x, s.x); s.x = fma(a.y, h.y, s.x);
+        s.y = fma(-a.x, h.y, s.y); s.y = fma(-a.y, h.x, s.y);
+    }
+    return cmake(s.y, -s.x);          // -i * s
+}
+__device__ __forceinline__ cplx heom_sys_any(const cplx* Hs, int n, const cplx* ya, int i, int j) {
+    switch (n) {
+        case 2: return heom_sys_t<2>(Hs, ya, i, j);
+        case 3: return heom_sys_t<3>(Hs, ya, i, j);
+        case 7: return heom_sys_t<7>(Hs, ya, i, j);
+        default: return heom_sys(Hs, n, ya, i, j);
+    }
+}
+
 // RK4 stage algebra (lime/phys.py:636-649) for one element; returns the next stage vector element
 __device__ __forceinline__ cplx heom_rk_update(int stage, cplx k, cplx& r, cplx& ac, double dt) {
     const double hdt = 0.5 * dt;
@@ -257,7 +281,7 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     __syncthreads();
     cplx k = cmake(0, 0);
     if (act) {
-        k = heom_sys(Hs, n, ys, i, j);
+        k = heom_sys_any(Hs, n, ys, i, j);
         const double damp = heom_damp(d, par, ado);
         k.x = fma(-damp, yv.x, k.x);
         k.y = fma(-damp, yv.y, k.y);
@@ -550,7 +574,7 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
             const cplx yv = yin[own];
             if (g < a.apc) ys[threadIdx.x] = yv;
             __syncthreads();
-            cplx k = heom_sys(Hs, n, ys + (size_t)g * nn, i, j);
+            cplx k = heom_sys_any(Hs, n, ys + (size_t)g * nn, i, j);
             k.x = fma(-damp, yv.x, k.x);
             k.y = fma(-damp, yv.y, k.y);
 #pragma unroll
@@ -591,6 +615,8 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
             }
     }
 }
+
+#include "heom_flow.cuh"
 
 // on-chip kernel: one CTA per hierarchy, all nsteps fused.  smem: Hs[nn], y0,y1 [nhe*nn] (+ L,R if dense Q)
 struct HeomChipArgs {
@@ -1059,6 +1085,8 @@ struct limeb200_heom_s {
     DevBuf dH, dQ, dqstart, dqmodes, dems, demm, demv, ddamp, dcdn, dcdnR, dnu, dstates, ddn, dup;
     int max_modes_per_elem = 0;
     DevBuf s_y, s_acc, dbar;
+    DevBuf s_T;                         // dataflow path: two tagged stage vectors (32 B per element each)
+    unsigned long long flow_tag = 1;    // next unused stage tag (monotonic over the launches of the plan)
     long long launches = 0;
     long long smem_optin = 0;
     int sm_count = 148;
@@ -1194,7 +1222,7 @@ int limeb200_heom_destroy(limeb200_heom_t p) {
     return LB_OK;
 }
 int limeb200_heom_set_path(limeb200_heom_t p, int path) {
-    LB_REQUIRE(p && path >= 0 && path <= 3, "bad arguments");
+    LB_REQUIRE(p && path >= 0 && path <= 4, "bad arguments");
     p->path_req = path;
     return LB_OK;
 }
@@ -1293,6 +1321,61 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     return LB_OK;
 }
 
+// ---- dataflow-synchronised persistent kernel (heom_flow.cuh)
+static bool heom_flow_supported(limeb200_heom_t p) {
+    const long long total = p->nhe * p->n * p->n;
+    return p->diagq && p->npar == 1 && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << 30) &&
+           p->n * p->n <= 1024 && p->row_hi > p->row_lo;
+}
+struct HeomFlowCfg { void (*kern)(HeomFlowArgs) = nullptr; int apc = 1, threads = 32, grid = 1; size_t smem = 0; };
+static int heom_flow_config(limeb200_heom_t p, HeomFlowCfg& c) {
+    const int nn = p->n * p->n;
+    const long long nown = p->row_hi - p->row_lo;
+    int coop = 0;
+    LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
+    if (!coop || !heom_flow_supported(p)) return LB_ERR_UNSUPPORTED;
+    // one CTA per SM, contiguous balanced blocks of ADOs, each walked in equal tiles of <= 1024 threads; a block that
+    // fits 576 threads takes the variant compiled for 576 threads (113 registers instead of 64: no spills)
+    long long per = ceil_div(nown, (long long)p->sm_count);
+    const bool small = per * nn <= 576;
+    const int apc_max = std::max(1, (small ? 576 : 1024) / nn);
+    const long long ntile = ceil_div(per, (long long)apc_max);
+    c.apc = (int)ceil_div(per, ntile);
+    c.threads = ceil_div(c.apc * nn, 32) * 32;
+    if (small)
+        c.kern = p->n == 7 ? heom_flow_kernel<7, 576> : p->n == 3 ? heom_flow_kernel<3, 576>
+               : p->n == 2 ? heom_flow_kernel<2, 576> : heom_flow_kernel<0, 576>;
+    else
+        c.kern = p->n == 7 ? heom_flow_kernel<7, 1024> : p->n == 3 ? heom_flow_kernel<3, 1024>
+               : p->n == 2 ? heom_flow_kernel<2, 1024> : heom_flow_kernel<0, 1024>;
+    c.grid = (int)ceil_div(nown, per);
+    c.smem = (size_t)(2 + c.apc) * nn * 16;
+    LB_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+    int occ = 0;
+    LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.kern, c.threads, c.smem));
+    if (occ < 1 || c.grid > occ * p->sm_count) return LB_ERR_UNSUPPORTED;
+    return LB_OK;
+}
+// fa: T / Tp / npeer / peer_mask / tag0 / outputs filled by the caller; T[0] must already hold the tagged state
+static int heom_flow_launch(limeb200_heom_t p, HeomFlowArgs& fa, cplx* rho, double dt, int nsteps, cudaStream_t st) {
+    HeomFlowCfg c;
+    int r = heom_flow_config(p, c);
+    if (r != LB_OK) return r;
+    const long long total = p->nhe * p->n * p->n;
+    if (p->s_acc.bytes < (size_t)total * 16) LB_CUDA(p->s_acc.alloc((size_t)total * 16));
+    if (!p->dbar.p) LB_CUDA(p->dbar.alloc(64));
+    LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
+    fa.d = p->dev();
+    fa.row_lo = p->row_lo; fa.row_hi = p->row_hi;
+    fa.apc = c.apc; fa.nsteps = nsteps; fa.dt = dt;
+    fa.rho = rho; fa.acc = p->s_acc.as<cplx>();
+    fa.err = p->dbar.as<unsigned>() + 2;
+    void* kargs[] = {&fa};
+    LB_CUDA(cudaLaunchCooperativeKernel((void*)c.kern, dim3(c.grid), dim3(c.threads), kargs, c.smem, st));
+    p->launches += 1;
+    return LB_OK;
+}
+
 int limeb200_heom_stage(limeb200_heom_t p, int stage, double* d_rho, const double* d_yin,
                         double* d_ynext, double* d_acc, int B, double dt, void* stream) {
     LB_REQUIRE(p && d_rho && d_yin && d_ynext && d_acc, "null argument");
@@ -1384,6 +1467,32 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     // (capacities are tracked in bytes: the sharded entry point allocates s_acc only)
     if (p->s_y.bytes < (size_t)2 * B * total * 16) LB_CUDA(p->s_y.alloc((size_t)2 * B * total * 16));
     if (p->s_acc.bytes < (size_t)B * total * 16) LB_CUDA(p->s_acc.alloc((size_t)B * total * 16));
+    if ((path == 4 || (path == 3 && p->path_req == 0 && !getenv("LIMEB200_HEOM_NO_FLOW"))) && B == 1) {
+        // dataflow-synchronised persistent kernel: no barrier, every value carries its stage tag
+        HeomFlowCfg c;
+        int rc = heom_flow_config(p, c);
+        if (rc == LB_OK) {
+            if (p->s_T.bytes < (size_t)4 * total * 16) {
+                LB_CUDA(p->s_T.alloc((size_t)4 * total * 16));
+                LB_CUDA(cudaMemsetAsync(p->s_T.p, 0, (size_t)4 * total * 16, st));
+            }
+            HeomFlowArgs fa;
+            memset(&fa, 0, sizeof(fa));
+            fa.T[0] = p->s_T.as<ulonglong2>(); fa.T[1] = p->s_T.as<ulonglong2>() + (size_t)2 * total;
+            fa.tag0 = p->flow_tag;
+            p->flow_tag += 4ull * nsteps + 4;
+            fa.E = E; fa.traj_every = traj_every;
+            fa.eT = (const cplx*)d_eT; fa.obs = E > 0 ? (cplx*)d_obs : nullptr; fa.traj = (cplx*)d_traj;
+            heom_flow_pack_kernel<<<std::min<long long>(ceil_div(total, 256LL), 148 * 8), 256, 0, st>>>(
+                (const cplx*)d_ado, total, fa.tag0, fa.T[0]);
+            rc = heom_flow_launch(p, fa, (cplx*)d_ado, dt, nsteps, st);
+            if (rc == LB_OK) { p->path = 4; return LB_OK; }
+        }
+        if (rc != LB_ERR_UNSUPPORTED) return rc;
+        LB_REQUIRE(p->path_req != 4, "the dataflow path needs diagonal coupling operators, one hierarchy and a cooperative launch");
+        path = 3; p->path = 3;
+    }
+    LB_REQUIRE(path != 4, "the dataflow path takes one hierarchy (B = 1)");
     if (path == 3) {
         // persistent cooperative kernel: all steps in one launch, one grid barrier per stage
         HeomPersistArgs pa;
@@ -1494,14 +1603,66 @@ int limeb200_heom_run_sharded(limeb200_heom_t p, int rank, int world, void* cons
     if (r == LB_ERR_UNSUPPORTED) { limeb200::set_error("persistent sharded kernel cannot be launched on this device"); return r; }
     return r;
 }
+/* dataflow variant of the sharded propagator: tagged stage vectors instead of barriers (heom_flow.cuh) */
+int limeb200_heom_flow_supported(limeb200_heom_t p) {
+    LB_REQUIRE(p, "null plan");
+    LB_CUDA(cudaSetDevice(p->device));
+    HeomFlowCfg c;
+    return heom_flow_config(p, c) == LB_OK ? 1 : 0;
+}
+int limeb200_heom_flow_pack(limeb200_heom_t p, const double* d_y, void* d_T0, unsigned long long tag, void* stream) {
+    LB_REQUIRE(p && d_y && d_T0, "null argument");
+    LB_CUDA(cudaSetDevice(p->device));
+    const long long total = p->nhe * p->n * p->n;
+    heom_flow_pack_kernel<<<(int)std::min<long long>(ceil_div(total, 256LL), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        (const cplx*)d_y, total, tag, (ulonglong2*)d_T0);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+int limeb200_heom_flow_unpack(limeb200_heom_t p, const void* d_T0, unsigned long long tag, double* d_y, void* stream) {
+    LB_REQUIRE(p && d_y && d_T0, "null argument");
+    LB_CUDA(cudaSetDevice(p->device));
+    const long long total = p->nhe * p->n * p->n;
+    if (!p->dbar.p) { LB_CUDA(p->dbar.alloc(64)); LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, (cudaStream_t)stream)); }
+    heom_flow_unpack_kernel<<<(int)std::min<long long>(ceil_div(total, 256LL), 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+        (const ulonglong2*)d_T0, total, tag, (cplx*)d_y, p->dbar.as<unsigned>() + 2);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+int limeb200_heom_flow_run_sharded(limeb200_heom_t p, int rank, int world, void* const* d_T0, void* const* d_T1,
+                                   double* d_rho, const unsigned char* d_peer_mask, double dt, int nsteps,
+                                   unsigned long long tag0, void* stream) {
+    LB_REQUIRE(p && d_T0 && d_T1 && d_rho, "null argument");
+    LB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8");
+    LB_REQUIRE(nsteps >= 0 && tag0 >= 1, "bad nsteps / tag0");
+    LB_CUDA(cudaSetDevice(p->device));
+    p->launches = 0;
+    if (nsteps == 0) return LB_OK;
+    HeomFlowArgs fa;
+    memset(&fa, 0, sizeof(fa));
+    fa.T[0] = (ulonglong2*)d_T0[rank]; fa.T[1] = (ulonglong2*)d_T1[rank];
+    int q = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        fa.Tp[0][q] = (ulonglong2*)d_T0[r]; fa.Tp[1][q] = (ulonglong2*)d_T1[r];
+        ++q;
+    }
+    fa.npeer = world - 1;
+    fa.peer_mask = d_peer_mask;
+    fa.tag0 = tag0;
+    int r = heom_flow_launch(p, fa, (cplx*)d_rho, dt, nsteps, (cudaStream_t)stream);
+    if (r == LB_ERR_UNSUPPORTED) limeb200::set_error("the dataflow sharded kernel does not support this plan");
+    return r;
+}
+
 /* 1 when a bounded spin of the last sharded run timed out (a peer never arrived) */
 int limeb200_heom_sharded_error(limeb200_heom_t p, void* stream) {
     LB_REQUIRE(p, "null plan");
     if (!p->dbar.p) return 0;
-    unsigned w[3] = {0, 0, 0};
-    LB_CUDA(cudaMemcpyAsync(w, p->dbar.p, 12, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    unsigned w4[4] = {0, 0, 0, 0};
+    LB_CUDA(cudaMemcpyAsync(w4, p->dbar.p, 16, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     LB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    return (int)w[2];
+    return (int)(w4[2] | (w4[3] << 1));       // bit 0: a wait timed out; bit 1: unpack found a stale tag
 }
 
 int limeb200_heom_dl_euler(const double* h_H, const double* h_sz, int n, int nado,

@@ -17,6 +17,11 @@ Two data paths:
                   CUDA-IPC peer pointers, into the stage vectors of the peers that read it over NVLink; the stages are
                   separated by a one-hop barrier (every CTA counts itself on every peer with one remote reduction and
                   polls only its own memory).  torch.distributed is used only to exchange the IPC handles.
+  exchange='flow' (default where it applies: diagonal coupling operators) the dataflow kernel of
+                  csrc/heom_flow.cuh: NO barrier between stages.  Every stage-vector entry carries a 64-bit stage tag
+                  in the same 16-byte words as its value; owners store new entries locally and into the buffers of the
+                  ranks that read them, consumers poll exactly the entries they need in their own memory -- one one-way
+                  NVLink traversal per stage instead of store acknowledgement + flag + barrier.
   exchange='nccl' CUDA stage kernel -> NCCL all-gather, 4 x per step, captured in a CUDA graph.
 `stage_fn` is a seam for the world_size-2 gloo tests of this host logic (they plug a CPU stage
 function built from the oracle); the product path always uses the CUDA plan.
@@ -56,7 +61,7 @@ def partition(nhe, world):
 class ShardedHEOM:
     def __init__(self, H, Q, coup_strength, cut_freq, temperature, N_exp=2, N_cut=4,
                  pref_dn=-1j, pref_up=-1j, group=None, stage_fn=None, device=None, use_graph=True,
-                 exchange='p2p', halo_only=True):
+                 exchange='auto', halo_only=True):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -80,7 +85,7 @@ class ShardedHEOM:
         self.states, self.dn, self.up = engine.heom_tables([N_cut + 1] * self.nmodes, N_cut)
         self.nhe = self.states.shape[0]
         self.chunk, self.ranges = partition(self.nhe, self.world)
-        if exchange == 'p2p' and stage_fn is None:
+        if exchange in ('p2p', 'flow', 'auto') and stage_fn is None:
             # checked identically on every rank BEFORE any IPC set-up, so that all ranks raise together
             if self.world > 8:
                 raise ValueError('exchange="p2p" supports at most 8 ranks (one NVSwitch box); use exchange="nccl"')
@@ -93,6 +98,7 @@ class ShardedHEOM:
         self._stage_fn = stage_fn
         self.use_graph = use_graph
         self.exchange = exchange if stage_fn is None else 'collective'
+        self._tag = 1
         self._peer = None
         self._epoch = 0
         # fused path: new stage values travel only to the peers that own a neighbour of the ADO (plus one full
@@ -104,6 +110,17 @@ class ShardedHEOM:
             self.plan = engine.HeomPlan(self.H, self.Q, self.qmap, self.c, self.nu, self.states, self.dn, self.up,
                                         pref_dn=pref_dn, pref_up=pref_up, row_range=(self.lo, self.hi),
                                         device_index=self.dev.index)
+            if self.exchange in ('auto', 'flow'):
+                from .._lib import lib
+                ok = bool(lib().limeb200_heom_flow_supported(self.plan._h) == 1)
+                if self.world > 1:                      # every rank must take the same path
+                    flags = [None] * self.world
+                    dist.all_gather_object(flags, ok, group=self.group)
+                    ok = all(flags)
+                if self.exchange == 'flow' and not ok:
+                    raise ValueError("exchange='flow' needs diagonal coupling operators with at most 4 modes per matrix "
+                                     "element; use exchange='p2p'")
+                self.exchange = 'flow' if ok else 'p2p'
         else:
             self.dev = torch.device('cpu') if device is None else device
             self.plan = None
@@ -136,7 +153,9 @@ class ShardedHEOM:
         from .._lib import lib, check
         nbytes = self.nhe_pad * self.n * self.n * 16
         mine, handles = [], []
-        for size in (nbytes, nbytes, 256):
+        flow = self.exchange == 'flow'
+        # flow: two TAGGED stage vectors (32 bytes per element) and no flag array (third buffer unused)
+        for size in ((2 * nbytes, 2 * nbytes, 256) if flow else (nbytes, nbytes, 256)):
             ptr = C.c_void_p()
             h = (C.c_ubyte * 64)()
             check(lib().limeb200_peer_alloc(self.dev.index, size, C.byref(ptr), h))
@@ -161,7 +180,7 @@ class ShardedHEOM:
                     opened.append(q.value)
         arr = [(C.c_void_p * self.world)(*ptrs[k]) for k in range(3)]
         # arrivals per stage of every rank = CTAs of its persistent kernel (the one-hop barrier counts them)
-        g = check(lib().limeb200_heom_persist_grid(self.plan._h, 1))
+        g = 1 if flow else check(lib().limeb200_heom_persist_grid(self.plan._h, 1))
         grids = [None] * self.world
         if self.world > 1:
             dist.all_gather_object(grids, int(g), group=self.group)
@@ -218,10 +237,53 @@ class ShardedHEOM:
             dist.barrier(group=self.group)       # nobody reuses the buffers before everyone has copied out
         return ado
 
+    def _run_flow(self, ado, dt, nsteps):
+        """dataflow kernel: pack the full state into the tagged buffer, synchronise the ranks, ONE launch, synchronise,
+        unpack (the last stage delivered every owner's rows to every rank)"""
+        import ctypes as C
+        from .._lib import lib, check, LimeB200Error
+        if self._peer is None:
+            self._peer_setup()
+        pr = self._peer
+        rho = torch.zeros((1, self.nhe_pad, self.n, self.n), dtype=torch.complex128, device=ado.device)
+        rho[:, :self.nhe] = ado
+        st = torch.cuda.current_stream(ado.device)
+        sp = C.c_void_p(st.cuda_stream)
+        tag0 = self._tag
+        self._tag += 4 * nsteps + 4
+        check(lib().limeb200_heom_flow_pack(self.plan._h, C.c_void_p(rho.data_ptr()), C.c_void_p(pr['mine'][0]),
+                                            C.c_ulonglong(tag0), sp))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)        # every rank's buffer holds the tagged state before anyone stores into it
+        if self.peer_mask is not None and self._d_mask is None:
+            self._d_mask = torch.from_numpy(self.peer_mask).to(ado.device)
+        mptr = C.c_void_p(self._d_mask.data_ptr()) if self._d_mask is not None else None
+        check(lib().limeb200_heom_flow_run_sharded(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1],
+                                                   C.c_void_p(rho.data_ptr()), mptr, float(dt), int(nsteps),
+                                                   C.c_ulonglong(tag0), sp))
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)        # all peers' last-stage stores have landed
+        check(lib().limeb200_heom_flow_unpack(self.plan._h, C.c_void_p(pr['mine'][0]), C.c_ulonglong(tag0 + 4 * nsteps),
+                                              C.c_void_p(rho.data_ptr()), sp))
+        err = lib().limeb200_heom_sharded_error(self.plan._h, sp)
+        if err:
+            raise LimeB200Error('sharded HEOM run (dataflow kernel): %s' %
+                                ('a value never arrived (wait timed out)' if err & 1 else 'stale entries in the final state'))
+        ado.copy_(rho[:, :self.nhe])
+        torch.cuda.synchronize()
+        self.last_launches = 1
+        if self.world > 1:
+            dist.barrier(group=self.group)
+        return ado
+
     def run_device(self, ado, dt, nsteps):
         """ado: [1, N_he, n, n] complex128 on self.dev, identical on every rank; advanced in place by
         nsteps RK4 steps (every rank ends up with the full hierarchy)."""
         assert ado.shape == (1, self.nhe, self.n, self.n) and ado.dtype == torch.complex128
+        if self.exchange == 'flow' and self._stage_fn is None and nsteps > 0:
+            return self._run_flow(ado, dt, nsteps)
         if self.exchange == 'p2p' and self._stage_fn is None and nsteps > 0:
             return self._run_p2p(ado, dt, nsteps)
         shape = (1, self.nhe_pad, self.n, self.n)

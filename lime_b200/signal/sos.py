@@ -52,8 +52,23 @@ def _U(E, gamma, x, y, tau, extra=None):
 
 
 def _finish(out, single):
-    r = out.cpu().numpy()
+    r = _dev.d2h_owned(out) if out.numel() >= (1 << 16) else out.cpu().numpy()
     return r[0] if single else r
+
+
+def _fp(*arrays):
+    """content fingerprint of small host inputs (energies, dipoles, index lists, grids) for the plan cache"""
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for a in arrays:
+        b = np.ascontiguousarray(np.asarray(a if not isinstance(a, range) else list(a)))
+        h.update(str((b.shape, b.dtype.str)).encode())
+        h.update(b.view(np.uint8).reshape(-1))
+    return h.hexdigest()
+
+
+_PE_CACHE = {}
+_PE_CACHE_MAX = 4
 
 
 def _check_grid(n1, n3):
@@ -119,13 +134,20 @@ def _pe_eval(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts
         T = 1 if single else len(tau2)
         z = np.zeros((T, n3, n1), dtype=complex)
         return z[0] if single else z
-    W, P, (eA, gA) = _pe_terms(evals, dip, tau2, g_idx, e_idx, f_idx, gamma, parts)
-    z1, z3 = _z(omega1), _z(omega3)
-    A = _simple_factor(z1, eA, gA)                 # [1,R,n1]  G_ab(omega1)
-    Bf = engine.sos_factor(z3, W, P)               # [T,R,n3]
-    out = engine.sos_outer(Bf, A, W.shape[0])      # [T,n3,n1]
+    # the O(states^3) weights, poles and grids are a pure function of the inputs: the uploaded plan (PhotonEchoGrid) is
+    # cached on their CONTENT, so that repeated evaluations on one system (scans over anything else, re-plots) cost the
+    # O(grid) device work and the transfer of the result only
+    key = (_fp(evals, dip, gamma, list(g_idx), list(e_idx), list(f_idx), omega1, omega3, tau2), tuple(parts),
+           torch.cuda.current_device() if torch.cuda.is_available() else None)
+    grid = _PE_CACHE.pop(key, None)
+    if grid is None:
+        grid = PhotonEchoGrid(evals, dip, omega1, omega3, tau2, g_idx, e_idx, f_idx, gamma, parts=parts)
+        while len(_PE_CACHE) >= _PE_CACHE_MAX:
+            _PE_CACHE.pop(next(iter(_PE_CACHE)))
+    _PE_CACHE[key] = grid
+    out = grid.run()
     if return_device:
-        return out
+        return out.clone()                         # the plan's output buffer is overwritten by the next evaluation
     return _finish(out, single)
 
 

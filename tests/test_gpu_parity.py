@@ -283,7 +283,7 @@ def test_heom_dl_exact(cuda):
     assert relerr(traj, g['traj']) <= TOL
 
 
-@pytest.mark.parametrize('path', [1, 2, 3])
+@pytest.mark.parametrize('path', [1, 2, 3, 4])
 def test_heom_spin_boson_multi_index(cuda, path):
     """config-3 shape: K=2 Matsubara terms, depth 12 -> 91 ADOs, 312 couplings (diagonal Q)"""
     from lime_b200.heom.heom import HEOM
@@ -351,10 +351,10 @@ def test_heom_rhs_against_reference_rule_matrix(cuda, name):
         assert relerr(out.reshape(-1), y) <= TOL, path
 
 
-@pytest.mark.parametrize('path', [2, 3])
+@pytest.mark.parametrize('path', [2, 3, 4])
 def test_heom_config4_full_size(cuda, path):
     """config 4 at its real size: FMO, 7 baths x K = 2, depth 4 -> 3060 ADOs of 7x7, 19 040 couplings; 50 RK4 steps
-    of the stage-wise (2) and persistent (3) kernels against the oracle"""
+    of the stage-wise (2), barrier-persistent (3) and dataflow-persistent (4) kernels against the oracle"""
     from lime_b200 import builders
     from lime_b200.heom.heom import HEOM
     from lime_b200.units import au2fs
