@@ -190,7 +190,7 @@ int limeb200_heom_destroy(limeb200_heom_t plan);
 /* 0 auto, 1 on-chip (one CTA per hierarchy, all steps fused), 2 one launch per RK4 stage,
  * 3 persistent cooperative kernel (all steps in one launch, one grid barrier per stage),
  * 4 dataflow-synchronised persistent kernel (one hierarchy, diagonal coupling operators: tagged stage
- *   vectors, no barrier; the default for a single large hierarchy when it applies)              */
+ *   vectors, no barrier; opt-in on one GPU, the default of the ADO-sharded multi-GPU propagator)   */
 int limeb200_heom_set_path(limeb200_heom_t plan, int path);
 int limeb200_heom_get_path(limeb200_heom_t plan);
 /* nsteps RK4 steps (lime/phys.py:636-649) of B hierarchies d_ado[B][nhe][n][n], in place.
@@ -246,7 +246,7 @@ int limeb200_heom_run_sharded(limeb200_heom_t plan, int rank, int world, void* c
  *                        tag0 .. tag0 + 4 nsteps: the next run must use a larger tag0
  *   flow_unpack        : d_y <- values of d_T0 (after the ranks have synchronised on the host), checking every tag
  *   limeb200_heom_sharded_error reports bit 0 = a wait timed out, bit 1 = unpack met a stale tag               */
-int limeb200_heom_flow_supported(limeb200_heom_t plan);
+int limeb200_heom_flow_supported(limeb200_heom_t plan);   /* 0 no, 1 tiled variant, 2 register-resident variant */
 int limeb200_heom_flow_pack(limeb200_heom_t plan, const double* d_y, void* d_T0, unsigned long long tag, void* stream);
 int limeb200_heom_flow_unpack(limeb200_heom_t plan, const void* d_T0, unsigned long long tag, double* d_y, void* stream);
 int limeb200_heom_flow_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_T0, void* const* d_T1,

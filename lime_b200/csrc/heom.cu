@@ -1327,15 +1327,41 @@ static bool heom_flow_supported(limeb200_heom_t p) {
     return p->diagq && p->npar == 1 && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << 30) &&
            p->n * p->n <= 1024 && p->row_hi > p->row_lo;
 }
-struct HeomFlowCfg { void (*kern)(HeomFlowArgs) = nullptr; int apc = 1, threads = 32, grid = 1; size_t smem = 0; };
+struct HeomFlowCfg { void (*kern)(HeomFlowArgs) = nullptr; int apc = 1, threads = 32, grid = 1; size_t smem = 0; bool cached = false; };
 static int heom_flow_config(limeb200_heom_t p, HeomFlowCfg& c) {
     const int nn = p->n * p->n;
     const long long nown = p->row_hi - p->row_lo;
     int coop = 0;
     LB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, p->device));
     if (!coop || !heom_flow_supported(p)) return LB_ERR_UNSUPPORTED;
-    // one CTA per SM, contiguous balanced blocks of ADOs, each walked in equal tiles of <= 1024 threads; a block that
-    // fits 576 threads takes the variant compiled for 576 threads (113 registers instead of 64: no spills)
+    // (a) register-resident variant, one or two elements per thread for the whole run: the owned ADOs fit one tile per
+    //     CTA on one (<= 1024 threads, x EPT) or two (<= 576 threads) CTAs per SM
+    if (p->nhe * nn < (1LL << HEOM_FLOW_IDXBITS) && !getenv("LIMEB200_HEOM_FLOW_TILED")) {
+        const long long apc1 = ceil_div(nown, (long long)p->sm_count), apc2 = ceil_div(nown, 2LL * p->sm_count);
+        int apc = 0, per_sm = 1, ept = 1;
+        if (apc1 * nn <= 576) { apc = (int)apc1; }
+        else if (apc2 * nn <= 576) { apc = (int)apc2; per_sm = 2; }
+        else if (apc1 * nn <= 1024) { apc = (int)apc1; }
+        else if (apc1 * nn <= 2048) { apc = (int)apc1; ept = 2; }
+        if (apc > 0) {
+            const int threads = ceil_div((int)ceil_div(apc * nn, ept), 32) * 32;
+            const int cls = ept == 2 ? 3 : threads > 576 ? 2 : per_sm == 2 ? 1 : 0;
+#define LB_FLOWC(NN) (cls == 3 ? heom_flow_cached_kernel<NN, 1024, 1, 2> : cls == 2 ? heom_flow_cached_kernel<NN, 1024, 1, 1> \
+                      : cls == 1 ? heom_flow_cached_kernel<NN, 576, 2, 1> : heom_flow_cached_kernel<NN, 576, 1, 1>)
+            c.kern = p->n == 7 ? LB_FLOWC(7) : p->n == 3 ? LB_FLOWC(3) : p->n == 2 ? LB_FLOWC(2) : LB_FLOWC(0);
+#undef LB_FLOWC
+            c.apc = apc; c.threads = threads; c.cached = true;
+            c.grid = (int)ceil_div(nown, (long long)apc);
+            c.smem = (size_t)(2 + apc) * nn * 16 + (size_t)nn * HEOM_FLOW_NE * 16 + (size_t)ept * HEOM_FLOW_NE * threads * 4;
+            LB_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
+            int occ = 0;
+            LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.kern, c.threads, c.smem));
+            if (occ >= 1 && c.grid <= occ * p->sm_count) return LB_OK;
+            c.cached = false;
+        }
+    }
+    // (b) tiled variant: one CTA per SM, contiguous balanced blocks of ADOs, each walked in equal tiles of <= 1024 threads;
+    //     a block that fits 576 threads takes the variant compiled for 576 threads (more registers, no spills)
     long long per = ceil_div(nown, (long long)p->sm_count);
     const bool small = per * nn <= 576;
     const int apc_max = std::max(1, (small ? 576 : 1024) / nn);
@@ -1467,7 +1493,10 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     // (capacities are tracked in bytes: the sharded entry point allocates s_acc only)
     if (p->s_y.bytes < (size_t)2 * B * total * 16) LB_CUDA(p->s_y.alloc((size_t)2 * B * total * 16));
     if (p->s_acc.bytes < (size_t)B * total * 16) LB_CUDA(p->s_acc.alloc((size_t)B * total * 16));
-    if ((path == 4 || (path == 3 && p->path_req == 0 && !getenv("LIMEB200_HEOM_NO_FLOW"))) && B == 1) {
+    // (measured on one GPU, config 4: 6.7e7 ADO-steps/s against 9.4e7 of the barrier kernel -- tagged entries double the
+    //  L2 bytes of the neighbour gather, which costs more than the grid barrier it saves; the dataflow kernel pays off
+    //  where the barrier crosses NVLink, so on one GPU it is opt-in: path 4 or LIMEB200_HEOM_FLOW)
+    if ((path == 4 || (path == 3 && p->path_req == 0 && getenv("LIMEB200_HEOM_FLOW"))) && B == 1) {
         // dataflow-synchronised persistent kernel: no barrier, every value carries its stage tag
         HeomFlowCfg c;
         int rc = heom_flow_config(p, c);
@@ -1608,7 +1637,8 @@ int limeb200_heom_flow_supported(limeb200_heom_t p) {
     LB_REQUIRE(p, "null plan");
     LB_CUDA(cudaSetDevice(p->device));
     HeomFlowCfg c;
-    return heom_flow_config(p, c) == LB_OK ? 1 : 0;
+    if (heom_flow_config(p, c) != LB_OK) return 0;
+    return c.cached ? 2 : 1;        // 2: the register-resident variant applies (the latency-bound regime it is built for)
 }
 int limeb200_heom_flow_pack(limeb200_heom_t p, const double* d_y, void* d_T0, unsigned long long tag, void* stream) {
     LB_REQUIRE(p && d_y && d_T0, "null argument");

@@ -213,3 +213,163 @@ heom_flow_unpack_kernel(const ulonglong2* __restrict__ T0, long long count, unsi
         y[e] = cmake(__longlong_as_double((long long)a.x), __longlong_as_double((long long)b.x));
     }
 }
+
+// ---- register / shared-memory resident variant: EPT matrix elements per thread for the whole run ---------------
+// The latency-bound case (up to ~2000 elements per SM: the 3060-ADO FMO hierarchy on 1-8 GPUs, the 38 760-ADO one on
+// 8).  rho, the RK4 accumulator and the current stage value of an element live in registers; its <= 8 neighbour
+// entries are cached in shared memory as ONE packed word each (entry index | n_k << 26; the coefficient is
+// n_k x a per-(matrix element, slot) constant kept in a 6 KB table), computed once.  A stage is: publish the own
+// ADOs through shared memory for -i[H, .], then per element poll the 8 tagged neighbour entries (all in flight, only
+// untagged ones re-read), and publish the new tagged entry locally and into the reading peers.  No barrier, no round
+// trip through global memory for the state.
+#define HEOM_FLOW_IDXBITS 26
+template <int NN_, int MAXT, int MINB, int EPT>
+__global__ void __launch_bounds__(MAXT, MINB)
+heom_flow_cached_kernel(HeomFlowArgs a) {
+    extern __shared__ double2 smem[];
+    const HeomDev& d = a.d;
+    const int n = NN_ ? NN_ : d.n, nn = n * n, T = blockDim.x;
+    cplx* Hs = smem;                                        // [nn]
+    cplx* ys = Hs + nn;                                     // [apc * nn]
+    cplx* r0s = ys + (size_t)a.apc * nn;                    // [nn]
+    cplx* ctab = r0s + nn;                                  // [nn][NE] coefficient per unit n_k
+    unsigned* eoff = reinterpret_cast<unsigned*>(ctab + (size_t)nn * HEOM_FLOW_NE);     // [EPT][NE][T]
+    for (int l = threadIdx.x; l < nn; l += T) Hs[l] = d.H[l];
+    for (int l = threadIdx.x; l < nn * HEOM_FLOW_NE; l += T) ctab[l] = cmake(0, 0);
+    __syncthreads();
+    for (int l = threadIdx.x; l < nn; l += T) {
+        int q = 0;
+        for (int t = d.em_start[l]; t < d.em_start[l + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
+            const int m = d.em_mode[t];
+            const double2 v = d.em_v[t];
+            ctab[l * HEOM_FLOW_NE + 2 * q] = heom_dn_coef(d, 0, m, 1.0, v);
+            ctab[l * HEOM_FLOW_NE + 2 * q + 1] = cscale(v.x - v.y, d.pref_up);
+        }
+    }
+    const long long nown = a.row_hi - a.row_lo;
+    const bool obs_cta = (a.obs || a.traj) && a.row_lo == 0 && blockIdx.x == 0;
+    bool act[EPT];
+    unsigned own[EPT], pmask[EPT];
+    int idx[EPT], gg[EPT];
+    cplx rreg[EPT], areg[EPT], ycur[EPT];
+    double damp[EPT];
+#pragma unroll
+    for (int u = 0; u < EPT; ++u) {
+        const int l = threadIdx.x + u * T;
+        gg[u] = l / nn;
+        idx[u] = l - gg[u] * nn;
+        const long long item = (long long)blockIdx.x * a.apc + gg[u];
+        act[u] = gg[u] < a.apc && item < nown;
+        const long long ado = a.row_lo + (act[u] ? item : 0);
+        own[u] = (unsigned)(ado * nn + idx[u]);
+        rreg[u] = act[u] ? a.rho[own[u]] : cmake(0, 0);
+        areg[u] = cmake(0, 0);
+        ycur[u] = rreg[u];
+        damp[u] = act[u] ? heom_damp(d, 0, ado) : 0.0;
+        pmask[u] = (a.peer_mask && act[u]) ? a.peer_mask[ado] : 0xffu;
+#pragma unroll
+        for (int s = 0; s < HEOM_FLOW_NE; ++s) eoff[(u * HEOM_FLOW_NE + s) * T + threadIdx.x] = own[u];
+        if (act[u]) {
+            const int* st = d.states + ado * d.nmodes;
+            const int* dn = d.dn + ado * d.nmodes;
+            const int* up = d.up + ado * d.nmodes;
+            int q = 0;
+            for (int t = d.em_start[idx[u]]; t < d.em_start[idx[u] + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
+                const int m = d.em_mode[t];
+                const int id = dn[m], iu = up[m];
+                if (id >= 0)
+                    eoff[(u * HEOM_FLOW_NE + 2 * q) * T + threadIdx.x] =
+                        ((unsigned)id * (unsigned)nn + (unsigned)idx[u]) | ((unsigned)st[m] << HEOM_FLOW_IDXBITS);
+                if (iu >= 0)        // waited for even when the coefficient vanishes: keeps the coupling graph symmetric
+                    eoff[(u * HEOM_FLOW_NE + 2 * q + 1) * T + threadIdx.x] =
+                        ((unsigned)iu * (unsigned)nn + (unsigned)idx[u]) | (1u << HEOM_FLOW_IDXBITS);
+            }
+        }
+    }
+    const long long limit = 10000000000LL;
+    __syncthreads();
+    for (int step = 0; step < a.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            const unsigned long long want = a.tag0 + 4ull * step + stage;
+            const ulonglong2* Tin = a.T[stage & 1];
+            ulonglong2* Tout = a.T[(stage + 1) & 1];
+            const bool last = (step == a.nsteps - 1 && stage == 3);
+#pragma unroll
+            for (int u = 0; u < EPT; ++u)
+                if (gg[u] < a.apc) ys[threadIdx.x + u * T] = ycur[u];
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < EPT; ++u) {
+                if (!act[u]) continue;
+                double vx[HEOM_FLOW_NE], vy[HEOM_FLOW_NE];
+                unsigned word[HEOM_FLOW_NE];
+#pragma unroll
+                for (int s = 0; s < HEOM_FLOW_NE; ++s) word[s] = eoff[(u * HEOM_FLOW_NE + s) * T + threadIdx.x];
+                {
+                    const long long t0 = clock64();
+                    unsigned pending = (1u << HEOM_FLOW_NE) - 1u, spins = 0;
+                    do {        // only the entries that were not tagged yet are read again
+#pragma unroll
+                        for (int s = 0; s < HEOM_FLOW_NE; ++s)
+                            if ((pending >> s) & 1u) {
+                                const ulonglong2* e = Tin + 2 * (size_t)(word[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u));
+                                const ulonglong2 w0 = flow_ld(e), w1 = flow_ld(e + 1);
+                                vx[s] = __longlong_as_double((long long)w0.x);
+                                vy[s] = __longlong_as_double((long long)w1.x);
+                                if (w0.y == want && w1.y == want) pending &= ~(1u << s);
+                            }
+                        if (pending && ((++spins & 1023u) == 0) && (clock64() - t0 > limit || *(volatile unsigned*)a.err)) {
+                            atomicExch(a.err, 1u);
+                            pending = 0;
+                        }
+                    } while (pending);
+                }
+                const int i = idx[u] / n, j = idx[u] - i * n;
+                cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)gg[u] * nn, i, j)
+                             : heom_sys(Hs, n, ys + (size_t)gg[u] * nn, i, j);
+                k.x = fma(-damp[u], ycur[u].x, k.x);
+                k.y = fma(-damp[u], ycur[u].y, k.y);
+#pragma unroll
+                for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+                    const double nk = (double)(word[s] >> HEOM_FLOW_IDXBITS);
+                    cfma(k, cscale(nk, ctab[idx[u] * HEOM_FLOW_NE + s]), cmake(vx[s], vy[s]));
+                }
+                const cplx yn = heom_rk_update(stage, k, rreg[u], areg[u], a.dt);
+                flow_st(Tout + 2 * (size_t)own[u], yn.x, want + 1);
+                flow_st(Tout + 2 * (size_t)own[u] + 1, yn.y, want + 1);
+                if (a.npeer) {
+                    const unsigned m = last ? 0xffu : pmask[u];
+                    for (int q = 0; q < a.npeer; ++q)
+                        if ((m >> q) & 1u) {
+                            ulonglong2* tp = a.Tp[(stage + 1) & 1][q];
+                            flow_st(tp + 2 * (size_t)own[u], yn.x, want + 1);
+                            flow_st(tp + 2 * (size_t)own[u] + 1, yn.y, want + 1);
+                        }
+                }
+                ycur[u] = yn;
+                if (stage == 3 && obs_cta && own[u] < (unsigned)nn) r0s[idx[u]] = rreg[u];
+            }
+            __syncthreads();
+        }
+        if (obs_cta) {
+            const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = T >> 5;
+            if (a.obs)
+                for (int e = warp; e < a.E; e += nw) {
+                    cplx v = cmake(0, 0);
+                    for (int l = lane; l < nn; l += 32) cfma(v, __ldg(a.eT + (size_t)e * nn + l), r0s[l]);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        v.x += __shfl_down_sync(0xffffffffu, v.x, o);
+                        v.y += __shfl_down_sync(0xffffffffu, v.y, o);
+                    }
+                    if (lane == 0) a.obs[(size_t)step * a.E + e] = v;
+                }
+            if (a.traj && ((step + 1) % a.traj_every) == 0)
+                for (int l = threadIdx.x; l < nn; l += T) a.traj[(size_t)(step / a.traj_every) * nn + l] = r0s[l];
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < EPT; ++u)
+        if (act[u]) a.rho[own[u]] = rreg[u];
+}

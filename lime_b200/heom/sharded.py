@@ -112,15 +112,20 @@ class ShardedHEOM:
                                         device_index=self.dev.index)
             if self.exchange in ('auto', 'flow'):
                 from .._lib import lib
-                ok = bool(lib().limeb200_heom_flow_supported(self.plan._h) == 1)
+                # 0: not supported (dense coupling operators ...), 1: tiled variant, 2: register-resident variant.
+                # 'auto' takes the dataflow kernel in the regime it is built for (2: a few thousand elements per SM, where
+                # the cross-GPU barrier dominates a stage) and the barrier kernel with peer stores for larger shards, which
+                # are throughput-bound (measured at 2 ranks, 38 760 ADOs: 9.1e7 tiled dataflow vs 1.27e8 ADO-steps/s)
+                level = int(lib().limeb200_heom_flow_supported(self.plan._h))
                 if self.world > 1:                      # every rank must take the same path
-                    flags = [None] * self.world
-                    dist.all_gather_object(flags, ok, group=self.group)
-                    ok = all(flags)
-                if self.exchange == 'flow' and not ok:
+                    levels = [None] * self.world
+                    dist.all_gather_object(levels, level, group=self.group)
+                    level = min(levels)
+                if self.exchange == 'flow' and level < 1:
                     raise ValueError("exchange='flow' needs diagonal coupling operators with at most 4 modes per matrix "
                                      "element; use exchange='p2p'")
-                self.exchange = 'flow' if ok else 'p2p'
+                if self.exchange == 'auto':
+                    self.exchange = 'flow' if (level == 2 and self.world > 1) else 'p2p'
         else:
             self.dev = torch.device('cpu') if device is None else device
             self.plan = None
