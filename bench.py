@@ -160,7 +160,7 @@ class JCLindblad:
         self.alg_bytes_per_unit = 2 * 16 * self.N * self.N          # read rho_n, write rho_{n+1}
         self.units_per_step = self.B * self.rk
         self.launches = 0
-        self.spot_check = not getattr(args, 'no_spot_check', False)
+        self.spot_check = not getattr(args, 'no_spot_check', False) and rank == 0       # rank 0's block of points
         if need_gpu:
             import torch
             from lime_b200 import oqs

@@ -1084,6 +1084,7 @@ struct limeb200_heom_s {
     cplx pref_up;
     DevBuf dH, dQ, dqstart, dqmodes, dems, demm, demv, ddamp, dcdn, dcdnR, dnu, dstates, ddn, dup;
     int max_modes_per_elem = 0;
+    int max_nk = 0;                     // largest occupation number in the index table
     DevBuf s_y, s_acc, dbar;
     DevBuf s_T;                         // dataflow path: two tagged stage vectors (32 B per element each)
     unsigned long long flow_tag = 1;    // next unused stage tag (monotonic over the launches of the plan)
@@ -1210,6 +1211,7 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
     LB_CUDA(p->dcdn.upload(cdn.data(), cdn.size() * 16));
     LB_CUDA(p->dcdnR.upload(cdnR.data(), cdnR.size() * 16));
     LB_CUDA(p->dnu.upload(h_nu, (size_t)npar * nmodes * 8));
+    for (long long l = 0; l < nhe * nmodes; ++l) p->max_nk = std::max(p->max_nk, states[l]);
     LB_CUDA(p->dstates.upload(states, (size_t)nhe * nmodes * 4));
     LB_CUDA(p->ddn.upload(dn, (size_t)nhe * nmodes * 4));
     LB_CUDA(p->dup.upload(up, (size_t)nhe * nmodes * 4));
@@ -1324,7 +1326,7 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
 // ---- dataflow-synchronised persistent kernel (heom_flow.cuh)
 static bool heom_flow_supported(limeb200_heom_t p) {
     const long long total = p->nhe * p->n * p->n;
-    return p->diagq && p->npar == 1 && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << 30) &&
+    return p->diagq && p->npar == 1 && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << 30) && p->max_nk < 64 &&
            p->n * p->n <= 1024 && p->row_hi > p->row_lo;
 }
 struct HeomFlowCfg { void (*kern)(HeomFlowArgs) = nullptr; int apc = 1, threads = 32, grid = 1; size_t smem = 0; bool cached = false; };
@@ -1352,7 +1354,8 @@ static int heom_flow_config(limeb200_heom_t p, HeomFlowCfg& c) {
 #undef LB_FLOWC
             c.apc = apc; c.threads = threads; c.cached = true;
             c.grid = (int)ceil_div(nown, (long long)apc);
-            c.smem = (size_t)(2 + apc) * nn * 16 + (size_t)nn * HEOM_FLOW_NE * 16 + (size_t)ept * HEOM_FLOW_NE * threads * 4;
+            c.smem = (size_t)(2 + apc) * nn * 16 + (size_t)nn * HEOM_FLOW_NE * (p->max_nk + 1) * 16 +
+                     (size_t)ept * HEOM_FLOW_NE * threads * 4 + (ept == 1 ? (size_t)HEOM_FLOW_NE * threads * 16 : 0);
             LB_CUDA(cudaFuncSetAttribute(c.kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem));
             int occ = 0;
             LB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, c.kern, c.threads, c.smem));
@@ -1393,7 +1396,7 @@ static int heom_flow_launch(limeb200_heom_t p, HeomFlowArgs& fa, cplx* rho, doub
     LB_CUDA(cudaMemsetAsync(p->dbar.p, 0, 64, st));
     fa.d = p->dev();
     fa.row_lo = p->row_lo; fa.row_hi = p->row_hi;
-    fa.apc = c.apc; fa.nsteps = nsteps; fa.dt = dt;
+    fa.apc = c.apc; fa.nsteps = nsteps; fa.dt = dt; fa.maxn = p->max_nk;
     fa.rho = rho; fa.acc = p->s_acc.as<cplx>();
     fa.err = p->dbar.as<unsigned>() + 2;
     void* kargs[] = {&fa};

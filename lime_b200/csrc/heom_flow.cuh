@@ -30,6 +30,7 @@ struct HeomFlowArgs {
     HeomDev d;
     long long row_lo, row_hi;        // owned ADO range of this rank
     int apc;                         // ADOs per tile
+    int maxn;                        // largest occupation number n_k of the hierarchy
     int nsteps, E, traj_every;
     double dt;
     ulonglong2* T[2];                // local tagged stage vectors: entry e -> words 2e, 2e + 1
@@ -217,8 +218,8 @@ heom_flow_unpack_kernel(const ulonglong2* __restrict__ T0, long long count, unsi
 // ---- register / shared-memory resident variant: EPT matrix elements per thread for the whole run ---------------
 // The latency-bound case (up to ~2000 elements per SM: the 3060-ADO FMO hierarchy on 1-8 GPUs, the 38 760-ADO one on
 // 8).  rho, the RK4 accumulator and the current stage value of an element live in registers; its <= 8 neighbour
-// entries are cached in shared memory as ONE packed word each (entry index | n_k << 26; the coefficient is
-// n_k x a per-(matrix element, slot) constant kept in a 6 KB table), computed once.  A stage is: publish the own
+// entries are cached in shared memory as ONE packed word each (entry index | n_k << 26; the finished coefficient is
+// looked up in a per-(matrix element, slot, n_k) table of a few tens of KB), computed once.  A stage is: publish the own
 // ADOs through shared memory for -i[H, .], then per element poll the 8 tagged neighbour entries (all in flight, only
 // untagged ones re-read), and publish the new tagged entry locally and into the reading peers.  No barrier, no round
 // trip through global memory for the state.
@@ -232,18 +233,24 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
     cplx* Hs = smem;                                        // [nn]
     cplx* ys = Hs + nn;                                     // [apc * nn]
     cplx* r0s = ys + (size_t)a.apc * nn;                    // [nn]
-    cplx* ctab = r0s + nn;                                  // [nn][NE] coefficient per unit n_k
-    unsigned* eoff = reinterpret_cast<unsigned*>(ctab + (size_t)nn * HEOM_FLOW_NE);     // [EPT][NE][T]
+    const int NK = a.maxn + 1;
+    cplx* ctab = r0s + nn;                                  // [nn][NE][NK] finished coefficient for n_k = 0 .. maxn
+    // EPT == 1: there is room to cache the finished coefficients too ([NE][T]), which saves the n_k conversion and
+    // two multiplications per neighbour and stage
+    constexpr bool FULLCF = (EPT == 1);
+    cplx* ecf = ctab + (size_t)nn * HEOM_FLOW_NE * NK;      // [NE][T] (FULLCF only)
+    unsigned* eoff = reinterpret_cast<unsigned*>(ecf + (FULLCF ? (size_t)HEOM_FLOW_NE * T : 0));     // [EPT][NE][T]
     for (int l = threadIdx.x; l < nn; l += T) Hs[l] = d.H[l];
-    for (int l = threadIdx.x; l < nn * HEOM_FLOW_NE; l += T) ctab[l] = cmake(0, 0);
+    for (int l = threadIdx.x; l < nn * HEOM_FLOW_NE * NK; l += T) ctab[l] = cmake(0, 0);
     __syncthreads();
     for (int l = threadIdx.x; l < nn; l += T) {
         int q = 0;
         for (int t = d.em_start[l]; t < d.em_start[l + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
             const int m = d.em_mode[t];
             const double2 v = d.em_v[t];
-            ctab[l * HEOM_FLOW_NE + 2 * q] = heom_dn_coef(d, 0, m, 1.0, v);
-            ctab[l * HEOM_FLOW_NE + 2 * q + 1] = cscale(v.x - v.y, d.pref_up);
+            for (int nk = 1; nk < NK; ++nk)     // down-coupling: n_k (q_i c_k - q_j conj c_k), exactly as the other kernels form it
+                ctab[(l * HEOM_FLOW_NE + 2 * q) * NK + nk] = heom_dn_coef(d, 0, m, (double)nk, v);
+            if (NK > 1) ctab[(l * HEOM_FLOW_NE + 2 * q + 1) * NK + 1] = cscale(v.x - v.y, d.pref_up);     // up-coupling: slot "n_k" = 1
         }
     }
     const long long nown = a.row_hi - a.row_lo;
@@ -288,6 +295,13 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
     }
     const long long limit = 10000000000LL;
     __syncthreads();
+    if (FULLCF) {
+#pragma unroll
+        for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+            const unsigned w = eoff[s * T + threadIdx.x];
+            ecf[s * T + threadIdx.x] = ctab[(idx[0] * HEOM_FLOW_NE + s) * NK + (w >> HEOM_FLOW_IDXBITS)];
+        }
+    }
     for (int step = 0; step < a.nsteps; ++step) {
 #pragma unroll 1
         for (int stage = 0; stage < 4; ++stage) {
@@ -307,23 +321,26 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
 #pragma unroll
                 for (int s = 0; s < HEOM_FLOW_NE; ++s) word[s] = eoff[(u * HEOM_FLOW_NE + s) * T + threadIdx.x];
                 {
+                    // all 16 loads of a round are in flight together; a round is repeated until every entry is tagged
+                    // (re-reading only the untagged entries was measured slower: the per-entry branches serialise the loads)
                     const long long t0 = clock64();
-                    unsigned pending = (1u << HEOM_FLOW_NE) - 1u, spins = 0;
-                    do {        // only the entries that were not tagged yet are read again
+                    bool ready;
+                    unsigned spins = 0;
+                    do {
+                        ready = true;
 #pragma unroll
-                        for (int s = 0; s < HEOM_FLOW_NE; ++s)
-                            if ((pending >> s) & 1u) {
-                                const ulonglong2* e = Tin + 2 * (size_t)(word[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u));
-                                const ulonglong2 w0 = flow_ld(e), w1 = flow_ld(e + 1);
-                                vx[s] = __longlong_as_double((long long)w0.x);
-                                vy[s] = __longlong_as_double((long long)w1.x);
-                                if (w0.y == want && w1.y == want) pending &= ~(1u << s);
-                            }
-                        if (pending && ((++spins & 1023u) == 0) && (clock64() - t0 > limit || *(volatile unsigned*)a.err)) {
-                            atomicExch(a.err, 1u);
-                            pending = 0;
+                        for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+                            const ulonglong2* e = Tin + 2 * (size_t)(word[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u));
+                            const ulonglong2 w0 = flow_ld(e), w1 = flow_ld(e + 1);
+                            vx[s] = __longlong_as_double((long long)w0.x);
+                            vy[s] = __longlong_as_double((long long)w1.x);
+                            ready = ready && w0.y == want && w1.y == want;
                         }
-                    } while (pending);
+                        if (!ready && ((++spins & 1023u) == 0) && (clock64() - t0 > limit || *(volatile unsigned*)a.err)) {
+                            atomicExch(a.err, 1u);
+                            ready = true;
+                        }
+                    } while (!ready);
                 }
                 const int i = idx[u] / n, j = idx[u] - i * n;
                 cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)gg[u] * nn, i, j)
@@ -332,8 +349,11 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
                 k.y = fma(-damp[u], ycur[u].y, k.y);
 #pragma unroll
                 for (int s = 0; s < HEOM_FLOW_NE; ++s) {
-                    const double nk = (double)(word[s] >> HEOM_FLOW_IDXBITS);
-                    cfma(k, cscale(nk, ctab[idx[u] * HEOM_FLOW_NE + s]), cmake(vx[s], vy[s]));
+                    if (FULLCF) {
+                        cfma(k, ecf[s * T + threadIdx.x], cmake(vx[s], vy[s]));
+                    } else {
+                        cfma(k, ctab[(idx[u] * HEOM_FLOW_NE + s) * NK + (word[s] >> HEOM_FLOW_IDXBITS)], cmake(vx[s], vy[s]));
+                    }
                 }
                 const cplx yn = heom_rk_update(stage, k, rreg[u], areg[u], a.dt);
                 flow_st(Tout + 2 * (size_t)own[u], yn.x, want + 1);

@@ -449,6 +449,434 @@ def test_redfield_green_functions(cuda):
         sol2.correlation_2op_1t(rr, a, b, t)
 
 
+def test_heom_dataflow_kernel_tiles_and_trajectory(cuda, monkeypatch):
+    """path 4, tiled variant, on a hierarchy large enough that a CTA walks several tiles (FMO depth 5: 11 628 ADOs -> 79
+    per CTA, 4 tiles of 20), random non-Hermitian ADOs, observables + tier-0 trajectory, against the barrier kernel"""
+    from lime_b200 import builders
+    import lime_b200.heom.heom as hh
+    Hm, Q, lam, gam, kT = builders.fmo_heom_inputs()
+    h = hh.HEOM(Hm, Q, lam, gam, kT, N_exp=2, N_cut=5)
+    rng = np.random.default_rng(12)
+    ado0 = 0.1 * (rng.standard_normal((h.nhe, 7, 7)) + 1j * rng.standard_normal((h.nhe, 7, 7)))
+    dt = 20.0
+    h.plan.set_path(3)
+    o3, b3, t3 = h.plan.run(ado0, dt, 12, e_ops=[Q[0], Hm], traj_every=4)
+    h.plan.set_path(4)
+    o4, b4, t4 = h.plan.run(ado0, dt, 12, e_ops=[Q[0], Hm], traj_every=4)
+    assert h.plan.path == 4
+    assert relerr(o4, o3) <= 1e-13 and relerr(b4, b3) <= 1e-13 and relerr(t4, t3) <= 1e-13
+    o4b, _, _ = h.plan.run(o4, dt, 3)              # a second launch on the same plan: tags continue
+    h.plan.set_path(3)
+    o3b, _, _ = h.plan.run(o3, dt, 3)
+    assert relerr(o4b, o3b) <= 1e-13
+    # the tiled variant forced on a hierarchy that would take the register-resident one
+    monkeypatch.setenv('LIMEB200_HEOM_FLOW_TILED', '1')
+    h2 = hh.HEOM(Hm, Q, lam, gam, kT, N_exp=2, N_cut=3)
+    a0 = 0.1 * (rng.standard_normal((h2.nhe, 7, 7)) + 1j * rng.standard_normal((h2.nhe, 7, 7)))
+    h2.plan.set_path(4)
+    p4, q4, _ = h2.plan.run(a0, dt, 9, e_ops=[Q[1]])
+    monkeypatch.delenv('LIMEB200_HEOM_FLOW_TILED')
+    h2.plan.set_path(3)
+    p3, q3, _ = h2.plan.run(a0, dt, 9, e_ops=[Q[1]])
+    assert relerr(p4, p3) <= 1e-13 and relerr(q4, q3) <= 1e-13
+
+
+def test_heom_dataflow_kernel_two_elements_per_thread(cuda):
+    """path 4, register-resident variant with TWO matrix elements per thread: 7 sites, 11 bath modes (four baths with
+    two exponentials, three with one), depth 5 -> 4368 ADOs = 30 per SM; against the barrier kernel (path 3) and the
+    oracle"""
+    from lime_b200 import builders, engine
+    from lime_b200.heom.heom import _calc_matsubara_params
+    Hm, Q, lam, gam, kT = builders.fmo_heom_inputs()
+    qmap = [0, 0, 1, 1, 2, 2, 3, 3, 4, 5, 6]
+    c, nu = [], []
+    for b in range(7):
+        cb, nub = _calc_matsubara_params(2, lam * (1 + 0.1 * b), gam, kT)
+        k = 2 if b < 4 else 1
+        c += cb[:k]
+        nu += nub[:k]
+    states, dn, up = engine.heom_tables([6] * 11, 5)
+    assert states.shape[0] == 4368
+    plan = engine.HeomPlan(Hm, np.stack(Q).astype(complex), qmap, np.array(c), np.array(nu), states, dn, up)
+    rng = np.random.default_rng(3)
+    ado0 = 0.1 * (rng.standard_normal((4368, 7, 7)) + 1j * rng.standard_normal((4368, 7, 7)))
+    plan.set_path(3)
+    o3, b3, _ = plan.run(ado0, 15.0, 10, e_ops=[Q[2]])
+    plan.set_path(4)
+    o4, b4, _ = plan.run(ado0, 15.0, 10, e_ops=[Q[2]])
+    assert plan.path == 4
+    assert relerr(o4, o3) <= 1e-13 and relerr(b4, b3) <= 1e-13
+    st = states.astype(np.int64)
+    ado_o, _, _ = lo.heom_rk4(ado0, Hm, np.stack(Q).astype(complex), qmap, np.array(c), np.array(nu), st,
+                              dn.astype(np.int64), up.astype(np.int64), 15.0, 2)
+    o2, _, _ = plan.run(ado0, 15.0, 2)
+    assert relerr(o2, ado_o) <= TOL
+
+
+@pytest.mark.parametrize('path', [0, 2, 3])
+def test_heom_fmo_shape_stagewise_and_batch(cuda, path):
+    """config-4 shape at reduced depth: 7 sites, 7 baths x K=2, depth 2 (120 ADOs of 7x7);
+    projector coupling operators (diagonal-Q gather path); batch of 3 hierarchies"""
+    from lime_b200 import engine
+    import lime_b200.heom.heom as hh
+    n = 7
+    H = cases.rand_herm(n, 21, 0.5) + np.diag(np.arange(n) * 0.3)
+    Q = [np.diag((np.arange(n) == j).astype(float)) for j in range(n)]
+    h = hh.HEOM(H, Q, 0.05, 0.6, 1.2, N_exp=2, N_cut=2)
+    assert h.nhe == 120
+    st = h.states.astype(np.int64)
+    rng = np.random.default_rng(5)
+    ado0 = rng.standard_normal((3, h.nhe, n, n)) + 1j * rng.standard_normal((3, h.nhe, n, n))
+    ado0 *= 0.1
+    h.plan.set_path(path)
+    out, obs, traj = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
+    assert relerr(traj[-1], out[:, 0]) == 0
+    for b in range(3):
+        ado_o, obs_o, _ = lo.heom_rk4(ado0[b], H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                      h.up.astype(np.int64), 0.02, 10, e_ops=[H])
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+
+
+def test_heom_parameter_batch(cuda):
+    """[ext] config-3 throughput variant: hierarchies differing in (lambda, beta)"""
+    from lime_b200 import engine
+    from lime_b200.heom.heom import _calc_matsubara_params
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=5)
+    states, dn, up = engine.heom_tables([depth + 1] * K, depth)
+    pars = [(0.1, 1.0), (0.2, 0.7), (0.3, 1.4), (0.05, 2.0)]
+    cs, nus = [], []
+    for lam_b, T_b in pars:
+        c, nu = _calc_matsubara_params(K, lam_b, gam, T_b)
+        cs.append(c)
+        nus.append(nu)
+    plan = engine.HeomPlan(H, sz, [0] * K, np.array(cs), np.array(nus), states, dn, up)
+    ado0 = np.zeros((len(pars), states.shape[0], 2, 2), dtype=complex)
+    ado0[:, 0] = rho0
+    out, obs, _ = plan.run(ado0, 0.01, 40, e_ops=[sz])
+    for b in range(len(pars)):
+        ado_o, obs_o, _ = lo.heom_rk4(ado0[b], H, sz[None], [0] * K, cs[b], nus[b], states.astype(np.int64),
+                                      dn.astype(np.int64), up.astype(np.int64), 0.01, 40, e_ops=[sz])
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+
+
+# ---------------------------------------------------------------- SOS
+def test_sos_all_pathways(cuda):
+    from lime_b200.signal import sos
+    g = golden('sos')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    w1, w3, w2, w1b, t2 = g['w1'], g['w3'], g['w2'], g['w1b'], float(g['t2'])
+    au2ev = 27.211386
+    assert relerr(sos.GSB(E, dip, w1, w3, t2, g_idx, e_idx, gamma), g['GSB']) <= TOL
+    assert relerr(sos.SE(E, dip, w1, w3, t2, g_idx, e_idx, gamma), g['SE']) <= TOL
+    assert relerr(sos.ESA(E, dip, w1, w3, t2, g_idx, e_idx, f_idx, gamma), g['ESA']) <= TOL
+    pe = sos._photon_echo(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma)
+    assert pe.shape == (12, 12) and pe.dtype == np.complex128
+    assert relerr(pe, g['PE']) <= TOL
+    assert relerr(sos._SE(E, dip, -w1, w3, t2, g_idx, e_idx, gamma, dephasing=0.01 / au2ev), g['SE_t3']) <= TOL
+    assert relerr(sos._ESA(E, dip, -w1, w3, t2, g_idx, e_idx, f_idx, gamma, dephasing=0.01 / au2ev), g['ESA_t3']) <= TOL
+    kw = dict(g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, gamma=gamma)
+    assert relerr(sos.DQC_R1(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, **kw), g['R1_t3']) <= TOL
+    assert relerr(sos.DQC_R2(E, dip, omega1=w1b, omega2=w2, tau3=1e-6, **kw), g['R2_t3']) <= TOL
+    assert relerr(sos.DQC_R1(E, dip, omega2=w2, omega3=w1b, tau1=50.0, **kw), g['R1_t1']) <= TOL
+    assert relerr(sos.DQC_R2(E, dip, omega2=w2, omega3=w1b, tau1=50.0, **kw), g['R2_t1']) <= TOL
+    assert relerr(sos.TPA2D(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D']) <= TOL
+    assert relerr(sos.TPA2D_time_order(E, dip, w2, w1b, g_idx, e_idx, f_idx, gamma), g['TPA2D_to']) <= TOL
+    with pytest.raises(Exception):
+        sos.DQC_R2(E, dip, omega2=w2, **kw)
+
+
+def test_sos_waiting_time_batch_and_ragged_grid(cuda):
+    """[ext] vector of waiting times in one launch; non-multiple-of-tile grid; N=32 config-5 shape"""
+    from lime_b200.signal import sos
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system(N=32, ne=15, seed=0)
+    au2ev, au2fs = 27.211386, 2.41888432651e-2
+    w = np.linspace(1.4, 2.1, 45) / au2ev
+    T = np.linspace(0, 630, 5) / au2fs
+    pe = sos._photon_echo(E, dip, -w, w, T, g_idx, e_idx, f_idx, gamma)
+    assert pe.shape == (5, 45, 45)
+    for t in (0, 2, 4):
+        assert relerr(pe[t], lo.photon_echo_core(E, dip, -w, w, T[t], g_idx, e_idx, f_idx, gamma)) <= TOL
+    # linearity in the dipole scale: S ~ mu^4
+    pe2 = sos._photon_echo(E, 2.0 * dip, -w, w, T[1], g_idx, e_idx, f_idx, gamma)
+    assert relerr(pe2, 16.0 * pe[1]) <= 1e-12
+    # [ext] device-resident evaluation (what bench.py times) gives the same numbers, repeatedly
+    grid = sos.PhotonEchoGrid(E, dip, -w, w, T, g_idx, e_idx, f_idx, gamma)
+    assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
+    assert relerr(grid.run().cpu().numpy(), pe) <= 1e-14
+
+
+def test_time_domain_2des(cuda):
+    """lime/signal/2DES.py:37-247 (G, ESA, GSB, SE in the time domain) against the frozen outputs of the
+    reference functions themselves and against the oracle; scalars, vectors, waiting-time batch"""
+    from lime_b200.signal import twodes
+    g = golden('twodes_time')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    t1, t3, tw = g['t1'], g['t3'], float(g['t2'])
+    twodes.en, twodes.decay = None, None
+    assert relerr(twodes.ESA(E, dip, g_idx, e_idx, f_idx, gamma, t1[None, :], tw, t3[:, None]), g['ESA']) <= TOL
+    assert relerr(twodes.GSB(E, dip, g_idx, e_idx, gamma, t1, tw, t3), g['GSB']) <= TOL
+    assert relerr(twodes.SE(E, dip, g_idx, e_idx, t1, tw, t3, gamma=gamma), g['SE']) <= TOL
+    # module globals as in lime
+    twodes.en, twodes.decay = E, gamma
+    try:
+        assert relerr(twodes.SE(None, dip, g_idx, e_idx, t1, tw, t3), g['SE']) <= TOL
+        assert relerr(twodes.G(2, 0, t3), lo.td_G(E, gamma, 2, 0, t3)) <= 1e-13
+        assert abs(twodes.G(1, 0, 3.0) - lo.td_G(E, gamma, 1, 0, 3.0)) <= 1e-13
+        assert twodes.G(1, 0, -1.0) == 0
+    finally:
+        twodes.en, twodes.decay = None, None
+    # scalar delays and a batch of waiting times
+    s = twodes.ESA(E, dip, g_idx, e_idx, f_idx, gamma, 10.0, tw, 20.0)
+    assert abs(s - lo.td_ESA(E, gamma, dip, g_idx, e_idx, f_idx, 10.0, tw, 20.0)) <= TOL * abs(s)
+    tws = np.array([0.0, 25.0, 80.0])
+    b = twodes.GSB(E, dip, g_idx, e_idx, gamma, t1, tws, t3)
+    assert b.shape == (3, len(t3), len(t1))
+    for k, t2 in enumerate(tws):
+        assert relerr(b[k], lo.td_GSB(E, gamma, dip, g_idx, e_idx, t1[None, :], t2, t3[:, None])) <= TOL
+
+
+def test_redfield_two_level_batch_thread_per_vector_kernel(cuda):
+    """config-1 throughput variant: the Redfield tensor of examples/redfield.py on a batch large enough to
+    take the thread-per-vector kernel; checked against the oracle on a few members"""
+    from lime_b200.oqs import Redfield_solver
+    H, a_ops, spectra, rho0, dt, Nt, e_ops, tlist = cases.redfield_example()
+    s = Redfield_solver(H, c_ops=a_ops, spectra=spectra)
+    R, evecs = s.redfield_tensor()
+    batch = cases.rand_dm_batch(5000, 2, 9)
+    out, obs = s.evolve_batch(batch, dt, 40, e_ops=e_ops)
+    assert obs.shape == (40, 5000, 1)
+    for b in (0, 17, 4999):
+        o, rl = lo.redfield(R, batch[b], evecs=evecs, Nt=40, dt=dt, e_ops=e_ops)
+        assert relerr(obs[:, b], o) <= TOL
+        assert relerr(evecs @ out[b] @ evecs.conj().T, rl[-1]) <= TOL
+
+
+@pytest.mark.parametrize('no_dmma', [False, True])
+def test_lindblad_dense_stage_64_tile_ragged(cuda, monkeypatch, no_dmma):
+    """dense stage-wise path at a size that is no multiple of the 64x64 tile: the FP64 tensor-core kernel
+    (qme_dense_stage_dmma, N >= 96) and, with LIMEB200_DENSE_NO_DMMA, the register-tiled DFMA kernel it replaced"""
+    from lime_b200 import oqs
+    if no_dmma:
+        monkeypatch.setenv('LIMEB200_DENSE_NO_DMMA', '1')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=101, M=2, E=1, seed=77)
+    H = H / 10.0
+    o, rl = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=6, dt=0.01)
+    plan = oqs._lindblad_plan(H, c_ops, e_ops, path=2)
+    rf, ob, _ = plan.run(rho0, 0.01, 6)
+    assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+    assert relerr(plan.rhs(rho0), lo.liouvillian(rho0, H, c_ops)) <= 1e-12
+
+
+@pytest.mark.parametrize('no_dmma', [False, True])
+def test_lindblad_dense_config2prime_full_size(cuda, monkeypatch, no_dmma):
+    """config 2' at its named size: N = 256, M = 2 dense operators, a batch of 3, 4 RK4 steps (DMMA and DFMA kernels);
+    and the 32x32-tile kernel below N = 96 with the DMMA path disabled"""
+    from lime_b200 import oqs
+    if no_dmma:
+        monkeypatch.setenv('LIMEB200_DENSE_NO_DMMA', '1')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=256, M=2, E=2, seed=123)
+    H = H / 20.0
+    c_ops = [c / 4.0 for c in c_ops]
+    plan = oqs._lindblad_plan(H, c_ops, e_ops, path=2)
+    r0 = np.stack([rho0, cases.rand_dm(256, 5), cases.rand_dm(256, 6)])
+    rf, ob, _ = plan.run(r0, 0.01, 4)
+    for b in (0, 2):
+        o, rl = lo.lindblad(H, r0[b], c_ops, e_ops=e_ops, Nt=4, dt=0.01)
+        assert relerr(ob[:, b], o) <= TOL and relerr(rf[b], rl[-1]) <= TOL
+    if no_dmma:
+        H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=80, M=1, E=1, seed=9)
+        o, rl = lo.lindblad(H / 8.0, rho0, c_ops, e_ops=e_ops, Nt=5, dt=0.01)
+        plan = oqs._lindblad_plan(H / 8.0, c_ops, e_ops, path=2)
+        rf, ob, _ = plan.run(rho0, 0.01, 5)
+        assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+
+
+def test_lindblad_config2_full_batch(cuda):
+    """config 2 at its real batch: 4096 coupling x detuning points of N = 128 in ONE launch (the launch bench.py
+    times), 12 RK4 steps; three of the points against the oracle, Tr rho = 1 on all of them"""
+    import torch
+    from lime_b200 import builders, oqs
+    pat, vals, c_ops, e_ops, rho0 = builders.jc_grid()
+    assert vals.shape[0] == 4096
+    plan, B = oqs._lindblad_plan_batch((pat, vals), c_ops, e_ops)
+    assert plan.path == 6
+    rho = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(rho0, (4096, 128, 128)))).cuda()
+    obs, _ = plan.run_device(rho, 0.01, 12)
+    tr = torch.einsum('bii->b', rho).cpu().numpy()
+    assert np.max(np.abs(tr - 1)) < 1e-12
+    gs = np.linspace(0.01, 0.2, 64)
+    dets = np.linspace(-0.2, 0.2, 64)
+    for b in (0, 2077, 4095):
+        Ho, co, eo = lo.jaynes_cummings(1.0, 1.0 + dets[b % 64], gs[b // 64], 64, 0.05)
+        o, rl = lo.lindblad(Ho.toarray(), rho0, [c.toarray() for c in co], [e.toarray() for e in eo], Nt=12, dt=0.01)
+        assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
+
+
+def test_heom_config3_long_run(cuda):
+    """config 3 (spin-boson, K = 2, depth 12, dt = 0.01): 4000 RK4 steps of the single hierarchy stay within
+    1e-10 of the oracle (thread-per-ADO kernel, one launch)"""
+    from lime_b200.heom.heom import HEOM
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=12)
+    h = HEOM(H, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    res = h.evolve(rho0, 0.01, 4000, e_ops=[sz], store_states=False)
+    st = h.states.astype(np.int64)
+    ado_o, obs_o, _ = lo.heom_rk4(h.initial(rho0), H, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64),
+                                  h.up.astype(np.int64), 0.01, 4000, e_ops=[sz])
+    assert relerr(res.ado, ado_o) <= TOL and relerr(res.observables, obs_o) <= TOL
+    assert abs(np.trace(res.ado[0]) - 1) < 1e-11
+
+
+def test_heom_config3_1e5_steps_one_launch(cuda):
+    """config 3 at its named length: 1e5 RK4 steps of the 91-ADO hierarchy in ONE launch.  The oracle needs minutes for
+    that, so the full length is checked through properties: splitting the run into 25 launches of 4000 steps (whose
+    first segment IS checked against the oracle above) gives the bit-identical state, the trace stays 1, tier 0 stays
+    Hermitian and the populations approach a stationary value"""
+    from lime_b200.heom.heom import HEOM
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=12)
+    h = HEOM(H, sz, lam, gam, T, N_exp=K, N_cut=depth)
+    one, obs1, _ = h.plan.run(h.initial(rho0), 0.01, 100000, e_ops=[sz])
+    seg = h.initial(rho0)
+    for _ in range(25):
+        seg, _, _ = h.plan.run(seg, 0.01, 4000)
+    assert np.array_equal(one, seg)
+    assert abs(np.trace(one[0]) - 1) < 1e-10 and relerr(one[0], one[0].conj().T) < 1e-12
+    assert abs(obs1[-1, 0] - obs1[-2000, 0]) < 1e-6 and np.all(np.isfinite(one))
+
+
+def test_heom_parameter_batch_thread_per_ado_kernel(cuda):
+    """batch large enough (>= 2 hierarchies per SM) to take the thread-per-ADO kernel; per-hierarchy bath parameters"""
+    from lime_b200 import engine
+    from lime_b200.heom.heom import _calc_matsubara_params
+    H, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=6)
+    states, dn, up = engine.heom_tables([depth + 1] * K, depth)
+    B = 600
+    lams = np.linspace(0.05, 0.4, B)
+    Ts = np.linspace(0.6, 2.0, B)
+    cs, nus = [], []
+    for lam_b, T_b in zip(lams, Ts):
+        c, nu = _calc_matsubara_params(K, lam_b, gam, T_b)
+        cs.append(c)
+        nus.append(nu)
+    plan = engine.HeomPlan(H, sz, [0] * K, np.array(cs), np.array(nus), states, dn, up)
+    ado0 = np.zeros((B, states.shape[0], 2, 2), dtype=complex)
+    ado0[:, 0] = rho0
+    sx = np.array([[0, 1.], [1, 0]])
+    out, obs, traj = plan.run(ado0, 0.01, 30, e_ops=[sz, sx], traj_every=10)
+    assert plan.path == 1
+    for b in (0, 299, 599):
+        ado_o, obs_o, tr_o = lo.heom_rk4(ado0[b], H, sz[None], [0] * K, cs[b], nus[b], states.astype(np.int64),
+                                         dn.astype(np.int64), up.astype(np.int64), 0.01, 30, e_ops=[sz, sx], store=True)
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+        assert relerr(traj[:, b], np.array([tr_o[9], tr_o[19], tr_o[29]])) <= TOL
+
+
+def test_liouvillian_eigen_solver(cuda):
+    """superoperator.Lindblad_solver (lime/superoperator.py:456-773).  Frozen reference outputs
+    (another host may round the LAPACK eigenvectors differently: 1e-8) and the oracle on this host (1e-10);
+    the device part is the DMMA ZGEMM"""
+    from lime_b200.superoperator import Lindblad_solver
+    from lime_b200 import engine
+    g = golden('super_lindblad')
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=3, M=2, E=2, seed=61)
+    A, B, C = g['A'], g['B'], g['C']
+    tl, taul, wl = g['tl'], g['taul'], g['wl']
+    s = Lindblad_solver(H, c_ops)
+    with pytest.raises(TypeError):
+        s.evolve(rho0, tl, e_ops)
+    s.eigenstates()
+    o = lo.SuperLindblad(H, c_ops)
+    o.eigenstates()
+    got = {'evolve': s.evolve(rho0, tl, e_ops).observables,
+           'c2_1t': s.correlation_2op_1t(rho0, [A, B], tl), 'c2_1w': s.correlation_2op_1w(rho0, [A, B], wl),
+           'c3_1t': s.correlation_3op_1t(rho0, [A, B, C], tl), 'c3_1w': s.correlation_3op_1w(rho0, [A, B, C], wl),
+           'c3_2t': s.correlation_3op_2t(rho0, [A, B, C], tl, taul),
+           'c4_2t': s.correlation_4op_2t(rho0, [A, B, C, A], tl, taul)}
+    want = {'evolve': o.evolve(rho0, tl, e_ops),
+            'c2_1t': o.correlation_2op_1t(rho0, [A, B], tl), 'c2_1w': o.correlation_2op_1w(rho0, [A, B], wl),
+            'c3_1t': o.correlation_3op_1t(rho0, [A, B, C], tl), 'c3_1w': o.correlation_3op_1w(rho0, [A, B, C], wl),
+            'c3_2t': o.correlation_3op_2t(rho0, [A, B, C], tl, taul),
+            'c4_2t': o.correlation_4op_2t(rho0, [A, B, C, A], tl, taul)}
+    for k in got:
+        assert got[k].shape == g[k].shape, k
+        assert relerr(got[k], want[k]) <= TOL, k
+        assert relerr(got[k], g[k]) <= 1e-8, k
+    assert got['c3_2t'].shape == (len(taul), len(tl))
+    with pytest.raises(ValueError):
+        s.correlation_4op_2t(rho0, [A, B, C], tl, taul)
+    # the GEMM primitive itself, ragged and batched shapes
+    rng = np.random.default_rng(3)
+    for (m, n, k, b) in [(1, 1, 1, 1), (70, 33, 129, 1), (64, 64, 64, 3), (5, 200, 17, 2)]:
+        a = rng.standard_normal((b, m, k)) + 1j * rng.standard_normal((b, m, k))
+        bb = rng.standard_normal((k, n)) + 1j * rng.standard_normal((k, n))
+        c = engine.zgemm(a, bb).cpu().numpy()
+        assert relerr(c, a @ bb) <= 1e-13
+
+
+def test_sesolver_wavefunction_path(cuda):
+    """lime.mol.SESolver (RK4 of the Schroedinger equation and its correlation functions)
+    against frozen outputs of the reference and the oracle"""
+    from lime_b200.mol import SESolver
+    g = golden('sesolver')
+    H = cases.rand_herm(5, 81)
+    psi0 = cases.rand_cplx(5, 82)[:, 0]
+    psi0 = psi0 / np.linalg.norm(psi0)
+    e_ops = [cases.rand_herm(5, 83), cases.rand_herm(5, 84)]
+    ops = [g['A'], g['B'], g['C']]
+    s = SESolver(H)
+    r = s.run(psi0=psi0, dt=0.01, Nt=40, e_ops=e_ops, nout=2)
+    assert r.observables.shape == (20, 2) and len(r.psilist) == 20
+    assert relerr(r.observables, g['obs']) <= TOL and relerr(np.array(r.psilist), g['psilist']) <= TOL
+    assert relerr(s.correlation_3op_1t(psi0, ops, 0.01, 12), g['c3_1t']) <= TOL
+    assert relerr(s.correlation_3op_2t(psi0, ops, 0.01, 5, 6), g['c3_2t']) <= TOL
+    assert relerr(s.correlation_4op_2t(psi0, ops + [ops[0]], 0.01, 4, 3), g['c4_2t']) <= TOL
+    U = s.propagator(0.01, 6)
+    import scipy.linalg
+    assert len(U) == 6 and relerr(U[5], scipy.linalg.expm(-1j * H * 0.05)) <= 1e-9      # RK4 truncation error
+    with pytest.raises(NotImplementedError):
+        s.run(psi0=psi0, pulse=object(), edip=H)
+
+
+def test_sos_mol_wrappers_and_tpa(cuda, tmp_path):
+    """photon_echo / photon_echo_t3 (Mol-based wrappers with their np.savez side effect) and the single-frequency
+    TPA, lime/signal/sos.py:199-228, 731-902, against frozen reference outputs"""
+    from lime_b200.signal import sos
+    g = golden('sos_mol')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    mol = cases.DuckMol(E, dip, gamma, dephasing=0.01 / 27.211386)
+    wp = g['wp']
+    pe = sos.photon_echo(mol, wp, wp, t2=30.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=str(tmp_path / 's'))
+    assert relerr(pe, g['PE']) <= TOL
+    saved = np.load(str(tmp_path / 's.npz'))
+    assert np.array_equal(saved['arr_2'], pe)
+    t3 = sos.photon_echo_t3(mol, wp, wp, 20.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=str(tmp_path / 't'))
+    assert relerr(t3, g['PE_t3']) <= TOL
+    se, esa = sos.photon_echo_t3(mol, wp, wp, 20.0, g_idx=g_idx, e_idx=e_idx, f_idx=f_idx, fname=None, separate=True)
+    assert relerr(se + esa, g['PE_t3']) <= TOL
+    tpa = np.array([sos.TPA(E, dip, w, g_idx, e_idx, f_idx, gamma) for w in g['wtpa']])
+    assert relerr(tpa, g['TPA']) <= TOL
+    mol.gamma = None
+    with pytest.raises(ValueError):
+        sos.photon_echo(mol, wp, wp)
+
+
+def test_fft_module(cuda):
+    """lime/fft.py (fft, ifft, fft2 = library FFT + lime's shift/scale/phase epilogue on the
+    device; dft, dft2 = separable sums as tensor-core GEMMs) against frozen reference outputs"""
+    from lime_b200 import fft as lfft
+    g = golden('fft')
+    xg, f1, f2 = g['xg'], g['f1'], g['f2']
+    out, freq = lfft.fft(f1, xg)
+    assert relerr(out, g['fft']) <= 1e-12 and np.array_equal(freq, g['fft_freq'])
+    out0, _ = lfft.fft(f1.T.copy(), xg, axis=0)
+    assert relerr(out0, g['fft'].T) <= 1e-12
+    out, freq = lfft.ifft(f1[0], xg)
+    assert relerr(out, g['ifft']) <= 1e-12 and np.array_equal(freq, g['ifft_freq'])
+    fx, fy, out = lfft.fft2(f2, 0.1, 0.2)
+    assert relerr(out, g['fft2']) <= 1e-12 and np.array_equal(fy, g['fft2_fy'])
+    assert relerr(lfft.dft(xg, f1[1], g['kxs']), g['dft']) <= 1e-12
+    assert relerr(lfft.dft2(g['xs'], g['ys'], g['fxy'], g['kxs'], g['kys']), g['dft2']) <= 1e-12
+
+
 # ---------------------------------------------------------------- RKF45 (north_star; lime ships only examples/rkf45_test.py)
 def test_rkf45_lime_example_problems(cuda):
     """examples/rkf45_test.py:72-119 (test04), :153-202 (test05), :283-330 (test06, single-step mode) through the

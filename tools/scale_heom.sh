@@ -1,7 +1,7 @@
 # sharded FMO hierarchy only: dataflow kernel vs barrier kernel at N ranks (N = $NG)
 NG=${NG:-2}
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG "$@" --no-cpu 2>>gpurun_out/scale_heom.err | grep "^{" ; }
-for ex in flow p2p; do
+for ex in ${EX:-flow p2p}; do
   run --workload heom_fmo --depth 4 --rk-steps 400 --exchange $ex --steps 3 --warmup 3 >> gpurun_out/r02_scale_heom_$NG.jsonl
   run --workload heom_fmo --depth 6 --rk-steps 50 --exchange $ex --steps 3 --warmup 3 >> gpurun_out/r02_scale_heom_$NG.jsonl
 done
