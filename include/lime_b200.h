@@ -289,6 +289,11 @@ int limeb200_sos_tpa2d(const double* d_E, const double* d_dip, const double* d_g
                        const int* d_eidx, int ne, const int* d_fidx, int nf,
                        const double* d_omegap, int np, const double* d_omega1, int n1,
                        int time_order, double* d_out, void* stream);
+/* ETPA double time integrals, _etpa lime/signal/sos.py:1171-1223: the second contraction
+ *   d_out[c][f] = sum_a exp(i (d_Ef[f] - d_alpha[c]) d_t2[a]) d_V[a][c]      (complex d_V [n2][C], d_out [C][nf])
+ * with V = (theta o (J + J^T)) . U1 from limeb200_zgemm, c = (pump frequency, intermediate state)              */
+int limeb200_etpa_reduce(const double* d_V, const double* d_t2, int n2, const double* d_alpha, int C,
+                         const double* d_Ef, int nf, double* d_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,7 @@ SIGNATURES = {
     'limeb200_sos_factor': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'limeb200_sos_factor_time': (c_int, [c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),
     'limeb200_sos_outer': (c_int, [c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_dbl, c_int, c_vp, c_vp]),
+    'limeb200_etpa_reduce': (c_int, [c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_vp]),
     'limeb200_sos_tpa2d': (c_int, [c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int, c_vp, c_int,
                                    c_int, c_vp, c_vp]),
 }

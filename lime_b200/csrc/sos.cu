@@ -133,6 +133,39 @@ sos_tpa2d_kernel(const double* __restrict__ E, const double* __restrict__ dip, c
     out[(size_t)i * n1 + j] = sig;
 }
 
+
+// ETPA double time integral, second contraction (lime/signal/sos.py:1171-1223):
+//   out[c][f] = sum_a exp(i (Ef[f] - alpha[c]) t2[a]) V[a][c]
+// V = (theta o (J + J^T)) . U1 comes from limeb200_zgemm; one CTA per column c = (pump frequency, intermediate state)
+__global__ void __launch_bounds__(256)
+etpa_reduce_kernel(const cplx* __restrict__ V, const double* __restrict__ t2, int n2, const double* __restrict__ alpha,
+                   int C, const double* __restrict__ Ef, int nf, cplx* __restrict__ out) {
+    __shared__ cplx red[8];
+    const int c = blockIdx.x;
+    const double al = alpha[c];
+    for (int f = 0; f < nf; ++f) {
+        const double w = Ef[f] - al;
+        cplx acc = cmake(0, 0);
+        for (int a = threadIdx.x; a < n2; a += blockDim.x) {
+            double sn, cs;
+            sincos(w * t2[a], &sn, &cs);
+            cfma(acc, cmake(cs, sn), V[(size_t)a * C + c]);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_down_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_down_sync(0xffffffffu, acc.y, o);
+        }
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            cplx t = red[0];
+            for (int w8 = 1; w8 < (int)(blockDim.x >> 5); ++w8) t = cadd(t, red[w8]);
+            out[(size_t)c * nf + f] = t;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -186,6 +219,15 @@ int limeb200_sos_tpa2d(const double* d_E, const double* d_dip, const double* d_g
     dim3 grid(ceil_div(n1, 256), np);
     sos_tpa2d_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(d_E, d_dip, d_gamma, N, d_eidx, ne, d_fidx, nf,
                                                             d_omegap, np, d_omega1, n1, time_order, d_out);
+    LB_CUDA(cudaGetLastError());
+    return LB_OK;
+}
+
+int limeb200_etpa_reduce(const double* d_V, const double* d_t2, int n2, const double* d_alpha, int C,
+                         const double* d_Ef, int nf, double* d_out, void* stream) {
+    LB_REQUIRE(d_V && d_t2 && d_alpha && d_Ef && d_out, "null argument");
+    LB_REQUIRE(n2 >= 1 && C >= 1 && nf >= 1, "bad sizes");
+    etpa_reduce_kernel<<<C, 256, 0, (cudaStream_t)stream>>>((const cplx*)d_V, d_t2, n2, d_alpha, C, d_Ef, nf, (cplx*)d_out);
     LB_CUDA(cudaGetLastError());
     return LB_OK;
 }

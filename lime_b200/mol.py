@@ -73,9 +73,82 @@ def _quantum_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=[], t0=0.0, nout=1, store_s
     return result
 
 
+def driven_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=None, nout=1, t0=0.0, return_result=True, sparse=True,
+                    strict_parity=False):
+    """Laser-driven wave-function dynamics, lime/mol.py:1473-1588: H = [H0, [H1, f1], ...], H(t) = H0 - sum_i f_i(t) H_i
+    evaluated at the start time of the current block of `nout` steps (lime advances t once per block) and frozen over the
+    four RK4 stages; entry 0 of the output is
+    the initial state, entry k the state after k * nout steps, k < Nt // nout.
+
+    The whole loop is one launch of the driven master-equation kernel (limeb200_qme_run with per-step drive
+    coefficients): psi is column 0 of an N x N state with generator G(t) = -i H(t) and NO right generator, so that
+    d/dt column = -i H(t) column.
+
+    lime's calcH reads `Ht = H[0]; Ht += ...` (lime/mol.py:1510-1517); lime only runs with scipy.sparse operands here
+    (its psi is a CSR column; an ndarray Hamiltonian raises ValueError), and for those `+=` rebinds Ht, so H(t) is
+    evaluated afresh each step -- which is what happens here for sparse AND dense operands.  strict_parity=True applies
+    the accumulation an aliased ndarray H[0] would see.  return_result=False writes psi.dat / obs.dat as lime does and
+    returns None."""
+    from . import engine, _dev
+    e_ops = [] if e_ops is None else e_ops
+    H0 = _dev.as_c128(H[0])
+    N = H0.shape[0]
+    psi0v = np.asarray(psi0.toarray() if hasattr(psi0, 'toarray') else psi0, dtype=complex).reshape(-1)
+    nd = len(H) - 1
+
+    def sample(nsteps, first):
+        # lime advances t once per block of nout steps (`t += dt * nout` after the inner loop, lime/mol.py:1541-1547):
+        # every step of a block sees H at the block's start time
+        times = t0 + dt * nout * ((np.arange(nsteps) + first) // nout)
+        f = np.array([[complex(H[i][1](t)) for i in range(1, len(H))] for t in times], dtype=complex).reshape(nsteps, nd)
+        return np.cumsum(f, axis=0) if strict_parity else f
+
+    plan = engine.QmePlan(N)
+    plan.set_generator(-1j * H0)
+    plan.set_right_generator(np.zeros((N, N), dtype=complex))
+    for i in range(1, len(H)):
+        Hi = _dev.as_c128(H[i][0])
+        plan.add_drive(1j * Hi, np.zeros((N, N), dtype=complex))
+    plan.finalize()
+    rho = np.zeros((N, N), dtype=complex)
+    rho[:, 0] = psi0v
+
+    def expect(psi):
+        return [np.vdot(psi, (e @ psi) if not hasattr(e, 'toarray') else e.dot(psi)) for e in e_ops]
+
+    if return_result:
+        nblk = Nt // nout
+        nsteps = max(nblk - 1, 0) * nout
+        result = Result(dt=dt, Nt=Nt, psi0=psi0, t0=t0, nout=nout)
+        observables = np.zeros((nblk, len(e_ops)), dtype=complex)
+        if nblk > 0:
+            observables[0, :] = expect(psi0v)
+        if nsteps > 0:
+            _, _, traj = plan.run(rho, dt, nsteps, coef=sample(nsteps, 0), traj_every=nout)
+            for k in range(1, nblk):
+                psi = traj[k - 1][:, 0]
+                observables[k, :] = expect(psi)
+                result.psilist.append(psi.copy())
+        result.observables = observables
+        return result
+    nblk = int(Nt / nout)
+    nsteps = nblk * nout
+    with open('psi.dat', 'w') as f_dm, open('obs.dat', 'w') as f_obs:
+        if nsteps > 0:
+            _, _, traj = plan.run(rho, dt, nsteps, coef=sample(nsteps, 0), traj_every=nout)
+            fmt = '{} ' * (len(e_ops) + 1) + '\n'
+            fmt_dm = '{} ' * (N + 1) + '\n'
+            for k in range(nblk):
+                psi = traj[k][:, 0]
+                t = t0 + dt * nout * (k + 1)
+                f_dm.write(fmt_dm.format(t, *psi))
+                f_obs.write(fmt.format(t, *expect(psi)))
+    return None
+
+
 class SESolver:
-    """time-dependent Schroedinger equation, lime/mol.py:1094-1277 (time-independent Hamiltonians; the laser-driven
-    branch `driven_dynamics` is not on the density-matrix path and raises NotImplementedError)"""
+    """time-dependent Schroedinger equation, lime/mol.py:1094-1277: time-independent Hamiltonians through the Liouville
+    RK4 kernel, laser-driven ones (`pulse=`) through `driven_dynamics`"""
 
     def __init__(self, H=None):
         self.H = H
@@ -86,8 +159,15 @@ class SESolver:
             psi0 = self.groundstate
         if pulse is not None:
             if edip is None:
-                raise ValueError('Electric dipole must be provided for laser-driven dynamics.')
-            raise NotImplementedError('laser-driven wave-function dynamics (lime.mol.driven_dynamics) is not built')
+                raise ValueError('Electric dipole must be provided for \
+                                 laser-driven dynamics.')
+            if isinstance(pulse, list):
+                H = [self.H]
+                for i in range(len(pulse)):
+                    H.append([edip[i], pulse[i].efield])
+            else:
+                H = [self.H, [edip, pulse.efield]]
+            return driven_dynamics(H=H, psi0=psi0, dt=dt, Nt=Nt, e_ops=e_ops, nout=nout, t0=t0)
         return _quantum_dynamics(self.H, psi0, dt=dt, Nt=Nt, e_ops=e_ops, nout=nout, t0=t0)
 
     def propagator(self, dt, Nt):

@@ -175,14 +175,13 @@ class PhotonEchoGrid:
         return A, Bf
 
     def run(self, use_graph=True):
-        """the three launches are captured in a CUDA graph on the second call (at 256 x 256 x 64 the kernels
-        take ~50 us, less than three individual launches from Python)"""
+        """the three launches are replayed from a CUDA graph (at 256 x 256 x 64 the kernels take ~50 us, less than three
+        individual launches from Python); the graph is captured in the FIRST call, right after a plain warm-up pass, so
+        that every later call is a replay"""
         if not use_graph:
             self._launch()
         elif self._graph is None:
-            self._keep = self._launch()                  # first call: plain launches (also the warm-up)
-            self._graph = False
-        elif self._graph is False:
+            self._keep = self._launch()                  # plain launches: warm-up (module load, allocator)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -426,3 +425,65 @@ def TPA(E, dip, omegap, g_idx, e_idx, f_idx, gamma, degenerate=True):
     if not degenerate:
         raise UnboundLocalError("omega1 is not defined for degenerate=False (as in lime)")
     return float(_tpa2d(E, dip, [omegap], [omegap * 0.5], e_idx, f_idx, gamma, False)[0, 0])
+
+
+# ---------------------------------------------------------------------------------------
+# entangled two-photon absorption: double time integrals
+# ---------------------------------------------------------------------------------------
+def _etpa(omegaps, Es, edip, jta, t1, t2, g_idx, e_idx, f_idx):
+    """ETPA signal from the joint temporal amplitude, lime/signal/sos.py:1171-1223:
+
+        signal[j] = sum_{f,e} mu_eg mu_fe  sum_{T1,T2} theta(T2 - T1) e^{i d2 T2 + i d1 T1} (jta + jta^T)[T2, T1],
+        d2 = E_f - E_e - w_j/2,  d1 = E_e - E_g - w_j/2,  theta(0) = 1/2
+
+    (lime's two terms have the same detunings because omega1 = omega2 = omegap/2; they differ in jta vs jta.T).
+    lime evaluates the full n2 x n1 double sum for every (pump frequency, e, f) in Python loops.  The sum factorises:
+    V = (theta o (jta + jta^T)) . U1 with U1[b, (j,e)] = e^{i d1 t1_b} is ONE complex GEMM on the FP64 tensor cores
+    (limeb200_zgemm), and the remaining contraction over T2 with e^{i d2 t2_a} is limeb200_etpa_reduce.
+    As in lime, `g_idx` must select ONE ground state (its `Es[g]` / `edip[e, g]` only broadcast for a single index) and
+    jta must be square (it is transposed)."""
+    import ctypes as C
+    from .._lib import lib, check
+    omegaps = np.asarray(omegaps, dtype=float).reshape(-1)
+    Es = np.asarray(Es, dtype=float)
+    edip = np.asarray(edip)
+    t1 = np.asarray(t1, dtype=float)
+    t2 = np.asarray(t2, dtype=float)
+    jta = np.asarray(jta)
+    g = np.atleast_1d(np.asarray(g_idx, dtype=int))
+    if g.size != 1:
+        raise ValueError('operands could not be broadcast together: _etpa needs a single ground state (lime indexes Es[g_idx])')
+    g = int(g[0])
+    e_idx = np.array(list(e_idx), dtype=int)
+    f_idx = np.array(list(f_idx), dtype=int)
+    T1, T2 = np.meshgrid(t1, t2)
+    theta = np.heaviside(T2 - T1, 0.5)
+    if jta.shape != theta.shape or jta.shape != jta.T.shape:
+        raise ValueError('operands could not be broadcast together with shapes %s %s' % (theta.shape, jta.shape))
+    nw, ne, nf = len(omegaps), len(e_idx), len(f_idx)
+    signal = np.zeros(nw, dtype=complex)
+    if ne == 0 or nf == 0 or nw == 0:
+        return signal
+    M = np.ascontiguousarray(theta * (jta + jta.T), dtype=np.complex128)                 # [n2, n1]
+    d1 = (Es[e_idx][None, :] - Es[g]) - 0.5 * omegaps[:, None]                         # [nw, ne]
+    U1 = np.ascontiguousarray(np.exp(1j * t1[:, None] * d1.reshape(1, -1)))             # [n1, nw*ne]
+    V = engine.zgemm(M, U1).contiguous()                                                # [n2, nw*ne] on the device
+    dev = V.device
+    alpha = _dev.to_dev((Es[e_idx][None, :] + 0.5 * omegaps[:, None]).reshape(-1), np.float64, dev)
+    dEf = _dev.to_dev(Es[f_idx], np.float64, dev)
+    dt2 = _dev.to_dev(t2, np.float64, dev)
+    out = torch.empty((nw * ne, nf), dtype=torch.complex128, device=dev)
+    check(lib().limeb200_etpa_reduce(_dev.ptr(V), _dev.ptr(dt2), len(t2), _dev.ptr(alpha), nw * ne, _dev.ptr(dEf), nf,
+                                     _dev.ptr(out), _dev.stream_ptr(dev)))
+    S = out.cpu().numpy().reshape(nw, ne, nf)
+    D = edip[e_idx, g][:, None] * edip[f_idx[None, :], e_idx[:, None]]                  # mu_eg mu_fe  [ne, nf]
+    return np.einsum('jef,ef->j', S, D)
+
+
+def etpa(omegaps, mol, epp, g_idx, e_idx, f_idx):
+    """lime/signal/sos.py:1139-1167: ETPA signal of `mol` for the biphoton state `epp` (its get_jta() supplies the
+    joint temporal amplitude on the host)"""
+    Es = mol.eigenenergies()
+    edip = mol.edip
+    t1, t2, jta = epp.get_jta()
+    return _etpa(omegaps, Es, edip, jta, t1, t2, g_idx, e_idx, f_idx)

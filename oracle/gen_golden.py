@@ -341,6 +341,39 @@ def main():
     note('sesolver', **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'sesolver.npz'), A=ops[0], B=ops[1], C=ops[2], **g)
 
+
+    # ---- laser-driven wave-function dynamics, SESolver.run(pulse=...) -> driven_dynamics, lime/mol.py:1094-1171,1473-1560
+    class _Pulse:                       # the two attributes SESolver.run uses of lime.optics.Pulse: .efield(t)
+        def __init__(self, a, w, tc, sig):
+            self.a, self.w, self.tc, self.sig = a, w, tc, sig
+
+        def efield(self, t):
+            return self.a * np.exp(-(t - self.tc) ** 2 / 2. / self.sig ** 2) * np.exp(-1j * self.w * (t - self.tc))
+    Hd = cases.rand_herm(5, 181)
+    mu = cases.rand_herm(5, 182)
+    mu2 = cases.rand_herm(5, 183)
+    psi0 = cases.rand_cplx(5, 184)[:, 0]
+    psi0 = psi0 / np.linalg.norm(psi0)
+    e_sp = [csr_matrix(cases.rand_herm(5, 185)), csr_matrix(cases.rand_herm(5, 186))]
+    p1, p2 = _Pulse(0.3, 1.1, 0.15, 0.1), _Pulse(0.2, 0.4, 0.25, 0.2)
+    rs = quiet(lmol.SESolver(csr_matrix(Hd)).run, psi0=psi0, dt=0.01, Nt=40, e_ops=e_sp, nout=2, edip=csr_matrix(mu), pulse=p1)
+    rl = quiet(lmol.SESolver(csr_matrix(Hd)).run, psi0=psi0, dt=0.01, Nt=30, e_ops=e_sp, nout=1,
+               edip=[csr_matrix(mu), csr_matrix(mu2)], pulse=[p1, p2])
+    dense_fails = 'ok'
+    try:                                    # an ndarray Hamiltonian cannot be combined with lime's sparse psi: ValueError
+        quiet(lmol.SESolver(Hd.copy()).run, psi0=psi0, dt=0.01, Nt=20, e_ops=e_sp, nout=1, edip=mu, pulse=p1)
+    except Exception as exc:
+        dense_fails = type(exc).__name__
+    tovec = lambda pl: np.array([np.asarray(p.toarray() if hasattr(p, 'toarray') else p).reshape(-1) for p in pl])
+    g = {'obs1': rs.observables, 'psi1': tovec(rs.psilist), 'obs2': rl.observables, 'psi2': tovec(rl.psilist)}
+    e_d = [e.toarray() for e in e_sp]
+    o1, pl1 = lo.driven_dynamics([Hd, [mu, p1.efield]], psi0, dt=0.01, Nt=40, e_ops=e_d, nout=2)
+    o2, pl2 = lo.driven_dynamics([Hd, [mu, p1.efield], [mu2, p2.efield]], psi0, dt=0.01, Nt=30, e_ops=e_d, nout=1)
+    o = {'obs1': o1, 'psi1': np.array(pl1), 'obs2': o2, 'psi2': np.array(pl2)}
+    note('sesolver_driven', dense_H_raises_ValueError=float(dense_fails != 'ValueError'), **{k: relerr(o[k], g[k]) for k in g})
+    np.savez_compressed(os.path.join(GOLD, 'sesolver_driven.npz'), Hd=Hd, mu=mu, mu2=mu2, psi0=psi0, e0=e_d[0], e1=e_d[1],
+                        pulses=np.array([[0.3, 1.1, 0.15, 0.1], [0.2, 0.4, 0.25, 0.2]]), **g)
+
     # ---- time-domain response functions, lime/signal/2DES.py:37-247 (the module cannot be imported:
     # it runs undefined names at :249-263; the function definitions themselves are exec'd verbatim here)
     src = open('/root/reference/lime/signal/2DES.py').read().split('\n')
@@ -478,6 +511,22 @@ def main():
     note('api_r2', cor_file_identical=float(cor_txt != open(fn2).read()), gf_eom_raises_TypeError=float(gf_eom != 'TypeError'),
          **{k: relerr(o[k], g[k]) for k in g})
     np.savez_compressed(os.path.join(GOLD, 'api_r2.npz'), A=A, B=B, tg=tg, wg=wg, cor_txt=np.array(cor_txt), **g)
+
+
+    # ---- ETPA double time integrals, sos._etpa (lime/signal/sos.py:1171-1223), SURVEY 8f item 4
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    rg = np.random.default_rng(21)
+    nt = 24
+    t1e = np.linspace(-40.0, 60.0, nt)
+    t2e = np.linspace(-40.0, 60.0, nt)
+    jta = (rg.standard_normal((nt, nt)) + 1j * rg.standard_normal((nt, nt))) * np.exp(-(t1e[None, :] ** 2 + t2e[:, None] ** 2) / 900.0)
+    wps = np.linspace(0.12, 0.16, 5)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        et_ref = quiet(sos._etpa, wps, E, dip, jta, t1e, t2e, list(g_idx), list(e_idx), list(f_idx))
+        et_o = lo.etpa_core(wps, E, dip, jta, t1e, t2e, list(g_idx), list(e_idx), list(f_idx))
+    note('etpa', etpa=relerr(et_o, et_ref))
+    np.savez_compressed(os.path.join(GOLD, 'etpa.npz'), wps=wps, t1=t1e, t2=t2e, jta=jta, etpa=et_ref)
 
     with open(os.path.join(GOLD, 'PINNING.json'), 'w') as f:
         json.dump({'generated_by': 'oracle/gen_golden.py', 'reference': 'binggu56/lime @ /root/reference',

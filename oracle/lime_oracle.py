@@ -284,6 +284,26 @@ def lindblad_correlation_3op_2t(H, c_ops, rho0, ops, dt, Nt, Ntau):
     return corr
 
 
+def etpa_core(omegaps, Es, edip, jta, t1, t2, g_idx, e_idx, f_idx):
+    """_etpa, lime/signal/sos.py:1171-1223: the double time integrals as lime's loops write them"""
+    T1, T2 = np.meshgrid(t1, t2)
+    theta = np.heaviside(T2 - T1, 0.5)
+    signal = np.zeros(len(omegaps), dtype=complex)
+    g = g_idx
+    for j, omegap in enumerate(omegaps):
+        omega1 = omega2 = omegap / 2.
+        for f in f_idx:
+            for e in e_idx:
+                detuning2 = Es[f] - Es[e] - omega2
+                detuning1 = Es[e] - Es[g] - omega1
+                D = edip[e, g] * edip[f, e]
+                signal[j] += (D * np.sum(theta * np.exp(1j * detuning2 * T2 + 1j * detuning1 * T1) * jta)).item()
+                detuning2 = Es[f] - Es[e] - omega1
+                detuning1 = Es[e] - Es[g] - omega2
+                signal[j] += (D * np.sum(theta * np.exp(1j * detuning2 * T2 + 1j * detuning1 * T1) * jta.T)).item()
+    return signal
+
+
 # --------------------------------------------------------------------------
 # L2 superoperator algebra (row-major vec)           lime/superoperator.py
 # --------------------------------------------------------------------------
@@ -1033,6 +1053,36 @@ def quantum_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=[], t0=0.0, nout=1):
     for k1 in range(1, Nt // nout):
         for k2 in range(nout):
             psi = rk4(psi, tdse, dt, H)
+        observables[k1, :] = [obs_psi(psi, e) for e in e_ops]
+        psilist.append(psi.copy())
+    return observables, psilist
+
+
+def driven_dynamics(H, psi0, dt=0.001, Nt=1, e_ops=None, nout=1, t0=0.0, strict=False):
+    """laser-driven wave-function dynamics (return_result=True), lime/mol.py:1473-1560: H = [H0, [H1, f1], ...],
+    Ht = H0 - sum_i f_i(t) H_i at the start time of the current block of nout steps.  lime only runs with scipy.sparse
+    operands here (its psi is a CSR column; an ndarray H raises), and for those `Ht = H[0]; Ht += ...` REBINDS Ht, so the
+    drive does not accumulate; strict=True models the accumulation an ndarray H[0] would see (unreachable in lime)."""
+    e_ops = [] if e_ops is None else e_ops
+    psi = np.array(psi0, dtype=complex)
+    H0 = np.array(H[0].toarray() if issparse(H[0]) else H[0], dtype=complex)
+
+    def calcH(t):
+        nonlocal H0
+        Ht = H0 if strict else H0.copy()
+        for i in range(1, len(H)):
+            Hi = H[i][0].toarray() if issparse(H[i][0]) else np.asarray(H[i][0])
+            Ht += -H[i][1](t) * Hi
+        return Ht
+    observables = np.zeros((Nt // nout, len(e_ops)), dtype=complex)
+    psilist = [np.array(psi0)]
+    t = t0
+    observables[0, :] = [obs_psi(psi, e) for e in e_ops]
+    for k1 in range(1, Nt // nout):
+        for k2 in range(nout):
+            ht = calcH(t)            # lime evaluates at the block's start time for every step of the block (t += dt*nout after)
+            psi = rk4(psi, tdse, dt, ht)
+        t += dt * nout
         observables[k1, :] = [obs_psi(psi, e) for e in e_ops]
         psilist.append(psi.copy())
     return observables, psilist

@@ -860,8 +860,8 @@ def test_sos_mol_wrappers_and_tpa(cuda, tmp_path):
 
 
 def test_fft_module(cuda):
-    """lime/fft.py (fft, ifft, fft2 = library FFT + lime's shift/scale/phase epilogue on the
-    device; dft, dft2 = separable sums as tensor-core GEMMs) against frozen reference outputs"""
+    """lime/fft.py -- fft, ifft, fft2 as ONE tensor-core GEMM with the Fourier matrix (shift, scale and
+    phase folded in; no FFT library), dft, dft2 as separable GEMMs -- against frozen reference outputs"""
     from lime_b200 import fft as lfft
     g = golden('fft')
     xg, f1, f2 = g['xg'], g['f1'], g['f2']
@@ -875,6 +875,103 @@ def test_fft_module(cuda):
     assert relerr(out, g['fft2']) <= 1e-12 and np.array_equal(fy, g['fft2_fy'])
     assert relerr(lfft.dft(xg, f1[1], g['kxs']), g['dft']) <= 1e-12
     assert relerr(lfft.dft2(g['xs'], g['ys'], g['fxy'], g['kxs'], g['kys']), g['dft2']) <= 1e-12
+    # odd lengths, a 2-D input through ifft (lime shifts every axis), rectangular fft2 -- against the NumPy formulas of lime
+    rng = np.random.default_rng(6)
+    for n in (7, 33):
+        x = np.linspace(0.3, 2.0, n)
+        f = rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))
+        dx = x[1] - x[0]
+        fr = 2 * np.pi * np.fft.fftshift(np.fft.fftfreq(n, d=dx))
+        ref = np.fft.fftshift(np.fft.fft(f, axis=-1), axes=(-1,)) * dx * np.exp(-1j * fr * x[0])
+        assert relerr(lfft.fft(f, x)[0], ref) <= 1e-12
+        fi = 2 * np.pi * np.fft.ifftshift(np.fft.fftfreq(n, d=dx))
+        ref = np.fft.ifftshift(np.fft.ifft(f, axis=-1)) * dx / 2 / np.pi * n * np.exp(1j * fi * x[0])
+        assert relerr(lfft.ifft(f, x)[0], ref) <= 1e-12
+        f22 = rng.standard_normal((n, n + 2)) + 0j
+        assert relerr(lfft.fft2(f22, 0.1, 0.3)[2], np.fft.fftshift(np.fft.fft2(f22)) * 0.03) <= 1e-12
+
+
+def test_sesolver_laser_driven(cuda, tmp_path, monkeypatch):
+    """SESolver.run(pulse=...) / driven_dynamics (lime/mol.py:1094-1171, 1473-1588): one launch of the driven kernel,
+    single pulse with nout = 2 (lime holds H at the block's start time), two pulses, sparse and dense operands, the
+    psi.dat / obs.dat branch"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import mol
+    from test_oracle_vs_golden import _GoldPulse
+    g = golden('sesolver_driven')
+    p1, p2 = [_GoldPulse(*r) for r in g['pulses']]
+    e_d = [g['e0'], g['e1']]
+    r = mol.SESolver(csr_matrix(g['Hd'])).run(psi0=g['psi0'], dt=0.01, Nt=40, e_ops=[csr_matrix(e) for e in e_d], nout=2,
+                                              edip=csr_matrix(g['mu']), pulse=p1)
+    assert relerr(r.observables, g['obs1']) <= TOL and relerr(np.array(r.psilist), g['psi1']) <= TOL
+    assert np.array_equal(r.times, 0.0 + np.arange(20) * 0.02)
+    r = mol.SESolver(g['Hd']).run(psi0=g['psi0'], dt=0.01, Nt=30, e_ops=e_d, nout=1, edip=[g['mu'], g['mu2']], pulse=[p1, p2])
+    assert relerr(r.observables, g['obs2']) <= TOL and relerr(np.array(r.psilist), g['psi2']) <= TOL
+    with pytest.raises(ValueError):
+        mol.SESolver(g['Hd']).run(psi0=g['psi0'], pulse=p1)
+    monkeypatch.chdir(tmp_path)
+    assert mol.driven_dynamics([g['Hd'], [g['mu'], p1.efield]], g['psi0'], dt=0.01, Nt=6, e_ops=e_d, return_result=False) is None
+    rows = np.genfromtxt(tmp_path / 'obs.dat', dtype=complex)
+    o, _ = lo.driven_dynamics([g['Hd'], [g['mu'], p1.efield]], g['psi0'], dt=0.01, Nt=8, e_ops=e_d, nout=1)
+    assert rows.shape == (6, 3) and relerr(rows[:, 1:], o[1:7]) <= TOL
+
+
+def test_etpa_double_time_integrals(cuda):
+    """sos._etpa (lime/signal/sos.py:1171-1223): tensor-core GEMM + reduction kernel against the frozen reference output,
+    and a rectangular-free larger grid against the oracle loops"""
+    from lime_b200.signal import sos
+    g = golden('etpa')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    out = sos._etpa(g['wps'], E, dip, g['jta'], g['t1'], g['t2'], list(g_idx), list(e_idx), list(f_idx))
+    assert relerr(out, g['etpa']) <= TOL
+    rng = np.random.default_rng(4)
+    nt = 70
+    t = np.linspace(-30, 90, nt)
+    jta = rng.standard_normal((nt, nt)) + 1j * rng.standard_normal((nt, nt))
+    wps = np.linspace(0.1, 0.2, 9)
+    ref = lo.etpa_core(wps, E, dip, jta, t, t, list(g_idx), list(e_idx), list(f_idx))
+    assert relerr(sos._etpa(wps, E, dip, jta, t, t, list(g_idx), list(e_idx), list(f_idx)), ref) <= TOL
+    assert np.array_equal(sos._etpa(wps, E, dip, jta, t, t, list(g_idx), [], list(f_idx)), np.zeros(9))
+    with pytest.raises(ValueError):
+        sos._etpa(wps, E, dip, jta, t, t, [0, 1], list(e_idx), list(f_idx))
+
+
+def test_phys_algebra_helpers_device_path(cuda):
+    """comm / anticomm / commutator / anticommutator (lime/phys.py:736-752): dense operands from N = 64 on take the
+    batched FP64 tensor-core GEMM; small, sparse and mismatched operands behave as in lime"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import phys
+    A, B = cases.rand_cplx(96, 1), cases.rand_cplx(96, 2)
+    assert relerr(phys.comm(A, B), A @ B - B @ A) <= 1e-13
+    assert relerr(phys.anticomm(A, B), A @ B + B @ A) <= 1e-13
+    assert relerr(phys.commutator(A, B), A @ B - B @ A) <= 1e-13
+    assert relerr(phys.anticommutator(A, B), A @ B + B @ A) <= 1e-13
+    Ar, Br = A.real.copy(), B.real.copy()
+    c = phys.comm(Ar, Br)
+    assert c.dtype == np.float64 and relerr(c, Ar @ Br - Br @ Ar) <= 1e-13
+    a, b = cases.rand_cplx(5, 3), cases.rand_cplx(5, 4)
+    assert np.array_equal(phys.comm(a, b), np.dot(a, b) - np.dot(b, a))
+    sa, sb = csr_matrix(a), csr_matrix(b)
+    assert relerr(phys.commutator(sa, sb).toarray(), a @ b - b @ a) <= 1e-15
+    with pytest.raises(AssertionError):
+        phys.comm(A, a)
+    assert np.array_equal(phys.dag(a), a.conj().T)
+    # lime-style user loop over rk4(rho, liouvillian, ...) (lime/phys.py:100-105): the operator plan is built once
+    from lime_b200 import oqs
+    H, c_ops, e_ops, rho0 = cases.lindblad_dense(n=6)
+    oqs.clear_plan_cache()
+    rho = rho0.copy()
+    for _ in range(5):
+        out = phys.rk4(rho, oqs.liouvillian, 0.01, H, c_ops)
+        assert out is rho
+    assert len(oqs._PLAN_CACHE) == 1
+    _, rl = lo.lindblad(H, rho0, c_ops, [], Nt=5, dt=0.01)
+    assert relerr(rho, rl[-1]) <= TOL
+    H2 = H.copy()
+    H2[0, 0] += 0.5                                   # a changed operator is a different plan (content fingerprint)
+    oqs.liouvillian(rho0, H2, c_ops)
+    assert len(oqs._PLAN_CACHE) == 2
+    assert relerr(oqs.liouvillian(rho0, H2, c_ops), lo.liouvillian(rho0, H2, c_ops)) <= 1e-13
 
 
 # ---------------------------------------------------------------- RKF45 (north_star; lime ships only examples/rkf45_test.py)

@@ -222,6 +222,34 @@ def test_round2_api_rows(tmp_path):
     assert relerr(lo.getG(1j * R, g['tg'], w=g['wg'], domain='freq'), g['G_freq']) <= 1e-12
 
 
+class _GoldPulse:
+    def __init__(self, a, w, tc, sig):
+        self.a, self.w, self.tc, self.sig = a, w, tc, sig
+
+    def efield(self, t):
+        return self.a * np.exp(-(t - self.tc) ** 2 / 2. / self.sig ** 2) * np.exp(-1j * self.w * (t - self.tc))
+
+
+def test_sesolver_driven():
+    """SESolver.run(pulse=...) -> driven_dynamics, lime/mol.py:1094-1171, 1473-1560"""
+    g = golden('sesolver_driven')
+    p1, p2 = [_GoldPulse(*r) for r in g['pulses']]
+    e_d = [g['e0'], g['e1']]
+    o1, pl1 = lo.driven_dynamics([g['Hd'], [g['mu'], p1.efield]], g['psi0'], dt=0.01, Nt=40, e_ops=e_d, nout=2)
+    assert relerr(o1, g['obs1']) <= TOL and relerr(np.array(pl1), g['psi1']) <= TOL
+    o2, pl2 = lo.driven_dynamics([g['Hd'], [g['mu'], p1.efield], [g['mu2'], p2.efield]], g['psi0'], dt=0.01, Nt=30,
+                                 e_ops=e_d, nout=1)
+    assert relerr(o2, g['obs2']) <= TOL and relerr(np.array(pl2), g['psi2']) <= TOL
+
+
+def test_etpa_double_time_integrals():
+    """sos._etpa, lime/signal/sos.py:1171-1223"""
+    g = golden('etpa')
+    E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
+    out = lo.etpa_core(g['wps'], E, dip, g['jta'], g['t1'], g['t2'], list(g_idx), list(e_idx), list(f_idx))
+    assert relerr(out, g['etpa']) <= TOL
+
+
 def test_sos():
     g = golden('sos')
     E, dip, gamma, g_idx, e_idx, f_idx = cases.sos_system()
