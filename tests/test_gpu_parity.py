@@ -832,8 +832,8 @@ def test_sesolver_wavefunction_path(cuda):
     U = s.propagator(0.01, 6)
     import scipy.linalg
     assert len(U) == 6 and relerr(U[5], scipy.linalg.expm(-1j * H * 0.05)) <= 1e-9      # RK4 truncation error
-    with pytest.raises(NotImplementedError):
-        s.run(psi0=psi0, pulse=object(), edip=H)
+    with pytest.raises(ValueError):                      # laser-driven branch: edip is mandatory (lime/mol.py:1153-1156)
+        s.run(psi0=psi0, pulse=object())
 
 
 def test_sos_mol_wrappers_and_tpa(cuda, tmp_path):
