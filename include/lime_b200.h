@@ -81,6 +81,10 @@ int limeb200_qme_set_observables(limeb200_qme_t plan, const double* h_e, int E);
  * 4 sparse cluster-resident (generic ELL), 5 sparse cluster-resident register-tiled
  * (at most 4 off-diagonal entries per row of G, one entry per row of X_s/Z_s, N <= 128);
  * tests force each path                                                                  */
+/* The generator (and sandwich) batch index is the RK4 STEP instead of the density matrix: values [nsteps][nnz] of a
+ * time-dependent sparse generator, frozen over the four stages of a step -- _lindblad_driven with CSR operands,
+ * lime/oqs.py:1691-1800 (Hermitian H(t): real drive envelopes).  Selects the sparse global-scratch kernel.    */
+int limeb200_qme_set_step_values(limeb200_qme_t plan, int on);
 int limeb200_qme_set_path(limeb200_qme_t plan, int path);
 /* analyse operators, choose the kernel, upload.  B_hint sizes scratch (may grow later). */
 int limeb200_qme_finalize(limeb200_qme_t plan);

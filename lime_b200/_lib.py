@@ -27,6 +27,7 @@ SIGNATURES = {
     'limeb200_qme_set_right_generator_dense': (c_int, [c_vp, c_vp, c_int]),
     'limeb200_qme_add_drive_dense': (c_int, [c_vp, c_vp, c_vp]),
     'limeb200_qme_set_observables': (c_int, [c_vp, c_vp, c_int]),
+    'limeb200_qme_set_step_values': (c_int, [c_vp, c_int]),
     'limeb200_qme_set_path': (c_int, [c_vp, c_int]),
     'limeb200_qme_finalize': (c_int, [c_vp]),
     'limeb200_qme_get_path': (c_int, [c_vp]),

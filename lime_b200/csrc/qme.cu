@@ -35,6 +35,7 @@ struct limeb200_qme_s {
     int path_req = 0, path = 0;
     bool finalized = false;
     int nb = 1;
+    bool step_vals = false;                     // the operator batch index is the RK4 step (time-dependent generator)
     HostOp G, Gr;                               // left generator, optional right generator (default G^H)
     std::vector<HostOp> X, Z;
     std::vector<std::vector<hcplx>> D, Dr;      // drives, dense: G_k += c D, Gr_k += c Dr (or conj(c) D^H)
@@ -727,6 +728,12 @@ int limeb200_qme_set_observables(limeb200_qme_t p, const double* h_e, int E) {
     p->E = E;
     return LB_OK;
 }
+int limeb200_qme_set_step_values(limeb200_qme_t p, int on) {
+    LB_REQUIRE(p, "null plan");
+    LB_REQUIRE(!p->finalized, "plan already finalized");
+    p->step_vals = on != 0;
+    return LB_OK;
+}
 int limeb200_qme_set_path(limeb200_qme_t p, int path) {
     LB_REQUIRE(p, "null plan");
     LB_REQUIRE(!p->finalized, "plan already finalized");
@@ -769,6 +776,11 @@ int limeb200_qme_finalize(limeb200_qme_t p) {
     const bool sparse_ok = (nd == 0) && !p->Gr.given && S <= QME_MAXS && wg <= 16 && wprod <= 16;
     const bool dense_mem_ok = (double)nb * NN * 16.0 * (2 + 2 * S) < 8e9;
     int path = p->path_req;
+    if (p->step_vals) {
+        // per-step generator values: the global-scratch sparse kernel is the one that re-reads the values every step
+        LB_REQUIRE(sparse_ok, "per-step operator values need sparse operands without dense drives");
+        path = 3;
+    }
     if (path == 0) {
         if (N >= 24 && sparse_ok && wg * 4 <= N) path = 5;          // structured mid/large N
         else if (N <= 64 && dense_mem_ok) path = 1;
@@ -1011,7 +1023,7 @@ __global__ void qme_permute(const cplx* __restrict__ src, cplx* __restrict__ dst
 }
 
 void fill_ell_args(limeb200_qme_t p, QmeEllArgs& a, int B) {
-    a.N = p->N; a.S = (int)p->X.size(); a.E = p->E; a.B = B; a.nb = p->nb;
+    a.N = p->N; a.S = (int)p->X.size(); a.E = p->E; a.B = B; a.nb = p->nb; a.step_vals = p->step_vals ? 1 : 0;
     a.G.w = p->wG; a.G.col = p->dGcol.as<int>(); a.G.val = p->dGval.as<cplx>();
     for (int s = 0; s < a.S; ++s) {
         a.X[s].w = p->wX[s]; a.X[s].col = p->dXcol[s].as<int>(); a.X[s].val = p->dXval[s].as<cplx>();
@@ -1163,7 +1175,8 @@ int limeb200_qme_run(limeb200_qme_t p, double* d_rho, int B, double dt, int nste
     LB_REQUIRE(p && p->finalized, "plan not finalized");
     LB_REQUIRE(p->device >= 0, "analysis-only plan (device -1) cannot run: there is no CPU fallback");
     LB_REQUIRE(d_rho && B >= 1 && nsteps >= 0, "bad arguments");
-    LB_REQUIRE(p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
+    LB_REQUIRE(p->step_vals || p->nb == 1 || p->nb == B, "operator batch %d != B %d", p->nb, B);
+    LB_REQUIRE(!p->step_vals || nsteps <= p->nb, "per-step operator values cover %d steps, %d requested", p->nb, nsteps);
     LB_REQUIRE(p->D.empty() || d_coef, "drive operators present but d_coef is NULL");
     LB_REQUIRE(!d_traj || traj_every >= 1, "traj_every must be >= 1");
     LB_CUDA(cudaSetDevice(p->device));

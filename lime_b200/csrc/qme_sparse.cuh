@@ -42,6 +42,7 @@ struct QmeEllArgs {
     cplx* traj;
     double dt;
     // cluster kernel geometry
+    int step_vals;          // operator values are indexed by the RK4 STEP (time-dependent generator), not by the batch point
     int rows_per_cta;       // owned rows per CTA
     int halo;               // rows needed above/below the owned block
 };
@@ -111,13 +112,15 @@ qme_ell_global(QmeEllArgs a) {
     __shared__ cplx red[32];
     const int N = a.N, NN = N * N;
     const int b = blockIdx.x;
-    const size_t vb = (a.nb > 1) ? (size_t)b : 0;
     cplx* rho = a.rho + (size_t)b * NN;
     cplx* y0 = a.ybuf + (size_t)b * NN;
     cplx* y1 = a.ybuf + ((size_t)a.B + b) * NN;
     cplx* acc = a.accbuf + (size_t)b * NN;
     const double dt = a.dt, hdt = 0.5 * a.dt;
     for (int step = 0; step < a.nsteps; ++step) {
+        // driven problems (_lindblad_driven with CSR operands, lime/oqs.py:1691-1800): one set of generator values per
+        // step, frozen over the four stages
+        const size_t vb = a.step_vals ? (size_t)step : ((a.nb > 1) ? (size_t)b : 0);
         for (int stage = 0; stage < 4; ++stage) {
             const cplx* yin = (stage == 0) ? rho : ((stage == 2) ? y1 : y0);
             cplx* yout = (stage == 1) ? y1 : y0;

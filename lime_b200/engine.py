@@ -76,6 +76,10 @@ class QmePlan:
         ip, ix, d, nnz, nb = _csr_parts(pattern, data)
         check(lib().limeb200_qme_set_generator_csr(self._h, hptr(ip), hptr(ix), hptr(d), nnz, nb))
 
+    def set_step_values(self, on=True):
+        """the generator batch index is the RK4 step (time-dependent sparse generator)"""
+        check(lib().limeb200_qme_set_step_values(self._h, 1 if on else 0))
+
     def add_sandwich(self, X, Z=None):
         Z = X if Z is None else Z
         if issparse(X) and issparse(Z):

@@ -193,6 +193,47 @@ def _lindblad_driven(H, rho0, c_ops=None, e_ops=None, Nt=1, dt=0.005, t0=0.,
                  dtype=complex).reshape(Nt, nd)
     if strict_parity:
         f = np.cumsum(f, axis=0)
+    # CSR operands with real drive envelopes (Hermitian H(t)): the sparse kernel with ONE set of generator values per step,
+    # G_k = -i (H0 - sum_i f_i(t_k) H_i) - 1/2 sum l^dag l on the union sparsity pattern (limeb200_qme_set_step_values).
+    # Complex envelopes (lime's Pulse.efield) make H(t) non-Hermitian: that case needs the separate right generator of
+    # the dense kernel below.
+    if (Nt > 0 and issparse(H[0]) and all(issparse(H[i][0]) for i in range(1, len(H))) and _all_sparse(c_ops)
+            and np.all(f.imag == 0) and _is_hermitian(H[0]) and all(_is_hermitian(H[i][0]) for i in range(1, len(H)))):
+        Hs = [csr_matrix(H[0]).astype(complex)] + [csr_matrix(H[i][0]).astype(complex) for i in range(1, len(H))]
+        ls = [csr_matrix(l).astype(complex) for l in c_ops]
+        diss = csr_matrix((N, N), dtype=complex)
+        for l in ls:
+            diss = diss - 0.5 * (l.conj().T @ l)
+        upat = csr_matrix((N, N))
+        for m in Hs + [diss]:
+            a = abs(m)
+            a.data[:] = 1.0
+            upat = upat + a
+        upat = csr_matrix(upat)
+        upat.sum_duplicates()
+        upat.sort_indices()
+        rows = np.repeat(np.arange(N), np.diff(upat.indptr))
+        cols = upat.indices
+        onto = [np.asarray(m.todense())[rows, cols] for m in Hs]
+        dvals = np.asarray(diss.todense())[rows, cols]
+        vals = (-1j * onto[0] + dvals)[None, :] + sum((1j * f[:, i - 1].real)[:, None] * onto[i][None, :]
+                                                      for i in range(1, len(H)))
+        upat.data[:] = 1.0
+        plan = engine.QmePlan(N)
+        plan.set_generator_csr_batch(upat, np.ascontiguousarray(vals, dtype=np.complex128))
+        for l in ls:
+            plan.add_sandwich(l, l)
+        plan.set_step_values(True)
+        plan.set_observables(e_ops)
+        plan.finalize()
+        rho_f, obs, traj = plan.run(_dev.as_c128(rho0), dt, Nt, traj_every=1 if return_result else 0)
+        if return_result:
+            result = Result(dt=dt, Nt=Nt, rho0=rho0)
+            result.observables = obs if obs is not None else np.zeros((Nt, 0), dtype=complex)
+            result.rholist = [traj[k] for k in range(Nt)]
+            return result
+        _write_obs_file('obs.dat', times, obs if obs is not None else np.zeros((Nt, 0), dtype=complex))
+        return rho_f
     # H(t_k) = H0 - sum_i f_i H_i  ->  G_k = G0 + sum_i f_i (i H_i),  Gr_k = Gr0 + sum_i f_i (-i H_i);
     # f_i may be complex (lime's Pulse.efield), H(t) is then not Hermitian and lime still
     # evaluates the plain commutator

@@ -342,6 +342,18 @@ def main():
     np.savez_compressed(os.path.join(GOLD, 'sesolver.npz'), A=ops[0], B=ops[1], C=ops[2], **g)
 
 
+
+    # ---- _lindblad_driven with CSR operands (and a CSR rho0, the only way lime runs them), real drive envelope
+    Hj, cj, ej, rj = cases.jc_point(ncav=6)
+    H1 = np.kron(np.array([[0, 1.], [1, 0]]), np.identity(6))
+    fdr = lambda t: 0.2 * np.exp(-(t - 0.2) ** 2 / 0.02) * np.cos(3 * t)
+    rdr = quiet(oqs._lindblad_driven, [csr_matrix(Hj), [csr_matrix(H1), fdr]], csr_matrix(rj), c_ops=[csr_matrix(c) for c in cj],
+                e_ops=[csr_matrix(e) for e in ej], Nt=40, dt=0.01, t0=0.05)
+    odr, rldr = lo.lindblad_driven([Hj.copy(), [H1, fdr]], rj, cj, ej, Nt=40, dt=0.01, t0=0.05)
+    note('lindblad_driven_csr', obs=relerr(odr, rdr.observables), rho=relerr(rldr[-1], rdr.rholist[-1].toarray()))
+    np.savez_compressed(os.path.join(GOLD, 'lindblad_driven_csr.npz'), H1=H1, obs=rdr.observables,
+                        rho_final=rdr.rholist[-1].toarray(), rho_mid=rdr.rholist[19].toarray())
+
     # ---- laser-driven wave-function dynamics, SESolver.run(pulse=...) -> driven_dynamics, lime/mol.py:1094-1171,1473-1560
     class _Pulse:                       # the two attributes SESolver.run uses of lime.optics.Pulse: .efield(t)
         def __init__(self, a, w, tc, sig):

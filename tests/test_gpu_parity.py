@@ -201,6 +201,34 @@ def test_lindblad_driven(cuda):
     assert relerr(res.observables, o) <= TOL and relerr(res.rholist[-1], rl[-1]) <= TOL
 
 
+def test_lindblad_driven_csr_operands(cuda):
+    """_lindblad_driven with CSR operands and a real envelope: the sparse kernel with one set of generator values per
+    step (limeb200_qme_set_step_values); a complex envelope falls to the dense kernel with its own right generator"""
+    from scipy.sparse import csr_matrix
+    from lime_b200 import oqs
+    g = golden('lindblad_driven_csr')
+    Hj, cj, ej, rj = cases.jc_point(ncav=6)
+    fdr = lambda t: 0.2 * np.exp(-(t - 0.2) ** 2 / 0.02) * np.cos(3 * t)
+    Hl = [csr_matrix(Hj), [csr_matrix(g['H1']), fdr]]
+    res = oqs._lindblad_driven(Hl, csr_matrix(rj), c_ops=[csr_matrix(c) for c in cj], e_ops=[csr_matrix(e) for e in ej],
+                               Nt=40, dt=0.01, t0=0.05)
+    assert relerr(res.observables, g['obs']) <= TOL
+    assert relerr(res.rholist[-1], g['rho_final']) <= TOL and relerr(res.rholist[19], g['rho_mid']) <= TOL
+    # same problem, larger cavity (N = 64: the cluster / tile regime for static operators), sparse vs oracle
+    Hb, cb, eb, rb = cases.jc_point(ncav=32)
+    H1b = np.kron(np.array([[0, 1.], [1, 0]]), np.identity(32))
+    o, rl = lo.lindblad_driven([Hb.copy(), [H1b, fdr]], rb, cb, eb, Nt=25, dt=0.01, t0=0.0)
+    res = oqs._lindblad_driven([csr_matrix(Hb), [csr_matrix(H1b), fdr]], rb, c_ops=[csr_matrix(c) for c in cb], e_ops=eb,
+                               Nt=25, dt=0.01)
+    assert relerr(res.observables, o) <= TOL and relerr(res.rholist[-1], rl[-1]) <= TOL
+    # complex envelope with CSR operands: dense kernel
+    fc = lambda t: 0.2 * np.exp(-(t - 0.2) ** 2 / 0.02) * np.exp(-3j * t)
+    o, rl = lo.lindblad_driven([Hj.copy(), [g['H1'], fc]], rj, cj, ej, Nt=20, dt=0.01, t0=0.0)
+    res = oqs._lindblad_driven([csr_matrix(Hj), [csr_matrix(g['H1']), fc]], rj, c_ops=[csr_matrix(c) for c in cj], e_ops=ej,
+                               Nt=20, dt=0.01)
+    assert relerr(res.observables, o) <= TOL and relerr(res.rholist[-1], rl[-1]) <= TOL
+
+
 def test_lindblad_correlations(cuda):
     from lime_b200.oqs import Lindblad_solver
     g = golden('lindblad_corr')

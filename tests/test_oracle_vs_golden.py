@@ -230,6 +230,15 @@ class _GoldPulse:
         return self.a * np.exp(-(t - self.tc) ** 2 / 2. / self.sig ** 2) * np.exp(-1j * self.w * (t - self.tc))
 
 
+def test_lindblad_driven_csr_operands():
+    """_lindblad_driven with scipy.sparse operands (lime/oqs.py:1691-1800): `Ht += ...` rebinds, no accumulation"""
+    g = golden('lindblad_driven_csr')
+    Hj, cj, ej, rj = cases.jc_point(ncav=6)
+    fdr = lambda t: 0.2 * np.exp(-(t - 0.2) ** 2 / 0.02) * np.cos(3 * t)
+    o, rl = lo.lindblad_driven([Hj.copy(), [g['H1'], fdr]], rj, cj, ej, Nt=40, dt=0.01, t0=0.05)
+    assert relerr(o, g['obs']) <= TOL and relerr(rl[-1], g['rho_final']) <= TOL and relerr(rl[19], g['rho_mid']) <= TOL
+
+
 def test_sesolver_driven():
     """SESolver.run(pulse=...) -> driven_dynamics, lime/mol.py:1094-1171, 1473-1560"""
     g = golden('sesolver_driven')
