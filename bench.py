@@ -608,7 +608,7 @@ class HeomFMO(HeomBase):
                 self.nhe = self.h.nhe
                 self.exchange = self.h.exchange
                 self.kernel = ('heom_flow_kernel (dataflow: tagged stage vectors, peer stores, no barrier)' if self.h.exchange == 'flow'
-                               else 'heom_persist_cached_kernel (fused peer stores + one-hop barrier)' if self.h.exchange == 'p2p'
+                               else 'heom_persist_kernel / heom_persist_cached_kernel (fused peer stores + one-hop barrier)' if self.h.exchange == 'p2p'
                                else 'heom_stage_kernel + NCCL all_gather (CUDA graph)')
             else:
                 self.h = HEOM(self.Hm, self.Q, self.lam, self.gam, self.kT, N_exp=2, N_cut=self.depth)
