@@ -608,6 +608,7 @@ class HeomFMO(HeomBase):
                 self.nhe = self.h.nhe
                 self.exchange = self.h.exchange
                 self.kernel = ('heom_flow_kernel (dataflow: tagged stage vectors, peer stores, no barrier)' if self.h.exchange == 'flow'
+                               else 'heom_persist_kernel (grid barrier inside the GPU, tagged halo over NVLink between GPUs)' if self.h.exchange == 'halo'
                                else 'heom_persist_kernel / heom_persist_cached_kernel (fused peer stores + one-hop barrier)' if self.h.exchange == 'p2p'
                                else 'heom_stage_kernel + NCCL all_gather (CUDA graph)')
             else:
@@ -1098,7 +1099,7 @@ def main():
     ap.add_argument('--batch', type=int, default=0, help='units per GPU (0 = workload default)')
     ap.add_argument('--size', type=int, default=0, help='Hilbert dimension for lindblad_dense (0 = 256)')
     ap.add_argument('--depth', type=int, default=0, help='HEOM depth for heom_fmo (0 = 4)')
-    ap.add_argument('--exchange', default='auto', choices=['auto', 'flow', 'p2p', 'nccl'],
+    ap.add_argument('--exchange', default='auto', choices=['auto', 'flow', 'halo', 'p2p', 'nccl'],
                     help='sharded heom_fmo: dataflow kernel (auto/flow), barrier kernel with peer stores (p2p) or stage kernel + NCCL all-gather')
     ap.add_argument('--cpu-seconds', type=float, default=8.0, help='per-process budget of the cpu_baseline sample')
     ap.add_argument('--no-cpu', action='store_true')

@@ -256,6 +256,13 @@ int limeb200_heom_flow_unpack(limeb200_heom_t plan, const void* d_T0, unsigned l
 int limeb200_heom_flow_run_sharded(limeb200_heom_t plan, int rank, int world, void* const* d_T0, void* const* d_T1,
                                    double* d_rho, const unsigned char* d_peer_mask, double dt, int nsteps,
                                    unsigned long long tag0, void* stream);
+/* Hybrid of the two: the barrier kernel (plain 16-byte elements, grid barrier) INSIDE each GPU, the tagged halo of the
+ * dataflow kernel BETWEEN the GPUs -- rows owned by other ranks are polled in the tagged inbox d_T0 / d_T1 (buffers and
+ * tags as for flow_run_sharded; use flow_pack before and flow_unpack after), no cross-GPU barrier.  For shards that
+ * are too large for the dataflow kernel's one-element-per-thread regime.                                             */
+int limeb200_heom_run_sharded_halo(limeb200_heom_t plan, int rank, int world, void* const* d_T0, void* const* d_T1,
+                                   double* d_rho, const unsigned char* d_peer_mask, double dt, int nsteps,
+                                   unsigned long long tag0, void* stream);
 /* 1 when a bounded spin of the last sharded run timed out (a peer never arrived), else 0 */
 int limeb200_heom_sharded_error(limeb200_heom_t plan, void* stream);
 

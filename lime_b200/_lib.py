@@ -66,6 +66,7 @@ SIGNATURES = {
     'limeb200_heom_flow_pack': (c_int, [c_vp, c_vp, c_vp, C.c_ulonglong, c_vp]),
     'limeb200_heom_flow_unpack': (c_int, [c_vp, c_vp, C.c_ulonglong, c_vp, c_vp]),
     'limeb200_heom_flow_run_sharded': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_ulonglong, c_vp]),
+    'limeb200_heom_run_sharded_halo': (c_int, [c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_dbl, c_int, C.c_ulonglong, c_vp]),
     'limeb200_heom_sharded_error': (c_int, [c_vp, c_vp]),
     'limeb200_heom_dl_euler': (c_int, [c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_int, c_dbl, c_int, c_vp, c_vp]),
     'limeb200_sos_factor': (c_int, [c_vp, c_int, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_vp]),

@@ -147,6 +147,14 @@ struct HeomStageArgs {
     cplx* peer_next[7];     // the same element of every peer GPU's stage vector (NVLink stores)
     const unsigned char* peer_mask;   // [nhe] bit q set: peer slot q reads this ADO (null or send_all: every peer)
     int send_all;
+    // hybrid sharding (tagged halo): rows owned by OTHER ranks are not in yin but in a tagged inbox -- entry e = two
+    // 16-byte words {value bits, 64-bit stage tag} written by the owner over NVLink -- and are polled there; new values
+    // go to the peers' inboxes as tagged entries instead of plain elements.  Null tag_in: everything is in yin.
+    const ulonglong2* tag_in;
+    ulonglong2* tag_out_peer[7];
+    ulonglong2* tag_out_own;          // own inbox, written at the last stage of a run only (uniform unpack)
+    unsigned long long tag_want;      // tag of the stage input
+    unsigned* tag_err;
 };
 
 // L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
@@ -193,6 +201,44 @@ __device__ __forceinline__ void heom_bath_diag(const HeomDev& d, int par, const 
         const cplx yu = y[(size_t)max(iu, 0) * d.nn + idx];
         if (id >= 0) cfma(k, heom_dn_coef(d, par, m, (double)st[m], v), yd);
         if (iu >= 0) cfma(k, cscale(v.x - v.y, d.pref_up), yu);
+    }
+}
+
+// value of element `e` of the stage input: from yin when its ADO is owned by this rank, else from the tagged inbox
+// (polled until the owner's entry for this stage has arrived; bounded, sets *err on time-out)
+__device__ __forceinline__ cplx heom_read_halo(const HeomStageArgs& a, const cplx* y, long long ado_nb, size_t e) {
+    if (!a.tag_in || (ado_nb >= a.row_lo && ado_nb < a.row_hi)) return y[e];
+    const ulonglong2* p = a.tag_in + 2 * e;
+    ulonglong2 w0, w1;
+    const long long t0 = clock64();
+    unsigned spins = 0;
+    while (true) {
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0.x), "=l"(w0.y) : "l"(p) : "memory");
+        asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w1.x), "=l"(w1.y) : "l"(p + 1) : "memory");
+        if (w0.y == a.tag_want && w1.y == a.tag_want) break;
+        if (((++spins & 1023u) == 0) && (clock64() - t0 > 10000000000LL || *(volatile unsigned*)a.tag_err)) {
+            atomicExch(a.tag_err, 1u);
+            break;
+        }
+    }
+    return cmake(__longlong_as_double((long long)w0.x), __longlong_as_double((long long)w1.x));
+}
+__device__ __forceinline__ void heom_store_tagged(ulonglong2* T, size_t e, cplx v, unsigned long long tag) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(T + 2 * e), "l"((unsigned long long)__double_as_longlong(v.x)), "l"(tag) : "memory");
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(T + 2 * e + 1), "l"((unsigned long long)__double_as_longlong(v.y)), "l"(tag) : "memory");
+}
+// bath part with a tagged halo: as heom_bath_diag, but every existing neighbour is READ (and so waited for) even when
+// its coefficient vanishes -- that keeps the read graph symmetric, which is what makes the inbox ping-pong safe
+__device__ __forceinline__ void heom_bath_diag_halo(const HeomStageArgs& a, int par, const int* st, const int* dn,
+                                                    const int* up, int idx, const cplx* y, cplx& k) {
+    const HeomDev& d = a.d;
+    const int t1 = __ldg(d.em_start + idx + 1);
+    for (int t = __ldg(d.em_start + idx); t < t1; ++t) {
+        const int m = __ldg(d.em_mode + t);
+        const double2 v = __ldg(d.em_v + t);
+        const int id = dn[m], iu = up[m];
+        if (id >= 0) cfma(k, heom_dn_coef(d, par, m, (double)st[m], v), heom_read_halo(a, y, id, (size_t)id * d.nn + idx));
+        if (iu >= 0) cfma(k, cscale(v.x - v.y, d.pref_up), heom_read_halo(a, y, iu, (size_t)iu * d.nn + idx));
     }
 }
 
@@ -291,7 +337,7 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const int* dn = tabs ? tabs + (size_t)(3 * g + 1) * nm : d.dn + ado * nm;
     const int* up = tabs ? tabs + (size_t)(3 * g + 2) * nm : d.up + ado * nm;
     if (d.diagq) {
-        if (act) heom_bath_diag(d, par, st, dn, up, idx, y, k);
+        if (act) { if (a.tag_in) heom_bath_diag_halo(a, par, st, dn, up, idx, y, k); else heom_bath_diag(d, par, st, dn, up, idx, y, k); }
     } else {
         for (int q = 0; q < d.nq; ++q) {
             cplx L = cmake(0, 0), R = cmake(0, 0);
@@ -318,7 +364,11 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
         if (a.npeer) {
             const unsigned m = (a.send_all || !a.peer_mask) ? 0xffu : a.peer_mask[ado];
             for (int r = 0; r < a.npeer; ++r)
-                if ((m >> r) & 1u) a.peer_next[r][o] = yn;
+                if ((m >> r) & 1u) {
+                    if (a.tag_in) heom_store_tagged(a.tag_out_peer[r], o, yn, a.tag_want + 1);
+                    else a.peer_next[r][o] = yn;
+                }
+            if (a.tag_in && a.send_all) heom_store_tagged(a.tag_out_own, o, yn, a.tag_want + 1);
         }
         if (a.stage == 3) a.rho[o] = *rreg;
         return;
@@ -331,7 +381,11 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     if (a.npeer) {
         const unsigned m = (a.send_all || !a.peer_mask) ? 0xffu : a.peer_mask[ado];
         for (int p = 0; p < a.npeer; ++p)
-            if ((m >> p) & 1u) a.peer_next[p][o] = yn;
+            if ((m >> p) & 1u) {
+                if (a.tag_in) heom_store_tagged(a.tag_out_peer[p], o, yn, a.tag_want + 1);
+                else a.peer_next[p][o] = yn;
+            }
+        if (a.tag_in && a.send_all) heom_store_tagged(a.tag_out_own, o, yn, a.tag_want + 1);
     }
 }
 
@@ -359,6 +413,11 @@ struct HeomPersistArgs {
     unsigned* flagp[7];               // peers' flag arrays; peer q's slot for this rank is flagp[q][rank]
     unsigned* flags;                  // this rank's flag array [world]: flags[q] counts the CTA arrivals of rank q
     unsigned peer_grid[7];            // CTAs of the persistent kernel on peer slot q (its arrivals per stage)
+    // hybrid sharding: local grid barrier + tagged halo inboxes (T[b] local, Tp[b][q] the peers'), tags tag0 + stage count
+    int hybrid;
+    ulonglong2* T[2];
+    ulonglong2* Tp[2][7];
+    unsigned long long tag0;
     const unsigned char* peer_mask;   // [nhe] which peer slots need each owned ADO (null: all); the last stage of the
                                       // run always goes to every peer so that each rank ends with the full state
 };
@@ -463,6 +522,13 @@ heom_persist_kernel(HeomPersistArgs p) {
             a.peer_mask = p.peer_mask;
             a.send_all = (step == p.nsteps - 1 && stage == 3) ? 1 : 0;
             for (int q = 0; q < p.world - 1; ++q) a.peer_next[q] = (stage & 1) ? p.y0p[q] : p.y1p[q];
+            if (p.hybrid) {
+                a.tag_in = p.T[stage & 1];
+                a.tag_out_own = p.T[(stage + 1) & 1];
+                for (int q = 0; q < p.world - 1; ++q) a.tag_out_peer[q] = p.Tp[(stage + 1) & 1][q];
+                a.tag_want = p.tag0 + 4ull * step + stage;
+                a.tag_err = p.barrier + 2;
+            }
             if (fixed) {
                 if (blockIdx.x < ntiles) heom_stage_tile(a, (long long)blockIdx.x * a.apc, smem, tabs, &rreg, &areg);
             } else {
@@ -472,8 +538,8 @@ heom_persist_kernel(HeomPersistArgs p) {
                 }
             }
             bar_target += gridDim.x;
-            if (p.world > 1) heom_world_barrier(p, bar_target, p.epoch + 4u * step + stage + 1u);
-            else heom_grid_barrier(p.barrier, bar_target);
+            if (p.world > 1 && !p.hybrid) heom_world_barrier(p, bar_target, p.epoch + 4u * step + stage + 1u);
+            else heom_grid_barrier(p.barrier, bar_target);      // hybrid: the ranks are coupled through the tagged halo only
         }
         // y0 == rho_{n+1}; tier-0 observables / trajectory: one warp per (hierarchy, observable)
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -1258,7 +1324,7 @@ struct HeomPersistCfg {
     size_t smem = 0;
     bool one_tile_per_cta = false;
 };
-static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c) {
+static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c, bool allow_cached = true) {
     const int nn = p->n * p->n;
     const long long total = p->nhe * nn;
     const long long nown = p->row_hi - p->row_lo;
@@ -1282,7 +1348,7 @@ static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c) {
     c.smem = (size_t)(1 + 3 * c.apc) * nn * 16 + (size_t)3 * c.apc * p->nmodes * 4;
     c.one_tile_per_cta = ceil_div(nitems, (long long)c.apc) <= (long long)per_sm * p->sm_count;
     const size_t smem_c = (size_t)(1 + c.apc) * nn * 16 + (size_t)HEOM_PC_NE * c.threads * 20;
-    if (p->diagq && c.one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
+    if (allow_cached && p->diagq && c.one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
         (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
         c.kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
         c.smem = smem_c;
@@ -1302,7 +1368,7 @@ static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c) {
 static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho, int B, double dt, int nsteps,
                                cudaStream_t st, bool require_one_tile_per_cta = false) {
     HeomPersistCfg c;
-    int r = heom_persist_config(p, B, c);
+    int r = heom_persist_config(p, B, c, !pa.hybrid);      // the tagged-halo mode lives in the generic tile code
     if (r != LB_OK) return r;
     // larger problems gain nothing from persistence (the per-stage launches are already long) and
     // run better with the smaller CTAs of the stage-wise kernel
@@ -1687,6 +1753,40 @@ int limeb200_heom_flow_run_sharded(limeb200_heom_t p, int rank, int world, void*
     fa.tag0 = tag0;
     int r = heom_flow_launch(p, fa, (cplx*)d_rho, dt, nsteps, (cudaStream_t)stream);
     if (r == LB_ERR_UNSUPPORTED) limeb200::set_error("the dataflow sharded kernel does not support this plan");
+    return r;
+}
+
+/* hybrid sharded propagator: barrier kernel inside each GPU, tagged halo between the GPUs (no cross-GPU barrier) */
+int limeb200_heom_run_sharded_halo(limeb200_heom_t p, int rank, int world, void* const* d_T0, void* const* d_T1,
+                                   double* d_rho, const unsigned char* d_peer_mask, double dt, int nsteps,
+                                   unsigned long long tag0, void* stream) {
+    LB_REQUIRE(p && d_T0 && d_T1 && d_rho, "null argument");
+    LB_REQUIRE(world >= 1 && world <= 8 && rank >= 0 && rank < world, "world must be 1..8");
+    LB_REQUIRE(p->npar == 1 && p->diagq, "the tagged-halo propagator takes one hierarchy with diagonal coupling operators");
+    LB_REQUIRE(nsteps >= 0 && tag0 >= 1, "bad nsteps / tag0");
+    LB_CUDA(cudaSetDevice(p->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    p->launches = 0;
+    if (nsteps == 0) return LB_OK;
+    const long long total = p->nhe * p->n * p->n;
+    if (p->s_y.bytes < (size_t)2 * total * 16) LB_CUDA(p->s_y.alloc((size_t)2 * total * 16));
+    if (p->s_acc.bytes < (size_t)total * 16) LB_CUDA(p->s_acc.alloc((size_t)total * 16));
+    HeomPersistArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world; pa.rank = rank; pa.hybrid = 1; pa.tag0 = tag0;
+    pa.peer_mask = d_peer_mask;
+    pa.y0 = p->s_y.as<cplx>(); pa.y1 = p->s_y.as<cplx>() + (size_t)total;
+    pa.T[0] = (ulonglong2*)d_T0[rank]; pa.T[1] = (ulonglong2*)d_T1[rank];
+    int q = 0;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        pa.Tp[0][q] = (ulonglong2*)d_T0[r]; pa.Tp[1][q] = (ulonglong2*)d_T1[r];
+        ++q;
+    }
+    // local rows of the stage input come from y0; d_rho holds the full state on entry
+    LB_CUDA(cudaMemcpyAsync(pa.y0, d_rho, (size_t)total * 16, cudaMemcpyDeviceToDevice, st));
+    int r = heom_launch_persist(p, pa, (cplx*)d_rho, 1, dt, nsteps, st);
+    if (r == LB_ERR_UNSUPPORTED) limeb200::set_error("persistent sharded kernel cannot be launched on this device");
     return r;
 }
 

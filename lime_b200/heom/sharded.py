@@ -22,6 +22,9 @@ Two data paths:
                   in the same 16-byte words as its value; owners store new entries locally and into the buffers of the
                   ranks that read them, consumers poll exactly the entries they need in their own memory -- one one-way
                   NVLink traversal per stage instead of store acknowledgement + flag + barrier.
+  exchange='halo' (default for larger shards with diagonal coupling operators) hybrid: the barrier kernel with plain
+                  16-byte elements and a grid barrier INSIDE each GPU, the tagged halo of the dataflow kernel BETWEEN the
+                  GPUs (rows owned by other ranks are polled in a tagged inbox; no cross-GPU barrier).
   exchange='nccl' CUDA stage kernel -> NCCL all-gather, 4 x per step, captured in a CUDA graph.
 `stage_fn` is a seam for the world_size-2 gloo tests of this host logic (they plug a CPU stage
 function built from the oracle); the product path always uses the CUDA plan.
@@ -85,7 +88,7 @@ class ShardedHEOM:
         self.states, self.dn, self.up = engine.heom_tables([N_cut + 1] * self.nmodes, N_cut)
         self.nhe = self.states.shape[0]
         self.chunk, self.ranges = partition(self.nhe, self.world)
-        if exchange in ('p2p', 'flow', 'auto') and stage_fn is None:
+        if exchange in ('p2p', 'flow', 'halo', 'auto') and stage_fn is None:
             # checked identically on every rank BEFORE any IPC set-up, so that all ranks raise together
             if self.world > 8:
                 raise ValueError('exchange="p2p" supports at most 8 ranks (one NVSwitch box); use exchange="nccl"')
@@ -110,7 +113,7 @@ class ShardedHEOM:
             self.plan = engine.HeomPlan(self.H, self.Q, self.qmap, self.c, self.nu, self.states, self.dn, self.up,
                                         pref_dn=pref_dn, pref_up=pref_up, row_range=(self.lo, self.hi),
                                         device_index=self.dev.index)
-            if self.exchange in ('auto', 'flow'):
+            if self.exchange in ('auto', 'flow', 'halo'):
                 from .._lib import lib
                 # 0: not supported (dense coupling operators ...), 1: tiled variant, 2: register-resident variant.
                 # 'auto' takes the dataflow kernel in the regime it is built for (2: a few thousand elements per SM, where
@@ -121,11 +124,11 @@ class ShardedHEOM:
                     levels = [None] * self.world
                     dist.all_gather_object(levels, level, group=self.group)
                     level = min(levels)
-                if self.exchange == 'flow' and level < 1:
-                    raise ValueError("exchange='flow' needs diagonal coupling operators with at most 4 modes per matrix "
-                                     "element; use exchange='p2p'")
+                if self.exchange in ('flow', 'halo') and level < 1:
+                    raise ValueError("exchange='%s' needs diagonal coupling operators with at most 4 modes per matrix "
+                                     "element; use exchange='p2p'" % self.exchange)
                 if self.exchange == 'auto':
-                    self.exchange = 'flow' if (level == 2 and self.world > 1) else 'p2p'
+                    self.exchange = 'p2p' if (level < 1 or self.world == 1) else ('flow' if level == 2 else 'halo')
         else:
             self.dev = torch.device('cpu') if device is None else device
             self.plan = None
@@ -158,7 +161,7 @@ class ShardedHEOM:
         from .._lib import lib, check
         nbytes = self.nhe_pad * self.n * self.n * 16
         mine, handles = [], []
-        flow = self.exchange == 'flow'
+        flow = self.exchange in ('flow', 'halo')
         # flow: two TAGGED stage vectors (32 bytes per element) and no flag array (third buffer unused)
         for size in ((2 * nbytes, 2 * nbytes, 256) if flow else (nbytes, nbytes, 256)):
             ptr = C.c_void_p()
@@ -264,9 +267,9 @@ class ShardedHEOM:
         if self.peer_mask is not None and self._d_mask is None:
             self._d_mask = torch.from_numpy(self.peer_mask).to(ado.device)
         mptr = C.c_void_p(self._d_mask.data_ptr()) if self._d_mask is not None else None
-        check(lib().limeb200_heom_flow_run_sharded(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1],
-                                                   C.c_void_p(rho.data_ptr()), mptr, float(dt), int(nsteps),
-                                                   C.c_ulonglong(tag0), sp))
+        run = lib().limeb200_heom_flow_run_sharded if self.exchange == 'flow' else lib().limeb200_heom_run_sharded_halo
+        check(run(self.plan._h, self.rank, self.world, pr['arr'][0], pr['arr'][1], C.c_void_p(rho.data_ptr()), mptr,
+                  float(dt), int(nsteps), C.c_ulonglong(tag0), sp))
         torch.cuda.synchronize()
         if self.world > 1:
             dist.barrier(group=self.group)        # all peers' last-stage stores have landed
@@ -287,7 +290,7 @@ class ShardedHEOM:
         """ado: [1, N_he, n, n] complex128 on self.dev, identical on every rank; advanced in place by
         nsteps RK4 steps (every rank ends up with the full hierarchy)."""
         assert ado.shape == (1, self.nhe, self.n, self.n) and ado.dtype == torch.complex128
-        if self.exchange == 'flow' and self._stage_fn is None and nsteps > 0:
+        if self.exchange in ('flow', 'halo') and self._stage_fn is None and nsteps > 0:
             return self._run_flow(ado, dt, nsteps)
         if self.exchange == 'p2p' and self._stage_fn is None and nsteps > 0:
             return self._run_p2p(ado, dt, nsteps)

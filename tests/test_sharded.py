@@ -173,7 +173,7 @@ def test_sharded_heom_single_rank_persistent_kernel(cuda):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('exchange', ['flow', 'p2p', 'p2p_all', 'nccl'])
+@pytest.mark.parametrize('exchange', ['flow', 'halo', 'p2p', 'p2p_all', 'nccl'])
 def test_sharded_heom_nccl_world2(exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
@@ -184,7 +184,7 @@ def test_sharded_heom_nccl_world2(exchange):
     assert np.array_equal(res[0][1], res[1][1])
 
 
-def _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, dt, runs, halo_only=True, flow=False):
+def _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, dt, runs, halo_only=True, flow=False, halo=False):
     """`world` ranks of the fused sharded kernel as `world` plans + streams on ONE GPU in one process: every rank's
     persistent kernel is resident at the same time (the grids are small), "peer" stores and the one-hop barrier go
     through ordinary device pointers instead of CUDA-IPC mappings.  Exercises limeb200_heom_run_sharded's cross-rank
@@ -210,8 +210,8 @@ def _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, dt, runs, halo
                              row_range=ranges[r], device_index=0) for r in range(world)]
     full = torch.zeros((1, nhe_pad, n, n), dtype=torch.complex128, device=dev)
     full[0, :nhe] = torch.from_numpy(ado0).to(dev)
-    if flow:
-        return _virtual_flow(world, plans, full, masks_of(dn, up, ranges, world, halo_only, dev), nhe, dt, runs), ranges
+    if flow or halo:
+        return _virtual_flow(world, plans, full, masks_of(dn, up, ranges, world, halo_only, dev), nhe, dt, runs, halo=halo), ranges
     y0 = [full.clone() for _ in range(world)]
     y1 = [torch.zeros_like(full) for _ in range(world)]
     rho = [full.clone() for _ in range(world)]
@@ -242,7 +242,7 @@ def masks_of(dn, up, ranges, world, halo_only, dev):
     return [torch.from_numpy(peer_masks(dn, up, ranges, r)).to(dev) if halo_only else None for r in range(world)]
 
 
-def _virtual_flow(world, plans, full, masks, nhe, dt, runs):
+def _virtual_flow(world, plans, full, masks, nhe, dt, runs, halo=False):
     """the dataflow kernel (tagged stage vectors, no barrier) with `world` ranks resident together on one GPU"""
     import ctypes as C
     from lime_b200._lib import lib, check
@@ -262,11 +262,11 @@ def _virtual_flow(world, plans, full, masks, nhe, dt, runs):
                                                 C.c_ulonglong(tag), None))
             rho[r].copy_(state)
         torch.cuda.synchronize()
+        run = lib().limeb200_heom_run_sharded_halo if halo else lib().limeb200_heom_flow_run_sharded
         for r in range(world):
-            check(lib().limeb200_heom_flow_run_sharded(plans[r]._h, r, world, arr[0], arr[1], C.c_void_p(rho[r].data_ptr()),
-                                                       C.c_void_p(masks[r].data_ptr()) if masks[r] is not None else None,
-                                                       float(dt), int(nsteps), C.c_ulonglong(tag),
-                                                       C.c_void_p(streams[r].cuda_stream)))
+            check(run(plans[r]._h, r, world, arr[0], arr[1], C.c_void_p(rho[r].data_ptr()),
+                      C.c_void_p(masks[r].data_ptr()) if masks[r] is not None else None,
+                      float(dt), int(nsteps), C.c_ulonglong(tag), C.c_void_p(streams[r].cuda_stream)))
         torch.cuda.synchronize()
         outs = []
         for r in range(world):
@@ -295,6 +295,39 @@ def test_sharded_dataflow_virtual_ranks_on_one_gpu(cuda, world, halo_only):
     for r, o in enumerate(outs):
         assert relerr(o, ref) <= 1e-10, r
         assert np.array_equal(o, outs[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 3])
+@pytest.mark.parametrize('halo_only', [True, False])
+def test_sharded_tagged_halo_virtual_ranks_on_one_gpu(cuda, world, halo_only):
+    """hybrid sharded propagator (grid barrier inside a rank, tagged halo between ranks), virtual ranks on one GPU"""
+    H, Q, lam, gam, T, depth, rho0 = _problem()
+    ref = _reference()
+    ado0 = np.zeros_like(ref)
+    ado0[0] = rho0
+    outs, ranges = _virtual_ranks_one_gpu(world, H, Q, lam, gam, T, depth, ado0, 0.01, [5, 7], halo_only=halo_only, halo=True)
+    for r, o in enumerate(outs):
+        assert relerr(o, ref) <= 1e-10, r
+        assert np.array_equal(o, outs[0])
+
+
+@pytest.mark.gpu
+def test_sharded_tagged_halo_fmo_depth3_long(cuda):
+    """hybrid propagator, FMO depth 3 over 3 virtual ranks, 200 steps, against the one-GPU barrier kernel"""
+    from lime_b200 import builders
+    from lime_b200.heom.heom import HEOM
+    from lime_b200.units import au2fs
+    Hm, Q, lam, gam, kT = builders.fmo_heom_inputs()
+    h = HEOM(Hm, Q, lam, gam, kT, N_exp=2, N_cut=3)
+    h.plan.set_path(3)
+    rho0 = np.zeros((7, 7), dtype=complex)
+    rho0[0, 0] = 1.0
+    dt = 0.5 / au2fs
+    one, _, _ = h.plan.run(h.initial(rho0), dt, 200)
+    outs, _ = _virtual_ranks_one_gpu(3, Hm, Q, lam, gam, kT, 3, h.initial(rho0), dt, [200], halo=True)
+    for o in outs:
+        assert relerr(o, one) <= 1e-12
 
 
 @pytest.mark.gpu
