@@ -22,7 +22,7 @@ Two data paths:
                   in the same 16-byte words as its value; owners store new entries locally and into the buffers of the
                   ranks that read them, consumers poll exactly the entries they need in their own memory -- one one-way
                   NVLink traversal per stage instead of store acknowledgement + flag + barrier.
-  exchange='halo' (default for larger shards with diagonal coupling operators) hybrid: the barrier kernel with plain
+  exchange='halo' (opt-in; measured slower than 'p2p', kept as the tested middle ground) hybrid: the barrier kernel with plain
                   16-byte elements and a grid barrier INSIDE each GPU, the tagged halo of the dataflow kernel BETWEEN the
                   GPUs (rows owned by other ranks are polled in a tagged inbox; no cross-GPU barrier).
   exchange='nccl' CUDA stage kernel -> NCCL all-gather, 4 x per step, captured in a CUDA graph.
@@ -128,7 +128,9 @@ class ShardedHEOM:
                     raise ValueError("exchange='%s' needs diagonal coupling operators with at most 4 modes per matrix "
                                      "element; use exchange='p2p'" % self.exchange)
                 if self.exchange == 'auto':
-                    self.exchange = 'p2p' if (level < 1 or self.world == 1) else ('flow' if level == 2 else 'halo')
+                    # ('halo' is never picked automatically: its per-neighbour polling serialises the gather -- 8.2e7 vs
+                    #  1.27e8 ADO-steps/s of the barrier kernel at 2 ranks, 38 760 ADOs)
+                    self.exchange = 'flow' if (level == 2 and self.world > 1) else 'p2p'
         else:
             self.dev = torch.device('cpu') if device is None else device
             self.plan = None

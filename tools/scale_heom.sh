@@ -1,9 +1,11 @@
-# sharded FMO hierarchy only: dataflow kernel vs barrier kernel at N ranks (N = $NG)
+# sharded FMO hierarchy: kernel variants at N ranks (N = $NG); EX = list of exchange modes, DEPTHS = list of depths
 NG=${NG:-2}
 run() { timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $NG "$@" --no-cpu 2>>gpurun_out/scale_heom.err | grep "^{" ; }
-for ex in ${EX:-flow p2p}; do
-  run --workload heom_fmo --depth 4 --rk-steps 400 --exchange $ex --steps 3 --warmup 3 >> gpurun_out/r02_scale_heom_$NG.jsonl
-  run --workload heom_fmo --depth 6 --rk-steps 50 --exchange $ex --steps 3 --warmup 3 >> gpurun_out/r02_scale_heom_$NG.jsonl
+for ex in ${EX:-auto p2p}; do
+  for d in ${DEPTHS:-4 6}; do
+    if [ $d = 4 ]; then rk=400; else rk=50; fi
+    run --workload heom_fmo --depth $d --rk-steps $rk --exchange $ex --steps 3 --warmup 3 >> gpurun_out/r02_scale_heom_$NG.jsonl
+  done
 done
 python - <<'PY'
 import json,os
