@@ -417,11 +417,12 @@ __device__ __forceinline__ void dmma8x8x4(double& d0, double& d1, double a, doub
 }
 
 #define QDM_KT 8
-#define QDM_LD 72        // 64 + 8 doubles of padding per k row
+#define QDM_LD 68        // 64 + 4 doubles of padding per k row: rows k, k+1, k+2, k+3 start 4 double-banks apart, so the 4 (k) x 4
+                         // (row) doubles a half-warp reads for one MMA fragment fall into 16 distinct banks (72 made k and k+2 collide)
 __global__ void __launch_bounds__(128, 2)
 qme_dense_stage_dmma(QmeStageArgs a) {
-    __shared__ double Ar[2][QDM_KT][QDM_LD], Ai[2][QDM_KT][QDM_LD];     // [buf][k][row]
-    __shared__ double Br[2][QDM_KT][QDM_LD], Bi[2][QDM_KT][QDM_LD];     // [buf][k][col]
+    __shared__ __align__(16) double Ar[2][QDM_KT][QDM_LD], Ai[2][QDM_KT][QDM_LD];     // [buf][k][row]
+    __shared__ __align__(16) double Br[2][QDM_KT][QDM_LD], Bi[2][QDM_KT][QDM_LD];     // [buf][k][col]
     const int N = a.N;
     const int Mr = a.Mr ? a.Mr : N, Nc = a.Nc ? a.Nc : N, Kd = a.Kd ? a.Kd : N;
     const int b = blockIdx.z;
@@ -454,10 +455,13 @@ qme_dense_stage_dmma(QmeStageArgs a) {
     };
     auto stash = [&](int buf) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            Ar[buf][la_k + u][la_r] = ra[u].x; Ai[buf][la_k + u][la_r] = ra[u].y;
-            Br[buf][lb_k][lb_c + u] = rb[u].x; Bi[buf][lb_k][lb_c + u] = rb[u].y;
-        }
+        for (int u = 0; u < 4; ++u) { Ar[buf][la_k + u][la_r] = ra[u].x; Ai[buf][la_k + u][la_r] = ra[u].y; }
+        // the 4 consecutive columns of a B row go out as two 16-byte stores per plane (scalar stores 32 bytes apart
+        // between lanes were a 4-way bank conflict)
+        *reinterpret_cast<double2*>(&Br[buf][lb_k][lb_c]) = make_double2(rb[0].x, rb[1].x);
+        *reinterpret_cast<double2*>(&Br[buf][lb_k][lb_c + 2]) = make_double2(rb[2].x, rb[3].x);
+        *reinterpret_cast<double2*>(&Bi[buf][lb_k][lb_c]) = make_double2(rb[0].y, rb[1].y);
+        *reinterpret_cast<double2*>(&Bi[buf][lb_k][lb_c + 2]) = make_double2(rb[2].y, rb[3].y);
     };
     fetch(0);
     stash(0);
