@@ -568,6 +568,45 @@ heom_persist_kernel(HeomPersistArgs p) {
     }
 }
 
+// The same two barriers split into ARRIVE (after a CTA's stores) and WAIT (before it reads other CTAs' values), so that
+// work which needs only the CTA's own data -- the -i[H, .] term of the NEXT stage -- runs while the arrivals propagate.
+__device__ __forceinline__ void heom_barrier_arrive(const HeomPersistArgs& p) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.barrier) : "memory");
+        if (p.world > 1) {
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (int q = 0; q < p.world - 1; ++q)
+                asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(p.flagp[q] + p.rank) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void heom_barrier_wait(const HeomPersistArgs& p, unsigned target, unsigned xcount) {
+    if (threadIdx.x == 0) {
+        const long long t0 = clock64();
+        const long long limit = 10000000000LL;
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.barrier) : "memory");
+        } while (v < target && (p.world == 1 || clock64() - t0 < limit));
+        if (p.world > 1) {
+            int slot = 0;
+            for (int q = 0; q < p.world; ++q) {
+                if (q == p.rank) continue;
+                const unsigned want = p.peer_grid[slot++] * xcount;
+                do {
+                    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p.flags + q) : "memory");
+                } while ((int)(v - want) < 0 && clock64() - t0 < limit);
+                if ((int)(v - want) < 0) atomicExch(p.barrier + 2, 1u);
+            }
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+        } else {
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        }
+    }
+    __syncthreads();
+}
+
 // Persistent kernel, diagonal Q, ONE element per thread for the whole run (apc ADOs per CTA,
 // every item has its own CTA slot): the element's <= NE neighbour offsets and coefficients are
 // computed once and kept in shared memory (structure-of-arrays, conflict-free), rho / the RK4
@@ -631,35 +670,10 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
     }
     __syncthreads();
     unsigned bar_target = 0;
-    for (int step = 0; step < p.nsteps; ++step) {
-#pragma unroll 1
-        for (int stage = 0; stage < 4; ++stage) {
-            const cplx* yin = (stage & 1) ? p.y1 : p.y0;
-            cplx* yout = (stage & 1) ? p.y0 : p.y1;
-            cplx nb[HEOM_PC_NE];
-#pragma unroll
-            for (int e = 0; e < HEOM_PC_NE; ++e) nb[e] = yin[eoff[e * T + threadIdx.x]];
-            const cplx yv = yin[own];
-            if (g < a.apc) ys[threadIdx.x] = yv;
-            __syncthreads();
-            cplx k = heom_sys_any(Hs, n, ys + (size_t)g * nn, i, j);
-            k.x = fma(-damp, yv.x, k.x);
-            k.y = fma(-damp, yv.y, k.y);
-#pragma unroll
-            for (int e = 0; e < HEOM_PC_NE; ++e) cfma(k, ecf[e * T + threadIdx.x], nb[e]);
-            const cplx yn = heom_rk_update(stage, k, rreg, areg, a.dt);
-            if (act) {
-                yout[own] = yn;
-                const unsigned m = (step == p.nsteps - 1 && stage == 3) ? 0xffu : pmask;
-                for (int q = 0; q < p.world - 1; ++q)
-                    if ((m >> q) & 1u) ((stage & 1) ? p.y0p[q] : p.y1p[q])[own] = yn;
-                if (stage == 3) a.rho[own] = rreg;
-            }
-            bar_target += gridDim.x;
-            if (p.world > 1) heom_world_barrier(p, bar_target, p.epoch + 4u * step + stage + 1u);
-            else heom_grid_barrier(p.barrier, bar_target);
-        }
-        // tier-0 observables / trajectory (a.rho was written before the barrier)
+    cplx ycur = rreg;                      // the element's value in the current stage vector (= its own last output)
+    // tier-0 observables / trajectory of a finished step (a.rho of every CTA is visible once that step's last barrier
+    // has been waited for)
+    auto outputs = [&](int step) {
         const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
         const int nwarps = (gridDim.x * blockDim.x) >> 5;
         if (p.obs)
@@ -681,6 +695,45 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
                 p.traj[((size_t)(step / p.traj_every) * a.B + bb) * nn + (l - bb * nn)] =
                     a.rho[(size_t)bb * d.nhe * nn + (l - bb * nn)];
             }
+    };
+    for (int step = 0; step < p.nsteps; ++step) {
+#pragma unroll 1
+        for (int stage = 0; stage < 4; ++stage) {
+            const cplx* yin = (stage & 1) ? p.y1 : p.y0;
+            cplx* yout = (stage & 1) ? p.y0 : p.y1;
+            // ---- the part of the right-hand side that needs only this CTA's own ADOs: -i[H, Y_a] and the damping.  It runs
+            // BEFORE the wait on the previous stage's barrier, i.e. while the other CTAs' arrivals propagate.
+            if (g < a.apc) ys[threadIdx.x] = ycur;
+            __syncthreads();
+            cplx k = heom_sys_any(Hs, n, ys + (size_t)g * nn, i, j);
+            k.x = fma(-damp, ycur.x, k.x);
+            k.y = fma(-damp, ycur.y, k.y);
+            if (step > 0 || stage > 0) {
+                heom_barrier_wait(p, bar_target, p.epoch + 4u * step + stage);
+                if (stage == 0) outputs(step - 1);
+            }
+            // ---- neighbour ADOs (other CTAs, other GPUs)
+            cplx nb[HEOM_PC_NE];
+#pragma unroll
+            for (int e = 0; e < HEOM_PC_NE; ++e) nb[e] = yin[eoff[e * T + threadIdx.x]];
+#pragma unroll
+            for (int e = 0; e < HEOM_PC_NE; ++e) cfma(k, ecf[e * T + threadIdx.x], nb[e]);
+            const cplx yn = heom_rk_update(stage, k, rreg, areg, a.dt);
+            if (act) {
+                yout[own] = yn;
+                const unsigned m = (step == p.nsteps - 1 && stage == 3) ? 0xffu : pmask;
+                for (int q = 0; q < p.world - 1; ++q)
+                    if ((m >> q) & 1u) ((stage & 1) ? p.y0p[q] : p.y1p[q])[own] = yn;
+                if (stage == 3) a.rho[own] = rreg;
+            }
+            ycur = yn;
+            bar_target += gridDim.x;
+            heom_barrier_arrive(p);
+        }
+    }
+    if (p.nsteps > 0) {
+        heom_barrier_wait(p, bar_target, p.epoch + 4u * p.nsteps);
+        outputs(p.nsteps - 1);
     }
 }
 

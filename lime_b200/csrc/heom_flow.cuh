@@ -316,6 +316,13 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 if (!act[u]) continue;
+                // -i[H, Y_a] and the damping need only this CTA's own ADOs: computed first, which also gives the producers of the
+                // neighbour entries time to publish them before the first poll round
+                const int i = idx[u] / n, j = idx[u] - i * n;
+                cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)gg[u] * nn, i, j)
+                             : heom_sys(Hs, n, ys + (size_t)gg[u] * nn, i, j);
+                k.x = fma(-damp[u], ycur[u].x, k.x);
+                k.y = fma(-damp[u], ycur[u].y, k.y);
                 double vx[HEOM_FLOW_NE], vy[HEOM_FLOW_NE];
                 unsigned word[HEOM_FLOW_NE];
 #pragma unroll
@@ -342,11 +349,6 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
                         }
                     } while (!ready);
                 }
-                const int i = idx[u] / n, j = idx[u] - i * n;
-                cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)gg[u] * nn, i, j)
-                             : heom_sys(Hs, n, ys + (size_t)gg[u] * nn, i, j);
-                k.x = fma(-damp[u], ycur[u].x, k.x);
-                k.y = fma(-damp[u], ycur[u].y, k.y);
 #pragma unroll
                 for (int s = 0; s < HEOM_FLOW_NE; ++s) {
                     if (FULLCF) {

@@ -119,6 +119,25 @@ def test_lindblad_batch_parameter_scan(cuda, path):
         assert relerr(rho_f[b], rl[-1]) <= TOL
 
 
+def test_evolve_batch_plan_cache_follows_operator_content(cuda):
+    """the plan cached on the solver is keyed on operator CONTENT: repeated calls reuse it, an in-place edit of the scan
+    values or of a collapse operator rebuilds it (no stale results)"""
+    from lime_b200 import builders, oqs
+    pat, vals, c_ops, e_ops, rho0 = builders.jaynes_cummings_batch(1.0, 1.0 + np.linspace(-0.1, 0.1, 6), np.linspace(0.02, 0.1, 6), 8, 0.05)
+    s = oqs.Lindblad_solver(None, c_ops=c_ops)
+    r1, o1, _ = s.evolve_batch(rho0, 0.01, 10, e_ops=e_ops, H_batch=(pat, vals))
+    plan1 = s._batch_plan[1]
+    r1b, o1b, _ = s.evolve_batch(rho0, 0.01, 10, e_ops=e_ops, H_batch=(pat, vals))
+    assert s._batch_plan[1] is plan1 and np.array_equal(r1, r1b)
+    vals[:, :] *= 1.1                                     # in-place edit: same objects, new physics
+    r2, o2, _ = s.evolve_batch(rho0, 0.01, 10, e_ops=e_ops, H_batch=(pat, vals))
+    assert s._batch_plan[1] is not plan1 and relerr(r2, r1) > 1e-6
+    Hs = [csr_matrix((vals[b], pat.indices, pat.indptr), shape=pat.shape) for b in range(6)]
+    for b in (0, 5):
+        o, rl = lo.lindblad(Hs[b].toarray(), rho0, [c.toarray() for c in c_ops], [e.toarray() for e in e_ops], Nt=10, dt=0.01)
+        assert relerr(r2[b], rl[-1]) <= TOL and relerr(o2[:, b], o) <= TOL
+
+
 def test_lindblad_non_hermitian_rho_and_ragged_sizes(cuda):
     """correlation functions propagate non-Hermitian 'density matrices'; odd N; N=1"""
     from lime_b200 import oqs
