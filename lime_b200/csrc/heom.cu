@@ -1358,6 +1358,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     if (nown <= 0) return LB_OK;
     const int nn = p->n * p->n;
     HeomStageArgs a;
+    memset(&a, 0, sizeof(a));          // (tagged-halo fields must be null here)
     a.npeer = 0; a.peer_mask = nullptr; a.send_all = 1;
     a.d = p->dev();
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;

@@ -316,32 +316,45 @@ heom_flow_cached_kernel(HeomFlowArgs a) {
 #pragma unroll
             for (int u = 0; u < EPT; ++u) {
                 if (!act[u]) continue;
-                // -i[H, Y_a] and the damping need only this CTA's own ADOs: computed first, which also gives the producers of the
-                // neighbour entries time to publish them before the first poll round
+                // first poll round: all 16 loads are ISSUED, then -i[H, Y_a] and the damping (which need only this CTA's own
+                // ADOs, through shared memory) are computed while they are in flight, then the tags are checked
+                unsigned word[HEOM_FLOW_NE];
+#pragma unroll
+                for (int s = 0; s < HEOM_FLOW_NE; ++s) word[s] = eoff[(u * HEOM_FLOW_NE + s) * T + threadIdx.x];
+                ulonglong2 w0[HEOM_FLOW_NE], w1[HEOM_FLOW_NE];
+#pragma unroll
+                for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+                    const ulonglong2* e = Tin + 2 * (size_t)(word[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u));
+                    w0[s] = flow_ld(e);
+                    w1[s] = flow_ld(e + 1);
+                }
                 const int i = idx[u] / n, j = idx[u] - i * n;
                 cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)gg[u] * nn, i, j)
                              : heom_sys(Hs, n, ys + (size_t)gg[u] * nn, i, j);
                 k.x = fma(-damp[u], ycur[u].x, k.x);
                 k.y = fma(-damp[u], ycur[u].y, k.y);
                 double vx[HEOM_FLOW_NE], vy[HEOM_FLOW_NE];
-                unsigned word[HEOM_FLOW_NE];
+                bool ready = true;
 #pragma unroll
-                for (int s = 0; s < HEOM_FLOW_NE; ++s) word[s] = eoff[(u * HEOM_FLOW_NE + s) * T + threadIdx.x];
-                {
-                    // all 16 loads of a round are in flight together; a round is repeated until every entry is tagged
+                for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+                    vx[s] = __longlong_as_double((long long)w0[s].x);
+                    vy[s] = __longlong_as_double((long long)w1[s].x);
+                    ready = ready && w0[s].y == want && w1[s].y == want;
+                }
+                if (!ready) {
+                    // further rounds: all loads of a round in flight together, repeated until every entry is tagged
                     // (re-reading only the untagged entries was measured slower: the per-entry branches serialise the loads)
                     const long long t0 = clock64();
-                    bool ready;
                     unsigned spins = 0;
                     do {
                         ready = true;
 #pragma unroll
                         for (int s = 0; s < HEOM_FLOW_NE; ++s) {
                             const ulonglong2* e = Tin + 2 * (size_t)(word[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u));
-                            const ulonglong2 w0 = flow_ld(e), w1 = flow_ld(e + 1);
-                            vx[s] = __longlong_as_double((long long)w0.x);
-                            vy[s] = __longlong_as_double((long long)w1.x);
-                            ready = ready && w0.y == want && w1.y == want;
+                            const ulonglong2 a0 = flow_ld(e), a1 = flow_ld(e + 1);
+                            vx[s] = __longlong_as_double((long long)a0.x);
+                            vy[s] = __longlong_as_double((long long)a1.x);
+                            ready = ready && a0.y == want && a1.y == want;
                         }
                         if (!ready && ((++spins & 1023u) == 0) && (clock64() - t0 > limit || *(volatile unsigned*)a.err)) {
                             atomicExch(a.err, 1u);
