@@ -81,6 +81,49 @@ __device__ __forceinline__ void tmem_ld32_wait(TmemRow& w) {
           "+r"(w.r[24]), "+r"(w.r[25]), "+r"(w.r[26]), "+r"(w.r[27])
         :: "memory");
 }
+// Variants without the "memory" clobber (template flag V & 1 of the kernel): tensor memory does not alias shared
+// memory, the TMEM accesses stay ordered among themselves because they are volatile, and every consumer of the
+// loaded words depends on the wait through its "+r" operands -- so the compiler may move the shared-memory loads of
+// the NEXT patch row above the FMA chain of the current one.
+__device__ __forceinline__ void tmem_ld32_wait_nc(TmemRow& w) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7]),
+          "+r"(w.r[8]), "+r"(w.r[9]), "+r"(w.r[10]), "+r"(w.r[11]), "+r"(w.r[12]), "+r"(w.r[13]), "+r"(w.r[14]), "+r"(w.r[15]),
+          "+r"(w.r[16]), "+r"(w.r[17]), "+r"(w.r[18]), "+r"(w.r[19]), "+r"(w.r[20]), "+r"(w.r[21]), "+r"(w.r[22]), "+r"(w.r[23]),
+          "+r"(w.r[24]), "+r"(w.r[25]), "+r"(w.r[26]), "+r"(w.r[27]));
+}
+__device__ __forceinline__ void tmem_st8_nc(unsigned taddr, const double (&d)[4]) {
+    unsigned r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { r[2 * i] = (unsigned)__double2loint(d[i]); r[2 * i + 1] = (unsigned)__double2hiint(d[i]); }
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]));
+}
+template <int IMM>
+__device__ __forceinline__ void st_async_c128_nc(unsigned raddr, cplx v, unsigned rbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0+%4], {%1, %2}, [%3];"
+                 ::"r"(raddr), "d"(v.x), "d"(v.y), "r"(rbar), "n"(IMM));
+}
+// plain arrival (release.cta) / bounded wait (acquire.cta) on a CTA-local mbarrier: the per-warp barriers of V & 2
+__device__ __forceinline__ void mbar_arrive_cta(unsigned bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// a protocol error must not hang the device: trap after ~2 s
+__device__ __forceinline__ void mbar_wait_bounded(unsigned bar, unsigned parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity))
+        if (clock64() - t0 > 4000000000ll) __trap();
+}
 __device__ __forceinline__ double tmem_dbl(const TmemRow& w, int i) {      // i-th double of the row record
     return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
 }
@@ -106,9 +149,12 @@ struct QmeTileCtx {
 };
 
 // One RK4 stage of one thread's patch.  STAGE is compile time: input buffer = STAGE & 1, output = the other one.
-template <int NP, int TR, int S, int STAGE>
+// V & 1: clobber-free tensor-memory / st.async statements and the sandwich sources loaded with the rest of the row's
+// operands (before the tensor-memory wait) -- same arithmetic, more scheduling freedom.
+template <int NP, int TR, int S, int STAGE, int V>
 __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
     constexpr int ROWB = NP * 16;
+    constexpr bool RLX = (V & 1) != 0;
     // ordinary shared-memory accesses (base register + immediate) that the compiler is free to schedule
     const unsigned in_off = (STAGE & 1) ? bufb : 0u;
     const unsigned out_off = (STAGE & 1) ? 0u : bufb;
@@ -143,7 +189,17 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
             k[u].x = fma(-c.cR[u], b.y, k[u].x);
             k[u].y = fma(c.cR[u], b.x, k[u].y);
         }
-        tmem_ld32_wait(tw);
+        cplx ysrc[S > 0 ? S : 1][2];
+        if (RLX) {
+#pragma unroll
+            for (int s = 0; s < S; ++s)
+#pragma unroll
+                for (int u = 0; u < 2; ++u)
+                    ysrc[s][u] = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
+            tmem_ld32_wait_nc(tw);
+        } else {
+            tmem_ld32_wait(tw);
+        }
         const double gdx = tmem_dbl(tw, 8), gdy = tmem_dbl(tw, 9), gup = tmem_dbl(tw, 10), gdn = tmem_dbl(tw, 11);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -164,7 +220,7 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
             const double xv = tmem_dbl(tw, 12 + s);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const cplx ys = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
+                const cplx ys = RLX ? ysrc[s][u] : *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
                 const double cf = xv * c.zv[s][u];
                 k[u].x = fma(cf, ys.x, k[u].x);
                 k[u].y = fma(cf, ys.y, k[u].y);
@@ -189,17 +245,28 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
                 st4[2 * u] = yn[u].x; st4[2 * u + 1] = yn[u].y;
             }
         }
-        tmem_st8(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
+        if (RLX) tmem_st8_nc(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
+        else tmem_st8(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
 #pragma unroll
         for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
         // boundary rows of a chunk also go into the neighbour CTA's halo row; the bytes are counted on its mbarrier
         if (r == 0 && c.up_dst) {
-            st_async_c128<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
-            st_async_c128<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
+            if (RLX) {
+                st_async_c128_nc<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
+                st_async_c128_nc<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
+            } else {
+                st_async_c128<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
+                st_async_c128<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
+            }
         }
         if (r == TR - 1 && c.dn_dst) {
-            st_async_c128<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
-            st_async_c128<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
+            if (RLX) {
+                st_async_c128_nc<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
+                st_async_c128_nc<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
+            } else {
+                st_async_c128<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
+                st_async_c128<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
+            }
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
@@ -207,16 +274,28 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base]
+// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base][warp dependency masks 32 x 4 B]
+// [per-warp stage barriers 32 x 2 x 8 B]
 static inline size_t qme_tile_smem(int NP, int P, int chunk, int C, int E) {
     const size_t nbr = (size_t)P * (chunk + 2);
     const size_t e = E > 0 ? E : 1;
-    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + 16;
+    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + 16 + 128 + 512;
 }
 
-template <int NP, int TR, int S>
+// V & 2 ("warp-level stage synchronisation"): the CTA barrier + everybody-waits-for-the-halo at the end of every
+// stage is replaced by per-warp mbarriers.  A warp's patch is read only by a few other warps (the row groups above /
+// below, the other column block, the patches its sandwich terms point at) and it reads only from those; the
+// relation is made symmetric (D_w = sources of w + readers of w), every warp arrives on the stage barrier of each
+// warp in D_w when its stage is stored and waits on its own barrier (count |D_w|) before the next stage.  Symmetry
+// gives read-after-write AND write-after-read safety on the two ping-pong buffers, and bounds the skew between
+// dependent warps to one stage -- hence two barriers per warp, indexed by the stage parity.  Only the warps that
+// read a halo row fed by a neighbour CTA (and warp 0, whose thread 0 arms the halo barrier) wait on the halo
+// mbarrier; they are exactly the warps that push rows to that neighbour (host check in build_tile_host), which is
+// what makes the cross-CTA write-after-read argument of the block-synchronised kernel carry over unchanged.
+template <int NP, int TR, int S, int V>
 __global__ void __launch_bounds__(512, 1)
 qme_tile_kernel(QmeTileArgs a) {
+    constexpr bool FG = (V & 2) != 0;
     extern __shared__ __align__(16) char smem_raw[];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -239,6 +318,8 @@ qme_tile_kernel(QmeTileArgs a) {
     const unsigned o_red = o_bar + 64;                // [E][32] cplx
     const unsigned o_part = o_red + Ee * 32 * 16;     // [2][C][E] cplx (rank 0)
     const unsigned o_tm = o_part + 2 * C * Ee * 16;
+    const unsigned o_dep = o_tm + 16;                 // [32] unsigned: source-warp masks
+    const unsigned o_wbar = o_dep + 128;              // [32][2] mbarriers: per-warp stage barriers
     cplx* buf0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* red = reinterpret_cast<cplx*>(smem_raw + o_red);
     cplx* part = reinterpret_cast<cplx*>(smem_raw + o_part);
@@ -341,14 +422,64 @@ qme_tile_kernel(QmeTileArgs a) {
         tmem_st8(c.trho + QME_TILE_TMW * r + 24, c4);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+
+    // ---- V & 2: who reads what.  Every lane maps the shared-memory words it reads in a stage to the warp that
+    // writes them (halo rows have no local writer), the warp ORs the lanes.
+    unsigned dmask = 0, ndeps = 0;
+    bool halo_wait = (C > 1);
+    const unsigned wbar0 = sbase + o_wbar;
+    if (FG) {
+        unsigned src = 0;
+        bool halo_read = false;
+        auto owner = [&](unsigned off) {               // byte offset inside buffer 0 -> writer warp
+            const int row = (int)(off / ROWB), pos = (int)(off % ROWB) / 16;
+            const int pp = row / (chunk + 2), t = row - pp * (chunk + 2);
+            if (t == 0) { halo_read |= (rank > 0); return; }
+            if (t == chunk + 1) { halo_read |= (rank < C - 1); return; }
+            src |= 1u << (((pp * chunk + t - 1) / TR) * CB + pos / 64);
+        };
+        for (int r = 0; r < TR + 2; ++r) { owner(c.own + r * ROWB); owner(c.own + r * ROWB + 512); }
+        for (int r = 1; r <= TR; ++r) { owner(c.nl + r * ROWB); owner(c.nr + r * ROWB); }
+        if (S > 0)
+            for (int s = 0; s < SS; ++s)
+                for (int u = 0; u < 2; ++u)
+                    for (int r = 0; r < TR; ++r) owner(c.xs[s][u] + r * ROWB);
+        src = __reduce_or_sync(0xffffffffu, src);
+        halo_read = __any_sync(0xffffffffu, halo_read);
+        unsigned* deps = reinterpret_cast<unsigned*>(smem_raw + o_dep);
+        if (lane == 0) deps[warp] = src;
+        __syncthreads();
+        const int W = T >> 5;
+        unsigned readers = 0;
+        for (int v = 0; v < W; ++v) readers |= ((deps[v] >> warp) & 1u) << v;
+        dmask = (src | readers) & ~(1u << warp);
+        ndeps = (unsigned)__popc(dmask);
+        if (lane == 0) {
+            mbar_init(wbar0 + 16 * warp, ndeps ? ndeps : 1u);
+            mbar_init(wbar0 + 16 * warp + 8, ndeps ? ndeps : 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        halo_wait = (C > 1) && (halo_read || warp == 0);
+        if (C == 1) __syncthreads();
+    }
+    // barrier addresses of parity 0 (0 = none): the one this lane arrives on, the one this warp waits on
+    const unsigned arr_bar = (FG && ((dmask >> lane) & 1u)) ? wbar0 + 16 * lane : 0u;
+    const unsigned own_bar = (FG && ndeps) ? wbar0 + 16 * warp : 0u;
     if (C > 1) cluster.sync();
 
     for (int step = 0; step < a.nsteps; ++step) {
 #define QME_TILE_STAGE(ST)                                                                           \
         if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * ((ST) & 1), halo_bytes);      \
-        qme_tile_stage<NP, TR, S, ST>(c, smem_raw, bufb);                                             \
-        __syncthreads();                                                                              \
-        if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));
+        qme_tile_stage<NP, TR, S, ST, V>(c, smem_raw, bufb);                                          \
+        if (FG) {                                                                                     \
+            __syncwarp();                                                                             \
+            if (arr_bar) mbar_arrive_cta(arr_bar + 8 * ((ST) & 1));                                   \
+            if (own_bar) mbar_wait_bounded(own_bar + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));    \
+            if (halo_wait) mbar_wait_bounded(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));     \
+        } else {                                                                                      \
+            __syncthreads();                                                                          \
+            if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));                 \
+        }
         QME_TILE_STAGE(0)
         if (C > 1 && a.obs && step > 0 && rank == 0) {
             // partial sums of the previous step (pushed by the other CTAs with st.async) are complete
@@ -367,6 +498,7 @@ qme_tile_kernel(QmeTileArgs a) {
 #undef QME_TILE_STAGE
         // buffer 0 now holds rho_{n+1} (own + halo rows)
         if (a.obs) {
+            if (FG) __syncthreads();      // the reduction reads every own row of the CTA
             for (int e = 0; e < a.E; ++e) {
                 cplx v = cmake(0, 0);
                 for (int n = a.eptr[e] + threadIdx.x; n < a.eptr[e + 1]; n += T)
@@ -432,9 +564,9 @@ qme_tile_kernel(QmeTileArgs a) {
     if (C > 1) cluster.sync();      // keep shared memory alive until the neighbours' remote stores are done
 }
 
-template <int NP, int TR, int S>
+template <int NP, int TR, int S, int V>
 static int qme_tile_launch_one(const QmeTileArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = qme_tile_kernel<NP, TR, S>;
+    auto kern = qme_tile_kernel<NP, TR, S, V>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int W = (a.P * a.chunk / TR) * (NP / 64);
     cudaLaunchConfig_t cfg = {};

@@ -1,13 +1,36 @@
 // explicit instantiations of the register-patch cluster propagator (see qme_tile.cuh)
 #include "qme_tile.cuh"
+#include <cstdlib>
+
+// kernel variant (qme_tile.cuh): bit 0 = clobber-free tensor-memory statements + early sandwich loads,
+// bit 1 = warp-level stage synchronisation instead of the CTA barrier.  LIMEB200_TILE_V overrides the default.
+#ifndef QME_TILE_DEFAULT_V
+#define QME_TILE_DEFAULT_V 0
+#endif
+int qme_tile_variant() {
+    const char* e = getenv("LIMEB200_TILE_V");
+    int v = QME_TILE_DEFAULT_V;
+    if (e && *e >= '0' && *e <= '3' && !e[1]) v = *e - '0';
+    return v;
+}
+
+template <int NP, int V>
+static int launch_s(const QmeTileArgs& a, int S, size_t smem, cudaStream_t st) {
+    if (S == 0) return qme_tile_launch_one<NP, 4, 0, V>(a, smem, st);
+    if (S == 1) return qme_tile_launch_one<NP, 4, 1, V>(a, smem, st);
+    return qme_tile_launch_one<NP, 4, 2, V>(a, smem, st);
+}
+template <int NP>
+static int launch_v(const QmeTileArgs& a, int S, size_t smem, cudaStream_t st) {
+    switch (qme_tile_variant()) {
+        case 1: return launch_s<NP, 1>(a, S, smem, st);
+        case 2: return launch_s<NP, 2>(a, S, smem, st);
+        case 3: return launch_s<NP, 3>(a, S, smem, st);
+        default: return launch_s<NP, 0>(a, S, smem, st);
+    }
+}
 
 int qme_tile_launch(const QmeTileArgs& a, int NP, int S, size_t smem, cudaStream_t st) {
-    if (NP == 128) {
-        if (S == 0) return qme_tile_launch_one<128, 4, 0>(a, smem, st);
-        if (S == 1) return qme_tile_launch_one<128, 4, 1>(a, smem, st);
-        return qme_tile_launch_one<128, 4, 2>(a, smem, st);
-    }
-    if (S == 0) return qme_tile_launch_one<64, 4, 0>(a, smem, st);
-    if (S == 1) return qme_tile_launch_one<64, 4, 1>(a, smem, st);
-    return qme_tile_launch_one<64, 4, 2>(a, smem, st);
+    if (NP == 128) return launch_v<128>(a, S, smem, st);
+    return launch_v<64>(a, S, smem, st);
 }

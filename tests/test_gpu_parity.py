@@ -759,6 +759,53 @@ def test_lindblad_config2_full_batch(cuda):
         assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
 
 
+@pytest.mark.parametrize('variant', [1, 2, 3])
+def test_lindblad_tile_kernel_variants(cuda, monkeypatch, variant):
+    """the scheduling / synchronisation variants of the register-patch kernel (LIMEB200_TILE_V: bit 0 clobber-free
+    tensor-memory statements, bit 1 warp-level stage barriers instead of the CTA barrier) do the same arithmetic:
+    identical to variant 0 and within tolerance of the oracle, small cutoffs (one CTA, ragged padding, clusters of
+    2 and 4), with / without observables and trajectory, and on the full 4096-point batch at full occupancy"""
+    import torch
+    from lime_b200 import builders, oqs
+    for ncav in (8, 16, 37, 64):
+        H, c_ops, e_ops, rho0 = cases.jc_point(ncav=ncav)
+        obs_o, rl_o = lo.lindblad(H, rho0, c_ops, e_ops=e_ops, Nt=60, dt=0.01)
+        Hs, cs = csr_matrix(H), [csr_matrix(c) for c in c_ops]
+        out = {}
+        for v in (0, variant):
+            monkeypatch.setenv('LIMEB200_TILE_V', str(v))
+            plan = oqs._lindblad_plan(Hs, cs, e_ops, path=6)
+            assert plan.path == 6
+            out[v] = plan.run(rho0, 0.01, 60, traj_every=20)
+            plan2 = oqs._lindblad_plan(Hs, cs, None, path=6)          # no observables: no CTA barrier at all
+            out[v] += (plan2.run(rho0, 0.01, 60)[0],)
+        rho_f, obs, traj, rho_n = out[variant]
+        assert relerr(obs, obs_o) <= TOL and relerr(rho_f, rl_o[-1]) <= TOL and relerr(rho_n, rl_o[-1]) <= TOL
+        assert relerr(traj, np.array([rl_o[19], rl_o[39], rl_o[59]])) <= TOL
+        for a, b in zip(out[variant], out[0]):
+            assert np.array_equal(a, b)
+    # no collapse operators (S = 0) and two of them (S = 2)
+    H, c_ops, e_ops, rho0 = cases.jc_point(ncav=16)
+    for cl in ([], [c_ops[0], 0.5 * c_ops[0]]):
+        o, rl = lo.lindblad(H, rho0, cl, e_ops=e_ops, Nt=30, dt=0.01)
+        monkeypatch.setenv('LIMEB200_TILE_V', str(variant))
+        plan = oqs._lindblad_plan(csr_matrix(H), [csr_matrix(c) for c in cl], e_ops, path=6)
+        rf, ob, _ = plan.run(rho0, 0.01, 30)
+        assert relerr(ob, o) <= TOL and relerr(rf, rl[-1]) <= TOL
+    # full batch, 200 steps: every CTA slot of the GPU busy, clusters of 4
+    pat, vals, c_ops, e_ops, rho0 = builders.jc_grid()
+    res = {}
+    for v in (0, variant):
+        monkeypatch.setenv('LIMEB200_TILE_V', str(v))
+        plan, B = oqs._lindblad_plan_batch((pat, vals), c_ops, e_ops)
+        assert plan.path == 6
+        rho = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(rho0, (4096, 128, 128)))).cuda()
+        obs, _ = plan.run_device(rho, 0.01, 200)
+        res[v] = (rho, obs)
+        del plan
+    assert torch.equal(res[0][0], res[variant][0]) and torch.equal(res[0][1], res[variant][1])
+
+
 def test_heom_config3_long_run(cuda):
     """config 3 (spin-boson, K = 2, depth 12, dt = 0.01): 4000 RK4 steps of the single hierarchy stay within
     1e-10 of the oracle (thread-per-ADO kernel, one launch)"""
