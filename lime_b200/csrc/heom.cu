@@ -1352,8 +1352,10 @@ int limeb200_heom_set_path(limeb200_heom_t p, int path) {
 int limeb200_heom_get_path(limeb200_heom_t p) { return p ? p->path : LB_ERR_ARG; }
 long long limeb200_heom_last_launches(limeb200_heom_t p) { return p ? p->launches : -1; }
 
+// b0: first hierarchy of the batch slice [b0, b0 + B) this launch works on (all batch-major pointers and the
+// per-hierarchy bath parameters are offset by it)
 static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx* yin, cplx* ynext, cplx* acc,
-                             int B, double dt, cudaStream_t st) {
+                             int B, double dt, cudaStream_t st, int b0 = 0) {
     const long long nown = p->row_hi - p->row_lo;
     if (nown <= 0) return LB_OK;
     const int nn = p->n * p->n;
@@ -1361,6 +1363,15 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     memset(&a, 0, sizeof(a));          // (tagged-halo fields must be null here)
     a.npeer = 0; a.peer_mask = nullptr; a.send_all = 1;
     a.d = p->dev();
+    if (b0 > 0) {
+        const size_t off = (size_t)b0 * p->nhe * nn;
+        if (rho) rho += off;
+        if (acc) acc += off;
+        yin += off; ynext += off;
+        if (p->npar > 1) {
+            a.d.cdn += (size_t)b0 * p->nmodes; a.d.cdnR += (size_t)b0 * p->nmodes; a.d.nu += (size_t)b0 * p->nmodes;
+        }
+    }
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
     a.apc = std::max(1, 256 / nn);
@@ -1667,17 +1678,36 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     cplx* y[2] = {p->s_y.as<cplx>(), p->s_y.as<cplx>() + (size_t)B * total};
     cplx* acc = p->s_acc.as<cplx>();
     LB_CUDA(cudaMemcpyAsync(y[0], rho, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
-    for (int step = 0; step < nsteps; ++step) {
-        for (int stage = 0; stage < 4; ++stage) {
-            int r = heom_launch_stage(p, stage, rho, y[stage & 1], y[(stage + 1) & 1], acc, B, dt, st);
-            if (r != LB_OK) return r;
-        }
-        const bool save = d_traj && ((step + 1) % traj_every) == 0;
-        if (E > 0 || save) {
-            heom_tier0_obs<<<B, 64, 0, st>>>(rho, total, nn, (const cplx*)d_eT, E,
-                                            E > 0 ? (cplx*)d_obs + (size_t)step * B * E : nullptr,
-                                            save ? (cplx*)d_traj + (size_t)(step / traj_every) * B * nn : nullptr);
-            p->launches++;
+    // L2 blocking over the batch: the four vectors a stage touches (rho, accumulator, two stage vectors) of a slice of
+    // `chunk` hierarchies stay in L2 across ALL steps of the launch when the slice is walked through the whole time
+    // loop before the next one starts, so DRAM sees every hierarchy once per call instead of ~5 vectors per stage
+    // (profiles/r01_heom_fmo_batch64_stage_v2.txt: 7.5x the algorithmic traffic).  LIMEB200_HEOM_NO_L2_CHUNK restores
+    // the batch-wide launches.
+    int chunk = B;
+    if (B > 1 && nsteps > 1 && !getenv("LIMEB200_HEOM_NO_L2_CHUNK")) {
+        int l2 = 0;
+        LB_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
+        const double ws = 4.0 * (double)total * 16.0;
+        const long long fit = (long long)(0.6 * (double)l2 / ws);
+        const long long min_items = 8LL * p->sm_count * std::max(1, 256 / nn);      // keep >= 8 CTAs per SM per launch
+        if (fit >= 1 && fit < B && fit * p->nhe >= min_items) chunk = (int)fit;
+        if (const char* e = getenv("LIMEB200_HEOM_L2_CHUNK"))        // forced slice size (tests, tuning)
+            if (atoi(e) >= 1) chunk = std::min(B, atoi(e));
+    }
+    for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int cb = std::min(chunk, B - b0);
+        for (int step = 0; step < nsteps; ++step) {
+            for (int stage = 0; stage < 4; ++stage) {
+                int r = heom_launch_stage(p, stage, rho, y[stage & 1], y[(stage + 1) & 1], acc, cb, dt, st, b0);
+                if (r != LB_OK) return r;
+            }
+            const bool save = d_traj && ((step + 1) % traj_every) == 0;
+            if (E > 0 || save) {
+                heom_tier0_obs<<<cb, 64, 0, st>>>(rho + (size_t)b0 * total, total, nn, (const cplx*)d_eT, E,
+                                                 E > 0 ? (cplx*)d_obs + ((size_t)step * B + b0) * E : nullptr,
+                                                 save ? (cplx*)d_traj + ((size_t)(step / traj_every) * B + b0) * nn : nullptr);
+                p->launches++;
+            }
         }
     }
     LB_CUDA(cudaGetLastError());

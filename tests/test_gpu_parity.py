@@ -606,6 +606,50 @@ def test_heom_parameter_batch(cuda):
         assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
 
 
+def test_heom_stagewise_batch_l2_slices(cuda, monkeypatch):
+    """stage-wise batch path walked in L2-sized slices of the batch (forced slice of 2 on a batch of 5: ragged last
+    slice): identical to the batch-wide launches -- shared bath parameters (FMO shape, observables + trajectory) and
+    per-hierarchy parameters (the slice offsets the parameter tables)"""
+    from lime_b200 import engine
+    import lime_b200.heom.heom as hh
+    from lime_b200.heom.heom import _calc_matsubara_params
+    n = 7
+    H = cases.rand_herm(n, 21, 0.5) + np.diag(np.arange(n) * 0.3)
+    Q = [np.diag((np.arange(n) == j).astype(float)) for j in range(n)]
+    h = hh.HEOM(H, Q, 0.05, 0.6, 1.2, N_exp=2, N_cut=2)
+    rng = np.random.default_rng(6)
+    ado0 = 0.1 * (rng.standard_normal((5, h.nhe, n, n)) + 1j * rng.standard_normal((5, h.nhe, n, n)))
+    h.plan.set_path(2)
+    res = {}
+    for mode in ('off', 'slices'):
+        if mode == 'off':
+            monkeypatch.setenv('LIMEB200_HEOM_NO_L2_CHUNK', '1')
+        else:
+            monkeypatch.delenv('LIMEB200_HEOM_NO_L2_CHUNK')
+            monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
+        res[mode] = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
+    for a, b in zip(res['off'], res['slices']):
+        assert np.array_equal(a, b)
+    ado_o, obs_o, _ = lo.heom_rk4(ado0[4], H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64), h.dn.astype(np.int64),
+                                  h.up.astype(np.int64), 0.02, 10, e_ops=[H])
+    assert relerr(res['slices'][0][4], ado_o) <= TOL and relerr(res['slices'][1][:, 4], obs_o) <= TOL
+    # per-hierarchy bath parameters
+    Hs, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=5)
+    states, dn, up = engine.heom_tables([depth + 1] * K, depth)
+    pars = [(0.1, 1.0), (0.2, 0.7), (0.3, 1.4), (0.05, 2.0), (0.15, 0.9)]
+    cs, nus = zip(*[_calc_matsubara_params(K, l, gam, t) for l, t in pars])
+    plan = engine.HeomPlan(Hs, sz, [0] * K, np.array(cs), np.array(nus), states, dn, up)
+    plan.set_path(2)
+    a0 = np.zeros((len(pars), states.shape[0], 2, 2), dtype=complex)
+    a0[:, 0] = rho0
+    out, obs, _ = plan.run(a0, 0.01, 40, e_ops=[sz])
+    assert plan.path == 2
+    for b in (0, 3, 4):
+        ado_o, obs_o, _ = lo.heom_rk4(a0[b], Hs, sz[None], [0] * K, cs[b], nus[b], states.astype(np.int64),
+                                      dn.astype(np.int64), up.astype(np.int64), 0.01, 40, e_ops=[sz])
+        assert relerr(out[b], ado_o) <= TOL and relerr(obs[:, b], obs_o) <= TOL
+
+
 # ---------------------------------------------------------------- SOS
 def test_sos_all_pathways(cuda):
     from lime_b200.signal import sos
