@@ -3,14 +3,18 @@
 #include <cstdlib>
 
 // kernel variant (qme_tile.cuh): bit 0 = clobber-free tensor-memory statements + early sandwich loads,
-// bit 1 = warp-level stage synchronisation instead of the CTA barrier.  LIMEB200_TILE_V overrides the default.
+// bit 1 = warp-level stage synchronisation instead of the CTA barrier, bit 2 = row coefficients from shared memory and
+// 16-word tensor-memory reads in stages 1-3 only (bit 0 is implied).  Built: 0, 1, 2, 3, 4, 6.  LIMEB200_TILE_V
+// overrides the default.
 #ifndef QME_TILE_DEFAULT_V
 #define QME_TILE_DEFAULT_V 0
 #endif
 int qme_tile_variant() {
     const char* e = getenv("LIMEB200_TILE_V");
     int v = QME_TILE_DEFAULT_V;
-    if (e && *e >= '0' && *e <= '3' && !e[1]) v = *e - '0';
+    if (e && *e >= '0' && *e <= '7' && !e[1]) v = *e - '0';
+    if (v == 5) v = 4;
+    if (v == 7) v = 6;
     return v;
 }
 
@@ -26,6 +30,8 @@ static int launch_v(const QmeTileArgs& a, int S, size_t smem, cudaStream_t st) {
         case 1: return launch_s<NP, 1>(a, S, smem, st);
         case 2: return launch_s<NP, 2>(a, S, smem, st);
         case 3: return launch_s<NP, 3>(a, S, smem, st);
+        case 4: return launch_s<NP, 4>(a, S, smem, st);
+        case 6: return launch_s<NP, 6>(a, S, smem, st);
         default: return launch_s<NP, 0>(a, S, smem, st);
     }
 }

@@ -803,10 +803,11 @@ def test_lindblad_config2_full_batch(cuda):
         assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3])
+@pytest.mark.parametrize('variant', [1, 2, 3, 4, 6])
 def test_lindblad_tile_kernel_variants(cuda, monkeypatch, variant):
     """the scheduling / synchronisation variants of the register-patch kernel (LIMEB200_TILE_V: bit 0 clobber-free
-    tensor-memory statements, bit 1 warp-level stage barriers instead of the CTA barrier) do the same arithmetic:
+    tensor-memory statements, bit 1 warp-level stage barriers instead of the CTA barrier, bit 2 row coefficients from
+    shared memory + 16-word tensor-memory reads in stages 1-3 only) do the same arithmetic:
     identical to variant 0 and within tolerance of the oracle, small cutoffs (one CTA, ragged padding, clusters of
     2 and 4), with / without observables and trajectory, and on the full 4096-point batch at full occupancy"""
     import torch
