@@ -739,6 +739,124 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
 
 #include "heom_flow.cuh"
 
+// ---- packed-neighbour stage kernel (diagonal coupling operators) -----------------------------------------------------
+// heom_stage_kernel walks the index tables for every element in every stage: ~850 thread instructions per element-stage
+// of the FMO hierarchy against ~100 FP64 operations (profiles/r01_heom_fmo_batch64_stage_v2.txt: issue 49 %, FP64 19 %,
+// l1tex 72 %).  Here the walk is done ONCE per plan: every element gets its <= 8 neighbour entries as packed 32-bit
+// words (entry index within a hierarchy | n_k << 26, as in heom_flow_cached_kernel), 32 bytes per element and shared by
+// all hierarchies of a batch, and the finished coefficients for n_k = 0 .. max come from a small table
+// [npar][nn][8][NK] (31 KB for the FMO hierarchy: L1 resident).  A stage of one element is then: 2 packed-word loads,
+// 8 independent neighbour loads, -i[H, .] through shared memory, 8 table look-ups + complex FMAs, the RK4 update.  A CTA
+// keeps the packed words in registers and walks HB hierarchies of the batch with them.  Same arithmetic, same order as
+// heom_stage_tile / heom_persist_cached_kernel (bit-identical results).
+#ifndef HEOM_FAST_DEFAULT_OCC
+#define HEOM_FAST_DEFAULT_OCC 3
+#endif
+struct HeomFastArgs {
+    HeomDev d;
+    int B, stage, HB, NK, apc;       // stage -1: plain right-hand side into ynext
+    long long row_lo, row_hi;
+    cplx* rho; const cplx* yin; cplx* ynext; cplx* acc;
+    double dt;
+    const uint4* pk;                 // [nhe * nn][2]
+    const cplx* ctab;                // [npar][nn][HEOM_FLOW_NE][NK]
+};
+
+__global__ void __launch_bounds__(256)
+heom_pack_kernel(HeomDev d, uint4* __restrict__ pk) {
+    const long long total = d.nhe * d.nn;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long ado = e / d.nn;
+        const int idx = (int)(e - ado * d.nn);
+        unsigned w[HEOM_FLOW_NE];
+#pragma unroll
+        for (int s = 0; s < HEOM_FLOW_NE; ++s) w[s] = (unsigned)e;           // own entry, n_k slot 0: coefficient 0
+        const int* st = d.states + ado * d.nmodes;
+        const int* dn = d.dn + ado * d.nmodes;
+        const int* up = d.up + ado * d.nmodes;
+        int q = 0;
+        for (int t = d.em_start[idx]; t < d.em_start[idx + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
+            const int m = d.em_mode[t];
+            const int id = dn[m], iu = up[m];
+            if (id >= 0) w[2 * q] = ((unsigned)id * (unsigned)d.nn + (unsigned)idx) | ((unsigned)st[m] << HEOM_FLOW_IDXBITS);
+            if (iu >= 0) w[2 * q + 1] = ((unsigned)iu * (unsigned)d.nn + (unsigned)idx) | (1u << HEOM_FLOW_IDXBITS);
+        }
+        pk[2 * e] = make_uint4(w[0], w[1], w[2], w[3]);
+        pk[2 * e + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    }
+}
+// ctab[par][idx][slot][nk]: down slots 2q hold n_k (q_i pref_dn c_k - q_j pref_dn conj c_k) formed exactly as
+// heom_dn_coef forms it, up slots 2q + 1 hold (q_i - q_j) pref_up at "n_k" = 1; everything else 0
+__global__ void __launch_bounds__(256)
+heom_ctab_kernel(HeomDev d, int NK, cplx* __restrict__ ctab) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= d.npar * d.nn) return;
+    const int par = l / d.nn, idx = l - par * d.nn;
+    cplx* c = ctab + (size_t)l * HEOM_FLOW_NE * NK;
+    for (int x = 0; x < HEOM_FLOW_NE * NK; ++x) c[x] = cmake(0, 0);
+    int q = 0;
+    for (int t = d.em_start[idx]; t < d.em_start[idx + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
+        const int m = d.em_mode[t];
+        const double2 v = d.em_v[t];
+        for (int nk = 1; nk < NK; ++nk) c[(2 * q) * NK + nk] = heom_dn_coef(d, par, m, (double)nk, v);
+        if (NK > 1) c[(2 * q + 1) * NK + 1] = cscale(v.x - v.y, d.pref_up);
+    }
+}
+
+template <int NN_, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+heom_stage_fast_kernel(HeomFastArgs a) {
+    extern __shared__ double2 smem[];
+    const HeomDev& d = a.d;
+    const int n = NN_ ? NN_ : d.n, nn = n * n, T = blockDim.x;
+    cplx* Hs = smem;                 // [nn]
+    cplx* ys = Hs + nn;              // [apc * nn]
+    for (int l = threadIdx.x; l < nn; l += T) Hs[l] = d.H[l];
+    const int g = threadIdx.x / nn, idx = threadIdx.x - g * nn;
+    const int i = idx / n, j = idx - i * n;
+    const long long ado = a.row_lo + (long long)blockIdx.x * a.apc + g;
+    const bool act = g < a.apc && ado < a.row_hi;
+    const size_t e = (size_t)(act ? ado : a.row_lo) * nn + (act ? idx : 0);      // element index inside one hierarchy
+    unsigned w[HEOM_FLOW_NE];
+    {
+        const uint4 p0 = __ldg(a.pk + 2 * e), p1 = __ldg(a.pk + 2 * e + 1);
+        w[0] = p0.x; w[1] = p0.y; w[2] = p0.z; w[3] = p0.w; w[4] = p1.x; w[5] = p1.y; w[6] = p1.z; w[7] = p1.w;
+    }
+    const size_t hstride = (size_t)d.nhe * nn;
+    const int b0 = blockIdx.y * a.HB, b1 = min(a.B, b0 + a.HB);
+    for (int b = b0; b < b1; ++b) {
+        const int par = d.npar > 1 ? b : 0;
+        const cplx* y = a.yin + (size_t)b * hstride;
+        const size_t o = (size_t)b * hstride + e;
+        // own value and the 8 neighbour values: independent loads, all in flight together
+        const cplx yv = y[e];
+        cplx nb[HEOM_FLOW_NE];
+#pragma unroll
+        for (int s = 0; s < HEOM_FLOW_NE; ++s) nb[s] = y[w[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u)];
+        if (b > b0) __syncthreads();          // the previous hierarchy's -i[H, .] has finished reading ys
+        if (g < a.apc) ys[threadIdx.x] = yv;
+        __syncthreads();
+        if (act) {
+            cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)g * nn, i, j) : heom_sys(Hs, n, ys + (size_t)g * nn, i, j);
+            const double damp = heom_damp(d, par, ado);
+            k.x = fma(-damp, yv.x, k.x);
+            k.y = fma(-damp, yv.y, k.y);
+            const cplx* ct = a.ctab + ((size_t)par * nn + idx) * HEOM_FLOW_NE * a.NK;
+#pragma unroll
+            for (int s = 0; s < HEOM_FLOW_NE; ++s) cfma(k, __ldg(ct + s * a.NK + (w[s] >> HEOM_FLOW_IDXBITS)), nb[s]);
+            if (a.stage < 0) {
+                a.ynext[o] = k;
+            } else {
+                cplx r = a.rho[o];
+                cplx ac = (a.stage == 0) ? cmake(0, 0) : a.acc[o];
+                const cplx yn = heom_rk_update(a.stage, k, r, ac, a.dt);
+                if (a.stage < 3) a.acc[o] = ac; else a.rho[o] = r;
+                a.ynext[o] = yn;
+            }
+        }
+    }
+}
+
 // on-chip kernel: one CTA per hierarchy, all nsteps fused.  smem: Hs[nn], y0,y1 [nhe*nn] (+ L,R if dense Q)
 struct HeomChipArgs {
     HeomDev d;
@@ -1208,6 +1326,8 @@ struct limeb200_heom_s {
     int max_nk = 0;                     // largest occupation number in the index table
     DevBuf s_y, s_acc, dbar;
     DevBuf s_T;                         // dataflow path: two tagged stage vectors (32 B per element each)
+    DevBuf d_pk, d_ctab;                // packed-neighbour stage kernel: per-element neighbour words, coefficient table
+    int fast_state = 0;                 // 0: not prepared, 1: ready, -1: not applicable
     unsigned long long flow_tag = 1;    // next unused stage tag (monotonic over the launches of the plan)
     long long launches = 0;
     long long smem_optin = 0;
@@ -1375,6 +1495,41 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
     a.apc = std::max(1, 256 / nn);
+    // packed-neighbour kernel (diagonal coupling operators): tables built on first use
+    if (p->fast_state == 0) {
+        const long long total = p->nhe * nn;
+        p->fast_state = (p->diagq && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << HEOM_FLOW_IDXBITS) &&
+                         p->max_nk < 64 && nn <= 256) ? 1 : -1;
+        if (p->fast_state == 1) {
+            const int NK = p->max_nk + 1;
+            LB_CUDA(p->d_pk.alloc((size_t)total * 32));
+            LB_CUDA(p->d_ctab.alloc((size_t)p->npar * nn * HEOM_FLOW_NE * NK * 16));
+            heom_pack_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256LL), 148 * 16), 256, 0, st>>>(p->dev(), p->d_pk.as<uint4>());
+            heom_ctab_kernel<<<ceil_div(p->npar * nn, 256), 256, 0, st>>>(p->dev(), NK, p->d_ctab.as<cplx>());
+            LB_CUDA(cudaGetLastError());
+        }
+    }
+    if (p->fast_state == 1 && !getenv("LIMEB200_HEOM_NO_FAST_STAGE")) {
+        HeomFastArgs f;
+        f.d = a.d; f.B = B; f.stage = stage; f.NK = p->max_nk + 1; f.apc = a.apc;
+        f.HB = std::min(B, 4);
+        f.row_lo = p->row_lo; f.row_hi = p->row_hi;
+        f.rho = rho; f.yin = yin; f.ynext = ynext; f.acc = acc; f.dt = dt;
+        f.pk = p->d_pk.as<uint4>();
+        f.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_FLOW_NE * f.NK : 0);
+        const dim3 fgrid((unsigned)ceil_div(nown, (long long)f.apc), (unsigned)ceil_div(B, f.HB));
+        const int threads = ceil_div(f.apc * nn, 32) * 32;
+        const size_t fsmem = (size_t)(1 + f.apc) * nn * 16;
+        // resident CTAs per SM the kernel is compiled for (register budget 128 / 80 / 64): LIMEB200_HEOM_FAST_OCC = 2, 3, 4
+        static const int occ = [] { const char* e = getenv("LIMEB200_HEOM_FAST_OCC"); const int v = e ? atoi(e) : HEOM_FAST_DEFAULT_OCC;
+                                    return (v >= 2 && v <= 4) ? v : HEOM_FAST_DEFAULT_OCC; }();
+#define LB_FAST(NN) (occ == 2 ? heom_stage_fast_kernel<NN, 2> : occ == 4 ? heom_stage_fast_kernel<NN, 4> : heom_stage_fast_kernel<NN, 3>)
+        void (*fk)(HeomFastArgs) = p->n == 7 ? LB_FAST(7) : p->n == 3 ? LB_FAST(3) : p->n == 2 ? LB_FAST(2) : LB_FAST(0);
+#undef LB_FAST
+        fk<<<fgrid, threads, fsmem, st>>>(f);
+        p->launches++;
+        return LB_OK;
+    }
     size_t smem = (size_t)(1 + 3 * a.apc) * nn * 16;
     dim3 grid((unsigned)ceil_div(nown * B, (long long)a.apc));
     if (smem > 48 * 1024)
@@ -1678,21 +1833,20 @@ int limeb200_heom_run(limeb200_heom_t p, double* d_ado, int B, double dt, int ns
     cplx* y[2] = {p->s_y.as<cplx>(), p->s_y.as<cplx>() + (size_t)B * total};
     cplx* acc = p->s_acc.as<cplx>();
     LB_CUDA(cudaMemcpyAsync(y[0], rho, (size_t)B * total * 16, cudaMemcpyDeviceToDevice, st));
-    // L2 blocking over the batch: the four vectors a stage touches (rho, accumulator, two stage vectors) of a slice of
-    // `chunk` hierarchies stay in L2 across ALL steps of the launch when the slice is walked through the whole time
-    // loop before the next one starts, so DRAM sees every hierarchy once per call instead of ~5 vectors per stage
-    // (profiles/r01_heom_fmo_batch64_stage_v2.txt: 7.5x the algorithmic traffic).  LIMEB200_HEOM_NO_L2_CHUNK restores
-    // the batch-wide launches.
+    // Optional L2 blocking over the batch (LIMEB200_HEOM_L2_CHUNK = slice size, 0 = sized to L2): a slice of `chunk`
+    // hierarchies is walked through the whole time loop before the next one starts, so that the four vectors a stage
+    // touches stay in L2.  Measured with heom_stage_kernel on the batch of 64 FMO hierarchies it LOSES 7 % (9.33e7 vs
+    // 1.00e8 ADO-steps/s): that kernel is issue / latency bound, not DRAM bound, and smaller launches cost more than the
+    // saved traffic buys -- so it is opt-in.
     int chunk = B;
-    if (B > 1 && nsteps > 1 && !getenv("LIMEB200_HEOM_NO_L2_CHUNK")) {
+    if (B > 1 && nsteps > 1 && getenv("LIMEB200_HEOM_L2_CHUNK")) {
         int l2 = 0;
         LB_CUDA(cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, p->device));
         const double ws = 4.0 * (double)total * 16.0;
         const long long fit = (long long)(0.6 * (double)l2 / ws);
         const long long min_items = 8LL * p->sm_count * std::max(1, 256 / nn);      // keep >= 8 CTAs per SM per launch
-        if (fit >= 1 && fit < B && fit * p->nhe >= min_items) chunk = (int)fit;
-        if (const char* e = getenv("LIMEB200_HEOM_L2_CHUNK"))        // forced slice size (tests, tuning)
-            if (atoi(e) >= 1) chunk = std::min(B, atoi(e));
+        if (fit >= 1 && fit < B && fit * p->nhe >= min_items) chunk = (int)fit;      // LIMEB200_HEOM_L2_CHUNK=0: automatic
+        if (atoi(getenv("LIMEB200_HEOM_L2_CHUNK")) >= 1) chunk = std::min(B, atoi(getenv("LIMEB200_HEOM_L2_CHUNK")));
     }
     for (int b0 = 0; b0 < B; b0 += chunk) {
         const int cb = std::min(chunk, B - b0);

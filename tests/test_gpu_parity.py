@@ -607,9 +607,10 @@ def test_heom_parameter_batch(cuda):
 
 
 def test_heom_stagewise_batch_l2_slices(cuda, monkeypatch):
-    """stage-wise batch path walked in L2-sized slices of the batch (forced slice of 2 on a batch of 5: ragged last
-    slice): identical to the batch-wide launches -- shared bath parameters (FMO shape, observables + trajectory) and
-    per-hierarchy parameters (the slice offsets the parameter tables)"""
+    """stage-wise batch path: (i) the packed-neighbour stage kernel (default for diagonal coupling operators) agrees
+    with the table-walking one to rounding; (ii) walked in slices of the batch (opt-in; forced slice of 2 on a batch of
+    5: ragged last slice) it is identical to the batch-wide launches -- shared bath parameters (FMO shape, observables +
+    trajectory) and per-hierarchy parameters (the slice offsets the parameter and coefficient tables)"""
     from lime_b200 import engine
     import lime_b200.heom.heom as hh
     from lime_b200.heom.heom import _calc_matsubara_params
@@ -621,15 +622,19 @@ def test_heom_stagewise_batch_l2_slices(cuda, monkeypatch):
     ado0 = 0.1 * (rng.standard_normal((5, h.nhe, n, n)) + 1j * rng.standard_normal((5, h.nhe, n, n)))
     h.plan.set_path(2)
     res = {}
-    for mode in ('off', 'slices'):
-        if mode == 'off':
-            monkeypatch.setenv('LIMEB200_HEOM_NO_L2_CHUNK', '1')
-        else:
-            monkeypatch.delenv('LIMEB200_HEOM_NO_L2_CHUNK')
+    for mode in ('off', 'slices', 'generic'):
+        monkeypatch.delenv('LIMEB200_HEOM_L2_CHUNK', raising=False)
+        monkeypatch.delenv('LIMEB200_HEOM_NO_FAST_STAGE', raising=False)
+        if mode == 'slices':
             monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
+        if mode == 'generic':           # the table-walking stage kernel instead of the packed-neighbour one
+            monkeypatch.setenv('LIMEB200_HEOM_NO_FAST_STAGE', '1')
         res[mode] = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
     for a, b in zip(res['off'], res['slices']):
         assert np.array_equal(a, b)
+    for a, b in zip(res['off'], res['generic']):          # same operations in the same order (coefficients tabulated)
+        assert relerr(a, b) <= 1e-14
+    monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
     ado_o, obs_o, _ = lo.heom_rk4(ado0[4], H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64), h.dn.astype(np.int64),
                                   h.up.astype(np.int64), 0.02, 10, e_ops=[H])
     assert relerr(res['slices'][0][4], ado_o) <= TOL and relerr(res['slices'][1][:, 4], obs_o) <= TOL
