@@ -155,7 +155,14 @@ struct HeomStageArgs {
     ulonglong2* tag_out_own;          // own inbox, written at the last stage of a run only (uniform unpack)
     unsigned long long tag_want;      // tag of the stage input
     unsigned* tag_err;
+    // packed neighbour lists (built once per plan, see heom_pack_kernel): per element 8 words entry | n_k << 26 and the
+    // finished coefficients ctab[par][idx][slot][n_k]; null: walk the index tables
+    const uint4* pk;
+    const cplx* ctab;
+    int NK;
 };
+#define HEOM_PK_NE 8
+#define HEOM_PK_IDXBITS 26
 
 // L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
 // st/dn/up: the ADO's rows of the index tables (global memory, or a shared-memory copy)
@@ -337,7 +344,24 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
     const int* dn = tabs ? tabs + (size_t)(3 * g + 1) * nm : d.dn + ado * nm;
     const int* up = tabs ? tabs + (size_t)(3 * g + 2) * nm : d.up + ado * nm;
     if (d.diagq) {
-        if (act) { if (a.tag_in) heom_bath_diag_halo(a, par, st, dn, up, idx, y, k); else heom_bath_diag(d, par, st, dn, up, idx, y, k); }
+        if (act) {
+            if (a.tag_in) {
+                heom_bath_diag_halo(a, par, st, dn, up, idx, y, k);
+            } else if (a.pk) {
+                // packed gather: same neighbours, same coefficients, same order as heom_bath_diag
+                const size_t e = (size_t)ado * nn + idx;
+                const uint4 p0 = __ldg(a.pk + 2 * e), p1 = __ldg(a.pk + 2 * e + 1);
+                const unsigned w[HEOM_PK_NE] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+                cplx nb[HEOM_PK_NE];
+#pragma unroll
+                for (int s = 0; s < HEOM_PK_NE; ++s) nb[s] = y[w[s] & ((1u << HEOM_PK_IDXBITS) - 1u)];
+                const cplx* ct = a.ctab + ((size_t)par * nn + idx) * HEOM_PK_NE * a.NK;
+#pragma unroll
+                for (int s = 0; s < HEOM_PK_NE; ++s) cfma(k, __ldg(ct + s * a.NK + (w[s] >> HEOM_PK_IDXBITS)), nb[s]);
+            } else {
+                heom_bath_diag(d, par, st, dn, up, idx, y, k);
+            }
+        }
     } else {
         for (int q = 0; q < d.nq; ++q) {
             cplx L = cmake(0, 0), R = cmake(0, 0);
@@ -752,6 +776,7 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
 #ifndef HEOM_FAST_DEFAULT_OCC
 #define HEOM_FAST_DEFAULT_OCC 3
 #endif
+static_assert(HEOM_PK_NE == HEOM_FLOW_NE && HEOM_PK_IDXBITS == HEOM_FLOW_IDXBITS, "one packed-word format");
 struct HeomFastArgs {
     HeomDev d;
     int B, stage, HB, NK, apc;       // stage -1: plain right-hand side into ynext
@@ -1348,6 +1373,7 @@ struct limeb200_heom_s {
 
 extern "C" {
 
+static int heom_fast_prepare(limeb200_heom_t p);
 int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int nmodes, int nq, long long nhe,
                                  const double* h_H, const double* h_Q, const int* qmap,
                                  const double* h_c, const double* h_nu, int npar,
@@ -1456,6 +1482,10 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
     LB_CUDA(p->dstates.upload(states, (size_t)nhe * nmodes * 4));
     LB_CUDA(p->ddn.upload(dn, (size_t)nhe * nmodes * 4));
     LB_CUDA(p->dup.upload(up, (size_t)nhe * nmodes * 4));
+    {
+        const int r = heom_fast_prepare(p.get());
+        if (r != LB_OK) return r;
+    }
     *plan = p.release();
     return LB_OK;
 }
@@ -1474,6 +1504,31 @@ long long limeb200_heom_last_launches(limeb200_heom_t p) { return p ? p->launche
 
 // b0: first hierarchy of the batch slice [b0, b0 + B) this launch works on (all batch-major pointers and the
 // per-hierarchy bath parameters are offset by it)
+// 0: walk the index tables (heom_bath_diag), 1: generic tile code with the packed gather, 2: heom_stage_fast_kernel.
+// LIMEB200_HEOM_STAGE_MODE overrides (tests, comparisons); LIMEB200_HEOM_NO_FAST_STAGE = mode 0.
+static int heom_stage_mode(limeb200_heom_t p) {
+    if (p->fast_state != 1 || getenv("LIMEB200_HEOM_NO_FAST_STAGE")) return 0;
+    const char* e = getenv("LIMEB200_HEOM_STAGE_MODE");
+    if (e && *e >= '0' && *e <= '2' && !e[1]) return *e - '0';
+    return 2;
+}
+// tables of the packed-neighbour stage kernel; called once when the plan is created (never inside a stream capture)
+static int heom_fast_prepare(limeb200_heom_t p) {
+    const int nn = p->n * p->n;
+    const long long total = p->nhe * nn;
+    p->fast_state = (p->diagq && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << HEOM_FLOW_IDXBITS) &&
+                     p->max_nk < 64 && nn <= 256) ? 1 : -1;
+    if (p->fast_state != 1) return LB_OK;
+    const int NK = p->max_nk + 1;
+    LB_CUDA(p->d_pk.alloc((size_t)total * 32));
+    LB_CUDA(p->d_ctab.alloc((size_t)p->npar * nn * HEOM_FLOW_NE * NK * 16));
+    heom_pack_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256LL), 148 * 16), 256>>>(p->dev(), p->d_pk.as<uint4>());
+    heom_ctab_kernel<<<ceil_div(p->npar * nn, 256), 256>>>(p->dev(), NK, p->d_ctab.as<cplx>());
+    LB_CUDA(cudaGetLastError());
+    LB_CUDA(cudaDeviceSynchronize());
+    return LB_OK;
+}
+
 static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx* yin, cplx* ynext, cplx* acc,
                              int B, double dt, cudaStream_t st, int b0 = 0) {
     const long long nown = p->row_hi - p->row_lo;
@@ -1495,24 +1550,16 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     a.B = B; a.stage = stage; a.row_lo = p->row_lo; a.row_hi = p->row_hi;
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
     a.apc = std::max(1, 256 / nn);
-    // packed-neighbour kernel (diagonal coupling operators): tables built on first use
-    if (p->fast_state == 0) {
-        const long long total = p->nhe * nn;
-        p->fast_state = (p->diagq && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << HEOM_FLOW_IDXBITS) &&
-                         p->max_nk < 64 && nn <= 256) ? 1 : -1;
-        if (p->fast_state == 1) {
-            const int NK = p->max_nk + 1;
-            LB_CUDA(p->d_pk.alloc((size_t)total * 32));
-            LB_CUDA(p->d_ctab.alloc((size_t)p->npar * nn * HEOM_FLOW_NE * NK * 16));
-            heom_pack_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256LL), 148 * 16), 256, 0, st>>>(p->dev(), p->d_pk.as<uint4>());
-            heom_ctab_kernel<<<ceil_div(p->npar * nn, 256), 256, 0, st>>>(p->dev(), NK, p->d_ctab.as<cplx>());
-            LB_CUDA(cudaGetLastError());
-        }
+    // packed-neighbour kernel (diagonal coupling operators; tables built by heom_fast_prepare at plan creation)
+    const int mode = heom_stage_mode(p);
+    if (mode >= 1) {
+        a.pk = p->d_pk.as<uint4>(); a.NK = p->max_nk + 1;
+        a.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_PK_NE * a.NK : 0);
     }
-    if (p->fast_state == 1 && !getenv("LIMEB200_HEOM_NO_FAST_STAGE")) {
+    if (mode == 2) {
         HeomFastArgs f;
         f.d = a.d; f.B = B; f.stage = stage; f.NK = p->max_nk + 1; f.apc = a.apc;
-        f.HB = std::min(B, 4);
+        f.HB = std::max(std::min(B, 4), ceil_div(B, 65535));
         f.row_lo = p->row_lo; f.row_hi = p->row_hi;
         f.rho = rho; f.yin = yin; f.ynext = ynext; f.acc = acc; f.dt = dt;
         f.pk = p->d_pk.as<uint4>();
@@ -1570,7 +1617,7 @@ static int heom_persist_config(limeb200_heom_t p, int B, HeomPersistCfg& c, bool
     c.smem = (size_t)(1 + 3 * c.apc) * nn * 16 + (size_t)3 * c.apc * p->nmodes * 4;
     c.one_tile_per_cta = ceil_div(nitems, (long long)c.apc) <= (long long)per_sm * p->sm_count;
     const size_t smem_c = (size_t)(1 + c.apc) * nn * 16 + (size_t)HEOM_PC_NE * c.threads * 20;
-    if (allow_cached && p->diagq && c.one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
+    if (allow_cached && !getenv("LIMEB200_HEOM_NO_CACHED") && p->diagq && c.one_tile_per_cta && 2 * p->max_modes_per_elem <= HEOM_PC_NE &&
         (long long)B * total < (1LL << 31) && smem_c * per_sm + 2048 <= (size_t)p->smem_optin) {
         c.kern = per_sm == 2 ? heom_persist_cached_kernel<576, 2> : heom_persist_cached_kernel<1024, 1>;
         c.smem = smem_c;
@@ -1600,6 +1647,9 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
     pa.s.dt = dt;
     pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
+    if (heom_stage_mode(p) >= 1 && !pa.hybrid) {       // the generic persistent kernel gathers through the packed lists too
+        pa.s.pk = p->d_pk.as<uint4>(); pa.s.ctab = p->d_ctab.as<cplx>(); pa.s.NK = p->max_nk + 1;
+    }
     pa.s.apc = c.apc;
     pa.nsteps = nsteps;
     if (!p->dbar.p) LB_CUDA(p->dbar.alloc(512));

@@ -634,6 +634,23 @@ def test_heom_stagewise_batch_l2_slices(cuda, monkeypatch):
         assert np.array_equal(a, b)
     for a, b in zip(res['off'], res['generic']):          # same operations in the same order (coefficients tabulated)
         assert relerr(a, b) <= 1e-14
+    # the generic tile code with the packed gather (mode 1): stage-wise kernel and the generic persistent kernel
+    # (the one the ADO-sharded barrier path runs on large shards; LIMEB200_HEOM_NO_CACHED keeps the cached kernel out)
+    monkeypatch.delenv('LIMEB200_HEOM_NO_FAST_STAGE', raising=False)
+    monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', '1')
+    for a, b in zip(res['off'], h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)):
+        assert relerr(a, b) <= 1e-14
+    monkeypatch.setenv('LIMEB200_HEOM_NO_CACHED', '1')
+    h.plan.set_path(3)
+    for m in ('0', '1'):
+        monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', m)
+        out3 = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
+        assert h.plan.path == 3
+        for a, b in zip(res['off'], out3):
+            assert relerr(a, b) <= 1e-14
+    monkeypatch.delenv('LIMEB200_HEOM_NO_CACHED')
+    monkeypatch.delenv('LIMEB200_HEOM_STAGE_MODE')
+    h.plan.set_path(2)
     monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
     ado_o, obs_o, _ = lo.heom_rk4(ado0[4], H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64), h.dn.astype(np.int64),
                                   h.up.astype(np.int64), 0.02, 10, e_ops=[H])
