@@ -141,6 +141,27 @@ __device__ __forceinline__ void tmem_ld16_wait(TmemRow16& w) {
 __device__ __forceinline__ double tmem_dbl(const TmemRow16& w, int i) {
     return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
 }
+// 8-word load (one patch row of the stage vector; V & 8)
+struct TmemRow8 { unsigned r[8]; };
+__device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, TmemRow8& w) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(w.r[0]), "=r"(w.r[1]), "=r"(w.r[2]), "=r"(w.r[3]), "=r"(w.r[4]), "=r"(w.r[5]), "=r"(w.r[6]), "=r"(w.r[7])
+        : "r"(taddr));
+}
+// wait for every outstanding tensor-memory load of the thread; both records are operands so that no consumer moves up
+__device__ __forceinline__ void tmem_ld_wait(TmemRow16& a, TmemRow8& b) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(a.r[0]), "+r"(a.r[1]), "+r"(a.r[2]), "+r"(a.r[3]), "+r"(a.r[4]), "+r"(a.r[5]), "+r"(a.r[6]), "+r"(a.r[7]),
+          "+r"(a.r[8]), "+r"(a.r[9]), "+r"(a.r[10]), "+r"(a.r[11]), "+r"(a.r[12]), "+r"(a.r[13]), "+r"(a.r[14]), "+r"(a.r[15]),
+          "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]), "+r"(b.r[3]), "+r"(b.r[4]), "+r"(b.r[5]), "+r"(b.r[6]), "+r"(b.r[7]));
+}
+__device__ __forceinline__ void tmem_ld_wait(TmemRow8& b) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+        : "+r"(b.r[0]), "+r"(b.r[1]), "+r"(b.r[2]), "+r"(b.r[3]), "+r"(b.r[4]), "+r"(b.r[5]), "+r"(b.r[6]), "+r"(b.r[7]));
+}
+__device__ __forceinline__ double tmem_dbl(const TmemRow8& w, int i) {
+    return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
+}
 __device__ __forceinline__ double tmem_dbl(const TmemRow& w, int i) {      // i-th double of the row record
     return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
 }
@@ -405,6 +426,136 @@ __device__ __forceinline__ void qme_tile_stage_s(const QmeTileCtx<NP, TR, S>& c,
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// V & 8 (with V & 4): the thread's OWN rows of the stage vector come from tensor memory as well.  The measurements of
+// round 2 (tools/ubench/tmem_bw.cu: tcgen05.ld 439 B/clk per SM, tcgen05.st 619 B/clk, against 128 B/clk of shared
+// memory; ncu: 42.7 shared-memory wavefronts per warp and patch row, shared-memory pipe 63-77 %; variants 2/4/6 all
+// slower in proportion to the wavefronts they add) say the kernel is bound by the shared-memory pipe and that tensor
+// memory is the cheap port.  Of the (TR + 2) x 2 window loads of a stage, TR x 2 re-read values the SAME thread stored in
+// the previous stage; they now live in a third tensor-memory slot per row ([rho 8][acc 8][y 8]), updated in place
+// (row r + 1 is fetched one row ahead, before row r is overwritten), and only the two halo rows of the window, the
+// left / right / sandwich neighbours and the row coefficients still come from shared memory: 31 wavefronts per warp and
+// patch row instead of 42.7.  The values still go to shared memory too -- the other threads read them there.
+template <int NP, int TR, int S, int STAGE>
+__device__ __forceinline__ void qme_tile_stage_t(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
+    constexpr int ROWB = NP * 16;
+    const unsigned in_off = (STAGE & 1) ? bufb : 0u;
+    const unsigned out_off = (STAGE & 1) ? 0u : bufb;
+    const char* pown = smem + (c.own + in_off);
+    const char* pl = smem + (c.nl + in_off);
+    const char* pr = smem + (c.nr + in_off);
+    const char* prc = smem + c.rowc;
+    char* pout = smem + (c.own + out_off);
+    const double cy = (STAGE == 2) ? c.dt : c.hdt;
+
+    cplx wp[2], wc[2], wn[2];
+    TmemRow8 ty;
+    tmem_ld8_issue(c.trho + 16, ty);                       // own row 0 of the stage input
+#pragma unroll
+    for (int u = 0; u < 2; ++u) wp[u] = *reinterpret_cast<const cplx*>(pown + 512 * u);     // row above the patch
+    tmem_ld_wait(ty);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) wc[u] = cmake(tmem_dbl(ty, 2 * u), tmem_dbl(ty, 2 * u + 1));
+#pragma unroll
+    for (int r = 0; r < TR; ++r) {
+        TmemRow16 tw;
+        if (STAGE != 0) tmem_ld16_issue(c.trho + QME_TILE_TMW * r, tw);
+        if (r + 1 < TR) {
+            tmem_ld8_issue(c.trho + QME_TILE_TMW * (r + 1) + 16, ty);
+        } else {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) wn[u] = *reinterpret_cast<const cplx*>(pown + (TR + 1) * ROWB + 512 * u);   // row below
+        }
+        const cplx yl = *reinterpret_cast<const cplx*>(pl + (r + 1) * ROWB);
+        const cplx yr = *reinterpret_cast<const cplx*>(pr + (r + 1) * ROWB);
+        const double2 gd = *reinterpret_cast<const double2*>(prc + r * 48);
+        const double2 gud = *reinterpret_cast<const double2*>(prc + r * 48 + 16);
+        double2 xv2 = make_double2(0.0, 0.0);
+        if (S > 0) xv2 = *reinterpret_cast<const double2*>(prc + r * 48 + 32);
+        cplx ysrc[S > 0 ? S : 1][2];
+#pragma unroll
+        for (int s = 0; s < S; ++s)
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+                ysrc[s][u] = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
+        cplx k[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const cplx a = (u == 0) ? yl : wc[0];
+            const cplx b = (u == 0) ? wc[1] : yr;
+            k[u].x = -c.cL[u] * a.y;
+            k[u].y = c.cL[u] * a.x;
+            k[u].x = fma(-c.cR[u], b.y, k[u].x);
+            k[u].y = fma(c.cR[u], b.x, k[u].y);
+        }
+        if (STAGE != 0) {
+            if (r + 1 < TR) tmem_ld_wait(tw, ty); else tmem_ld16_wait(tw);
+        } else if (r + 1 < TR) {
+            tmem_ld_wait(ty);
+        }
+        if (r + 1 < TR) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) wn[u] = cmake(tmem_dbl(ty, 2 * u), tmem_dbl(ty, 2 * u + 1));
+        }
+        const double gdx = gd.x, gdy = gd.y, gup = gud.x, gdn = gud.y;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const double dr = gdx + c.cdr[u], di = gdy + c.cdi[u];
+            k[u].x = fma(dr, wc[u].x, k[u].x);
+            k[u].x = fma(-di, wc[u].y, k[u].x);
+            k[u].y = fma(dr, wc[u].y, k[u].y);
+            k[u].y = fma(di, wc[u].x, k[u].y);
+            k[u].x = fma(-gup, wp[u].y, k[u].x);
+            k[u].y = fma(gup, wp[u].x, k[u].y);
+            k[u].x = fma(-gdn, wn[u].y, k[u].x);
+            k[u].y = fma(gdn, wn[u].x, k[u].y);
+        }
+#pragma unroll
+        for (int s = 0; s < S; ++s) {
+            const double xv = (s == 0) ? xv2.x : xv2.y;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const double cf = xv * c.zv[s][u];
+                k[u].x = fma(cf, ysrc[s][u].x, k[u].x);
+                k[u].y = fma(cf, ysrc[s][u].y, k[u].y);
+            }
+        }
+        cplx yn[2];
+        double st4[4], sy4[4];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const double kx = k[u].x, ky = k[u].y;
+            if (STAGE == 0) {
+                st4[2 * u] = kx; st4[2 * u + 1] = ky;
+                yn[u] = cmake(fma(cy, kx, wc[u].x), fma(cy, ky, wc[u].y));
+            } else if (STAGE < 3) {
+                st4[2 * u] = fma(2.0, kx, tmem_dbl(tw, 4 + 2 * u));
+                st4[2 * u + 1] = fma(2.0, ky, tmem_dbl(tw, 5 + 2 * u));
+                yn[u] = cmake(fma(cy, kx, tmem_dbl(tw, 2 * u)), fma(cy, ky, tmem_dbl(tw, 2 * u + 1)));
+            } else {
+                yn[u].x = fma(c.w6, tmem_dbl(tw, 4 + 2 * u) + kx, tmem_dbl(tw, 2 * u));
+                yn[u].y = fma(c.w6, tmem_dbl(tw, 5 + 2 * u) + ky, tmem_dbl(tw, 2 * u + 1));
+                st4[2 * u] = yn[u].x; st4[2 * u + 1] = yn[u].y;
+            }
+            sy4[2 * u] = yn[u].x; sy4[2 * u + 1] = yn[u].y;
+        }
+        tmem_st8_nc(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
+        tmem_st8_nc(c.trho + QME_TILE_TMW * r + 16, sy4);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
+        if (r == 0 && c.up_dst) {
+            st_async_c128_nc<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
+            st_async_c128_nc<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
+        }
+        if (r == TR - 1 && c.dn_dst) {
+            st_async_c128_nc<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
+            st_async_c128_nc<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
 // shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base][warp dependency masks 32 x 4 B]
 // [per-warp stage barriers 32 x 2 x 8 B][row coefficients R x 48 B]
 static inline size_t qme_tile_smem(int NP, int P, int chunk, int C, int E) {
@@ -480,7 +631,7 @@ qme_tile_kernel(QmeTileArgs a) {
         buf0[NBR * NP + l] = cmake(0, 0);
     }
 
-    if (V & 4) {
+    if (V & 12) {
         const double* rc = a.rowc + ((size_t)vb * C + rank) * R * QME_TILE_ROWC;
         double* rs = reinterpret_cast<double*>(smem_raw + o_rowc);
         for (int l = threadIdx.x; l < R * QME_TILE_ROWC; l += T) rs[l] = rc[l];
@@ -556,7 +707,8 @@ qme_tile_kernel(QmeTileArgs a) {
         tmem_st8(c.trho + QME_TILE_TMW * r, rh);
         tmem_st8(c.trho + QME_TILE_TMW * r + 8, z4);
         c4[0] = rcp[0]; c4[1] = rcp[1]; c4[2] = rcp[2]; c4[3] = rcp[3];
-        tmem_st8(c.trho + QME_TILE_TMW * r + 16, c4);
+        if (V & 8) tmem_st8(c.trho + QME_TILE_TMW * r + 16, rh);      // third slot: the stage input (= rho before stage 0)
+        else tmem_st8(c.trho + QME_TILE_TMW * r + 16, c4);
         c4[0] = rcp[4]; c4[1] = rcp[5]; c4[2] = 0.0; c4[3] = 0.0;
         tmem_st8(c.trho + QME_TILE_TMW * r + 24, c4);
     }
@@ -609,7 +761,8 @@ qme_tile_kernel(QmeTileArgs a) {
     for (int step = 0; step < a.nsteps; ++step) {
 #define QME_TILE_STAGE(ST)                                                                           \
         if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * ((ST) & 1), halo_bytes);      \
-        if (V & 4) qme_tile_stage_s<NP, TR, S, ST>(c, smem_raw, bufb);                                \
+        if (V & 8) qme_tile_stage_t<NP, TR, S, ST>(c, smem_raw, bufb);                                \
+        else if (V & 4) qme_tile_stage_s<NP, TR, S, ST>(c, smem_raw, bufb);                           \
         else qme_tile_stage<NP, TR, S, ST, V>(c, smem_raw, bufb);                                     \
         if (FG) {                                                                                     \
             __syncwarp();                                                                             \

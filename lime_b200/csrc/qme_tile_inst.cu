@@ -4,15 +4,15 @@
 
 // kernel variant (qme_tile.cuh): bit 0 = clobber-free tensor-memory statements + early sandwich loads,
 // bit 1 = warp-level stage synchronisation instead of the CTA barrier, bit 2 = row coefficients from shared memory and
-// 16-word tensor-memory reads in stages 1-3 only (bit 0 is implied).  Built: 0, 1, 2, 3, 4, 6.  LIMEB200_TILE_V
-// overrides the default.
+// 16-word tensor-memory reads in stages 1-3 only (bit 0 is implied), bit 3 (with bit 2; value 8 = 12) = the thread's own rows of the stage
+// vector from tensor memory too.  Built: 0, 1, 2, 3, 4, 6, 8.  LIMEB200_TILE_V overrides the default.
 #ifndef QME_TILE_DEFAULT_V
 #define QME_TILE_DEFAULT_V 0
 #endif
 int qme_tile_variant() {
     const char* e = getenv("LIMEB200_TILE_V");
     int v = QME_TILE_DEFAULT_V;
-    if (e && *e >= '0' && *e <= '7' && !e[1]) v = *e - '0';
+    if (e && *e >= '0' && *e <= '8' && !e[1]) v = *e - '0';
     if (v == 5) v = 4;
     if (v == 7) v = 6;
     return v;
@@ -32,6 +32,7 @@ static int launch_v(const QmeTileArgs& a, int S, size_t smem, cudaStream_t st) {
         case 3: return launch_s<NP, 3>(a, S, smem, st);
         case 4: return launch_s<NP, 4>(a, S, smem, st);
         case 6: return launch_s<NP, 6>(a, S, smem, st);
+        case 8: return launch_s<NP, 12>(a, S, smem, st);
         default: return launch_s<NP, 0>(a, S, smem, st);
     }
 }

@@ -825,7 +825,7 @@ def test_lindblad_config2_full_batch(cuda):
         assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3, 4, 6])
+@pytest.mark.parametrize('variant', [1, 2, 3, 4, 6, 8])
 def test_lindblad_tile_kernel_variants(cuda, monkeypatch, variant):
     """the scheduling / synchronisation variants of the register-patch kernel (LIMEB200_TILE_V: bit 0 clobber-free
     tensor-memory statements, bit 1 warp-level stage barriers instead of the CTA barrier, bit 2 row coefficients from
