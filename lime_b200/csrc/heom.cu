@@ -1518,8 +1518,9 @@ static int heom_fast_prepare(limeb200_heom_t p) {
     const long long total = p->nhe * nn;
     p->fast_state = (p->diagq && 2 * p->max_modes_per_elem <= HEOM_FLOW_NE && total < (1LL << HEOM_FLOW_IDXBITS) &&
                      p->max_nk < 64 && nn <= 256) ? 1 : -1;
-    if (p->fast_state != 1) return LB_OK;
     const int NK = p->max_nk + 1;
+    if ((size_t)p->npar * nn * HEOM_FLOW_NE * NK * 16 > ((size_t)256 << 20)) p->fast_state = -1;     // per-hierarchy parameter sets: keep the table small
+    if (p->fast_state != 1) return LB_OK;
     LB_CUDA(p->d_pk.alloc((size_t)total * 32));
     LB_CUDA(p->d_ctab.alloc((size_t)p->npar * nn * HEOM_FLOW_NE * NK * 16));
     heom_pack_kernel<<<(unsigned)std::min<long long>(ceil_div(total, 256LL), 148 * 16), 256>>>(p->dev(), p->d_pk.as<uint4>());
