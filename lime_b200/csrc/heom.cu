@@ -163,6 +163,10 @@ struct HeomStageArgs {
 };
 #define HEOM_PK_NE 8
 #define HEOM_PK_IDXBITS 26
+// coefficient table layout ctab[par][slot][nk][idx], matrix element fastest (see heom_ctab_kernel)
+__device__ __forceinline__ size_t heom_ctab_index(int par, int slot, int nk, int idx, int NK, int nn) {
+    return (((size_t)par * HEOM_PK_NE + slot) * NK + nk) * nn + idx;
+}
 
 // L_q / R_q element (idx) of ADO a from the neighbours in stage vector y (dense-Q path)
 // st/dn/up: the ADO's rows of the index tables (global memory, or a shared-memory copy)
@@ -355,9 +359,9 @@ __device__ __forceinline__ void heom_stage_tile(const HeomStageArgs& a, long lon
                 cplx nb[HEOM_PK_NE];
 #pragma unroll
                 for (int s = 0; s < HEOM_PK_NE; ++s) nb[s] = y[w[s] & ((1u << HEOM_PK_IDXBITS) - 1u)];
-                const cplx* ct = a.ctab + ((size_t)par * nn + idx) * HEOM_PK_NE * a.NK;
 #pragma unroll
-                for (int s = 0; s < HEOM_PK_NE; ++s) cfma(k, __ldg(ct + s * a.NK + (w[s] >> HEOM_PK_IDXBITS)), nb[s]);
+                for (int s = 0; s < HEOM_PK_NE; ++s)
+                    cfma(k, __ldg(a.ctab + heom_ctab_index(par, s, (int)(w[s] >> HEOM_PK_IDXBITS), idx, a.NK, nn)), nb[s]);
             } else {
                 heom_bath_diag(d, par, st, dn, up, idx, y, k);
             }
@@ -773,9 +777,6 @@ heom_persist_cached_kernel(HeomPersistArgs p) {
 // 8 independent neighbour loads, -i[H, .] through shared memory, 8 table look-ups + complex FMAs, the RK4 update.  A CTA
 // keeps the packed words in registers and walks HB hierarchies of the batch with them.  Same arithmetic, same order as
 // heom_stage_tile / heom_persist_cached_kernel (bit-identical results).
-#ifndef HEOM_FAST_DEFAULT_OCC
-#define HEOM_FAST_DEFAULT_OCC 3
-#endif
 static_assert(HEOM_PK_NE == HEOM_FLOW_NE && HEOM_PK_IDXBITS == HEOM_FLOW_IDXBITS, "one packed-word format");
 struct HeomFastArgs {
     HeomDev d;
@@ -810,33 +811,69 @@ heom_pack_kernel(HeomDev d, uint4* __restrict__ pk) {
         pk[2 * e + 1] = make_uint4(w[4], w[5], w[6], w[7]);
     }
 }
-// ctab[par][idx][slot][nk]: down slots 2q hold n_k (q_i pref_dn c_k - q_j pref_dn conj c_k) formed exactly as
-// heom_dn_coef forms it, up slots 2q + 1 hold (q_i - q_j) pref_up at "n_k" = 1; everything else 0
+// ctab[par][slot][nk][idx] (matrix element fastest: the lanes of a warp read neighbouring entries; with the element
+// index slowest every lane hit its own 128-byte line and the look-ups alone saturated l1tex --
+// profiles/r02_heom_fmo_batch64_stage_fast_v1.txt: l1tex 94.7 %).  Down slots 2q hold n_k (q_i pref_dn c_k - q_j pref_dn
+// conj c_k) formed exactly as heom_dn_coef forms it, up slots 2q + 1 hold (q_i - q_j) pref_up at "n_k" = 1; the rest 0.
 __global__ void __launch_bounds__(256)
 heom_ctab_kernel(HeomDev d, int NK, cplx* __restrict__ ctab) {
     const int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l >= d.npar * d.nn) return;
     const int par = l / d.nn, idx = l - par * d.nn;
-    cplx* c = ctab + (size_t)l * HEOM_FLOW_NE * NK;
-    for (int x = 0; x < HEOM_FLOW_NE * NK; ++x) c[x] = cmake(0, 0);
+    for (int s = 0; s < HEOM_PK_NE; ++s)
+        for (int nk = 0; nk < NK; ++nk) ctab[heom_ctab_index(par, s, nk, idx, NK, d.nn)] = cmake(0, 0);
     int q = 0;
-    for (int t = d.em_start[idx]; t < d.em_start[idx + 1] && q < HEOM_FLOW_NE / 2; ++t, ++q) {
+    for (int t = d.em_start[idx]; t < d.em_start[idx + 1] && q < HEOM_PK_NE / 2; ++t, ++q) {
         const int m = d.em_mode[t];
         const double2 v = d.em_v[t];
-        for (int nk = 1; nk < NK; ++nk) c[(2 * q) * NK + nk] = heom_dn_coef(d, par, m, (double)nk, v);
-        if (NK > 1) c[(2 * q + 1) * NK + 1] = cscale(v.x - v.y, d.pref_up);
+        for (int nk = 1; nk < NK; ++nk) ctab[heom_ctab_index(par, 2 * q, nk, idx, NK, d.nn)] = heom_dn_coef(d, par, m, (double)nk, v);
+        if (NK > 1) ctab[heom_ctab_index(par, 2 * q + 1, 1, idx, NK, d.nn)] = cscale(v.x - v.y, d.pref_up);
     }
 }
 
-template <int NN_, int MINB>
-__global__ void __launch_bounds__(256, MINB)
+// -i [H, Y]_{ij} for a REAL Hamiltonian (Hr: n x n doubles): half the shared-memory bytes and half the FP64 work of the
+// complex form on the H side; same values (the dropped terms are products with Im H = 0)
+template <int NN_>
+__device__ __forceinline__ cplx heom_sys_real_t(const double* Hr, const cplx* ya, int i, int j) {
+    cplx s = cmake(0, 0);
+    const double* hrow = Hr + i * NN_;
+    const cplx* yrow = ya + i * NN_;
+#pragma unroll
+    for (int m = 0; m < NN_; ++m) {
+        const double h1 = hrow[m];
+        const cplx y1 = ya[m * NN_ + j];
+        s.x = fma(h1, y1.x, s.x);
+        s.y = fma(h1, y1.y, s.y);
+        const cplx a = yrow[m];
+        const double h2 = Hr[m * NN_ + j];
+        s.x = fma(-a.x, h2, s.x);
+        s.y = fma(-a.y, h2, s.y);
+    }
+    return cmake(s.y, -s.x);          // -i * s
+}
+
+// HR: the system Hamiltonian is real (needs NN_ != 0).  CB (shared bath parameters only): the coefficient of a slot is
+// n_k x base[slot][element] with the 8 x nn base coefficients (the n_k = 1 column of the table) in shared memory --
+// conflict-free reads, one conversion and two multiplications per neighbour -- instead of a look-up of the finished
+// coefficient in global memory / L1.  n_k x base is how heom_dn_coef forms the value, so the results are the same bits.
+template <int NN_, bool HR, bool CB>
+__global__ void __launch_bounds__(256, 3)
 heom_stage_fast_kernel(HeomFastArgs a) {
     extern __shared__ double2 smem[];
     const HeomDev& d = a.d;
     const int n = NN_ ? NN_ : d.n, nn = n * n, T = blockDim.x;
-    cplx* Hs = smem;                 // [nn]
+    cplx* Hs = smem;                 // [nn] (HR: the first nn doubles hold Re H)
+    double* Hr = reinterpret_cast<double*>(smem);
     cplx* ys = Hs + nn;              // [apc * nn]
-    for (int l = threadIdx.x; l < nn; l += T) Hs[l] = d.H[l];
+    cplx* base = ys + (size_t)a.apc * nn;     // [NE][nn] (CB)
+    for (int l = threadIdx.x; l < nn; l += T) {
+        if (HR) Hr[l] = d.H[l].x; else Hs[l] = d.H[l];
+    }
+    if (CB)
+        for (int l = threadIdx.x; l < HEOM_FLOW_NE * nn; l += T) {
+            const int s = l / nn;
+            base[l] = a.NK > 1 ? __ldg(a.ctab + heom_ctab_index(0, s, 1, l - s * nn, a.NK, nn)) : cmake(0, 0);
+        }
     const int g = threadIdx.x / nn, idx = threadIdx.x - g * nn;
     const int i = idx / n, j = idx - i * n;
     const long long ado = a.row_lo + (long long)blockIdx.x * a.apc + g;
@@ -848,6 +885,7 @@ heom_stage_fast_kernel(HeomFastArgs a) {
         w[0] = p0.x; w[1] = p0.y; w[2] = p0.z; w[3] = p0.w; w[4] = p1.x; w[5] = p1.y; w[6] = p1.z; w[7] = p1.w;
     }
     const size_t hstride = (size_t)d.nhe * nn;
+    const double damp1 = (act && d.damp) ? __ldg(d.damp + ado) : 0.0;      // shared bath parameters: one damping rate per ADO
     const int b0 = blockIdx.y * a.HB, b1 = min(a.B, b0 + a.HB);
     for (int b = b0; b < b1; ++b) {
         const int par = d.npar > 1 ? b : 0;
@@ -862,13 +900,16 @@ heom_stage_fast_kernel(HeomFastArgs a) {
         if (g < a.apc) ys[threadIdx.x] = yv;
         __syncthreads();
         if (act) {
-            cplx k = NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)g * nn, i, j) : heom_sys(Hs, n, ys + (size_t)g * nn, i, j);
-            const double damp = heom_damp(d, par, ado);
+            cplx k = HR ? heom_sys_real_t<(NN_ ? NN_ : 2)>(Hr, ys + (size_t)g * nn, i, j)
+                   : NN_ ? heom_sys_t<(NN_ ? NN_ : 2)>(Hs, ys + (size_t)g * nn, i, j) : heom_sys(Hs, n, ys + (size_t)g * nn, i, j);
+            const double damp = d.damp ? damp1 : heom_damp(d, par, ado);
             k.x = fma(-damp, yv.x, k.x);
             k.y = fma(-damp, yv.y, k.y);
-            const cplx* ct = a.ctab + ((size_t)par * nn + idx) * HEOM_FLOW_NE * a.NK;
 #pragma unroll
-            for (int s = 0; s < HEOM_FLOW_NE; ++s) cfma(k, __ldg(ct + s * a.NK + (w[s] >> HEOM_FLOW_IDXBITS)), nb[s]);
+            for (int s = 0; s < HEOM_FLOW_NE; ++s) {
+                if (CB) cfma(k, cscale((double)(w[s] >> HEOM_FLOW_IDXBITS), base[s * nn + idx]), nb[s]);
+                else cfma(k, __ldg(a.ctab + heom_ctab_index(par, s, (int)(w[s] >> HEOM_FLOW_IDXBITS), idx, a.NK, nn)), nb[s]);
+            }
             if (a.stage < 0) {
                 a.ynext[o] = k;
             } else {
@@ -1345,6 +1386,7 @@ struct limeb200_heom_s {
     long long nhe = 0, row_lo = 0, row_hi = 0;
     int path_req = 0, path = 0;
     bool diagq = false;
+    bool h_real = false;                // Im H == 0 everywhere: the packed-neighbour stage kernel takes the real -i[H, .] form
     cplx pref_up;
     DevBuf dH, dQ, dqstart, dqmodes, dems, demm, demv, ddamp, dcdn, dcdnR, dnu, dstates, ddn, dup;
     int max_modes_per_elem = 0;
@@ -1444,6 +1486,9 @@ int limeb200_heom_create_batched(limeb200_heom_t* plan, int device, int n, int n
     for (size_t i = 0; i < cdn.size(); ++i) { cdn[i] = pd * c[i]; cdnR[i] = pd * std::conj(c[i]); }
     p->pref_up = cmake(pref_up[0], pref_up[1]);
     LB_CUDA(p->dH.upload(h_H, (size_t)nn * 16));
+    p->h_real = true;
+    for (int l = 0; l < nn; ++l)
+        if (h_H[2 * l + 1] != 0.0) p->h_real = false;
     LB_CUDA(p->dQ.upload(h_Q, (size_t)nq * nn * 16));
     {   // per matrix element: the modes whose (diagonal) coupling operator touches row i or column j
         std::vector<int> ems(nn + 1, 0), emm;
@@ -1504,13 +1549,17 @@ long long limeb200_heom_last_launches(limeb200_heom_t p) { return p ? p->launche
 
 // b0: first hierarchy of the batch slice [b0, b0 + B) this launch works on (all batch-major pointers and the
 // per-hierarchy bath parameters are offset by it)
-// 0: walk the index tables (heom_bath_diag), 1: generic tile code with the packed gather, 2: heom_stage_fast_kernel.
+// 0: walk the index tables (heom_bath_diag), 1: generic tile code with the packed gather, 2: heom_stage_fast_kernel with
+// the finished-coefficient table in global memory, 3: the same with n_k x base coefficients from shared memory.
 // LIMEB200_HEOM_STAGE_MODE overrides (tests, comparisons); LIMEB200_HEOM_NO_FAST_STAGE = mode 0.
+#ifndef HEOM_STAGE_DEFAULT_MODE
+#define HEOM_STAGE_DEFAULT_MODE 0
+#endif
 static int heom_stage_mode(limeb200_heom_t p) {
     if (p->fast_state != 1 || getenv("LIMEB200_HEOM_NO_FAST_STAGE")) return 0;
     const char* e = getenv("LIMEB200_HEOM_STAGE_MODE");
-    if (e && *e >= '0' && *e <= '2' && !e[1]) return *e - '0';
-    return 2;
+    if (e && *e >= '0' && *e <= '3' && !e[1]) return *e - '0';
+    return HEOM_STAGE_DEFAULT_MODE;
 }
 // tables of the packed-neighbour stage kernel; called once when the plan is created (never inside a stream capture)
 static int heom_fast_prepare(limeb200_heom_t p) {
@@ -1557,7 +1606,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
         a.pk = p->d_pk.as<uint4>(); a.NK = p->max_nk + 1;
         a.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_PK_NE * a.NK : 0);
     }
-    if (mode == 2) {
+    if (mode >= 2) {
         HeomFastArgs f;
         f.d = a.d; f.B = B; f.stage = stage; f.NK = p->max_nk + 1; f.apc = a.apc;
         f.HB = std::max(std::min(B, 4), ceil_div(B, 65535));
@@ -1567,12 +1616,14 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
         f.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_FLOW_NE * f.NK : 0);
         const dim3 fgrid((unsigned)ceil_div(nown, (long long)f.apc), (unsigned)ceil_div(B, f.HB));
         const int threads = ceil_div(f.apc * nn, 32) * 32;
-        const size_t fsmem = (size_t)(1 + f.apc) * nn * 16;
-        // resident CTAs per SM the kernel is compiled for (register budget 128 / 80 / 64): LIMEB200_HEOM_FAST_OCC = 2, 3, 4
-        static const int occ = [] { const char* e = getenv("LIMEB200_HEOM_FAST_OCC"); const int v = e ? atoi(e) : HEOM_FAST_DEFAULT_OCC;
-                                    return (v >= 2 && v <= 4) ? v : HEOM_FAST_DEFAULT_OCC; }();
-#define LB_FAST(NN) (occ == 2 ? heom_stage_fast_kernel<NN, 2> : occ == 4 ? heom_stage_fast_kernel<NN, 4> : heom_stage_fast_kernel<NN, 3>)
-        void (*fk)(HeomFastArgs) = p->n == 7 ? LB_FAST(7) : p->n == 3 ? LB_FAST(3) : p->n == 2 ? LB_FAST(2) : LB_FAST(0);
+        const size_t fsmem = (size_t)(1 + f.apc + HEOM_FLOW_NE) * nn * 16;
+        // (compiled for 3 resident CTAs per SM, 80 registers; 2 / 4 CTAs measured within 2 % of it)
+        const bool hr = p->h_real && !getenv("LIMEB200_HEOM_COMPLEX_H");
+        const bool cb = p->npar == 1 && mode == 3;
+#define LB_FAST(NN) (hr ? (cb ? heom_stage_fast_kernel<NN, true, true> : heom_stage_fast_kernel<NN, true, false>) \
+                        : (cb ? heom_stage_fast_kernel<NN, false, true> : heom_stage_fast_kernel<NN, false, false>))
+        void (*fk)(HeomFastArgs) = p->n == 7 ? LB_FAST(7) : p->n == 3 ? LB_FAST(3) : p->n == 2 ? LB_FAST(2)
+                                 : (cb ? heom_stage_fast_kernel<0, false, true> : heom_stage_fast_kernel<0, false, false>);
 #undef LB_FAST
         fk<<<fgrid, threads, fsmem, st>>>(f);
         p->launches++;

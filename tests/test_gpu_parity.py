@@ -607,54 +607,51 @@ def test_heom_parameter_batch(cuda):
 
 
 def test_heom_stagewise_batch_l2_slices(cuda, monkeypatch):
-    """stage-wise batch path: (i) the packed-neighbour stage kernel (default for diagonal coupling operators) agrees
-    with the table-walking one to rounding; (ii) walked in slices of the batch (opt-in; forced slice of 2 on a batch of
-    5: ragged last slice) it is identical to the batch-wide launches -- shared bath parameters (FMO shape, observables +
-    trajectory) and per-hierarchy parameters (the slice offsets the parameter and coefficient tables)"""
+    """stage-wise batch path: (i) the packed-neighbour forms (LIMEB200_HEOM_STAGE_MODE 1: generic tile code with the
+    packed gather, 2: heom_stage_fast_kernel with the coefficient table, 3: with n_k x base coefficients from shared
+    memory) agree with the table-walking kernel (mode 0) to rounding, also in the generic persistent kernel; (ii) walked
+    in slices of the batch (opt-in; forced slice of 2 on a batch of 5: ragged last slice) the results are identical to the
+    batch-wide launches -- shared bath parameters (FMO shape, observables + trajectory) and per-hierarchy parameters
+    (the slice offsets the parameter and coefficient tables)"""
     from lime_b200 import engine
     import lime_b200.heom.heom as hh
     from lime_b200.heom.heom import _calc_matsubara_params
     n = 7
     H = cases.rand_herm(n, 21, 0.5) + np.diag(np.arange(n) * 0.3)
     Q = [np.diag((np.arange(n) == j).astype(float)) for j in range(n)]
-    h = hh.HEOM(H, Q, 0.05, 0.6, 1.2, N_exp=2, N_cut=2)
     rng = np.random.default_rng(6)
-    ado0 = 0.1 * (rng.standard_normal((5, h.nhe, n, n)) + 1j * rng.standard_normal((5, h.nhe, n, n)))
-    h.plan.set_path(2)
-    res = {}
-    for mode in ('off', 'slices', 'generic'):
-        monkeypatch.delenv('LIMEB200_HEOM_L2_CHUNK', raising=False)
-        monkeypatch.delenv('LIMEB200_HEOM_NO_FAST_STAGE', raising=False)
-        if mode == 'slices':
+    for Hsys in (H.real.astype(complex), H):          # real Hamiltonian (the real -i[H, .] form) and a complex one
+        h = hh.HEOM(Hsys, Q, 0.05, 0.6, 1.2, N_exp=2, N_cut=2)
+        ado0 = 0.1 * (rng.standard_normal((5, h.nhe, n, n)) + 1j * rng.standard_normal((5, h.nhe, n, n)))
+        h.plan.set_path(2)
+        res = {}
+        for mode in ('0', '1', '2', '3'):
+            monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', mode)
+            res[mode] = h.plan.run(ado0, 0.02, 10, e_ops=[Hsys], traj_every=5)
             monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
-        if mode == 'generic':           # the table-walking stage kernel instead of the packed-neighbour one
-            monkeypatch.setenv('LIMEB200_HEOM_NO_FAST_STAGE', '1')
-        res[mode] = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
-    for a, b in zip(res['off'], res['slices']):
-        assert np.array_equal(a, b)
-    for a, b in zip(res['off'], res['generic']):          # same operations in the same order (coefficients tabulated)
-        assert relerr(a, b) <= 1e-14
-    # the generic tile code with the packed gather (mode 1): stage-wise kernel and the generic persistent kernel
-    # (the one the ADO-sharded barrier path runs on large shards; LIMEB200_HEOM_NO_CACHED keeps the cached kernel out)
-    monkeypatch.delenv('LIMEB200_HEOM_NO_FAST_STAGE', raising=False)
-    monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', '1')
-    for a, b in zip(res['off'], h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)):
-        assert relerr(a, b) <= 1e-14
-    monkeypatch.setenv('LIMEB200_HEOM_NO_CACHED', '1')
-    h.plan.set_path(3)
-    for m in ('0', '1'):
-        monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', m)
-        out3 = h.plan.run(ado0, 0.02, 10, e_ops=[H], traj_every=5)
-        assert h.plan.path == 3
-        for a, b in zip(res['off'], out3):
-            assert relerr(a, b) <= 1e-14
-    monkeypatch.delenv('LIMEB200_HEOM_NO_CACHED')
-    monkeypatch.delenv('LIMEB200_HEOM_STAGE_MODE')
-    h.plan.set_path(2)
+            sl = h.plan.run(ado0, 0.02, 10, e_ops=[Hsys], traj_every=5)
+            monkeypatch.delenv('LIMEB200_HEOM_L2_CHUNK')
+            for a, b in zip(res[mode], sl):
+                assert np.array_equal(a, b)
+            for a, b in zip(res['0'], res[mode]):     # same operations in the same order (coefficients tabulated)
+                assert relerr(a, b) <= 1e-14
+        ado_o, obs_o, _ = lo.heom_rk4(ado0[4], Hsys, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64), h.dn.astype(np.int64),
+                                      h.up.astype(np.int64), 0.02, 10, e_ops=[Hsys])
+        for mode in ('0', '3'):
+            assert relerr(res[mode][0][4], ado_o) <= TOL and relerr(res[mode][1][:, 4], obs_o) <= TOL
+        # the generic persistent kernel (the one the ADO-sharded barrier path runs on large shards;
+        # LIMEB200_HEOM_NO_CACHED keeps the cached kernel out) with and without the packed gather
+        monkeypatch.setenv('LIMEB200_HEOM_NO_CACHED', '1')
+        h.plan.set_path(3)
+        for m in ('0', '1'):
+            monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', m)
+            out3 = h.plan.run(ado0, 0.02, 10, e_ops=[Hsys], traj_every=5)
+            assert h.plan.path == 3
+            for a, b in zip(res['0'], out3):
+                assert relerr(a, b) <= 1e-14
+        monkeypatch.delenv('LIMEB200_HEOM_NO_CACHED')
+    monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', '2')
     monkeypatch.setenv('LIMEB200_HEOM_L2_CHUNK', '2')
-    ado_o, obs_o, _ = lo.heom_rk4(ado0[4], H, h.Q, h.qmap, h.c, h.nu, h.states.astype(np.int64), h.dn.astype(np.int64),
-                                  h.up.astype(np.int64), 0.02, 10, e_ops=[H])
-    assert relerr(res['slices'][0][4], ado_o) <= TOL and relerr(res['slices'][1][:, 4], obs_o) <= TOL
     # per-hierarchy bath parameters
     Hs, sz, rho0, depth, K, lam, gam, T = cases.spin_boson_heom(depth=5)
     states, dn, up = engine.heom_tables([depth + 1] * K, depth)
