@@ -645,7 +645,10 @@ class HeomFMO(HeomBase):
     def kernel_name(self):
         if self.kernel:
             return self.kernel
-        return {1: 'heom_onchip_kernel', 2: 'heom_stage_kernel (one launch per RK4 stage)',
+        stage = ('heom_stage_fast_kernel (packed neighbour lists, n_k x base coefficients from shared memory; one launch '
+                 'per RK4 stage)' if self.B >= 4 else
+                 'heom_stage_kernel (packed neighbour lists + coefficient table; one launch per RK4 stage)')
+        return {1: 'heom_onchip_kernel', 2: stage,
                 3: 'heom_persist_cached_kernel / heom_persist_kernel (one cooperative launch per run)',
                 4: 'heom_flow_kernel (dataflow: tagged stage vectors, no barrier; one cooperative launch per run)'
                 }.get(self.h.plan.path, 'path %d' % self.h.plan.path)

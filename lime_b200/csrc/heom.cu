@@ -864,8 +864,8 @@ heom_stage_fast_kernel(HeomFastArgs a) {
     const int n = NN_ ? NN_ : d.n, nn = n * n, T = blockDim.x;
     cplx* Hs = smem;                 // [nn] (HR: the first nn doubles hold Re H)
     double* Hr = reinterpret_cast<double*>(smem);
-    cplx* ys = Hs + nn;              // [apc * nn]
-    cplx* base = ys + (size_t)a.apc * nn;     // [NE][nn] (CB)
+    cplx* ys0 = Hs + nn;             // [2][apc * nn]: double-buffered over the hierarchies of the CTA (one barrier each)
+    cplx* base = ys0 + (size_t)2 * a.apc * nn;     // [NE][nn] (CB)
     for (int l = threadIdx.x; l < nn; l += T) {
         if (HR) Hr[l] = d.H[l].x; else Hs[l] = d.H[l];
     }
@@ -896,7 +896,9 @@ heom_stage_fast_kernel(HeomFastArgs a) {
         cplx nb[HEOM_FLOW_NE];
 #pragma unroll
         for (int s = 0; s < HEOM_FLOW_NE; ++s) nb[s] = y[w[s] & ((1u << HEOM_FLOW_IDXBITS) - 1u)];
-        if (b > b0) __syncthreads();          // the previous hierarchy's -i[H, .] has finished reading ys
+        // (no second barrier: the buffer written now was last read two hierarchies ago, and every thread has passed
+        //  the barrier in between only after finishing those reads)
+        cplx* ys = ys0 + (size_t)((b - b0) & 1) * a.apc * nn;
         if (g < a.apc) ys[threadIdx.x] = yv;
         __syncthreads();
         if (act) {
@@ -1549,17 +1551,20 @@ long long limeb200_heom_last_launches(limeb200_heom_t p) { return p ? p->launche
 
 // b0: first hierarchy of the batch slice [b0, b0 + B) this launch works on (all batch-major pointers and the
 // per-hierarchy bath parameters are offset by it)
-// 0: walk the index tables (heom_bath_diag), 1: generic tile code with the packed gather, 2: heom_stage_fast_kernel with
-// the finished-coefficient table in global memory, 3: the same with n_k x base coefficients from shared memory.
-// LIMEB200_HEOM_STAGE_MODE overrides (tests, comparisons); LIMEB200_HEOM_NO_FAST_STAGE = mode 0.
-#ifndef HEOM_STAGE_DEFAULT_MODE
-#define HEOM_STAGE_DEFAULT_MODE 0
-#endif
-static int heom_stage_mode(limeb200_heom_t p) {
+// How a stage gathers the bath terms.  0: walk the index tables (heom_bath_diag), 1: generic tile code with the packed
+// gather, 2: heom_stage_fast_kernel with the finished-coefficient table in global memory, 3: the same with n_k x base
+// coefficients from shared memory.  Measured on B200 (profiles/r02_heom_stage_modes_pass3.jsonl, ADO-steps/s):
+//   batch of 64 FMO hierarchies (3060 ADOs each):  0: 1.01e8   1: 1.30e8   2: 1.40e8   3: 1.42e8
+//   one 38 760-ADO hierarchy:                       0: 8.50e7   1: 1.10e8   2: 9.48e7   3: 8.77e7
+// so batches (where a CTA reuses its packed words over 4 hierarchies) take mode 3 and single hierarchies mode 1 (61
+// registers, 4 CTAs per SM: the gather of a 30 MB stage vector is latency bound and wants the occupancy).  Per-hierarchy
+// bath parameters keep the table walk (their coefficient tables were not measured).  LIMEB200_HEOM_STAGE_MODE overrides.
+static int heom_stage_mode(limeb200_heom_t p, int B) {
     if (p->fast_state != 1 || getenv("LIMEB200_HEOM_NO_FAST_STAGE")) return 0;
     const char* e = getenv("LIMEB200_HEOM_STAGE_MODE");
     if (e && *e >= '0' && *e <= '3' && !e[1]) return *e - '0';
-    return HEOM_STAGE_DEFAULT_MODE;
+    if (p->npar > 1) return 0;
+    return B >= 4 ? 3 : 1;
 }
 // tables of the packed-neighbour stage kernel; called once when the plan is created (never inside a stream capture)
 static int heom_fast_prepare(limeb200_heom_t p) {
@@ -1601,7 +1606,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
     a.rho = rho; a.yin = yin; a.ynext = ynext; a.acc = acc; a.dt = dt;
     a.apc = std::max(1, 256 / nn);
     // packed-neighbour kernel (diagonal coupling operators; tables built by heom_fast_prepare at plan creation)
-    const int mode = heom_stage_mode(p);
+    const int mode = heom_stage_mode(p, B);
     if (mode >= 1) {
         a.pk = p->d_pk.as<uint4>(); a.NK = p->max_nk + 1;
         a.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_PK_NE * a.NK : 0);
@@ -1616,7 +1621,7 @@ static int heom_launch_stage(limeb200_heom_t p, int stage, cplx* rho, const cplx
         f.ctab = p->d_ctab.as<cplx>() + (p->npar > 1 ? (size_t)b0 * nn * HEOM_FLOW_NE * f.NK : 0);
         const dim3 fgrid((unsigned)ceil_div(nown, (long long)f.apc), (unsigned)ceil_div(B, f.HB));
         const int threads = ceil_div(f.apc * nn, 32) * 32;
-        const size_t fsmem = (size_t)(1 + f.apc + HEOM_FLOW_NE) * nn * 16;
+        const size_t fsmem = (size_t)(1 + 2 * f.apc + HEOM_FLOW_NE) * nn * 16;
         // (compiled for 3 resident CTAs per SM, 80 registers; 2 / 4 CTAs measured within 2 % of it)
         const bool hr = p->h_real && !getenv("LIMEB200_HEOM_COMPLEX_H");
         const bool cb = p->npar == 1 && mode == 3;
@@ -1699,7 +1704,7 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
     pa.s.dt = dt;
     pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
-    if (heom_stage_mode(p) >= 1 && !pa.hybrid) {       // the generic persistent kernel gathers through the packed lists too
+    if (heom_stage_mode(p, 1) >= 1 && !pa.hybrid) {       // the generic persistent kernel gathers through the packed lists too
         pa.s.pk = p->d_pk.as<uint4>(); pa.s.ctab = p->d_ctab.as<cplx>(); pa.s.NK = p->max_nk + 1;
     }
     pa.s.apc = c.apc;

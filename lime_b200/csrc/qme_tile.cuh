@@ -81,17 +81,8 @@ __device__ __forceinline__ void tmem_ld32_wait(TmemRow& w) {
           "+r"(w.r[24]), "+r"(w.r[25]), "+r"(w.r[26]), "+r"(w.r[27])
         :: "memory");
 }
-// Variants without the "memory" clobber (template flag V & 1 of the kernel): tensor memory does not alias shared
-// memory, the TMEM accesses stay ordered among themselves because they are volatile, and every consumer of the
-// loaded words depends on the wait through its "+r" operands -- so the compiler may move the shared-memory loads of
-// the NEXT patch row above the FMA chain of the current one.
-__device__ __forceinline__ void tmem_ld32_wait_nc(TmemRow& w) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-        : "+r"(w.r[0]), "+r"(w.r[1]), "+r"(w.r[2]), "+r"(w.r[3]), "+r"(w.r[4]), "+r"(w.r[5]), "+r"(w.r[6]), "+r"(w.r[7]),
-          "+r"(w.r[8]), "+r"(w.r[9]), "+r"(w.r[10]), "+r"(w.r[11]), "+r"(w.r[12]), "+r"(w.r[13]), "+r"(w.r[14]), "+r"(w.r[15]),
-          "+r"(w.r[16]), "+r"(w.r[17]), "+r"(w.r[18]), "+r"(w.r[19]), "+r"(w.r[20]), "+r"(w.r[21]), "+r"(w.r[22]), "+r"(w.r[23]),
-          "+r"(w.r[24]), "+r"(w.r[25]), "+r"(w.r[26]), "+r"(w.r[27]));
-}
+// Clobber-free forms used by the tensor-memory-window variant (tensor memory does not alias shared memory; the
+// TMEM accesses stay ordered among themselves because they are volatile).
 __device__ __forceinline__ void tmem_st8_nc(unsigned taddr, const double (&d)[4]) {
     unsigned r[8];
 #pragma unroll
@@ -104,27 +95,7 @@ __device__ __forceinline__ void st_async_c128_nc(unsigned raddr, cplx v, unsigne
     asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f64 [%0+%4], {%1, %2}, [%3];"
                  ::"r"(raddr), "d"(v.x), "d"(v.y), "r"(rbar), "n"(IMM));
 }
-// plain arrival (release.cta) / bounded wait (acquire.cta) on a CTA-local mbarrier: the per-warp barriers of V & 2
-__device__ __forceinline__ void mbar_arrive_cta(unsigned bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned bar, unsigned parity) {
-    unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    return ok != 0;
-}
-// a protocol error must not hang the device: trap after ~2 s
-__device__ __forceinline__ void mbar_wait_bounded(unsigned bar, unsigned parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity))
-        if (clock64() - t0 > 4000000000ll) __trap();
-}
-// 16-word load (rho + accumulator only; V & 4)
+// 16-word load (rho + accumulator)
 struct TmemRow16 { unsigned r[16]; };
 __device__ __forceinline__ void tmem_ld16_issue(unsigned taddr, TmemRow16& w) {
     asm volatile(
@@ -141,7 +112,7 @@ __device__ __forceinline__ void tmem_ld16_wait(TmemRow16& w) {
 __device__ __forceinline__ double tmem_dbl(const TmemRow16& w, int i) {
     return __hiloint2double((int)w.r[2 * i + 1], (int)w.r[2 * i]);
 }
-// 8-word load (one patch row of the stage vector; V & 8)
+// 8-word load (one patch row of the stage vector)
 struct TmemRow8 { unsigned r[8]; };
 __device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, TmemRow8& w) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -182,18 +153,15 @@ struct QmeTileCtx {
     unsigned xs[S > 0 ? S : 1][2];     // ... of the sandwich source of patch row 0 at the source columns of u = 0, 1
     unsigned up_dst, dn_dst, up_bar, dn_bar;   // remote (shared::cluster) addresses, buffer 0, of the pushed rows; 0 = no push
     unsigned trho;                     // tensor-memory address of this thread's row records
-    unsigned rowc;                     // V & 4: byte offset (from the start of shared memory) of the patch's row coefficients
+    unsigned rowc;                     // TW: byte offset (from the start of shared memory) of the patch's row coefficients
     double cdr[2], cdi[2], cL[2], cR[2], zv[S > 0 ? S : 1][2];
     double hdt, dt, w6;
 };
 
 // One RK4 stage of one thread's patch.  STAGE is compile time: input buffer = STAGE & 1, output = the other one.
-// V & 1: clobber-free tensor-memory / st.async statements and the sandwich sources loaded with the rest of the row's
-// operands (before the tensor-memory wait) -- same arithmetic, more scheduling freedom.
-template <int NP, int TR, int S, int STAGE, int V>
+template <int NP, int TR, int S, int STAGE>
 __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
     constexpr int ROWB = NP * 16;
-    constexpr bool RLX = (V & 1) != 0;
     // ordinary shared-memory accesses (base register + immediate) that the compiler is free to schedule
     const unsigned in_off = (STAGE & 1) ? bufb : 0u;
     const unsigned out_off = (STAGE & 1) ? 0u : bufb;
@@ -228,17 +196,7 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
             k[u].x = fma(-c.cR[u], b.y, k[u].x);
             k[u].y = fma(c.cR[u], b.x, k[u].y);
         }
-        cplx ysrc[S > 0 ? S : 1][2];
-        if (RLX) {
-#pragma unroll
-            for (int s = 0; s < S; ++s)
-#pragma unroll
-                for (int u = 0; u < 2; ++u)
-                    ysrc[s][u] = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
-            tmem_ld32_wait_nc(tw);
-        } else {
-            tmem_ld32_wait(tw);
-        }
+        tmem_ld32_wait(tw);
         const double gdx = tmem_dbl(tw, 8), gdy = tmem_dbl(tw, 9), gup = tmem_dbl(tw, 10), gdn = tmem_dbl(tw, 11);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
@@ -259,7 +217,7 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
             const double xv = tmem_dbl(tw, 12 + s);
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
-                const cplx ys = RLX ? ysrc[s][u] : *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
+                const cplx ys = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
                 const double cf = xv * c.zv[s][u];
                 k[u].x = fma(cf, ys.x, k[u].x);
                 k[u].y = fma(cf, ys.y, k[u].y);
@@ -284,28 +242,17 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
                 st4[2 * u] = yn[u].x; st4[2 * u + 1] = yn[u].y;
             }
         }
-        if (RLX) tmem_st8_nc(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
-        else tmem_st8(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
+        tmem_st8(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
 #pragma unroll
         for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
         // boundary rows of a chunk also go into the neighbour CTA's halo row; the bytes are counted on its mbarrier
         if (r == 0 && c.up_dst) {
-            if (RLX) {
-                st_async_c128_nc<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
-                st_async_c128_nc<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
-            } else {
-                st_async_c128<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
-                st_async_c128<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
-            }
+            st_async_c128<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
+            st_async_c128<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
         }
         if (r == TR - 1 && c.dn_dst) {
-            if (RLX) {
-                st_async_c128_nc<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
-                st_async_c128_nc<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
-            } else {
-                st_async_c128<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
-                st_async_c128<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
-            }
+            st_async_c128<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
+            st_async_c128<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
@@ -313,120 +260,8 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// V & 4: the same stage with the tensor-memory traffic cut to what is lane-private.  A tcgen05.ld moves
-// 128 B per word and warp whatever the data; the B300 tables (B300_MICROARCH.md, "TMEM") give 64 B/clk per SM for
-// tensor-memory READS, so the 32-word row record of the kernel above costs 64 clk per warp and patch row = 4096 clk per
-// stage for 16 warps x 4 rows -- which is the measured stage time (3940 clk at 4.61e6 rho-steps/s): the kernel is bound
-// by the tensor-memory read port, not by latency.  Here (i) the row coefficients -- warp-uniform, so their copy in tensor
-// memory is replicated 32 times -- come from shared memory as three 16-byte broadcasts, (ii) stage 0 reads nothing from
-// tensor memory (its input IS rho, already in the sliding window), (iii) stages 1-3 read the 16 words rho + accumulator.
-// Tensor-memory reads per RK4 step: 3 x 16 words instead of 4 x 32.
-template <int NP, int TR, int S, int STAGE>
-__device__ __forceinline__ void qme_tile_stage_s(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
-    constexpr int ROWB = NP * 16;
-    const unsigned in_off = (STAGE & 1) ? bufb : 0u;
-    const unsigned out_off = (STAGE & 1) ? 0u : bufb;
-    const char* pown = smem + (c.own + in_off);
-    const char* pl = smem + (c.nl + in_off);
-    const char* pr = smem + (c.nr + in_off);
-    const char* prc = smem + c.rowc;
-    char* pout = smem + (c.own + out_off);
-    const double cy = (STAGE == 2) ? c.dt : c.hdt;
-
-    cplx wp[2], wc[2], wn[2];
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        wp[u] = *reinterpret_cast<const cplx*>(pown + 512 * u);
-        wc[u] = *reinterpret_cast<const cplx*>(pown + ROWB + 512 * u);
-    }
-#pragma unroll
-    for (int r = 0; r < TR; ++r) {
-        TmemRow16 tw;
-        if (STAGE != 0) tmem_ld16_issue(c.trho + QME_TILE_TMW * r, tw);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) wn[u] = *reinterpret_cast<const cplx*>(pown + (r + 2) * ROWB + 512 * u);
-        const cplx yl = *reinterpret_cast<const cplx*>(pl + (r + 1) * ROWB);
-        const cplx yr = *reinterpret_cast<const cplx*>(pr + (r + 1) * ROWB);
-        const double2 gd = *reinterpret_cast<const double2*>(prc + r * 48);            // G_ii
-        const double2 gud = *reinterpret_cast<const double2*>(prc + r * 48 + 16);      // Im G_i,i-1, Im G_i,i+1
-        double2 xv2 = make_double2(0.0, 0.0);
-        if (S > 0) xv2 = *reinterpret_cast<const double2*>(prc + r * 48 + 32);         // X_0, X_1 row entries
-        cplx ysrc[S > 0 ? S : 1][2];
-#pragma unroll
-        for (int s = 0; s < S; ++s)
-#pragma unroll
-            for (int u = 0; u < 2; ++u)
-                ysrc[s][u] = *reinterpret_cast<const cplx*>(smem + (c.xs[s][u] + in_off) + r * ROWB);
-        cplx k[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const cplx a = (u == 0) ? yl : wc[0];
-            const cplx b = (u == 0) ? wc[1] : yr;
-            k[u].x = -c.cL[u] * a.y;
-            k[u].y = c.cL[u] * a.x;
-            k[u].x = fma(-c.cR[u], b.y, k[u].x);
-            k[u].y = fma(c.cR[u], b.x, k[u].y);
-        }
-        const double gdx = gd.x, gdy = gd.y, gup = gud.x, gdn = gud.y;
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const double dr = gdx + c.cdr[u], di = gdy + c.cdi[u];
-            k[u].x = fma(dr, wc[u].x, k[u].x);
-            k[u].x = fma(-di, wc[u].y, k[u].x);
-            k[u].y = fma(dr, wc[u].y, k[u].y);
-            k[u].y = fma(di, wc[u].x, k[u].y);
-            k[u].x = fma(-gup, wp[u].y, k[u].x);
-            k[u].y = fma(gup, wp[u].x, k[u].y);
-            k[u].x = fma(-gdn, wn[u].y, k[u].x);
-            k[u].y = fma(gdn, wn[u].x, k[u].y);
-        }
-#pragma unroll
-        for (int s = 0; s < S; ++s) {
-            const double xv = (s == 0) ? xv2.x : xv2.y;
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                const double cf = xv * c.zv[s][u];
-                k[u].x = fma(cf, ysrc[s][u].x, k[u].x);
-                k[u].y = fma(cf, ysrc[s][u].y, k[u].y);
-            }
-        }
-        if (STAGE != 0) tmem_ld16_wait(tw);
-        cplx yn[2];
-        double st4[4];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const double kx = k[u].x, ky = k[u].y;
-            if (STAGE == 0) {
-                st4[2 * u] = kx; st4[2 * u + 1] = ky;
-                yn[u] = cmake(fma(cy, kx, wc[u].x), fma(cy, ky, wc[u].y));
-            } else if (STAGE < 3) {
-                st4[2 * u] = fma(2.0, kx, tmem_dbl(tw, 4 + 2 * u));
-                st4[2 * u + 1] = fma(2.0, ky, tmem_dbl(tw, 5 + 2 * u));
-                yn[u] = cmake(fma(cy, kx, tmem_dbl(tw, 2 * u)), fma(cy, ky, tmem_dbl(tw, 2 * u + 1)));
-            } else {
-                yn[u].x = fma(c.w6, tmem_dbl(tw, 4 + 2 * u) + kx, tmem_dbl(tw, 2 * u));
-                yn[u].y = fma(c.w6, tmem_dbl(tw, 5 + 2 * u) + ky, tmem_dbl(tw, 2 * u + 1));
-                st4[2 * u] = yn[u].x; st4[2 * u + 1] = yn[u].y;
-            }
-        }
-        tmem_st8_nc(c.trho + QME_TILE_TMW * r + (STAGE == 3 ? 0 : 8), st4);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) *reinterpret_cast<cplx*>(pout + (r + 1) * ROWB + 512 * u) = yn[u];
-        if (r == 0 && c.up_dst) {
-            st_async_c128_nc<0>(c.up_dst + out_off, yn[0], c.up_bar + 8 * (STAGE & 1));
-            st_async_c128_nc<512>(c.up_dst + out_off, yn[1], c.up_bar + 8 * (STAGE & 1));
-        }
-        if (r == TR - 1 && c.dn_dst) {
-            st_async_c128_nc<0>(c.dn_dst + out_off, yn[0], c.dn_bar + 8 * (STAGE & 1));
-            st_async_c128_nc<512>(c.dn_dst + out_off, yn[1], c.dn_bar + 8 * (STAGE & 1));
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) { wp[u] = wc[u]; wc[u] = wn[u]; }
-    }
-    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-
-// V & 8 (with V & 4): the thread's OWN rows of the stage vector come from tensor memory as well.  The measurements of
+// TW ("tensor-memory window", opt-in: LIMEB200_TILE_V=8): the thread's OWN rows of the stage vector come from tensor
+// memory, and the warp-uniform row coefficients from shared memory as three 16-byte broadcasts.  The measurements of
 // round 2 (tools/ubench/tmem_bw.cu: tcgen05.ld 439 B/clk per SM, tcgen05.st 619 B/clk, against 128 B/clk of shared
 // memory; ncu: 42.7 shared-memory wavefronts per warp and patch row, shared-memory pipe 63-77 %; variants 2/4/6 all
 // slower in proportion to the wavefronts they add) say the kernel is bound by the shared-memory pipe and that tensor
@@ -556,28 +391,16 @@ __device__ __forceinline__ void qme_tile_stage_t(const QmeTileCtx<NP, TR, S>& c,
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base][warp dependency masks 32 x 4 B]
-// [per-warp stage barriers 32 x 2 x 8 B][row coefficients R x 48 B]
+// shared memory: [buffer 0][buffer 1][4 mbarriers][red E*32][part 2*C*E][tmem base][row coefficients R x 48 B]
 static inline size_t qme_tile_smem(int NP, int P, int chunk, int C, int E) {
     const size_t nbr = (size_t)P * (chunk + 2);
     const size_t e = E > 0 ? E : 1;
-    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + 16 + 128 + 512 + (size_t)P * chunk * 48;
+    return 2 * nbr * NP * 16 + 64 + e * 32 * 16 + 2 * (size_t)C * e * 16 + 16 + (size_t)P * chunk * 48;
 }
 
-// V & 2 ("warp-level stage synchronisation"): the CTA barrier + everybody-waits-for-the-halo at the end of every
-// stage is replaced by per-warp mbarriers.  A warp's patch is read only by a few other warps (the row groups above /
-// below, the other column block, the patches its sandwich terms point at) and it reads only from those; the
-// relation is made symmetric (D_w = sources of w + readers of w), every warp arrives on the stage barrier of each
-// warp in D_w when its stage is stored and waits on its own barrier (count |D_w|) before the next stage.  Symmetry
-// gives read-after-write AND write-after-read safety on the two ping-pong buffers, and bounds the skew between
-// dependent warps to one stage -- hence two barriers per warp, indexed by the stage parity.  Only the warps that
-// read a halo row fed by a neighbour CTA (and warp 0, whose thread 0 arms the halo barrier) wait on the halo
-// mbarrier; they are exactly the warps that push rows to that neighbour (host check in build_tile_host), which is
-// what makes the cross-CTA write-after-read argument of the block-synchronised kernel carry over unchanged.
-template <int NP, int TR, int S, int V>
+template <int NP, int TR, int S, bool TW>
 __global__ void __launch_bounds__(512, 1)
 qme_tile_kernel(QmeTileArgs a) {
-    constexpr bool FG = (V & 2) != 0;
     extern __shared__ __align__(16) char smem_raw[];
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -600,9 +423,7 @@ qme_tile_kernel(QmeTileArgs a) {
     const unsigned o_red = o_bar + 64;                // [E][32] cplx
     const unsigned o_part = o_red + Ee * 32 * 16;     // [2][C][E] cplx (rank 0)
     const unsigned o_tm = o_part + 2 * C * Ee * 16;
-    const unsigned o_dep = o_tm + 16;                 // [32] unsigned: source-warp masks
-    const unsigned o_wbar = o_dep + 128;              // [32][2] mbarriers: per-warp stage barriers
-    const unsigned o_rowc = o_wbar + 512;             // [R][6] doubles: row coefficients (V & 4)
+    const unsigned o_rowc = o_tm + 16;                // [R][6] doubles: row coefficients (TW)
     cplx* buf0 = reinterpret_cast<cplx*>(smem_raw);
     cplx* red = reinterpret_cast<cplx*>(smem_raw + o_red);
     cplx* part = reinterpret_cast<cplx*>(smem_raw + o_part);
@@ -631,7 +452,7 @@ qme_tile_kernel(QmeTileArgs a) {
         buf0[NBR * NP + l] = cmake(0, 0);
     }
 
-    if (V & 12) {
+    if (TW) {
         const double* rc = a.rowc + ((size_t)vb * C + rank) * R * QME_TILE_ROWC;
         double* rs = reinterpret_cast<double*>(smem_raw + o_rowc);
         for (int l = threadIdx.x; l < R * QME_TILE_ROWC; l += T) rs[l] = rc[l];
@@ -707,72 +528,22 @@ qme_tile_kernel(QmeTileArgs a) {
         tmem_st8(c.trho + QME_TILE_TMW * r, rh);
         tmem_st8(c.trho + QME_TILE_TMW * r + 8, z4);
         c4[0] = rcp[0]; c4[1] = rcp[1]; c4[2] = rcp[2]; c4[3] = rcp[3];
-        if (V & 8) tmem_st8(c.trho + QME_TILE_TMW * r + 16, rh);      // third slot: the stage input (= rho before stage 0)
+        if (TW) tmem_st8(c.trho + QME_TILE_TMW * r + 16, rh);      // third slot: the stage input (= rho before stage 0)
         else tmem_st8(c.trho + QME_TILE_TMW * r + 16, c4);
         c4[0] = rcp[4]; c4[1] = rcp[5]; c4[2] = 0.0; c4[3] = 0.0;
         tmem_st8(c.trho + QME_TILE_TMW * r + 24, c4);
     }
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 
-    // ---- V & 2: who reads what.  Every lane maps the shared-memory words it reads in a stage to the warp that
-    // writes them (halo rows have no local writer), the warp ORs the lanes.
-    unsigned dmask = 0, ndeps = 0;
-    bool halo_wait = (C > 1);
-    const unsigned wbar0 = sbase + o_wbar;
-    if (FG) {
-        unsigned src = 0;
-        bool halo_read = false;
-        auto owner = [&](unsigned off) {               // byte offset inside buffer 0 -> writer warp
-            const int row = (int)(off / ROWB), pos = (int)(off % ROWB) / 16;
-            const int pp = row / (chunk + 2), t = row - pp * (chunk + 2);
-            if (t == 0) { halo_read |= (rank > 0); return; }
-            if (t == chunk + 1) { halo_read |= (rank < C - 1); return; }
-            src |= 1u << (((pp * chunk + t - 1) / TR) * CB + pos / 64);
-        };
-        for (int r = 0; r < TR + 2; ++r) { owner(c.own + r * ROWB); owner(c.own + r * ROWB + 512); }
-        for (int r = 1; r <= TR; ++r) { owner(c.nl + r * ROWB); owner(c.nr + r * ROWB); }
-        if (S > 0)
-            for (int s = 0; s < SS; ++s)
-                for (int u = 0; u < 2; ++u)
-                    for (int r = 0; r < TR; ++r) owner(c.xs[s][u] + r * ROWB);
-        src = __reduce_or_sync(0xffffffffu, src);
-        halo_read = __any_sync(0xffffffffu, halo_read);
-        unsigned* deps = reinterpret_cast<unsigned*>(smem_raw + o_dep);
-        if (lane == 0) deps[warp] = src;
-        __syncthreads();
-        const int W = T >> 5;
-        unsigned readers = 0;
-        for (int v = 0; v < W; ++v) readers |= ((deps[v] >> warp) & 1u) << v;
-        dmask = (src | readers) & ~(1u << warp);
-        ndeps = (unsigned)__popc(dmask);
-        if (lane == 0) {
-            mbar_init(wbar0 + 16 * warp, ndeps ? ndeps : 1u);
-            mbar_init(wbar0 + 16 * warp + 8, ndeps ? ndeps : 1u);
-            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        }
-        halo_wait = (C > 1) && (halo_read || warp == 0);
-        if (C == 1) __syncthreads();
-    }
-    // barrier addresses of parity 0 (0 = none): the one this lane arrives on, the one this warp waits on
-    const unsigned arr_bar = (FG && ((dmask >> lane) & 1u)) ? wbar0 + 16 * lane : 0u;
-    const unsigned own_bar = (FG && ndeps) ? wbar0 + 16 * warp : 0u;
     if (C > 1) cluster.sync();
 
     for (int step = 0; step < a.nsteps; ++step) {
 #define QME_TILE_STAGE(ST)                                                                           \
         if (C > 1 && threadIdx.x == 0) mbar_arrive_expect_tx(bar0 + 8 * ((ST) & 1), halo_bytes);      \
-        if (V & 8) qme_tile_stage_t<NP, TR, S, ST>(c, smem_raw, bufb);                                \
-        else if (V & 4) qme_tile_stage_s<NP, TR, S, ST>(c, smem_raw, bufb);                           \
-        else qme_tile_stage<NP, TR, S, ST, V>(c, smem_raw, bufb);                                     \
-        if (FG) {                                                                                     \
-            __syncwarp();                                                                             \
-            if (arr_bar) mbar_arrive_cta(arr_bar + 8 * ((ST) & 1));                                   \
-            if (own_bar) mbar_wait_bounded(own_bar + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));    \
-            if (halo_wait) mbar_wait_bounded(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));     \
-        } else {                                                                                      \
-            __syncthreads();                                                                          \
-            if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));                 \
-        }
+        if (TW) qme_tile_stage_t<NP, TR, S, ST>(c, smem_raw, bufb);                                   \
+        else qme_tile_stage<NP, TR, S, ST>(c, smem_raw, bufb);                                        \
+        __syncthreads();                                                                              \
+        if (C > 1) mbar_wait(bar0 + 8 * ((ST) & 1), (unsigned)(((ST) >> 1) & 1));
         QME_TILE_STAGE(0)
         if (C > 1 && a.obs && step > 0 && rank == 0) {
             // partial sums of the previous step (pushed by the other CTAs with st.async) are complete
@@ -791,7 +562,6 @@ qme_tile_kernel(QmeTileArgs a) {
 #undef QME_TILE_STAGE
         // buffer 0 now holds rho_{n+1} (own + halo rows)
         if (a.obs) {
-            if (FG) __syncthreads();      // the reduction reads every own row of the CTA
             for (int e = 0; e < a.E; ++e) {
                 cplx v = cmake(0, 0);
                 for (int n = a.eptr[e] + threadIdx.x; n < a.eptr[e + 1]; n += T)
@@ -857,9 +627,9 @@ qme_tile_kernel(QmeTileArgs a) {
     if (C > 1) cluster.sync();      // keep shared memory alive until the neighbours' remote stores are done
 }
 
-template <int NP, int TR, int S, int V>
+template <int NP, int TR, int S, bool TW>
 static int qme_tile_launch_one(const QmeTileArgs& a, size_t smem, cudaStream_t st) {
-    auto kern = qme_tile_kernel<NP, TR, S, V>;
+    auto kern = qme_tile_kernel<NP, TR, S, TW>;
     LB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int W = (a.P * a.chunk / TR) * (NP / 64);
     cudaLaunchConfig_t cfg = {};

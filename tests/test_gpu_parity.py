@@ -822,13 +822,13 @@ def test_lindblad_config2_full_batch(cuda):
         assert relerr(rho[b].cpu().numpy(), rl[-1]) <= TOL and relerr(obs[:, b].cpu().numpy(), o) <= TOL
 
 
-@pytest.mark.parametrize('variant', [1, 2, 3, 4, 6, 8])
+@pytest.mark.parametrize('variant', [8])
 def test_lindblad_tile_kernel_variants(cuda, monkeypatch, variant):
-    """the scheduling / synchronisation variants of the register-patch kernel (LIMEB200_TILE_V: bit 0 clobber-free
-    tensor-memory statements, bit 1 warp-level stage barriers instead of the CTA barrier, bit 2 row coefficients from
-    shared memory + 16-word tensor-memory reads in stages 1-3 only) do the same arithmetic:
-    identical to variant 0 and within tolerance of the oracle, small cutoffs (one CTA, ragged padding, clusters of
-    2 and 4), with / without observables and trajectory, and on the full 4096-point batch at full occupancy"""
+    """the tensor-memory-window variant of the register-patch kernel (LIMEB200_TILE_V=8: the thread's own rows of the
+    stage vector and nothing else come from tensor memory, row coefficients from shared memory) does the same
+    arithmetic: identical to the default kernel and within tolerance of the oracle, small cutoffs (one CTA, ragged
+    padding, clusters of 2 and 4), with / without observables and trajectory, and on the full 4096-point batch at full
+    occupancy"""
     import torch
     from lime_b200 import builders, oqs
     for ncav in (8, 16, 37, 64):
@@ -841,7 +841,7 @@ def test_lindblad_tile_kernel_variants(cuda, monkeypatch, variant):
             plan = oqs._lindblad_plan(Hs, cs, e_ops, path=6)
             assert plan.path == 6
             out[v] = plan.run(rho0, 0.01, 60, traj_every=20)
-            plan2 = oqs._lindblad_plan(Hs, cs, None, path=6)          # no observables: no CTA barrier at all
+            plan2 = oqs._lindblad_plan(Hs, cs, None, path=6)          # no observables
             out[v] += (plan2.run(rho0, 0.01, 60)[0],)
         rho_f, obs, traj, rho_n = out[variant]
         assert relerr(obs, obs_o) <= TOL and relerr(rho_f, rl_o[-1]) <= TOL and relerr(rho_n, rl_o[-1]) <= TOL

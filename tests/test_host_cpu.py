@@ -338,13 +338,3 @@ def test_rkf45_step_controller_host_logic(rkf45_on_host):
         U = v @ np.diag(np.exp(-1j * w * t)) @ v.conj().T
         assert np.max(np.abs(r - U @ rho0 @ U.conj().T)) < 1e-8
 
-
-def test_tile_kernel_warp_sync_protocol_model():
-    """the warp-level stage synchronisation of qme_tile_kernel (template flag V & 2): randomised-schedule model of the
-    protocol (per-warp mbarriers by stage parity, symmetric dependency sets, halo transaction barriers) -- every read
-    sees exactly the stage it expects, no deadlock; the model rejects the three obvious simplifications"""
-    import importlib.util, random
-    spec = importlib.util.spec_from_file_location('tile_sync_model', os.path.join(ROOT, 'tools', 'tile_sync_model.py'))
-    m = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(m)
-    assert m.main(60) >= 50
