@@ -368,6 +368,24 @@ def test_sharded_virtual_ranks_on_one_gpu(cuda, world, halo_only):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('mode', ['0', '1'])
+def test_sharded_virtual_ranks_generic_persistent_kernel(cuda, monkeypatch, mode):
+    """the GENERIC persistent kernel (what the barrier path runs on shards too large for the cached one; forced here with
+    LIMEB200_HEOM_NO_CACHED) across 3 virtual ranks: table walk (mode 0) and packed neighbour lists (mode 1, the
+    default) behind the same peer stores and one-hop barrier"""
+    monkeypatch.setenv('LIMEB200_HEOM_NO_CACHED', '1')
+    monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', mode)
+    H, Q, lam, gam, T, depth, rho0 = _problem()
+    ref = _reference()
+    ado0 = np.zeros_like(ref)
+    ado0[0] = rho0
+    outs, ranges = _virtual_ranks_one_gpu(3, H, Q, lam, gam, T, depth, ado0, 0.01, [5, 7], halo_only=True)
+    for r, o in enumerate(outs):
+        assert relerr(o, ref) <= 1e-10, r
+        assert np.array_equal(o, outs[0])
+
+
+@pytest.mark.gpu
 def test_sharded_virtual_ranks_fmo_depth3_long(cuda):
     """a larger hierarchy (FMO, depth 3: 680 ADOs of 7x7) over 4 virtual ranks for 200 steps against the one-GPU
     propagator of the same library: the barrier protocol over 800 stages"""
