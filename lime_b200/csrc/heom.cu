@@ -1704,8 +1704,15 @@ static int heom_launch_persist(limeb200_heom_t p, HeomPersistArgs& pa, cplx* rho
     pa.s.rho = rho; pa.s.acc = p->s_acc.as<cplx>(); pa.s.yin = nullptr; pa.s.ynext = nullptr;
     pa.s.dt = dt;
     pa.s.npeer = 0; pa.s.peer_mask = nullptr; pa.s.send_all = 1;
-    if (heom_stage_mode(p, 1) >= 1 && !pa.hybrid) {       // the generic persistent kernel gathers through the packed lists too
-        pa.s.pk = p->d_pk.as<uint4>(); pa.s.ctab = p->d_ctab.as<cplx>(); pa.s.NK = p->max_nk + 1;
+    // The generic persistent kernel keeps the table walk: with its 64-register budget (1024 threads per CTA) the packed
+    // gather spills and was measured 19 % SLOWER on the 38 760-ADO hierarchy over 2 GPUs (18.6 vs 15.1 ms per 50 steps,
+    // profiles/r02_bench_default_2gpu_packed_persist.json vs r02_bench_default_2gpu.json).  LIMEB200_HEOM_STAGE_MODE=1
+    // switches it on explicitly (tests).
+    {
+        const char* e = getenv("LIMEB200_HEOM_STAGE_MODE");
+        if (p->fast_state == 1 && e && e[0] == '1' && !e[1] && !pa.hybrid && !getenv("LIMEB200_HEOM_NO_FAST_STAGE")) {
+            pa.s.pk = p->d_pk.as<uint4>(); pa.s.ctab = p->d_ctab.as<cplx>(); pa.s.NK = p->max_nk + 1;
+        }
     }
     pa.s.apc = c.apc;
     pa.nsteps = nsteps;

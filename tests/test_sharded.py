@@ -371,8 +371,8 @@ def test_sharded_virtual_ranks_on_one_gpu(cuda, world, halo_only):
 @pytest.mark.parametrize('mode', ['0', '1'])
 def test_sharded_virtual_ranks_generic_persistent_kernel(cuda, monkeypatch, mode):
     """the GENERIC persistent kernel (what the barrier path runs on shards too large for the cached one; forced here with
-    LIMEB200_HEOM_NO_CACHED) across 3 virtual ranks: table walk (mode 0) and packed neighbour lists (mode 1, the
-    default) behind the same peer stores and one-hop barrier"""
+    LIMEB200_HEOM_NO_CACHED) across 3 virtual ranks: table walk (mode 0, the default there) and packed neighbour lists
+    (mode 1, opt-in: measured slower in this register-limited kernel) behind the same peer stores and one-hop barrier"""
     monkeypatch.setenv('LIMEB200_HEOM_NO_CACHED', '1')
     monkeypatch.setenv('LIMEB200_HEOM_STAGE_MODE', mode)
     H, Q, lam, gam, T, depth, rho0 = _problem()
