@@ -1083,7 +1083,7 @@ def run_ours(args):
 # and sizes (not measured in the bench run itself: ncu replays kernels, so it cannot share a run with the timed region);
 # key = (workload, units per launch); workloads / sizes without a capture report null
 TRAFFIC = {
-    ('jc_lindblad', 4096000): {'bytes': 1178027008 + 1183905280,
+    ('jc_lindblad', 4096000): {'bytes': 1178165248 + 1183468544,
                                'source': 'profiles/r02_traffic_jc_lindblad_default.csv (ncu --metrics dram__bytes_read.sum,'
                                          'dram__bytes_write.sum on one qme_tile_kernel launch of `python bench.py`: rho in, rho '
                                          'out, observables = 0.11 % of the algorithmic bytes; the state is on chip for 1000 steps)'},
