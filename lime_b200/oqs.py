@@ -333,12 +333,14 @@ class Lindblad_solver():
                          return_result=return_result)
 
     def evolve_batch(self, rho0, dt, Nt, e_ops=None, H_batch=None, store_every=0, path=None,
-                     device_index=None, return_device=False, pinned=False):
+                     device_index=None, return_device=False, pinned=False, obs_every=1):
         """[ext] propagate a batch of density matrices in one launch.
 
         rho0    : [B,N,N] (or [N,N], broadcast to the operator batch)
         H_batch : None (all share self.H) or a list/array of B Hamiltonians with the SAME
                   sparsity pattern (parameter scans: coupling x detuning grids)
+        obs_every : k > 1 returns the observables after steps k, 2k, ... only ([Nt // k, B, E]), sub-sampled on the
+                  device so that the device->host copy shrinks by k
         returns (rho_final [B,N,N], observables [Nt,B,E], rholist [Nt//store_every,B,N,N] or None)"""
         c_ops = [] if self.c_ops is None else list(self.c_ops)
         # the plan (operator analysis + upload) is kept on the solver and reused while the SAME operator objects are
@@ -368,8 +370,8 @@ class Lindblad_solver():
         if return_device:
             d = _dev.h2d(r, dev=plan.dev)
             obs, traj = plan.run_device(d, dt, Nt, traj_every=store_every)
-            return d, obs, traj
-        return plan.run(r, dt, Nt, traj_every=store_every, pinned=pinned)
+            return d, engine.subsample_steps(obs, obs_every), traj
+        return plan.run(r, dt, Nt, traj_every=store_every, pinned=pinned, obs_every=obs_every)
 
     # ---- correlation functions (quantum regression), lime/oqs.py:1196-1331 ---------
     def correlation_2op_1t(self, rho0, a_op, b_op, dt, Nt, output='cor.dat'):
@@ -641,10 +643,12 @@ class Redfield_solver:
             plan.set_path(path)
         return plan.finalize()
 
-    def evolve_batch(self, rho0, dt, Nt, e_ops=None, store_every=0, form='tensor'):
+    def evolve_batch(self, rho0, dt, Nt, e_ops=None, store_every=0, form='tensor', obs_every=1):
         """[ext] batch of initial states [B,N,N] (site basis) in one launch.
         form='tensor': vec(rho) propagated with the CSR tensor R (lime's form);
         form='operator': operator form (O(N^3) per right-hand side instead of O(N^4)).
+        obs_every = k > 1: observables after steps k, 2k, ... only ([Nt // k, B, E]; the device->host stream of a large
+        batch -- 16 bytes per step and state -- is what bounds this call end to end).
         Returns (rho_final [B,N,N] in the EIGENBASIS, observables [Nt,B,E])."""
         if self.R is None:
             self.redfield_tensor()
@@ -657,10 +661,10 @@ class Redfield_solver:
         e_eb = [transform(_dev.as_c128(e), v) for e in (e_ops or [])]
         if form == 'operator':
             plan = self.operator_plan(e_eb)
-            out, obs, _ = plan.run(r_eb, dt, Nt, traj_every=store_every)
+            out, obs, _ = plan.run(r_eb, dt, Nt, traj_every=store_every, obs_every=obs_every)
             return out, obs
         e_rows = [e.T.reshape(-1) for e in e_eb]
-        out, obs, _ = engine.liouville_rk4(self.R, r_eb.reshape(-1, N * N), dt, Nt, e_rows=e_rows)
+        out, obs, _ = engine.liouville_rk4(self.R, r_eb.reshape(-1, N * N), dt, Nt, e_rows=e_rows, obs_every=obs_every)
         return out.reshape(-1, N, N), obs
 
     def gf(self, t, w=None, secular=False, k=1, domain='time', method='EOM'):

@@ -1205,3 +1205,23 @@ def test_rkf45_device_resident_lindblad_and_heom(cuda):
     ado_o, _, _ = lo.heom_rk4(h.initial(rr), Hs, h.Q, h.qmap, h.c, h.nu, st, h.dn.astype(np.int64), h.up.astype(np.int64),
                               0.0005, 2000)
     assert relerr(out[-1][0].cpu().numpy(), ado_o) < 1e-8
+
+
+def test_batch_apis_obs_every(cuda):
+    """[ext] obs_every = k on the batch APIs returns exactly the observables after steps k, 2k, ... of the full run
+    (sub-sampled on the device before the copy; the final states are untouched)"""
+    from lime_b200.oqs import Lindblad_solver, Redfield_solver
+    H, c_ops, e_ops, rho0 = cases.jc_point(ncav=8)
+    s = Lindblad_solver(H, c_ops=c_ops)
+    batch = np.stack([rho0, cases.rand_dm(16, 3)])
+    rf, obs, _ = s.evolve_batch(batch, 0.01, 12, e_ops=e_ops)
+    for pinned in (False, True):
+        rf4, obs4, _ = s.evolve_batch(batch, 0.01, 12, e_ops=e_ops, obs_every=4, pinned=pinned)
+        assert obs4.shape == (3, 2, 2) and np.array_equal(obs4, obs[3::4]) and np.array_equal(rf4, rf)
+    Hs, a_ops, spectra, r0, dt, Nt, e_r, tlist = cases.redfield_example()
+    rs = Redfield_solver(Hs, c_ops=a_ops, spectra=spectra)
+    for form in ('tensor', 'operator'):
+        out, ob = rs.evolve_batch(np.stack([r0, r0]), dt, 12, e_ops=e_r, form=form)
+        out3, ob3 = rs.evolve_batch(np.stack([r0, r0]), dt, 12, e_ops=e_r, form=form, obs_every=3)
+        assert ob3.shape == (4, 2, 1) and np.array_equal(ob3, ob[2::3]) and np.array_equal(out3, out)
+

@@ -338,3 +338,43 @@ def test_rkf45_step_controller_host_logic(rkf45_on_host):
         U = v @ np.diag(np.exp(-1j * w * t)) @ v.conj().T
         assert np.max(np.abs(r - U @ rho0 @ U.conj().T)) < 1e-8
 
+
+def test_obs_every_plumbing_and_device_subsampling(monkeypatch):
+    """obs_every of the batch APIs: the sub-sampling helper keeps the samples after steps k, 2k, ... and both solvers
+    hand the argument down to the layer that copies the observables (checked with stand-in plans: no GPU needed)"""
+    from lime_b200 import engine, oqs
+    o = torch.arange(10 * 2 * 3, dtype=torch.float64).reshape(10, 2, 3)
+    assert engine.subsample_steps(o, 1) is o and engine.subsample_steps(None, 4) is None
+    r = engine.subsample_steps(o, 4)
+    assert r.is_contiguous() and torch.equal(r, o[[3, 7]])
+    assert engine.subsample_steps(o, 11).shape == (0, 2, 3)
+    seen = {}
+
+    class FakePlan:
+        dev = None
+
+        def run(self, rho0, dt, nsteps, **kw):
+            seen['run'] = kw
+            return 'rho', 'obs', 'traj'
+    monkeypatch.setattr(oqs, '_lindblad_plan', lambda *a, **k: FakePlan())
+    H, c_ops, e_ops, rho0 = cases.jc_point(ncav=4)
+    s = oqs.Lindblad_solver(H, c_ops=c_ops)
+    assert s.evolve_batch(rho0, 0.01, 8, e_ops=e_ops, obs_every=4) == ('rho', 'obs', 'traj')
+    assert seen['run']['obs_every'] == 4 and seen['run']['traj_every'] == 0
+    s.evolve_batch(rho0, 0.01, 8, e_ops=e_ops)
+    assert seen['run']['obs_every'] == 1
+    # Redfield: tensor form -> engine.liouville_rk4, operator form -> the plan's run
+    Hs, a_ops, spectra, r0, dt, Nt, e_r, tlist = cases.redfield_example()
+    rs = oqs.Redfield_solver(Hs, c_ops=a_ops, spectra=spectra)
+    rs.redfield_tensor()
+
+    def fake_rk4(R, v0, dt, nsteps, **kw):
+        seen['rk4'] = kw
+        return np.asarray(v0), None, None
+    monkeypatch.setattr(engine, 'liouville_rk4', fake_rk4)
+    rs.evolve_batch(r0, dt, 8, e_ops=e_r, obs_every=2)
+    assert seen['rk4']['obs_every'] == 2
+    monkeypatch.setattr(rs, 'operator_plan', lambda e: FakePlan())
+    rs.evolve_batch(r0, dt, 8, e_ops=e_r, obs_every=2, form='operator')
+    assert seen['run']['obs_every'] == 2
+
