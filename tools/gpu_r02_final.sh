@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: the kernel variants 1-6 and LIMEB200_HEOM_NO_L2_CHUNK this script times existed at commits 5c37e0c..4f25238 only
+# (results: profiles/r02_tile_variants_pass1.jsonl, r02_heom_batch64_l2_slices.jsonl); later trees ignore those values.
 # Round-2 final GPU pass (one gpurun call, 1 GPU): microbenchmark of the tensor-memory port, the GPU test suite,
 # timing of the qme_tile_kernel variants, the L2-sliced HEOM batch, the default bench line with the fastest variant,
 # and the ncu captures of that variant.  Everything lands in gpurun_out/ as it is produced.

@@ -1,4 +1,6 @@
 #!/bin/bash
+# NOTE: run at commit bb4ed64 (first heom_stage_fast_kernel, LIMEB200_HEOM_FAST_OCC); results in
+# profiles/r02_tile_variants_pass2.jsonl, r02_heom_stage_modes_pass2.jsonl.  LIMEB200_HEOM_FAST_OCC no longer exists.
 # Round-2 second GPU pass (one gpurun call, 1 GPU): test suite, qme_tile_kernel variant 8 against variant 0, the HEOM
 # stage-kernel modes (0 table walk, 1 packed gather in the generic tile code, 2 heom_stage_fast_kernel at 2 / 3 / 4 CTAs
 # per SM) on the 38 760-ADO hierarchy and on the batch of 64, the default bench line with the winners, ncu captures.
