@@ -261,15 +261,15 @@ __device__ __forceinline__ void qme_tile_stage(const QmeTileCtx<NP, TR, S>& c, c
 }
 
 // TW ("tensor-memory window", opt-in: LIMEB200_TILE_V=8): the thread's OWN rows of the stage vector come from tensor
-// memory, and the warp-uniform row coefficients from shared memory as three 16-byte broadcasts.  The measurements of
-// round 2 (tools/ubench/tmem_bw.cu: tcgen05.ld 439 B/clk per SM, tcgen05.st 619 B/clk, against 128 B/clk of shared
-// memory; ncu: 42.7 shared-memory wavefronts per warp and patch row, shared-memory pipe 63-77 %; variants 2/4/6 all
-// slower in proportion to the wavefronts they add) say the kernel is bound by the shared-memory pipe and that tensor
-// memory is the cheap port.  Of the (TR + 2) x 2 window loads of a stage, TR x 2 re-read values the SAME thread stored in
-// the previous stage; they now live in a third tensor-memory slot per row ([rho 8][acc 8][y 8]), updated in place
-// (row r + 1 is fetched one row ahead, before row r is overwritten), and only the two halo rows of the window, the
-// left / right / sandwich neighbours and the row coefficients still come from shared memory: 31 wavefronts per warp and
-// patch row instead of 42.7.  The values still go to shared memory too -- the other threads read them there.
+// memory, and the warp-uniform row coefficients from shared memory as three 16-byte broadcasts.  Tensor memory is the
+// cheap port (tools/ubench/tmem_bw.cu: tcgen05.ld 439 B/clk per SM, tcgen05.st 619 B/clk, against 128 B/clk of shared
+// memory).  Of the (TR + 2) x 2 window loads of a stage, TR x 2 re-read values the SAME thread stored in the previous
+// stage; here they live in a third tensor-memory slot per row ([rho 8][acc 8][y 8]), updated in place (row r + 1 is
+// fetched one row ahead, before row r is overwritten), and only the two halo rows of the window, the left / right /
+// sandwich neighbours and the row coefficients still come from shared memory: 31 wavefronts per warp and patch row
+// instead of 42.7.  The values still go to shared memory too -- the other threads read them there.
+// Measured: 4.66e6 against 4.62e6 rho-steps/s, i.e. nothing -- the kernel is bound by the latency of a warp's dependent
+// chain, not by the shared-memory pipe -- so this stays the opt-in form; identical bits.
 template <int NP, int TR, int S, int STAGE>
 __device__ __forceinline__ void qme_tile_stage_t(const QmeTileCtx<NP, TR, S>& c, char* smem, unsigned bufb) {
     constexpr int ROWB = NP * 16;
